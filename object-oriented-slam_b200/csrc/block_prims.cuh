@@ -1,0 +1,189 @@
+// block_prims.cuh -- CTA-wide primitives used by the per-object extraction kernels: deterministic reductions,
+// ordered (stable) stream compaction, and a stable LSD radix sort of (key, value) pairs living in global memory.
+// One CTA owns one object, so everything here synchronises with __syncthreads() only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace eslam {
+
+constexpr int kMaxWarps = 32;
+
+struct BlockScratch {            // shared-memory scratch, one per CTA
+  int warp_i[kMaxWarps + 1];
+  float warp_f[kMaxWarps * 6];
+  double warp_d[kMaxWarps * 9];
+  int bcast_i[8];
+  double bcast_d[16];
+};
+
+constexpr int kRadixWarps = 16;   // block_radix_sort supports CTAs of up to 512 threads
+struct RadixScratch {
+  unsigned int radix[kRadixWarps * 256];   // per-warp digit counters
+  unsigned int digit_base[256];
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+__device__ __forceinline__ int n_warps() { return (blockDim.x + 31) >> 5; }
+
+// exclusive prefix sum of one int per thread (thread order); returns exclusive prefix, total through `total`
+__device__ __forceinline__ int block_excl_scan(int v, BlockScratch &S, int &total) {
+  int lane = lane_id(), w = warp_id();
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) S.warp_i[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int nw = n_warps();
+    int x = (lane < nw) ? S.warp_i[lane] : 0;
+    int xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+    if (lane < nw) S.warp_i[lane] = xi - x;
+    if (lane == 31) S.warp_i[kMaxWarps] = xi;
+  }
+  __syncthreads();
+  int res = S.warp_i[w] + inc - v;
+  total = S.warp_i[kMaxWarps];
+  __syncthreads();
+  return res;
+}
+
+__device__ __forceinline__ int block_sum_int(int v, BlockScratch &S) { int tot; block_excl_scan(v, S, tot); return tot; }
+
+// K-wide deterministic fp64 sum (fixed butterfly + fixed warp order): every thread gets the result in out[]
+template <int K>
+__device__ __forceinline__ void block_sum_double(double *v, BlockScratch &S) {
+  int lane = lane_id(), w = warp_id(), nw = n_warps();
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) S.warp_d[w * K + k] = x;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double acc = 0;
+    for (int i = 0; i < nw; i++) acc += S.warp_d[i * K + k];
+    v[k] = acc;
+  }
+  __syncthreads();
+}
+
+// min/max of 3 floats (order independent => exact)
+__device__ __forceinline__ void block_minmax3(float *mn, float *mx, BlockScratch &S) {
+  int lane = lane_id(), w = warp_id(), nw = n_warps();
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float a = mn[k], b = mx[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o)); }
+    if (lane == 0) { S.warp_f[w * 6 + k] = a; S.warp_f[w * 6 + 3 + k] = b; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    float a = S.warp_f[k], b = S.warp_f[3 + k];
+    for (int i = 1; i < nw; i++) { a = fminf(a, S.warp_f[i * 6 + k]); b = fmaxf(b, S.warp_f[i * 6 + 3 + k]); }
+    mn[k] = a; mx[k] = b;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ double block_min_double(double v, BlockScratch &S) {
+  int lane = lane_id(), w = warp_id(), nw = n_warps();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) S.warp_d[w] = v;
+  __syncthreads();
+  double r = S.warp_d[0];
+  for (int i = 1; i < nw; i++) r = fmin(r, S.warp_d[i]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ unsigned block_max_u32(unsigned v, BlockScratch &S) {
+  int lane = lane_id(), w = warp_id(), nw = n_warps();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) S.warp_i[w] = (int)v;
+  __syncthreads();
+  unsigned r = (unsigned)S.warp_i[0];
+  for (int i = 1; i < nw; i++) r = max(r, (unsigned)S.warp_i[i]);
+  __syncthreads();
+  return r;
+}
+
+// Stable LSD radix sort of n (key,val) pairs, 8-bit digits, keys < 2^bits.  Warp w owns the contiguous chunk
+// [w*chunk, (w+1)*chunk); ranks inside a chunk come from __match_any_sync so equal keys keep their input order.
+// Result ends in (k0,v0).  k1/v1 are scratch of the same size.
+static __device__ void block_radix_sort(unsigned *k0, unsigned *v0, unsigned *k1, unsigned *v1, int n, int bits, RadixScratch &S) {
+  const int lane = lane_id(), w = warp_id(), nw = n_warps();
+  int chunk = (n + nw - 1) / nw;
+  chunk = (chunk + 31) & ~31;
+  const int beg = min(n, w * chunk), end = min(n, beg + chunk);
+  unsigned *ki = k0, *vi = v0, *ko = k1, *vo = v1;
+  int passes = (bits + 7) / 8;
+  if (passes < 1) passes = 1;
+  for (int p = 0; p < passes; p++) {
+    const int shift = p * 8;
+    for (int i = threadIdx.x; i < nw * 256; i += blockDim.x) S.radix[i] = 0;
+    __syncthreads();
+    unsigned *cnt = &S.radix[w * 256];
+    for (int i = beg; i < end; i += 32) {
+      int j = i + lane;
+      bool valid = j < end;
+      unsigned d = valid ? ((ki[j] >> shift) & 255u) : (256u + lane);
+      unsigned peers = __match_any_sync(0xffffffffu, d);
+      if (valid && (__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    // exclusive scan over (digit major, warp minor)
+    if (threadIdx.x < 256) {
+      unsigned run = 0;
+      for (int ww = 0; ww < nw; ww++) { unsigned c = S.radix[ww * 256 + threadIdx.x]; S.radix[ww * 256 + threadIdx.x] = run; run += c; }
+      S.digit_base[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (w == 0) {  // exclusive scan of the 256 digit totals
+      unsigned carry = 0;
+      for (int b = 0; b < 256; b += 32) {
+        unsigned x = S.digit_base[b + lane];
+        unsigned inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        S.digit_base[b + lane] = carry + inc - x;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    __syncthreads();
+    for (int i = beg; i < end; i += 32) {
+      int j = i + lane;
+      bool valid = j < end;
+      unsigned key = valid ? ki[j] : 0u, val = valid ? vi[j] : 0u;
+      unsigned d = valid ? ((key >> shift) & 255u) : (256u + lane);
+      unsigned peers = __match_any_sync(0xffffffffu, d);
+      unsigned base = valid ? (cnt[d] + S.digit_base[d]) : 0u;
+      unsigned rank = __popc(peers & ((1u << lane) - 1u));
+      __syncwarp();
+      if (valid && (__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
+      __syncwarp();
+      if (valid) { ko[base + rank] = key; vo[base + rank] = val; }
+    }
+    __syncthreads();
+    unsigned *t;
+    t = ki; ki = ko; ko = t;
+    t = vi; vi = vo; vo = t;
+  }
+  if (ki != k0) {  // odd number of passes: copy back
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { k0[i] = ki[i]; v0[i] = vi[i]; }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ int bits_for(unsigned maxval) { return maxval == 0 ? 1 : (32 - __clz(maxval)); }
+
+}  // namespace eslam

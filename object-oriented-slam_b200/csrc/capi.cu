@@ -1,0 +1,361 @@
+// capi.cu -- extern "C" boundary of libeslam_b200.so (include/eslam.h).  Host-side orchestration only: builds the
+// tiny per-object metadata, moves bulk data H2D/D2H for the *_host entry points and launches the kernels.
+// There is no CPU implementation of any hot-path stage in this library.
+#include <math.h>
+#include <new>
+#include "common.cuh"
+#include "extract_types.cuh"
+#include "internal.h"
+
+using namespace eslam;
+
+namespace {
+
+int symmetry_type_of_label(int label) {  // EllipsoidExtractor::LoadSymmetryPrior, src/pca/EllipsoidExtractor.cpp:52-79
+  switch (label) {
+    case 58: return 0;
+    case 59: case 62: case 57: case 66: case 63: case 64: case 41: return 1;
+    case 28: return 2;
+    default: return -1;
+  }
+}
+
+// host fp64 helpers for the two trivial pose utilities of the ABI (Frame.cpp:13-14, Plane.cpp:117-122)
+struct HQ { double x, y, z, w; };
+void h_rot(const HQ &q, const double v[3], double o[3]) {
+  double uv[3] = {q.y * v[2] - q.z * v[1], q.z * v[0] - q.x * v[2], q.x * v[1] - q.y * v[0]};
+  for (int i = 0; i < 3; i++) uv[i] += uv[i];
+  double c[3] = {q.y * uv[2] - q.z * uv[1], q.z * uv[0] - q.x * uv[2], q.x * uv[1] - q.y * uv[0]};
+  for (int i = 0; i < 3; i++) o[i] = v[i] + q.w * uv[i] + c[i];
+}
+
+ExtractParamsDev make_dev_params(const EslamHandle *h) {
+  ExtractParamsDev d;
+  const EslamParams &p = h->prm; const EslamCamera &c = h->cam;
+  d.fx = c.fx; d.fy = c.fy; d.cx = c.cx; d.cy = c.cy; d.scale = c.scale; d.depth_range = p.depth_range;
+  d.rows = c.rows; d.cols = c.cols;
+  d.voxel_leaf = (float)p.voxel_leaf; d.sym_leaf = (float)p.symmetry_grid;
+  for (int i = 0; i < 4; i++) d.plane[i] = h->plane_world[i];
+  d.plane_margin = p.plane_margin;
+  d.cluster_r2 = (float)(p.cluster_tolerance * p.cluster_tolerance);
+  d.cluster_cell = (float)(p.cluster_tolerance * 1.01);
+  d.min_cluster = p.min_cluster_size;
+  d.center_dis = p.center_dis;
+  d.sigma = p.symmetry_sigma;
+  d.symmetry_open = p.symmetry_open; d.symmetry_iters = p.symmetry_iters;
+  double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1};
+  for (int i = 0; i < 9; i++) d.K[i] = K[i];
+  return d;
+}
+
+// builds ObjMeta for a batch, (re)allocates the workspace, uploads the metadata
+int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const int *frame_of_obj, const double *bbox4, const int *label, const double *Twc7,
+                  bool want_dump, ExtractPtrs &P) {
+  if (!h->ex) h->ex = new ExtractWorkspace();
+  ExtractWorkspace &w = *h->ex;
+  w.meta_host.resize(n_obj);
+  long long off = 0;
+  for (int i = 0; i < n_obj; i++) {
+    ObjMeta &m = w.meta_host[i];
+    memset(&m, 0, sizeof(m));
+    m.frame = frame_of_obj[i]; m.label = label[i];
+    m.symtype = h->prm.symmetry_open ? symmetry_type_of_label(label[i]) : -1;
+    for (int k = 0; k < 4; k++) m.bbox[k] = bbox4[4 * i + k];
+    m.x1 = (int)m.bbox[0]; m.y1 = (int)m.bbox[1]; m.x2 = (int)m.bbox[2]; m.y2 = (int)m.bbox[3];
+    bool inside = m.frame >= 0 && m.frame < n_frames && m.x1 >= 0 && m.y1 >= 0 && m.x2 <= h->cam.cols && m.y2 <= h->cam.rows;
+    m.pre_status = inside ? 0 : ESLAM_OBJ_BBOX_OUTSIDE;
+    m.nx = (inside && m.x2 > m.x1) ? (m.x2 - m.x1 + 2) / 3 : 0;
+    m.ny = (inside && m.y2 > m.y1) ? (m.y2 - m.y1 + 2) / 3 : 0;
+    long long cap = (long long)m.nx * m.ny;
+    cap = (cap + 31) & ~31LL;
+    if (cap < 32) cap = 32;
+    m.off = (int)off; m.cap = (int)cap;
+    off += cap;
+    if (off > 0x7fffffffLL / 4) return ESLAM_ERR_CAPACITY;
+    if (inside) for (int k = 0; k < 7; k++) m.Twc[k] = Twc7[7 * m.frame + k];
+  }
+  w.cap_total = off; w.n_obj = n_obj;
+  const size_t CAP = (size_t)off;
+  ESLAM_CUDA_OK(h, w.meta.reserve(sizeof(ObjMeta) * (size_t)n_obj));
+  ESLAM_CUDA_OK(h, w.state.reserve(sizeof(ObjState) * (size_t)n_obj));
+  ESLAM_CUDA_OK(h, w.out.reserve(sizeof(EslamEllipsoidOut) * (size_t)n_obj));
+  ESLAM_CUDA_OK(h, w.ptsA.reserve(CAP * 16)); ESLAM_CUDA_OK(h, w.ptsB.reserve(CAP * 16)); ESLAM_CUDA_OK(h, w.ptsC.reserve(CAP * 16));
+  ESLAM_CUDA_OK(h, w.k0.reserve(CAP * 4)); ESLAM_CUDA_OK(h, w.k1.reserve(CAP * 4)); ESLAM_CUDA_OK(h, w.v0.reserve(CAP * 4)); ESLAM_CUDA_OK(h, w.v1.reserve(CAP * 4));
+  ESLAM_CUDA_OK(h, w.parent.reserve(CAP * 4)); ESLAM_CUDA_OK(h, w.count.reserve(CAP * 4));
+  ESLAM_CUDA_OK(h, w.objn.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.objnf.reserve(CAP * 16));
+  P.ptsA = w.ptsA.as<float4>(); P.ptsB = w.ptsB.as<float4>(); P.ptsC = w.ptsC.as<float4>();
+  P.k0 = w.k0.as<unsigned>(); P.k1 = w.k1.as<unsigned>(); P.v0 = w.v0.as<unsigned>(); P.v1 = w.v1.as<unsigned>();
+  P.parent = w.parent.as<int>(); P.count = w.count.as<int>();
+  P.objn = w.objn.as<double>(); P.objnf = w.objnf.as<float4>();
+  P.d_crop = P.d_voxel = P.d_world = P.d_sym = P.d_final = nullptr; P.d_label = nullptr;
+  if (want_dump) {
+    ESLAM_CUDA_OK(h, w.d_crop.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_voxel.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_world.reserve(CAP * 24));
+    ESLAM_CUDA_OK(h, w.d_sym.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_final.reserve(CAP * 96)); ESLAM_CUDA_OK(h, w.d_label.reserve(CAP * 4));
+    P.d_crop = w.d_crop.as<double>(); P.d_voxel = w.d_voxel.as<double>(); P.d_world = w.d_world.as<double>();
+    P.d_sym = w.d_sym.as<double>(); P.d_final = w.d_final.as<double>(); P.d_label = w.d_label.as<int>();
+  }
+  ESLAM_CUDA_OK(h, w.pin_meta.reserve(sizeof(ObjMeta) * (size_t)n_obj));
+  memcpy(w.pin_meta.p, w.meta_host.data(), sizeof(ObjMeta) * (size_t)n_obj);
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(w.meta.p, w.pin_meta.p, sizeof(ObjMeta) * (size_t)n_obj, cudaMemcpyHostToDevice, s));
+  return ESLAM_OK;
+}
+
+int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *depth_dev, size_t pitch, int n_obj, const int *frame_of_obj, const double *bbox4,
+                const int *label, const double *Twc7, bool want_dump, ExtractPtrs &P) {
+  if (!h->plane_set) { h->err = "supporting plane not set (eslam_set_supporting_plane)"; return ESLAM_ERR_NO_PLANE; }
+  if (n_obj <= 0 || n_frames <= 0 || !depth_dev || !frame_of_obj || !bbox4 || !label || !Twc7) return ESLAM_ERR_BAD_ARG;
+  if (pitch < (size_t)h->cam.cols) return ESLAM_ERR_BAD_ARG;
+  int rc = prepare_batch(h, s, n_frames, n_obj, frame_of_obj, bbox4, label, Twc7, want_dump, P);
+  if (rc) return rc;
+  ExtractParamsDev prm = make_dev_params(h);
+  size_t frame_stride = (size_t)h->cam.rows * pitch;
+  if ((rc = extract_launch(h, s, depth_dev, pitch, frame_stride, n_obj, prm, P))) return rc;
+  if ((rc = symmetry_finalize_launch(h, s, depth_dev, pitch, frame_stride, n_obj, prm, P))) return rc;
+  return ESLAM_OK;
+}
+
+int fetch_dump(EslamHandle *h, cudaStream_t s, int n_obj, const ExtractPtrs &P, const EslamEllipsoidOut *out, EslamStageDump *dump) {
+  ExtractWorkspace &w = *h->ex;
+  std::vector<ObjState> states(n_obj);
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(states.data(), w.state.p, sizeof(ObjState) * (size_t)n_obj, cudaMemcpyDeviceToHost, s));
+  ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
+  for (int i = 0; i < n_obj; i++) {
+    const ObjMeta &m = w.meta_host[i];
+    const ObjState &st = states[i];
+    EslamStageDump &d = dump[i];
+    const int cap = d.cap_points;
+    auto cp = [&](double *dst, const double *src_dev, size_t off_pts, int n) -> int {
+      if (!dst || n <= 0) return 0;
+      int k = n < cap ? n : cap;
+      cudaError_t e = cudaMemcpyAsync(dst, src_dev + 3 * off_pts, sizeof(double) * 3 * (size_t)k, cudaMemcpyDeviceToHost, s);
+      return e == cudaSuccess ? 0 : 1;
+    };
+    int bad = 0;
+    bad |= cp(d.crop_xyz, P.d_crop, m.off, out[i].n_crop);
+    bad |= cp(d.voxel_xyz, P.d_voxel, m.off, out[i].n_voxel);
+    bad |= cp(d.world_xyz, P.d_world, m.off, out[i].n_plane);
+    bad |= cp(d.sym_xyz, P.d_sym, m.off, out[i].n_sym);
+    bad |= cp(d.final_xyz, P.d_final, (size_t)4 * m.off, out[i].n_final);
+    if (d.cluster_label && out[i].n_plane > 0 && out[i].status != ESLAM_OBJ_NO_POINTS_AFTER_PLANE && out[i].status != ESLAM_OBJ_NO_CENTER) {
+      int k = out[i].n_plane < cap ? out[i].n_plane : cap;
+      if (cudaMemcpyAsync(d.cluster_label, P.d_label + m.off, sizeof(int) * (size_t)k, cudaMemcpyDeviceToHost, s) != cudaSuccess) bad = 1;
+    }
+    if (bad) { h->err = "dump copy failed"; return ESLAM_ERR_CUDA; }
+    for (int k = 0; k < 3; k++) { d.center_world[k] = st.center[k]; d.pca_center[k] = st.pca_center[k]; d.pca_eval[k] = st.pca_eval[k]; }
+    for (int k = 0; k < 9; k++) d.pca_rot[k] = st.pca_rot[k];
+    for (int k = 0; k < 7; k++) d.T_wo[k] = st.T_wo[k];
+    for (int sd = 0; sd < 9; sd++) {
+      d.seed_prob[sd] = st.seed_prob[sd]; d.seed_init_err[sd] = st.seed_init[sd]; d.seed_final_err[sd] = st.seed_final[sd]; d.seed_dual_dis[sd] = st.seed_dual[sd];
+      for (int k = 0; k < 4; k++) d.seed_plane[sd][k] = st.seed_plane[sd][k];
+    }
+  }
+  ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
+  return ESLAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eslam_abi_version(void) { return ESLAM_ABI_VERSION; }
+
+void eslam_default_params(EslamParams *p) {
+  p->depth_range = 6.0; p->voxel_leaf = 0.01; p->plane_margin = 0.05; p->cluster_tolerance = 0.02; p->min_cluster_size = 100; p->center_dis = 0.5;
+  p->symmetry_open = 1; p->symmetry_grid = 0.1; p->symmetry_sigma = 0.1; p->symmetry_iters = 5;
+  p->plane_min_size = 200; p->plane_angle_deg = 5.0; p->plane_dist = 0.1;
+  p->edge3d_scale = 10000.0; p->gravity_prior_open = 1; p->gravity_prior_scale = 100.0; p->border_pixels = 10; p->length_limit_pixels = 0;
+}
+void eslam_default_camera(EslamCamera *c) { c->fx = 535.4; c->fy = 539.2; c->cx = 320.1; c->cy = 247.6; c->scale = 5000.0; c->rows = 480; c->cols = 640; }
+
+int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHandle **out) {
+  if (!p || !c || !out) return ESLAM_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return ESLAM_ERR_NO_DEVICE;  // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return ESLAM_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ESLAM_ERR_NO_DEVICE;
+  EslamHandle *h = new (std::nothrow) EslamHandle();
+  if (!h) return ESLAM_ERR_CUDA;
+  h->prm = *p; h->cam = *c; h->device = device; h->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return ESLAM_ERR_CUDA; }
+  *out = h;
+  return ESLAM_OK;
+}
+
+void eslam_destroy(EslamHandle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->ex) {
+    ExtractWorkspace &w = *h->ex;
+    DevBuf *bufs[] = {&w.meta, &w.state, &w.out, &w.ptsA, &w.ptsB, &w.ptsC, &w.k0, &w.k1, &w.v0, &w.v1, &w.parent, &w.count, &w.objn, &w.objnf, &w.symscratch,
+                      &w.d_crop, &w.d_voxel, &w.d_world, &w.d_sym, &w.d_final, &w.d_label, &w.depth};
+    for (DevBuf *b : bufs) b->release();
+    w.pin_meta.release(); w.pin_out.release(); w.pin_depth.release();
+    delete h->ex;
+  }
+  graph_free(h);
+  plane_free(h);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char *eslam_last_error(EslamHandle *h) { return h ? h->err.c_str() : "null handle"; }
+long long eslam_launch_count(EslamHandle *h) { return h ? h->launches : 0; }
+
+size_t eslam_sizeof_params(void) { return sizeof(EslamParams); }
+size_t eslam_sizeof_camera(void) { return sizeof(EslamCamera); }
+size_t eslam_sizeof_ellipsoid_out(void) { return sizeof(EslamEllipsoidOut); }
+size_t eslam_sizeof_stage_dump(void) { return sizeof(EslamStageDump); }
+size_t eslam_sizeof_edge_batch(void) { return sizeof(EslamEdgeBatch); }
+size_t eslam_sizeof_lm_stats(void) { return sizeof(EslamLmStats); }
+
+// ---------------- ground plane ----------------
+int eslam_extract_ground_plane_dev(EslamHandle *h, void *stream, int n_frames, const uint16_t *depth_dev, size_t pitch, double *plane_cam_host, int *found_host,
+                                   int *n_inliers_host) {
+  if (!h || n_frames <= 0 || !depth_dev || !plane_cam_host || !found_host) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  return plane_extract(h, s, n_frames, depth_dev, pitch, plane_cam_host, found_host, n_inliers_host);
+}
+int eslam_extract_ground_plane_host(EslamHandle *h, int n_frames, const uint16_t *depth, size_t pitch, double *plane_cam, int *found, int *n_inliers) {
+  if (!h || n_frames <= 0 || !depth || !plane_cam || !found) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  if (!h->ex) h->ex = new ExtractWorkspace();
+  size_t bytes = (size_t)n_frames * h->cam.rows * pitch * sizeof(uint16_t);
+  ESLAM_CUDA_OK(h, h->ex->depth.reserve(bytes));
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(h->ex->depth.p, depth, bytes, cudaMemcpyHostToDevice, h->stream));
+  return plane_extract(h, h->stream, n_frames, h->ex->depth.as<uint16_t>(), pitch, plane_cam, found, n_inliers);
+}
+
+// test-only hook (not in include/eslam.h): intermediate buffers of the plane pipeline for stage-isolated parity tests
+int eslam_debug_plane_stage(EslamHandle *h, const uint16_t *depth, size_t pitch, int stage, void *out) {
+  if (!h || !depth || !out || stage < 1 || stage > 4) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  if (!h->ex) h->ex = new ExtractWorkspace();
+  size_t bytes = (size_t)h->cam.rows * pitch * sizeof(uint16_t);
+  ESLAM_CUDA_OK(h, h->ex->depth.reserve(bytes));
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(h->ex->depth.p, depth, bytes, cudaMemcpyHostToDevice, h->stream));
+  double pl[4]; int found = 0, inl = 0;
+  return plane_extract_dbg(h, h->stream, 1, h->ex->depth.as<uint16_t>(), pitch, pl, &found, &inl, stage, out);
+}
+
+void eslam_plane_to_world(const double pc[4], const double Twc[7], double pw[4]) {
+  // param = (Twc^T)^-1 * param with Twc = to_homogeneous_matrix() of the (possibly non-unit) quaternion pose:
+  // generic 4x4 inverse like the reference (src/core/Plane.cpp:117-122), no rigid-body shortcut.
+  const double x = Twc[3], y = Twc[4], z = Twc[5], w = Twc[6];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  double T[4][4] = {{1.0 - (tyy + tzz), txy - twz, txz + twy, Twc[0]},
+                    {txy + twz, 1.0 - (txx + tzz), tyz - twx, Twc[1]},
+                    {txz - twy, tyz + twx, 1.0 - (txx + tyy), Twc[2]},
+                    {0, 0, 0, 1}};
+  double a[4][8];
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { a[i][j] = T[j][i]; a[i][4 + j] = (i == j) ? 1.0 : 0.0; }   // transpose | I
+  for (int c = 0; c < 4; c++) {
+    int p = c; double best = fabs(a[c][c]);
+    for (int r = c + 1; r < 4; r++) if (fabs(a[r][c]) > best) { best = fabs(a[r][c]); p = r; }
+    if (p != c) for (int j = 0; j < 8; j++) { double t = a[p][j]; a[p][j] = a[c][j]; a[c][j] = t; }
+    double piv = a[c][c];
+    for (int j = 0; j < 8; j++) a[c][j] /= piv;
+    for (int r = 0; r < 4; r++) if (r != c) { double f = a[r][c]; if (f != 0.0) for (int j = 0; j < 8; j++) a[r][j] -= f * a[c][j]; }
+  }
+  for (int i = 0; i < 4; i++) { double s = a[i][4] * pc[0]; for (int k = 1; k < 4; k++) s += a[i][4 + k] * pc[k]; pw[i] = s; }
+}
+
+int eslam_set_supporting_plane(EslamHandle *h, const double pw[4]) {
+  if (!h || !pw) return ESLAM_ERR_BAD_ARG;
+  for (int i = 0; i < 4; i++) h->plane_world[i] = pw[i];
+  h->plane_set = true;
+  return ESLAM_OK;
+}
+
+int eslam_calibrate_measurement(const EslamParams *p, const EslamCamera *c, const double m[4]) {  // dataprocess_utils.cpp:150-190
+  int x_length = (int)(m[2] - m[0]), y_length = (int)(m[3] - m[1]);
+  if (x_length < p->length_limit_pixels || y_length < p->length_limit_pixels) return 1;
+  int correct = 0; const int b = p->border_pixels;
+  if (m[0] > b && m[0] < c->cols - 1 - b) correct++;
+  if (m[2] > b && m[2] < c->cols - 1 - b) correct++;
+  if (m[1] > b && m[1] < c->rows - 1 - b) correct++;
+  if (m[3] > b && m[3] < c->rows - 1 - b) correct++;
+  return correct != 4 ? 1 : 0;
+}
+
+// ---------------- ellipsoid extraction ----------------
+int eslam_estimate_ellipsoids_dev(EslamHandle *h, void *stream, int n_frames, const uint16_t *depth_dev, size_t pitch, int n_obj, const int *frame_of_obj,
+                                  const double *bbox4, const int *label, const double *Twc7) {
+  if (!h) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  ExtractPtrs P;
+  return run_extract(h, s, n_frames, depth_dev, pitch, n_obj, frame_of_obj, bbox4, label, Twc7, false, P);
+}
+int eslam_fetch_ellipsoids(EslamHandle *h, void *stream, int n_obj, EslamEllipsoidOut *out) {
+  if (!h || !h->ex || !out || n_obj <= 0 || n_obj > h->ex->n_obj) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(out, h->ex->out.p, sizeof(EslamEllipsoidOut) * (size_t)n_obj, cudaMemcpyDeviceToHost, s));
+  ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
+  return ESLAM_OK;
+}
+int eslam_estimate_ellipsoids_host(EslamHandle *h, int n_frames, const uint16_t *depth, size_t pitch, int n_obj, const int *frame_of_obj, const double *bbox4,
+                                   const int *label, const double *Twc7, EslamEllipsoidOut *out, EslamStageDump *dump) {
+  if (!h || !depth || !out || n_frames <= 0) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  cudaStream_t s = h->stream;
+  if (!h->ex) h->ex = new ExtractWorkspace();
+  size_t bytes = (size_t)n_frames * h->cam.rows * pitch * sizeof(uint16_t);
+  ESLAM_CUDA_OK(h, h->ex->depth.reserve(bytes));
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(h->ex->depth.p, depth, bytes, cudaMemcpyHostToDevice, s));
+  ExtractPtrs P;
+  int rc = run_extract(h, s, n_frames, h->ex->depth.as<uint16_t>(), pitch, n_obj, frame_of_obj, bbox4, label, Twc7, dump != nullptr, P);
+  if (rc) return rc;
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(out, h->ex->out.p, sizeof(EslamEllipsoidOut) * (size_t)n_obj, cudaMemcpyDeviceToHost, s));
+  ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
+  if (dump) return fetch_dump(h, s, n_obj, P, out, dump);
+  return ESLAM_OK;
+}
+
+// ---------------- initializer ----------------
+int eslam_init_quadric(EslamHandle *h, int n_obs, const double *Twc7, const double *det5, const double K[9], int rows, int cols, double e10[10], int *ok) {
+  if (!h || n_obs <= 0 || !Twc7 || !det5 || !K || !e10 || !ok) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  return init_quadric_device(h, h->stream, n_obs, Twc7, det5, K, rows, cols, e10, ok);
+}
+
+// ---------------- graph ----------------
+int eslam_edges_upload(EslamHandle *h, const EslamEdgeBatch *g, const double *ell) {
+  if (!h || !g || !ell) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  return graph_upload(h, g, ell, h->stream);
+}
+int eslam_edges_eval_dev(EslamHandle *h, void *stream) {
+  if (!h) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  return graph_eval(h, stream ? (cudaStream_t)stream : h->stream, true);
+}
+int eslam_edges_download(EslamHandle *h, double *res, double *jac, double *chi2) {
+  if (!h) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  return graph_download(h, res, jac, chi2, h->stream);
+}
+int eslam_edges_eval_host(EslamHandle *h, const EslamEdgeBatch *g, const double *ell, double *res, double *jac, double *chi2) {
+  int rc = eslam_edges_upload(h, g, ell);
+  if (rc) return rc;
+  if ((rc = graph_eval(h, h->stream, true))) return rc;
+  return graph_download(h, res, jac, chi2, h->stream);
+}
+int eslam_optimize_objects_host(EslamHandle *h, const EslamEdgeBatch *g, int iters, double *ell, EslamLmStats *stats) {
+  int rc = eslam_edges_upload(h, g, ell);
+  if (rc) return rc;
+  return graph_optimize(h, iters, ell, stats, h->stream);
+}
+
+void eslam_pose_inverse(const double T[7], double Ti[7]) {  // SE3Quat::inverse, se3quat.h:129-134
+  HQ qc{-T[3], -T[4], -T[5], T[6]};
+  double mt[3] = {T[0] * -1., T[1] * -1., T[2] * -1.}, o[3];
+  h_rot(qc, mt, o);
+  Ti[0] = o[0]; Ti[1] = o[1]; Ti[2] = o[2]; Ti[3] = qc.x; Ti[4] = qc.y; Ti[5] = qc.z; Ti[6] = qc.w;
+}
+
+}  // extern "C"

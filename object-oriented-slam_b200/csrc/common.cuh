@@ -1,0 +1,77 @@
+// common.cuh -- handle, device-buffer helpers and launch accounting shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/eslam.h"
+
+namespace eslam {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  // grow-only device buffer
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    size_t want = need + need / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) bytes = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct PinBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; bytes = 0;
+    size_t want = need + need / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) bytes = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct ExtractWorkspace;  // extract.cu
+struct GraphWorkspace;    // edges.cu
+struct PlaneWorkspace;    // plane.cu
+
+}  // namespace eslam
+
+struct EslamHandle {
+  EslamParams prm;
+  EslamCamera cam;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;  // owned stream used by the *_host entry points
+  bool plane_set = false;
+  double plane_world[4] = {0, 0, 1, 0};
+  long long launches = 0;
+  std::string err;
+  eslam::ExtractWorkspace *ex = nullptr;
+  eslam::GraphWorkspace *gr = nullptr;
+  eslam::PlaneWorkspace *pl = nullptr;
+};
+
+#define ESLAM_CUDA_OK(h, call)                                                                       \
+  do {                                                                                               \
+    cudaError_t _e = (call);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      char _b[512];                                                                                  \
+      snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      (h)->err = _b;                                                                                 \
+      return ESLAM_ERR_CUDA;                                                                         \
+    }                                                                                                \
+  } while (0)
+
+#define ESLAM_LAUNCHED(h) ((h)->launches++)

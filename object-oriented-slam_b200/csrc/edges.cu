@@ -1,0 +1,366 @@
+// edges.cu -- batched evaluation of the ellipsoid graph edges (residuals + g2o numeric Jacobians) and the
+// Levenberg-Marquardt driver for the object graph in mapping mode.
+//
+// Replaces, on the device:
+//   EdgeSE3EllipsoidProj / EdgeSE3Ellipsoid9DOF / EdgeEllipsoidGravityPlanePrior::computeError
+//        src/core/BasicEllipsoidEdges.cpp:68-77, :102-112, :129-152
+//   g2o numeric differentiation (delta = 1e-9 central differences)
+//        Thirdparty/g2o/g2o/core/base_binary_edge.hpp:131-205, base_unary_edge.hpp:82-123
+//   quadratic form H += J^T W J, b += -J^T W r      base_binary_edge.hpp:55-120, base_unary_edge.hpp:43-72
+//   OptimizationAlgorithmLevenberg::solve           Thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-164
+//   LinearSolverDense (Eigen LDLT)                  Thirdparty/g2o/g2o/solvers/linear_solver_dense.h:65-113
+//
+// Layout (HBM, SoA): type/frame/object int32[E]; meas f64[E*10]; info f64[E]; Tcw f64[F*7]; ellipsoids f64[No*10];
+// residuals f64[E*9]; jacobians f64[E*81] (dim x 9 row-major); chi2 f64[E].  All cameras are fixed (mapping mode,
+// Optimizer.cpp:126-137) so the Hessian is block diagonal: one 9x9 block per ellipsoid, accumulated in edge order.
+#include "common.cuh"
+#include "dmath.cuh"
+#include "internal.h"
+
+namespace eslam {
+
+struct GraphWorkspace {
+  int n_edges = 0, n_frames = 0, n_objects = 0;
+  DevBuf type, frame, object, meas, info, Tcw, K, ell, ell_trial, ell_backup;
+  DevBuf res, jac, chi2;
+  DevBuf obj_start, obj_edges;   // CSR: edges of each object in graph order
+  DevBuf H, b, x, xtmp, okflag, lm;  // H [No*81], b [No*9], x [No*9]
+  PinBuf pin;
+};
+
+struct LmState {  // lives in device memory, mirrored to pinned host memory after every decision
+  double lambda, ni, currentChi, tempChi, rho, iniChi;
+  int accepted, all_ok, pad0, pad1;
+};
+
+__device__ __forceinline__ int edge_dim(int t) { return t == ESLAM_EDGE_PROJ ? 4 : (t == ESLAM_EDGE_9DOF ? 9 : 1); }
+
+__device__ void edge_error(int type, const se3 &Tcw, const ellipsoid &obj, const double *meas, const double *K, double *err) {
+  if (type == ESLAM_EDGE_PROJ) {
+    double proj[4];
+    ell_bbox(obj, Tcw, K, proj);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { err[i] = 0; if (meas[i] >= 5) err[i] = proj[i] - meas[i]; }
+  } else if (type == ESLAM_EDGE_9DOF) {
+    se3 Twc = se3_inv(Tcw);
+    ellipsoid m = ell_load(meas);
+    ellipsoid g = m;
+    g.pose = se3_mul(Twc, m.pose);  // transform_from
+    ell_min_log_error(obj, g, err);
+  } else {
+    mat3 R = q_to_R(obj.pose.r);
+    d3 z = m3_col(R, 2);
+    d3 n = mk3(meas[0], meas[1], meas[2]);
+    double c = dot3(z, n) / norm3(z) / norm3(n);
+    if (c > 1) c = c - 0.0001;
+    else if (c < -1) c = c + 0.0001;
+    err[0] = acos(c) - 0;
+  }
+}
+
+// thread = (edge, slot); slot 0..8 -> Jacobian column (two perturbed evaluations), slot 9 -> residual + chi2.
+// blockDim.x must be a multiple of 10.  with_jac == 0 launches only slot 9.
+__global__ void __launch_bounds__(320) edge_eval_kernel(int n_edges, const int *__restrict__ type, const int *__restrict__ frame,
+                                                        const int *__restrict__ object, const double *__restrict__ meas,
+                                                        const double *__restrict__ info, const double *__restrict__ Tcw,
+                                                        const double *__restrict__ Kc, const double *__restrict__ ell,
+                                                        double *__restrict__ res, double *__restrict__ jac, double *__restrict__ chi2, int with_jac) {
+  const int slots = with_jac ? 10 : 1;
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int e = (int)(gid / slots);
+  int slot = with_jac ? (int)(gid % slots) : 9;
+  if (e >= n_edges) return;
+  int t = type[e];
+  int D = edge_dim(t);
+  double K[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) K[i] = Kc[i];
+  se3 T = se3_load(Tcw + 7 * (t == ESLAM_EDGE_GRAVITY ? 0 : frame[e]));
+  ellipsoid obj = ell_load(ell + 10 * object[e]);
+  const double *m = meas + 10 * (size_t)e;
+  if (slot == 9) {
+    double r[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) r[i] = 0;
+    edge_error(t, T, obj, m, K, r);
+    double w = info[e];
+    double c = 0;
+    for (int i = 0; i < D; i++) c += r[i] * (w * r[i]);
+    for (int i = 0; i < 9; i++) res[(size_t)e * 9 + i] = i < D ? r[i] : 0.0;
+    chi2[e] = c;
+  } else {
+    const double delta = 1e-9;
+    const double scalar = 1.0 / (2 * delta);
+    double add[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) add[i] = 0;
+    double e1[9], e2[9];
+    add[slot] = delta;
+    edge_error(t, T, ell_oplus(obj, add), m, K, e1);
+    add[slot] = -delta;
+    edge_error(t, T, ell_oplus(obj, add), m, K, e2);
+    for (int r = 0; r < 9; r++) jac[(size_t)e * 81 + r * 9 + slot] = r < D ? scalar * (e1[r] - e2[r]) : 0.0;
+  }
+}
+
+// one CTA (96 threads) per object: thread t < 81 owns H(i,j), t in [81,90) owns b(i); edges visited in graph order so the
+// fp64 accumulation order equals g2o's (activeEdges sorted by internalId, optimizable_graph.cpp:273).
+__global__ void __launch_bounds__(96) build_system_kernel(const int *__restrict__ obj_start, const int *__restrict__ obj_edges, const int *__restrict__ type,
+                                                          const double *__restrict__ info, const double *__restrict__ res, const double *__restrict__ jac,
+                                                          double *__restrict__ H, double *__restrict__ b) {
+  int o = blockIdx.x, t = threadIdx.x;
+  if (t >= 90) return;
+  int s = obj_start[o], epos = obj_start[o + 1];
+  double acc = 0.0;
+  if (t < 81) {
+    int i = t / 9, j = t % 9;
+    for (int k = s; k < epos; k++) {
+      int e = obj_edges[k];
+      int D = edge_dim(type[e]);
+      double w = info[e];
+      const double *J = jac + (size_t)e * 81;
+      double h = 0;
+      for (int r = 0; r < D; r++) { double pr = (J[r * 9 + i] * w) * J[r * 9 + j]; h = (r == 0) ? pr : h + pr; }
+      acc += h;
+    }
+    H[(size_t)o * 81 + t] = acc;
+  } else {
+    int i = t - 81;
+    for (int k = s; k < epos; k++) {
+      int e = obj_edges[k];
+      int ty = type[e];
+      int D = edge_dim(ty);
+      double w = info[e];
+      const double *J = jac + (size_t)e * 81;
+      const double *r_ = res + (size_t)e * 9;
+      double bi = 0;
+      for (int r = 0; r < D; r++) {
+        double pr = (ty == ESLAM_EDGE_GRAVITY) ? ((J[r * 9 + i] * w) * r_[r]) : (J[r * 9 + i] * (-(w * r_[r])));
+        bi = (r == 0) ? pr : bi + pr;
+      }
+      if (ty == ESLAM_EDGE_GRAVITY) acc -= bi; else acc += bi;
+    }
+    b[(size_t)o * 9 + i] = acc;
+  }
+}
+
+// sequential (graph-order) sum of the per-edge chi2 by one warp: lanes fetch 32 values, lane 0 adds them in order.
+__device__ double warp_ordered_sum(const double *v, int n) {
+  int lane = threadIdx.x & 31;
+  double acc = 0.0;
+  for (int base = 0; base < n; base += 32) {
+    double x = (base + lane < n) ? v[base + lane] : 0.0;
+    int cnt = min(32, n - base);
+    for (int k = 0; k < cnt; k++) {
+      double xk = __shfl_sync(0xffffffffu, x, k);
+      acc += xk;
+    }
+  }
+  return acc;  // every lane holds the same value
+}
+
+// iteration start: currentChi = sum chi2 (at est), lambda init on iteration 0 (computeLambdaInit :166-180)
+__global__ void lm_begin_kernel(LmState *st, const double *chi2, int n_edges, const double *H, int n_obj, int iteration) {
+  double chi = warp_ordered_sum(chi2, n_edges);
+  if (threadIdx.x == 0) {
+    st->currentChi = chi; st->tempChi = chi; st->iniChi = chi; st->rho = 0;
+    if (iteration == 0) {
+      double mx = 0;
+      for (int o = 0; o < n_obj; o++) for (int j = 0; j < 9; j++) mx = fmax(fabs(H[(size_t)o * 81 + j * 10]), mx);
+      st->lambda = 1e-5 * mx; st->ni = 2;
+    }
+    st->all_ok = 1;
+  }
+}
+
+// per object: solve (H + lambda I) x = b with Eigen-LDLT semantics
+__global__ void lm_solve_kernel(LmState *st, const double *H, const double *b, double *xtmp, int n_obj) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_obj) return;
+  double M[81], rhs[9], x[9];
+  double lambda = st->lambda;
+  for (int i = 0; i < 81; i++) M[i] = H[(size_t)o * 81 + i];
+  for (int i = 0; i < 9; i++) { M[i * 10] += lambda; rhs[i] = b[(size_t)o * 9 + i]; x[i] = 0; }
+  bool ok = ldlt_solve_small<9>(M, rhs, x);
+  if (!ok) atomicAnd(&st->all_ok, 0);
+  for (int i = 0; i < 9; i++) xtmp[(size_t)o * 9 + i] = x[i];
+}
+// commit x (only if every block was positive: a failed dense LDLT leaves g2o's _x untouched) and apply the update
+__global__ void lm_update_kernel(const LmState *st, const double *xtmp, double *x, const double *ell, double *ell_trial, int n_obj) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_obj) return;
+  double u[9];
+  bool ok = st->all_ok != 0;
+  for (int i = 0; i < 9; i++) { if (ok) x[(size_t)o * 9 + i] = xtmp[(size_t)o * 9 + i]; u[i] = x[(size_t)o * 9 + i]; }
+  ellipsoid e = ell_load(ell + 10 * (size_t)o);
+  ellipsoid r = ell_oplus(e, u);
+  ell_store(r, ell_trial + 10 * (size_t)o);
+}
+// rho test, lambda schedule, accept/reject (optimization_algorithm_levenberg.cpp:119-147)
+__global__ void lm_decide_kernel(LmState *st, const double *chi2, int n_edges, const double *x, const double *b, int n_obj, double *ell, const double *ell_trial,
+                                 LmState *host_copy) {
+  double tempChi = warp_ordered_sum(chi2, n_edges);
+  if (threadIdx.x == 0) {
+    if (!st->all_ok) tempChi = DBL_MAX;
+    double lambda = st->lambda;
+    double scale = 0;
+    for (int j = 0; j < 9 * n_obj; j++) scale += x[j] * (lambda * x[j] + b[j]);
+    scale += 1e-3;
+    double rho = (st->currentChi - tempChi);
+    rho /= scale;
+    int accepted = 0;
+    if (rho > 0 && isfinite(tempChi)) {
+      double alpha = 1. - pow((2 * rho - 1), 3.0);
+      alpha = fmin(alpha, 2. / 3.);
+      double sf = fmax(1. / 3., alpha);
+      st->lambda = lambda * sf; st->ni = 2; st->currentChi = tempChi; accepted = 1;
+    } else {
+      st->lambda = lambda * st->ni; st->ni = st->ni * 2;
+    }
+    st->tempChi = tempChi; st->rho = rho; st->accepted = accepted; st->all_ok = 1;
+    *host_copy = *st;
+  }
+  __syncwarp();
+  int accepted = __shfl_sync(0xffffffffu, (threadIdx.x == 0) ? st->accepted : 0, 0);
+  if (accepted) for (int i = threadIdx.x; i < 10 * n_obj; i += 32) ell[i] = ell_trial[i];
+}
+
+static int upload(EslamHandle *h, DevBuf &buf, const void *src, size_t bytes, cudaStream_t s) {
+  ESLAM_CUDA_OK(h, buf.reserve(bytes ? bytes : 8));
+  if (bytes) ESLAM_CUDA_OK(h, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, s));
+  return ESLAM_OK;
+}
+
+int graph_upload(EslamHandle *h, const EslamEdgeBatch *g, const double *ell, cudaStream_t s) {
+  if (!h->gr) h->gr = new GraphWorkspace();
+  GraphWorkspace &w = *h->gr;
+  if (g->n_edges < 0 || g->n_objects <= 0 || g->n_frames <= 0) return ESLAM_ERR_BAD_ARG;
+  for (int k = 0; k < g->n_edges; k++) {
+    if (g->object[k] < 0 || g->object[k] >= g->n_objects) return ESLAM_ERR_BAD_ARG;
+    if (g->type[k] != ESLAM_EDGE_GRAVITY && (g->frame[k] < 0 || g->frame[k] >= g->n_frames)) return ESLAM_ERR_BAD_ARG;
+    if (g->type[k] < 0 || g->type[k] > 2) return ESLAM_ERR_BAD_ARG;
+  }
+  w.n_edges = g->n_edges; w.n_frames = g->n_frames; w.n_objects = g->n_objects;
+  size_t E = (size_t)g->n_edges, No = (size_t)g->n_objects;
+  int rc;
+  if ((rc = upload(h, w.type, g->type, E * 4, s))) return rc;
+  if ((rc = upload(h, w.frame, g->frame, E * 4, s))) return rc;
+  if ((rc = upload(h, w.object, g->object, E * 4, s))) return rc;
+  if ((rc = upload(h, w.meas, g->meas, E * 80, s))) return rc;
+  if ((rc = upload(h, w.info, g->info, E * 8, s))) return rc;
+  if ((rc = upload(h, w.Tcw, g->Tcw, (size_t)g->n_frames * 56, s))) return rc;
+  if ((rc = upload(h, w.K, g->K, 72, s))) return rc;
+  if ((rc = upload(h, w.ell, ell, No * 80, s))) return rc;
+  // CSR of edges per object, preserving graph order
+  std::vector<int> start(No + 1, 0), list(E);
+  for (size_t k = 0; k < E; k++) start[g->object[k] + 1]++;
+  for (size_t o = 0; o < No; o++) start[o + 1] += start[o];
+  std::vector<int> fill(start.begin(), start.end() - 1);
+  for (size_t k = 0; k < E; k++) list[fill[g->object[k]]++] = (int)k;
+  ESLAM_CUDA_OK(h, w.obj_start.reserve((No + 1) * 4));
+  ESLAM_CUDA_OK(h, w.obj_edges.reserve(E * 4 + 8));
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(w.obj_start.p, start.data(), (No + 1) * 4, cudaMemcpyHostToDevice, s));
+  if (E) ESLAM_CUDA_OK(h, cudaMemcpyAsync(w.obj_edges.p, list.data(), E * 4, cudaMemcpyHostToDevice, s));
+  ESLAM_CUDA_OK(h, w.ell_trial.reserve(No * 80));
+  ESLAM_CUDA_OK(h, w.res.reserve(E * 72 + 8));
+  ESLAM_CUDA_OK(h, w.jac.reserve(E * 648 + 8));
+  ESLAM_CUDA_OK(h, w.chi2.reserve(E * 8 + 8));
+  ESLAM_CUDA_OK(h, w.H.reserve(No * 648));
+  ESLAM_CUDA_OK(h, w.b.reserve(No * 72));
+  ESLAM_CUDA_OK(h, w.x.reserve(No * 72));
+  ESLAM_CUDA_OK(h, w.xtmp.reserve(No * 72));
+  ESLAM_CUDA_OK(h, w.lm.reserve(sizeof(LmState)));
+  ESLAM_CUDA_OK(h, w.pin.reserve(sizeof(LmState)));
+  ESLAM_CUDA_OK(h, cudaMemsetAsync(w.x.p, 0, No * 72, s));
+  ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));  // host vectors go out of scope
+  return ESLAM_OK;
+}
+
+static int launch_eval(EslamHandle *h, cudaStream_t s, const double *ell, bool jac) {
+  GraphWorkspace &w = *h->gr;
+  if (w.n_edges == 0) return ESLAM_OK;
+  long long threads = (long long)w.n_edges * (jac ? 10 : 1);
+  int block = jac ? 320 : 256;
+  int grid = (int)((threads + block - 1) / block);
+  edge_eval_kernel<<<grid, block, 0, s>>>(w.n_edges, w.type.as<int>(), w.frame.as<int>(), w.object.as<int>(), w.meas.as<double>(), w.info.as<double>(),
+                                          w.Tcw.as<double>(), w.K.as<double>(), ell, w.res.as<double>(), w.jac.as<double>(), w.chi2.as<double>(), jac ? 1 : 0);
+  ESLAM_LAUNCHED(h);
+  ESLAM_CUDA_OK(h, cudaGetLastError());
+  return ESLAM_OK;
+}
+
+int graph_eval(EslamHandle *h, cudaStream_t s, bool jac) {
+  if (!h->gr) return ESLAM_ERR_BAD_ARG;
+  return launch_eval(h, s, h->gr->ell.as<double>(), jac);
+}
+
+int graph_download(EslamHandle *h, double *res, double *jac, double *chi2, cudaStream_t s) {
+  if (!h->gr) return ESLAM_ERR_BAD_ARG;
+  GraphWorkspace &w = *h->gr;
+  size_t E = (size_t)w.n_edges;
+  if (res && E) ESLAM_CUDA_OK(h, cudaMemcpyAsync(res, w.res.p, E * 72, cudaMemcpyDeviceToHost, s));
+  if (jac && E) ESLAM_CUDA_OK(h, cudaMemcpyAsync(jac, w.jac.p, E * 648, cudaMemcpyDeviceToHost, s));
+  if (chi2 && E) ESLAM_CUDA_OK(h, cudaMemcpyAsync(chi2, w.chi2.p, E * 8, cudaMemcpyDeviceToHost, s));
+  ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
+  return ESLAM_OK;
+}
+
+// SparseOptimizer::optimize(iters) with OptimizationAlgorithmLevenberg (sparse_optimizer.cpp:354-419)
+int graph_optimize(EslamHandle *h, int iters, double *ell_inout, EslamLmStats *stats, cudaStream_t s) {
+  if (!h->gr) return ESLAM_ERR_BAD_ARG;
+  GraphWorkspace &w = *h->gr;
+  const int No = w.n_objects, E = w.n_edges;
+  LmState *st = w.lm.as<LmState>();
+  LmState *hs = w.pin.as<LmState>();
+  EslamLmStats out; memset(&out, 0, sizeof(out));
+  int nBad = 0;
+  const int maxTrials = 10;
+  int rc;
+  for (int it = 0; it < iters; it++) {
+    if ((rc = launch_eval(h, s, w.ell.as<double>(), true))) return rc;   // computeActiveErrors + linearizeOplus
+    build_system_kernel<<<No, 96, 0, s>>>(w.obj_start.as<int>(), w.obj_edges.as<int>(), w.type.as<int>(), w.info.as<double>(), w.res.as<double>(),
+                                          w.jac.as<double>(), w.H.as<double>(), w.b.as<double>());
+    ESLAM_LAUNCHED(h);
+    lm_begin_kernel<<<1, 32, 0, s>>>(st, w.chi2.as<double>(), E, w.H.as<double>(), No, it);
+    ESLAM_LAUNCHED(h);
+    double rho = 0; int qmax = 0;
+    double iniChi = 0, currentChi = 0;
+    do {
+      lm_solve_kernel<<<(No + 31) / 32, 32, 0, s>>>(st, w.H.as<double>(), w.b.as<double>(), w.xtmp.as<double>(), No);
+      ESLAM_LAUNCHED(h);
+      lm_update_kernel<<<(No + 31) / 32, 32, 0, s>>>(st, w.xtmp.as<double>(), w.x.as<double>(), w.ell.as<double>(), w.ell_trial.as<double>(), No);
+      ESLAM_LAUNCHED(h);
+      if ((rc = launch_eval(h, s, w.ell_trial.as<double>(), false))) return rc;
+      lm_decide_kernel<<<1, 32, 0, s>>>(st, w.chi2.as<double>(), E, w.x.as<double>(), w.b.as<double>(), No, w.ell.as<double>(), w.ell_trial.as<double>(), hs);
+      ESLAM_LAUNCHED(h);
+      ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
+      rho = hs->rho; iniChi = hs->iniChi; currentChi = hs->currentChi;
+      if (it == 0 && qmax == 0) out.chi2_initial = iniChi;
+      qmax++;
+    } while (rho < 0 && qmax < maxTrials);
+    out.iterations++; out.trials_total += qmax; out.chi2_final = currentChi; out.lambda_final = hs->lambda;
+    bool terminate = false;
+    if (qmax == maxTrials || rho == 0) terminate = true;
+    else {
+      if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+      if (nBad >= 3) terminate = true;
+    }
+    if (terminate) { out.terminated = 1; break; }
+  }
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(ell_inout, w.ell.p, (size_t)No * 80, cudaMemcpyDeviceToHost, s));
+  ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
+  if (stats) *stats = out;
+  return ESLAM_OK;
+}
+
+void graph_free(EslamHandle *h) {
+  if (!h->gr) return;
+  GraphWorkspace &w = *h->gr;
+  DevBuf *bufs[] = {&w.type, &w.frame, &w.object, &w.meas, &w.info, &w.Tcw, &w.K, &w.ell, &w.ell_trial, &w.ell_backup, &w.res, &w.jac, &w.chi2,
+                    &w.obj_start, &w.obj_edges, &w.H, &w.b, &w.x, &w.xtmp, &w.okflag, &w.lm};
+  for (DevBuf *b : bufs) b->release();
+  w.pin.release();
+  delete h->gr; h->gr = nullptr;
+}
+
+}  // namespace eslam

@@ -1,0 +1,440 @@
+// extract.cu -- single-frame ellipsoid extraction, one CTA per (frame, bbox) object, batched over frames.
+//
+// Replaces EllipsoidExtractor::ExtractPointCloud + ProcessPCA + frame construction
+//   src/pca/EllipsoidExtractor.cpp:86-168 (crop, 1 cm voxel grid, to world, supporting-plane filter, centre, clusters)
+//   src/pca/EllipsoidExtractor.cpp:170-267, 308-347, 760-788 (PCA, chirality, gravity alignment, object frame)
+//   src/symmetry/PointCloudFilter.cpp:21-56, 249-261 ; src/core/Geometry.cpp:44-66,160-166
+// and the PCL calls behind them (VoxelGrid, EuclideanClusterExtraction, compute3DCentroid,
+// computeCovarianceMatrixNormalized) with B200-native data-parallel algorithms that give the SAME integer results:
+//   voxel grid        -> PCL voxel index, stable block radix sort, per-voxel float centroid in ascending point order
+//   euclidean cluster -> uniform hash grid (cell ~ tolerance) + lock-free union-find; membership == connected components
+//                        of {||p-q||^2 < r^2 in float}; order = size desc, then first index (PCL's discovery order)
+// Data layout: per-object slices of flat HBM arrays (ExtractPtrs); a CTA streams its slice, which stays L2 resident.
+#include "common.cuh"
+#include "dmath.cuh"
+#include "block_prims.cuh"
+#include "extract_types.cuh"
+#include "internal.h"
+
+namespace eslam {
+
+__device__ __forceinline__ int lower_bound_u32(const unsigned *a, int n, unsigned key) {
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ int vload(const int *p) { return *((const volatile int *)p); }
+__device__ int uf_find(int *parent, int i) {
+  int p = vload(parent + i);
+  while (p != i) { i = p; p = vload(parent + i); }
+  return i;
+}
+__device__ void uf_union(int *parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a); b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }   // hook the larger root under the smaller: final root == min index
+    int old = atomicCAS(parent + a, a, b);
+    if (old == a) return;
+  }
+}
+__device__ __forceinline__ float l2_simple(float4 a, float4 b) {  // flann::L2_Simple<float>, no contraction
+  float r = 0.0f, d;
+  d = __fsub_rn(a.x, b.x); r = __fadd_rn(r, __fmul_rn(d, d));
+  d = __fsub_rn(a.y, b.y); r = __fadd_rn(r, __fmul_rn(d, d));
+  d = __fsub_rn(a.z, b.z); r = __fadd_rn(r, __fmul_rn(d, d));
+  return r;
+}
+
+// PCL VoxelGrid indexing + stable sort.  On return k0[j]/v0[j] hold sorted voxel keys / original indices.
+__device__ void voxel_sort(const float4 *pts, int n, float leaf, unsigned *k0, unsigned *v0, unsigned *k1, unsigned *v1, BlockScratch &S, RadixScratch &RS) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float4 p = pts[i];
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  }
+  block_minmax3(mn, mx, S);
+  const float inv = __fdiv_rn(1.0f, leaf);
+  long long dx = (long long)__fmul_rn(__fsub_rn(mx[0], mn[0]), inv) + 1;
+  long long dy = (long long)__fmul_rn(__fsub_rn(mx[1], mn[1]), inv) + 1;
+  long long dz = (long long)__fmul_rn(__fsub_rn(mx[2], mn[2]), inv) + 1;
+  if (dx * dy * dz > 2147483647LL) {  // PCL returns the input unfiltered: every point is its own voxel
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { k0[i] = (unsigned)i; v0[i] = (unsigned)i; }
+    __syncthreads();
+    return;
+  }
+  int minb[3], divb[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    minb[a] = (int)floorf(__fmul_rn(mn[a], inv));
+    int maxb = (int)floorf(__fmul_rn(mx[a], inv));
+    divb[a] = maxb - minb[a] + 1;
+  }
+  const int mul1 = divb[0], mul2 = divb[0] * divb[1];
+  const float fb0 = (float)minb[0], fb1 = (float)minb[1], fb2 = (float)minb[2];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float4 p = pts[i];
+    int i0 = (int)__fsub_rn(floorf(__fmul_rn(p.x, inv)), fb0);
+    int i1 = (int)__fsub_rn(floorf(__fmul_rn(p.y, inv)), fb1);
+    int i2 = (int)__fsub_rn(floorf(__fmul_rn(p.z, inv)), fb2);
+    k0[i] = (unsigned)(i0 + i1 * mul1 + i2 * mul2);
+    v0[i] = (unsigned)i;
+  }
+  __syncthreads();
+  unsigned long long maxkey = (unsigned long long)divb[0] * (unsigned long long)divb[1] * (unsigned long long)divb[2];
+  int bits = (maxkey >= 0xffffffffULL) ? 32 : bits_for((unsigned)maxkey);
+  block_radix_sort(k0, v0, k1, v1, n, bits, RS);
+}
+
+// float centroid of the voxel whose first sorted position is j (members in ascending original index)
+__device__ __forceinline__ float4 voxel_centroid(const float4 *pts, const unsigned *k0, const unsigned *v0, int j, int n) {
+  unsigned key = k0[j];
+  float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+  int jj = j;
+  do {
+    float4 p = pts[v0[jj]];
+    sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
+    jj++;
+  } while (jj < n && k0[jj] == key);
+  float cnt = (float)(jj - j);
+  return make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 0.0f);
+}
+
+__global__ void __launch_bounds__(512, 1) extract_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride, const ObjMeta *__restrict__ metas,
+                                                      ObjState *__restrict__ states, ExtractParamsDev prm, ExtractPtrs W) {
+  __shared__ BlockScratch S;
+  __shared__ RadixScratch RS;
+  __shared__ int s_sel, s_K;
+  const int tid = threadIdx.x;
+  const ObjMeta m = metas[blockIdx.x];
+  ObjState &st = states[blockIdx.x];
+  if (tid == 0) {
+    st.status = m.pre_status;
+    st.n_crop = st.n_voxel = st.n_plane = st.n_clusters = st.n_cluster = st.n_sym = st.n_final = 0;
+    st.run_sym = 0; st.symtype = m.symtype; st.best_seed = -1;
+    for (int k = 0; k < 4; k++) st.bbox_i[k] = (int)m.bbox[k];
+    for (int s = 0; s < 9; s++) { st.seed_prob[s] = st.seed_init[s] = st.seed_final[s] = st.seed_dual[s] = 0; for (int k = 0; k < 4; k++) st.seed_plane[s][k] = 0; }
+  }
+  if (m.pre_status != 0) return;
+  float4 *A = W.ptsA + m.off, *B = W.ptsB + m.off, *Cc = W.ptsC + m.off;
+  unsigned *k0 = W.k0 + m.off, *k1 = W.k1 + m.off, *v0 = W.v0 + m.off, *v1 = W.v1 + m.off;
+  int *parent = W.parent + m.off, *count = W.count + m.off;
+  const uint16_t *img = depth + (size_t)m.frame * frame_stride;
+  const se3 Twc = se3_load(m.Twc);
+  const hom34 Twc_h = se3_hom(Twc);
+
+  // ---------------- S1: stride-3 crop + back-projection (PointCloudFilter.cpp:31-52) ----------------
+  int n1 = 0;
+  {
+    const int total = m.nx * m.ny;
+    for (int tile = 0; tile < total; tile += blockDim.x) {
+      int i = tile + tid;
+      bool keep = false;
+      double X = 0, Y = 0, Z = 0;
+      if (i < total) {
+        int iy = i / m.nx, ix = i - iy * m.nx;
+        int x = m.x1 + 3 * ix, y = m.y1 + 3 * iy;
+        unsigned short d = img[(size_t)y * pitch + x];
+        Z = d / prm.scale;
+        if (!(Z <= 0.1 || Z > prm.depth_range)) {
+          keep = true;
+          X = (x - prm.cx) * Z / prm.fx;
+          Y = (y - prm.cy) * Z / prm.fy;
+        }
+      }
+      int tot;
+      int ex = block_excl_scan(keep ? 1 : 0, S, tot);
+      if (keep) {
+        A[n1 + ex] = make_float4((float)X, (float)Y, (float)Z, 0.0f);   // QuadricPointCloudToPcl: double -> float
+        if (W.d_crop) { double *q = W.d_crop + 3 * (size_t)(m.off + n1 + ex); q[0] = X; q[1] = Y; q[2] = Z; }
+      }
+      n1 += tot;
+    }
+  }
+  __syncthreads();
+  // ---------------- S2 + S3 + S4: 1 cm voxel grid -> world -> supporting-plane filter ----------------
+  int n2 = 0, n3 = 0;
+  if (n1 > 0) {
+    voxel_sort(A, n1, prm.voxel_leaf, k0, v0, k1, v1, S, RS);
+    for (int tile = 0; tile < n1; tile += blockDim.x) {
+      int j = tile + tid;
+      bool head = false, keep = false;
+      d3 pc = mk3(0, 0, 0), pw = mk3(0, 0, 0);
+      if (j < n1) {
+        head = (j == 0) || (k0[j - 1] != k0[j]);
+        if (head) {
+          float4 c = voxel_centroid(A, k0, v0, j, n1);
+          pc = mk3((double)c.x, (double)c.y, (double)c.z);      // pclToQuadricPointCloud: float -> double
+          pw = hom_apply(Twc_h, pc);                               // transformPointCloud
+          keep = plane_signed_dist(prm.plane, pw) > prm.plane_margin;  // ApplySupportingPlaneFilter
+        }
+      }
+      int tot;
+      int packed = (head ? 1 : 0) | (keep ? 0x10000 : 0);
+      int ex = block_excl_scan(packed, S, tot);
+      int hr = ex & 0xffff, kr = ex >> 16;
+      if (head && W.d_voxel) { double *q = W.d_voxel + 3 * (size_t)(m.off + n2 + hr); q[0] = pc.x; q[1] = pc.y; q[2] = pc.z; }
+      if (keep) {
+        B[n3 + kr] = make_float4((float)pw.x, (float)pw.y, (float)pw.z, 0.0f);   // QuadricPointCloudToPclXYZ
+        if (W.d_world) { double *q = W.d_world + 3 * (size_t)(m.off + n3 + kr); q[0] = pw.x; q[1] = pw.y; q[2] = pw.z; }
+      }
+      n2 += tot & 0xffff; n3 += tot >> 16;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) { st.n_crop = n1; st.n_voxel = n2; st.n_plane = n3; }
+  if (n3 < 1) { if (tid == 0) st.status = ESLAM_OBJ_NO_POINTS_AFTER_PLANE; return; }
+
+  // ---------------- S5: GetCenter (EllipsoidExtractor.cpp:583-643) ----------------
+  if (tid == 0) {
+    int x = (int)((m.bbox[0] + m.bbox[2]) / 2.0);
+    int y = (int)((m.bbox[1] + m.bbox[3]) / 2.0);
+    const int point_num = 10;
+    int x_delta = (int)(fabs(m.bbox[0] - m.bbox[2]) / 4.0 / point_num);
+    int y_delta = (int)(fabs(m.bbox[1] - m.bbox[3]) / 4.0 / point_num);
+    double c0 = 0, c1 = 0, c2 = 0; int cnt = 0;
+    for (int x_id = -point_num / 2; x_id < point_num / 2; x_id++)
+      for (int y_id = -point_num / 2; y_id < point_num / 2; y_id++) {
+        int x_ = x + x_id * x_delta, y_ = y + y_id * y_delta;
+        if (x_ < 0 || y_ < 0 || x_ >= prm.cols || y_ >= prm.rows) continue;
+        unsigned short d = img[(size_t)y_ * pitch + x_];
+        float pz = (float)(d / prm.scale);
+        if ((double)pz <= 0.1 || (double)pz > prm.depth_range) continue;
+        float px = (float)((x_ - prm.cx) * (double)pz / prm.fx);
+        float py = (float)((y_ - prm.cy) * (double)pz / prm.fy);
+        c0 += (double)px; c1 += (double)py; c2 += (double)pz; cnt++;
+      }
+    int ok = cnt >= 2;
+    if (ok) {
+      double N = (double)cnt;
+      d3 cw = hom_apply(Twc_h, mk3(c0 / N, c1 / N, c2 / N));
+      S.bcast_d[0] = cw.x; S.bcast_d[1] = cw.y; S.bcast_d[2] = cw.z;
+      st.center[0] = cw.x; st.center[1] = cw.y; st.center[2] = cw.z;
+    }
+    S.bcast_i[0] = ok;
+  }
+  __syncthreads();
+  if (!S.bcast_i[0]) { if (tid == 0) st.status = ESLAM_OBJ_NO_CENTER; return; }
+  const d3 center = mk3(S.bcast_d[0], S.bcast_d[1], S.bcast_d[2]);
+  __syncthreads();
+
+  // ---------------- S6: Euclidean clustering (EllipsoidExtractor.cpp:646-737) ----------------
+  {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = tid; i < n3; i += blockDim.x) {
+      float4 p = B[i];
+      mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+      mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    }
+    block_minmax3(mn, mx, S);
+    float cs = prm.cluster_cell;
+    long long gx, gy, gz;
+    while (true) {
+      gx = (long long)((mx[0] - mn[0]) / cs) + 1; gy = (long long)((mx[1] - mn[1]) / cs) + 1; gz = (long long)((mx[2] - mn[2]) / cs) + 1;
+      if (gx * gy * gz < 2147483647LL) break;
+      cs *= 2.0f;
+    }
+    const int nx = (int)gx, ny = (int)gy, nz = (int)gz;
+    for (int i = tid; i < n3; i += blockDim.x) {
+      float4 p = B[i];
+      int cx = (int)((p.x - mn[0]) / cs), cy = (int)((p.y - mn[1]) / cs), cz = (int)((p.z - mn[2]) / cs);
+      k0[i] = (unsigned)((cz * ny + cy) * nx + cx);
+      v0[i] = (unsigned)i;
+      parent[i] = i; count[i] = 0;
+    }
+    __syncthreads();
+    block_radix_sort(k0, v0, k1, v1, n3, bits_for((unsigned)(gx * gy * gz)), RS);
+    const float r2 = prm.cluster_r2;
+    for (int pos = tid; pos < n3; pos += blockDim.x) {
+      int i = (int)v0[pos];
+      float4 p = B[i];
+      int cx = (int)((p.x - mn[0]) / cs), cy = (int)((p.y - mn[1]) / cs), cz = (int)((p.z - mn[2]) / cs);
+      int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
+      for (int dz = -1; dz <= 1; dz++) {
+        int zz = cz + dz; if (zz < 0 || zz >= nz) continue;
+        for (int dy = -1; dy <= 1; dy++) {
+          int yy = cy + dy; if (yy < 0 || yy >= ny) continue;
+          unsigned klo = (unsigned)((zz * ny + yy) * nx + xlo), khi = (unsigned)((zz * ny + yy) * nx + xhi);
+          int q = lower_bound_u32(k0, n3, klo);
+          for (; q < n3 && k0[q] <= khi; q++) {
+            int j = (int)v0[q];
+            if (j >= i) continue;
+            if (l2_simple(p, B[j]) < r2) uf_union(parent, i, j);   // RadiusResultSet::addPoint: dist < radius^2
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n3; i += blockDim.x) { int r = uf_find(parent, i); k1[i] = (unsigned)r; atomicAdd(count + r, 1); }
+    __syncthreads();
+    for (int i = tid; i < n3; i += blockDim.x) parent[i] = (int)k1[i];   // flattened labels (root = min index of the component)
+    __syncthreads();
+    // accepted clusters (size >= MinClusterSize), ascending root == PCL discovery order
+    int K = 0;
+    for (int tile = 0; tile < n3; tile += blockDim.x) {
+      int i = tile + tid;
+      bool acc = (i < n3) && (parent[i] == i) && (count[i] >= prm.min_cluster);
+      int tot;
+      int ex = block_excl_scan(acc ? 1 : 0, S, tot);
+      if (acc) v1[K + ex] = (unsigned)i;
+      K += tot;
+    }
+    __syncthreads();
+    if (tid == 0) {  // stable sort by size descending (EuclideanClusterExtraction::extract sorts clusters by size)
+      for (int a = 1; a < K; a++) {
+        unsigned r = v1[a]; int c = count[r]; int b = a - 1;
+        while (b >= 0 && count[v1[b]] < c) { v1[b + 1] = v1[b]; b--; }
+        v1[b + 1] = r;
+      }
+      st.n_clusters = K; s_K = K; s_sel = -1;
+    }
+    __syncthreads();
+    // first cluster whose minimum distance to the centre is < CenterDis (or the only cluster)  :696-714
+    for (int c = 0; c < K; c++) {
+      int root = (int)v1[c];
+      double mind = 999999;
+      for (int i = tid; i < n3; i += blockDim.x) {
+        if (parent[i] != root) continue;
+        float4 p = B[i];
+        double dx = center.x - (double)p.x, dy = center.y - (double)p.y, dz = center.z - (double)p.z;
+        double dis = sqrt(dx * dx + dy * dy + dz * dz);
+        mind = fmin(mind, dis);
+      }
+      mind = block_min_double(mind, S);
+      bool hit = mind < prm.center_dis;
+      if (tid == 0) { if (K == 1) s_sel = c; if (hit) s_sel = c; }
+      __syncthreads();
+      if (hit) break;
+    }
+    __syncthreads();
+    if (W.d_label) {
+      for (int i = tid; i < n3; i += blockDim.x) {
+        int lab = -1;
+        if (count[parent[i]] >= prm.min_cluster) for (int c = 0; c < K; c++) if ((int)v1[c] == parent[i]) { lab = c; break; }
+        W.d_label[m.off + i] = lab;
+      }
+    }
+  }
+  const int sel = s_sel;
+  if (sel < 0) { if (tid == 0) st.status = ESLAM_OBJ_NO_CLUSTER; return; }
+  int nc = 0;
+  {
+    const int root = (int)v1[sel];
+    for (int tile = 0; tile < n3; tile += blockDim.x) {
+      int i = tile + tid;
+      bool in = (i < n3) && (parent[i] == root);
+      int tot;
+      int ex = block_excl_scan(in ? 1 : 0, S, tot);
+      if (in) Cc[nc + ex] = B[i];
+      nc += tot;
+    }
+  }
+  __syncthreads();
+
+  // ---------------- S7 + S8: PCA, chirality, gravity alignment, object frame ----------------
+  {
+    double s3[3] = {0, 0, 0};
+    for (int i = tid; i < nc; i += blockDim.x) { float4 p = Cc[i]; s3[0] += (double)p.x; s3[1] += (double)p.y; s3[2] += (double)p.z; }
+    block_sum_double<3>(s3, S);
+    const double N = (double)nc;
+    const double c0 = s3[0] / N, c1 = s3[1] / N, c2 = s3[2] / N;   // compute3DCentroid
+    double cv[6] = {0, 0, 0, 0, 0, 0};  // (1,1) (1,2) (2,2) (0,0) (0,1) (0,2)  computeCovarianceMatrix dense branch
+    for (int i = tid; i < nc; i += blockDim.x) {
+      float4 p = Cc[i];
+      double px = (double)p.x - c0, py = (double)p.y - c1, pz = (double)p.z - c2;
+      cv[0] += py * py; cv[1] += py * pz; cv[2] += pz * pz;
+      cv[3] += px * px; cv[4] += py * px; cv[5] += pz * px;
+    }
+    block_sum_double<6>(cv, S);
+    if (tid == 0) {
+      mat3 cov;
+      cov.a[4] = cv[0] / N; cov.a[5] = cv[1] / N; cov.a[8] = cv[2] / N; cov.a[0] = cv[3] / N; cov.a[1] = cv[4] / N; cov.a[2] = cv[5] / N;
+      cov.a[3] = cov.a[1]; cov.a[6] = cov.a[2]; cov.a[7] = cov.a[5];
+      double ev[3]; mat3 rot;
+      eig3_sym(cov, ev, rot);
+      d3 cen = mk3((double)(float)c0, (double)(float)c1, (double)(float)c2);   // PointType c is float  (:184-191)
+      m3_setcol(rot, 2, cross3(m3_col(rot, 0), m3_col(rot, 1)));               // AdjustChirality
+      // AlignZAxisToGravity :207-267
+      d3 nrm = mk3(prm.plane[0], prm.plane[1], prm.plane[2]);
+      d3 zax = unit3(nrm);
+      double max_abs = 0; bool max_pos = false; int max_id = -1;
+      for (int i = 0; i < 3; i++) {
+        double ct = dot3(m3_col(rot, i), zax);
+        double a = fabs(ct);
+        if (a > max_abs) { max_abs = a; max_pos = ct > 0; max_id = i; }
+      }
+      if (max_id < 0) max_id = 0;
+      mat3 sw; double cs[3];
+      d3 zv = m3_col(rot, max_id);
+      if (!max_pos) zv = scl3(-1.0, zv);
+      m3_setcol(sw, 2, zv); cs[2] = ev[max_id];
+      int xi = (max_id + 1) % 3, yi = (max_id + 2) % 3;
+      m3_setcol(sw, 0, m3_col(rot, xi)); cs[0] = ev[xi];
+      m3_setcol(sw, 1, cross3(m3_col(sw, 2), m3_col(sw, 0))); cs[1] = ev[yi];
+      // ApplyGravityPrior / calibRotMatAccordingToGroundPlane :766-788
+      d3 zA = m3_col(sw, 2);
+      d3 axis = unit3(cross3(zA, nrm));
+      double cos_theta = dot3(nrm, zA) / norm3(nrm) / norm3(zA);
+      double theta = acos(cos_theta);
+      mat3 Rc = m3_mul(R_axis_angle(theta, axis), sw);
+      // normalised frame :327-346
+      d3 rx = unit3(m3_col(Rc, 0));
+      d3 ry = cross3(zax, rx);
+      mat3 Rwo; m3_setcol(Rwo, 0, rx); m3_setcol(Rwo, 1, ry); m3_setcol(Rwo, 2, zax);
+      se3 Two; Two.r = q_from_R(Rwo); Two.t = cen;
+      se3 Tow = se3_inv(Two);
+      se3 Toc = se3_mul(Tow, Twc);
+      st.pca_center[0] = cen.x; st.pca_center[1] = cen.y; st.pca_center[2] = cen.z;
+      for (int i = 0; i < 9; i++) st.pca_rot[i] = Rc.a[i];
+      st.pca_eval[0] = cs[0]; st.pca_eval[1] = cs[1]; st.pca_eval[2] = cs[2];
+      se3_store(Two, st.T_wo); se3_store(Toc, st.T_oc);
+      proj_matrix(se3_inv(Toc), prm.K, st.P);
+      st.n_cluster = nc;
+      hom34 h = se3_hom(Tow);
+      for (int i = 0; i < 12; i++) S.bcast_d[i] = h.m[i];
+    }
+    __syncthreads();
+  }
+  hom34 Tow_h;
+  for (int i = 0; i < 12; i++) Tow_h.m[i] = S.bcast_d[i];
+  __syncthreads();
+
+  // ---------------- symmetry grid (0.1 m) + transform to the object-normalised frame :322-347 ----------------
+  int M = 0;
+  voxel_sort(Cc, nc, prm.sym_leaf, k0, v0, k1, v1, S, RS);
+  double *objn = W.objn + 3 * (size_t)m.off;
+  float4 *objnf = W.objnf + m.off;
+  for (int tile = 0; tile < nc; tile += blockDim.x) {
+    int j = tile + tid;
+    bool head = false;
+    d3 po = mk3(0, 0, 0);
+    if (j < nc) {
+      head = (j == 0) || (k0[j - 1] != k0[j]);
+      if (head) { float4 c = voxel_centroid(Cc, k0, v0, j, nc); po = hom_apply(Tow_h, mk3((double)c.x, (double)c.y, (double)c.z)); }
+    }
+    int tot;
+    int ex = block_excl_scan(head ? 1 : 0, S, tot);
+    if (head) {
+      double *q = objn + 3 * (size_t)(M + ex); q[0] = po.x; q[1] = po.y; q[2] = po.z;
+      objnf[M + ex] = make_float4((float)po.x, (float)po.y, (float)po.z, 0.0f);   // initializeKDTree: double -> float
+      if (W.d_sym) { double *qq = W.d_sym + 3 * (size_t)(m.off + M + ex); qq[0] = po.x; qq[1] = po.y; qq[2] = po.z; }
+    }
+    M += tot;
+  }
+  if (tid == 0) {
+    st.n_sym = M;
+    st.run_sym = (prm.symmetry_open && m.symtype > 0 && M >= 1) ? 1 : 0;
+  }
+}
+
+int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int n_obj, const ExtractParamsDev &prm,
+                   const ExtractPtrs &ptrs) {
+  ExtractWorkspace &w = *h->ex;
+  extract_kernel<<<n_obj, 512, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>(), w.state.as<ObjState>(), prm, ptrs);
+  ESLAM_LAUNCHED(h);
+  ESLAM_CUDA_OK(h, cudaGetLastError());
+  return ESLAM_OK;
+}
+
+}  // namespace eslam

@@ -1,0 +1,67 @@
+// extract_types.cuh -- per-object metadata / state / workspace layout of the ellipsoid-extraction kernels.
+#pragma once
+#include "common.cuh"
+
+namespace eslam {
+
+struct ObjMeta {  // built on the host per batch (tiny), uploaded once
+  int frame, label, symtype, pre_status;
+  int x1, y1, x2, y2;   // int-truncated bbox (PointCloudFilter.cpp:26-29)
+  int nx, ny;           // number of stride-3 samples per axis
+  int off, cap;         // slice [off, off+cap) of every per-point workspace array
+  double bbox[4];
+  double Twc[7];
+};
+
+struct ObjState {  // device resident, one per object
+  int status;
+  int n_crop, n_voxel, n_plane, n_clusters, n_cluster, n_sym, n_final;
+  int run_sym, symtype, best_seed, pad;
+  int bbox_i[4];            // (int)bbox[k] as used by isInRange (SymmetrySolver.cpp:75)
+  double center[3];
+  double pca_center[3], pca_rot[9], pca_eval[3];
+  double T_wo[7];           // object frame before completion
+  double T_oc[7];           // camera pose in the object-normalised frame
+  double P[12];             // K[I|0] hom(T_oc^-1)
+  double seed_prob[9], seed_init[9], seed_final[9], seed_plane[9][4], seed_dual[9];
+};
+
+struct ExtractParamsDev {
+  double fx, fy, cx, cy, scale, depth_range;
+  int rows, cols;
+  float voxel_leaf, sym_leaf;
+  double plane[4];
+  double plane_margin;
+  float cluster_r2;          // (float)(tol*tol)
+  float cluster_cell;        // tol * 1.01
+  int min_cluster;
+  double center_dis;
+  double sigma;
+  int symmetry_open, symmetry_iters;
+  double K[9];
+};
+
+struct ExtractPtrs {  // device pointers of the per-point workspace (total capacity = sum of ObjMeta.cap)
+  float4 *ptsA;     // S1 crop (float), later scratch
+  float4 *ptsB;     // S3/S4 world points (float copy used by clustering)
+  float4 *ptsC;     // S6 selected cluster (float)
+  unsigned *k0, *k1, *v0, *v1;  // radix sort ping-pong
+  int *parent, *count;
+  double *objn;     // [cap*3] object-normalised cloud (double)
+  float4 *objnf;    // float copy for the NN search
+  // optional stage dump (device mirrors, NULL when no dump requested)
+  double *d_crop, *d_voxel, *d_world, *d_sym, *d_final;  // d_final has 4x capacity
+  int *d_label;
+};
+
+struct ExtractWorkspace {
+  DevBuf meta, state, out, ptsA, ptsB, ptsC, k0, k1, v0, v1, parent, count, objn, objnf, symscratch;
+  DevBuf d_crop, d_voxel, d_world, d_sym, d_final, d_label;
+  DevBuf depth;   // staging for the *_host entry point
+  PinBuf pin_meta, pin_out, pin_depth;
+  std::vector<ObjMeta> meta_host;
+  long long cap_total = 0;
+  int n_obj = 0;
+};
+
+}  // namespace eslam

@@ -1,0 +1,34 @@
+// internal.h -- C++ entry points between the translation units of libeslam_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/eslam.h"
+
+struct EslamHandle;
+namespace eslam {
+struct ExtractParamsDev;
+struct ExtractPtrs;
+
+// edges.cu
+int graph_upload(EslamHandle *h, const EslamEdgeBatch *g, const double *ell, cudaStream_t s);
+int graph_eval(EslamHandle *h, cudaStream_t s, bool jac);
+int graph_download(EslamHandle *h, double *res, double *jac, double *chi2, cudaStream_t s);
+int graph_optimize(EslamHandle *h, int iters, double *ell_inout, EslamLmStats *stats, cudaStream_t s);
+void graph_free(EslamHandle *h);
+
+// extract.cu / symmetry.cu
+int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int n_obj, const ExtractParamsDev &prm,
+                   const ExtractPtrs &ptrs);
+int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int n_obj,
+                             const ExtractParamsDev &prm, const ExtractPtrs &ptrs);
+
+// plane.cu
+int plane_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *depth_dev, size_t pitch, double *plane_cam_host, int *found_host,
+                  int *n_inliers_host);
+int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *depth_dev, size_t pitch, double *plane_cam_host, int *found_host,
+                      int *n_inliers_host, int debug_stage, void *debug_out);
+void plane_free(EslamHandle *h);
+
+// init_quadric.cu
+int init_quadric_device(EslamHandle *h, cudaStream_t s, int n_obs, const double *Twc7, const double *det5, const double K[9], int rows, int cols,
+                        double ellipsoid10[10], int *ok);
+}  // namespace eslam

@@ -1,0 +1,638 @@
+// plane.cu -- ground-plane extraction from full 640x480 depth frames, batched over frames.
+//
+// Replaces PlaneExtractor::extractPlanes / extractGroundPlane (src/plane/PlaneExtractor.cpp:22-107, :126-183) and the
+// PCL algorithms behind them (PCL is an external, unpinned dependency of the reference -- see oracle/orc_plane.h for the
+// restated upstream algorithms):
+//   pcl::IntegralImageNormalEstimation (AVERAGE_3D_GRADIENT)      -> points_kernel, integral_kernel, distmap_kernel, normals_kernel
+//   pcl::OrganizedConnectedComponentSegmentation + PlaneCoefficientComparator -> ccl_union_kernel / ccl_flatten_kernel (lock-free union-find)
+//   computeMeanAndCovarianceMatrix<float> + pcl::eigen33          -> fit_kernel (one warp per region, sequential float sums in raster order)
+//   OrganizedMultiPlaneSegmentation::refine (PlaneRefinementComparator) -> refine_kernel (row-sequential, scan-parallel inside a row)
+//   selection rules of extractGroundPlane                         -> select_kernel
+//
+// Exactness notes (why some stages look sequential): the reference's result depends on (a) the exact recurrence order of PCL's
+// double integral images, (b) float chamfer distances truncated with int(), (c) FLOAT accumulation of 9 moments over up to
+// ~250k pixels per region (rel. error ~1e-3 in the reference itself!) and (d) scan-order label propagation.  Each of these is
+// reproduced operation-for-operation, parallelised across frames / rows / regions instead of inside the dependent chain:
+//   (a) anti-diagonal wavefront: thread r owns image row r and runs 2 columns behind row r-1 (shared-memory ring),
+//   (b) row-sequential chamfer passes; the in-row recurrence is evaluated exactly with a 13-step window,
+//   (c) one warp per region walks the label image in raster order; lanes 0..8 own one float accumulator each,
+//   (d) per row: two block-wide max-scans resolve the left-to-right (right-to-left) propagation, vertical checks are parallel.
+// HBM layout per frame: pts float4[NP] (x,y,z,-), nrm float4[NP] (nx,ny,nz,plane_d), iiX/iiY double[(H+1)(W+1)3],
+// dm float[NP], parent/count/maxidx int[NP].  Algorithmic bytes: 2 B/pixel of depth in, 32 B out per frame.
+#include "common.cuh"
+#include "block_prims.cuh"
+#include "internal.h"
+#include <math.h>
+
+namespace eslam {
+
+constexpr int kMaxRegions = 4096;
+
+struct PlaneParamsDev {
+  double fx, fy, cx, cy, scale;
+  int rows, cols;
+  float dis_th;        // Plane.DistanceThreshold (float)
+  float ang_cos;       // cosf(0.017453 * AngTh)
+  int min_size;        // Plane.MinSize
+};
+
+struct PlaneFramePtrs {
+  float4 *pts, *nrm;
+  double *iiX, *iiY;
+  float *dm;
+  int *parent, *count, *maxidx;
+  int *cand_root;      // [F * kMaxRegions]
+  int *cand_n;         // [F]
+  float4 *cand_coef;   // [F * kMaxRegions]
+  int *cand_valid;     // [F * kMaxRegions]
+  int *cand_size;      // [F * kMaxRegions]  inlier count (grows during refinement)
+  double *out_plane;   // [F*4]
+  int *out_found, *out_inl;
+};
+
+struct PlaneWorkspace {
+  DevBuf pts, nrm, iiX, iiY, dm, parent, count, maxidx, cand_root, cand_n, cand_coef, cand_valid, cand_size, out_plane, out_found, out_inl;
+  PinBuf pin;
+  int chunk = 0;
+};
+
+// ---------------------------------------------------------------------------------------------- P1: back-projection
+__global__ void points_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride, PlaneParamsDev prm, PlaneFramePtrs W) {
+  const int NP = prm.rows * prm.cols;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int f = blockIdx.y;
+  if (idx >= NP) return;
+  int m = idx / prm.cols, n = idx - m * prm.cols;
+  unsigned short dv = depth[(size_t)f * frame_stride + (size_t)m * pitch + n];
+  double d = dv / prm.scale;
+  float z = (float)d;                                   // PointT p; p.z = d   (zero depth kept as (0,0,0), PlaneExtractor.cpp:36-47)
+  float x = (float)((n - prm.cx) * (double)z / prm.fx);
+  float y = (float)((m - prm.cy) * (double)z / prm.fy);
+  W.pts[(size_t)f * NP + idx] = make_float4(x, y, z, 0.0f);
+  W.parent[(size_t)f * NP + idx] = idx;
+  W.count[(size_t)f * NP + idx] = 0;
+  W.maxidx[(size_t)f * NP + idx] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------- P2: integral images (exact recurrence)
+// II(r+1,c+1) = ((II(r,c+1) + II(r+1,c)) - II(r,c)) + x(r,c)   in double, IntegralImage2D<float,3>::computeIntegralImages.
+// blockDim.x = rows rounded up to 32 (<= 1024); dynamic smem = rows * 4 * 6 doubles.
+__global__ void integral_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  extern __shared__ double ring[];   // [rows][4][6]
+  const int H = prm.rows, Wd = prm.cols, NP = H * Wd, IW = Wd + 1;
+  const int f = blockIdx.x;
+  const int r = threadIdx.x;
+  const float4 *pts = W.pts + (size_t)f * NP;
+  double *iiX = W.iiX + (size_t)f * (size_t)(H + 1) * IW * 3;
+  double *iiY = W.iiY + (size_t)f * (size_t)(H + 1) * IW * 3;
+  // row 0 and column 0 of the integral images are zero
+  for (int i = threadIdx.x; i < IW * 3; i += blockDim.x) { iiX[i] = 0.0; iiY[i] = 0.0; }
+  if (r < H) for (int k = 0; k < 3; k++) { iiX[((size_t)(r + 1) * IW) * 3 + k] = 0.0; iiY[((size_t)(r + 1) * IW) * 3 + k] = 0.0; }
+  double left[6] = {0, 0, 0, 0, 0, 0};
+  const bool inner_row = (r >= 1 && r <= H - 2);
+  const int steps = Wd + 2 * (H - 1);
+  float4 pl = make_float4(0, 0, 0, 0), pc = make_float4(0, 0, 0, 0), pr = make_float4(0, 0, 0, 0);  // P(r,c-1), P(r,c), P(r,c+1)
+  if (r < H) { pc = pts[(size_t)r * Wd]; if (Wd > 1) pr = pts[(size_t)r * Wd + 1]; }
+  for (int t = 0; t < steps; t++) {
+    int c = t - 2 * r;
+    if (r < H && c >= 0 && c < Wd) {
+      float v[6] = {0, 0, 0, 0, 0, 0};
+      if (inner_row && c >= 1 && c <= Wd - 2) {
+        float4 up = pts[(size_t)(r - 1) * Wd + c], dn = pts[(size_t)(r + 1) * Wd + c];
+        v[0] = __fsub_rn(pr.x, pl.x); v[1] = __fsub_rn(pr.y, pl.y); v[2] = __fsub_rn(pr.z, pl.z);
+        v[3] = __fsub_rn(dn.x, up.x); v[4] = __fsub_rn(dn.y, up.y); v[5] = __fsub_rn(dn.z, up.z);
+      }
+      double up1[6], ul[6];
+      if (r == 0) { for (int k = 0; k < 6; k++) { up1[k] = 0.0; ul[k] = 0.0; } }
+      else {
+        const double *a = &ring[((size_t)(r - 1) * 4 + (c & 3)) * 6];
+        for (int k = 0; k < 6; k++) up1[k] = a[k];
+        if (c == 0) { for (int k = 0; k < 6; k++) ul[k] = 0.0; }
+        else { const double *b = &ring[((size_t)(r - 1) * 4 + ((c - 1) & 3)) * 6]; for (int k = 0; k < 6; k++) ul[k] = b[k]; }
+      }
+      double *mine = &ring[((size_t)r * 4 + (c & 3)) * 6];
+      size_t o = ((size_t)(r + 1) * IW + (c + 1)) * 3;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        double val = __dadd_rn(__dsub_rn(__dadd_rn(up1[k], left[k]), ul[k]), (double)v[k]);
+        left[k] = val; mine[k] = val;
+      }
+      iiX[o] = left[0]; iiX[o + 1] = left[1]; iiX[o + 2] = left[2];
+      iiY[o] = left[3]; iiY[o + 1] = left[4]; iiY[o + 2] = left[5];
+      // slide the row window
+      pl = pc; pc = pr;
+      if (c + 2 < Wd) pr = pts[(size_t)r * Wd + c + 2];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- P3: depth-change + chamfer distance map
+__device__ __forceinline__ bool dc_viol(float d0, float d1) {   // depth-change test of computeFeature (max_depth_change_factor 0.05)
+  float ddc = __fmul_rn(__fmul_rn(0.05f, __fadd_rn(fabsf(d0), 1.0f)), 2.0f);
+  return fabsf(__fsub_rn(d0, d1)) > ddc || !isfinite(d0) || !isfinite(d1);
+}
+constexpr int kChamferWin = 13;
+// blockDim.x = cols rounded up to 32 (<= 1024): thread = column
+__global__ void distmap_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  __shared__ float s_prev[1024 + 2];
+  __shared__ float s_a[1024 + 2];
+  const int H = prm.rows, Wd = prm.cols, NP = H * Wd;
+  const int f = blockIdx.x, ci = threadIdx.x;
+  const float4 *pts = W.pts + (size_t)f * NP;
+  float *dm = W.dm + (size_t)f * NP;
+  const float big = (float)(Wd + H);
+  auto init_val = [&](int ri, int c) -> float {
+    float z = pts[(size_t)ri * Wd + c].z;
+    bool zero = false;
+    if (ri <= H - 2) {
+      if (c <= Wd - 2) { if (dc_viol(z, pts[(size_t)ri * Wd + c + 1].z)) zero = true; if (dc_viol(z, pts[(size_t)(ri + 1) * Wd + c].z)) zero = true; }
+      if (c >= 1) { if (dc_viol(pts[(size_t)ri * Wd + c - 1].z, z)) zero = true; }
+    }
+    if (ri >= 1 && c <= Wd - 2) { if (dc_viol(pts[(size_t)(ri - 1) * Wd + c].z, z)) zero = true; }
+    return zero ? 0.0f : big;
+  };
+  // ---- first pass (top-left to bottom-right)
+  float cur = 0.0f;
+  if (ci < Wd) { cur = init_val(0, ci); dm[ci] = cur; s_prev[ci] = cur; }
+  __syncthreads();
+  for (int ri = 1; ri < H; ri++) {
+    float center = 0.0f, a = 0.0f;
+    if (ci < Wd) {
+      center = init_val(ri, ci);
+      a = center;
+      if (ci >= 1) {
+        float upLeft = __fadd_rn(s_prev[ci - 1], 1.4f), up = __fadd_rn(s_prev[ci], 1.0f);
+        float upRight = (ci + 1 < Wd) ? __fadd_rn(s_prev[ci + 1], 1.4f) : 0.0f;
+        a = fminf(a, fminf(upLeft, up));
+        if (ci + 1 < Wd) a = fminf(a, upRight);
+      }
+      s_a[ci] = a;
+    }
+    __syncthreads();
+    if (ci < Wd) {
+      if (ci == Wd - 1 && ci >= 1) {   // previous_row[ci+1] runs into current_row[0] (never updated in this pass)
+        a = fminf(a, __fadd_rn(s_a[0], 1.4f));
+      }
+    }
+    __syncthreads();
+    if (ci == Wd - 1 && ci >= 1) s_a[ci] = a;
+    __syncthreads();
+    if (ci < Wd) {
+      float v;
+      if (ci == 0) v = a;
+      else {
+        int k0 = max(0, ci - kChamferWin);
+        v = s_a[k0];
+        for (int k = k0 + 1; k <= ci; k++) v = fminf(s_a[k], __fadd_rn(v, 1.0f));
+      }
+      cur = v;
+    }
+    __syncthreads();
+    if (ci < Wd) { s_prev[ci] = cur; dm[(size_t)ri * Wd + ci] = cur; }
+    __syncthreads();
+  }
+  // ---- second pass (bottom-right to top-left); s_prev holds the final row H-1
+  for (int ri = H - 2; ri >= 0; ri--) {
+    float fwd = 0.0f, a = 0.0f;
+    if (ci < Wd) {
+      fwd = dm[(size_t)ri * Wd + ci];
+      s_a[ci] = fwd;     // temporarily: forward values of this row (needed for the ci == 0 wrap: next_row[-1] == current_row[W-1])
+    }
+    __syncthreads();
+    if (ci < Wd) {
+      a = fwd;
+      if (ci <= Wd - 2) {
+        float lowerLeft = (ci >= 1) ? __fadd_rn(s_prev[ci - 1], 1.4f) : __fadd_rn(s_a[Wd - 1], 1.4f);
+        float lower = __fadd_rn(s_prev[ci], 1.0f), lowerRight = __fadd_rn(s_prev[ci + 1], 1.4f);
+        a = fminf(a, fminf(lowerLeft, fminf(lower, lowerRight)));
+      }
+    }
+    __syncthreads();
+    if (ci < Wd) s_a[ci] = a;
+    __syncthreads();
+    if (ci < Wd) {
+      float v;
+      if (ci == Wd - 1) v = a;
+      else {
+        int k0 = min(Wd - 1, ci + kChamferWin);
+        v = s_a[k0];
+        for (int k = k0 - 1; k >= ci; k--) v = fminf(s_a[k], __fadd_rn(v, 1.0f));
+      }
+      cur = v;
+    }
+    __syncthreads();
+    if (ci < Wd) { s_prev[ci] = cur; dm[(size_t)ri * Wd + ci] = cur; }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- P4: normals + plane_d
+__global__ void normals_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  const int H = prm.rows, Wd = prm.cols, NP = H * Wd, IW = Wd + 1;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int f = blockIdx.y;
+  if (idx >= NP) return;
+  int ri = idx / Wd, ci = idx - ri * Wd;
+  const float4 p = W.pts[(size_t)f * NP + idx];
+  const float nanf_ = __int_as_float(0x7fc00000);
+  float nx = nanf_, ny = nanf_, nz = nanf_;
+  const int border = 10;   // int(normal_smoothing_size_)
+  if (ri >= border && ri < H - border && ci >= border && ci < Wd - border && isfinite(p.z)) {
+    float smoothing = fminf(W.dm[(size_t)f * NP + idx], 10.0f);
+    if (smoothing > 2.0f) {
+      int rw = (int)smoothing, rw2 = rw / 2;
+      const double *iiX = W.iiX + (size_t)f * (size_t)(H + 1) * IW * 3;
+      const double *iiY = W.iiY + (size_t)f * (size_t)(H + 1) * IW * 3;
+      int sx = ci - rw2, sy = ri - rw2;
+      size_t ul = (size_t)sy * IW + sx, ur = ul + rw, ll = (size_t)(sy + rw) * IW + sx, lr = ll + rw;
+      double gx[3], gy[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        gx[k] = __dsub_rn(__dsub_rn(__dadd_rn(iiX[lr * 3 + k], iiX[ul * 3 + k]), iiX[ur * 3 + k]), iiX[ll * 3 + k]);
+        gy[k] = __dsub_rn(__dsub_rn(__dadd_rn(iiY[lr * 3 + k], iiY[ul * 3 + k]), iiY[ur * 3 + k]), iiY[ll * 3 + k]);
+      }
+      double n0 = __dsub_rn(__dmul_rn(gy[1], gx[2]), __dmul_rn(gy[2], gx[1]));   // gradient_y.cross(gradient_x)
+      double n1 = __dsub_rn(__dmul_rn(gy[2], gx[0]), __dmul_rn(gy[0], gx[2]));
+      double n2 = __dsub_rn(__dmul_rn(gy[0], gx[1]), __dmul_rn(gy[1], gx[0]));
+      double nl = __dadd_rn(__dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1)), __dmul_rn(n2, n2));
+      if (nl != 0.0) {
+        double s = sqrt(nl);
+        nx = (float)(n0 / s); ny = (float)(n1 / s); nz = (float)(n2 / s);
+        float vx = __fsub_rn(0.0f, p.x), vy = __fsub_rn(0.0f, p.y), vz = __fsub_rn(0.0f, p.z);   // flipNormalTowardsViewpoint, vp = 0
+        float cos_theta = __fadd_rn(__fadd_rn(__fmul_rn(vx, nx), __fmul_rn(vy, ny)), __fmul_rn(vz, nz));
+        if (cos_theta < 0) { nx *= -1; ny *= -1; nz *= -1; }
+      }
+    }
+  }
+  float pd = __fadd_rn(__fadd_rn(__fmul_rn(p.x, nx), __fmul_rn(p.y, ny)), __fmul_rn(p.z, nz));   // plane_d = p . n
+  W.nrm[(size_t)f * NP + idx] = make_float4(nx, ny, nz, pd);
+}
+
+// ---------------------------------------------------------------------------------------------- P5: connected components
+__device__ __forceinline__ int pvload(const int *p) { return *((const volatile int *)p); }
+__device__ int p_find(int *parent, int i) { int p = pvload(parent + i); while (p != i) { i = p; p = pvload(parent + i); } return i; }
+__device__ void p_union(int *parent, int a, int b) {
+  while (true) {
+    a = p_find(parent, a); b = p_find(parent, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }
+    if (atomicCAS(parent + a, a, b) == a) return;
+  }
+}
+__device__ __forceinline__ bool plane_compare(const float4 *pts, const float4 *nrm, int i1, int i2, float dis_th, float ang_cos) {
+  float z = pts[i1].z;                          // depth dependent threshold (setDistanceThreshold(.., true)), z_axis = (0,0,1)
+  float threshold = __fmul_rn(dis_th, __fmul_rn(z, z));
+  float4 a = nrm[i1], b = nrm[i2];
+  float dotn = __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+  return (fabsf(__fsub_rn(a.w, b.w)) < threshold) && (dotn > ang_cos);
+}
+__global__ void ccl_union_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  const int Wd = prm.cols, NP = prm.rows * prm.cols;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int f = blockIdx.y;
+  if (idx >= NP) return;
+  const float4 *pts = W.pts + (size_t)f * NP, *nrm = W.nrm + (size_t)f * NP;
+  int *parent = W.parent + (size_t)f * NP;
+  int ri = idx / Wd, ci = idx - ri * Wd;
+  if (ci >= 1 && plane_compare(pts, nrm, idx, idx - 1, prm.dis_th, prm.ang_cos)) p_union(parent, idx, idx - 1);
+  if (ri >= 1 && plane_compare(pts, nrm, idx, idx - Wd, prm.dis_th, prm.ang_cos)) p_union(parent, idx, idx - Wd);
+}
+__global__ void ccl_flatten_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  const int NP = prm.rows * prm.cols;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int f = blockIdx.y;
+  if (idx >= NP) return;
+  int *parent = W.parent + (size_t)f * NP;
+  int r = p_find(parent, idx);
+  atomicAdd(W.count + (size_t)f * NP + r, 1);
+  atomicMax(W.maxidx + (size_t)f * NP + r, idx);
+  W.dm[(size_t)f * NP + idx] = __int_as_float(r);   // dm is free now: stash the flattened label (written back below)
+}
+__global__ void ccl_commit_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  const int NP = prm.rows * prm.cols;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int f = blockIdx.y;
+  if (idx >= NP) return;
+  W.parent[(size_t)f * NP + idx] = __float_as_int(W.dm[(size_t)f * NP + idx]);
+}
+
+// ---------------------------------------------------------------------------------------------- P6: candidate regions (> 100 px), label order
+__global__ void candidates_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  __shared__ BlockScratch S;
+  const int NP = prm.rows * prm.cols;
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const int *parent = W.parent + (size_t)f * NP, *count = W.count + (size_t)f * NP;
+  int K = 0;
+  for (int tile = 0; tile < NP; tile += blockDim.x) {
+    int i = tile + tid;
+    bool acc = (i < NP) && parent[i] == i && (unsigned)count[i] > 100u;   // min_inliers_ = 100, strict
+    int tot;
+    int ex = block_excl_scan(acc ? 1 : 0, S, tot);
+    if (acc && K + ex < kMaxRegions) { W.cand_root[f * kMaxRegions + K + ex] = i; W.cand_size[f * kMaxRegions + K + ex] = count[i]; }
+    K += tot;
+  }
+  if (tid == 0) W.cand_n[f] = min(K, kMaxRegions);
+}
+
+// ---------------------------------------------------------------------------------------------- P7: plane fit (float, sequential raster order)
+__device__ void roots2f(float b, float c, float *roots) {
+  roots[0] = 0.0f;
+  float d = (float)((double)__fmul_rn(b, b) - 4.0 * (double)c);
+  if (d < 0.0f) d = 0.0f;
+  float sd = sqrtf(d);
+  roots[2] = __fmul_rn(0.5f, __fadd_rn(b, sd));
+  roots[1] = __fmul_rn(0.5f, __fsub_rn(b, sd));
+}
+__device__ void roots3f(const float *m /*3x3*/, float *roots) {   // pcl::computeRoots
+  float c0 = m[0] * m[4] * m[8] + 2.0f * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] - m[8] * m[1] * m[1];
+  float c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+  float c2 = m[0] + m[4] + m[8];
+  if (fabsf(c0) < 1.1920929e-07f) roots2f(c2, c1, roots);
+  else {
+    const float s_inv3 = (float)(1.0 / 3.0);
+    const float s_sqrt3 = sqrtf(3.0f);
+    float c2_over_3 = c2 * s_inv3;
+    float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+    if (a_over_3 > 0.0f) a_over_3 = 0.0f;
+    float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+    float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+    if (q > 0.0f) q = 0.0f;
+    float rho = sqrtf(-a_over_3);
+    float theta = atan2f(sqrtf(-q), half_b) * s_inv3;
+    float cos_theta = cosf(theta), sin_theta = sinf(theta);
+    roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
+    roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+    roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+    float t;
+    if (roots[0] >= roots[1]) { t = roots[0]; roots[0] = roots[1]; roots[1] = t; }
+    if (roots[1] >= roots[2]) { t = roots[1]; roots[1] = roots[2]; roots[2] = t; if (roots[0] >= roots[1]) { t = roots[0]; roots[0] = roots[1]; roots[1] = t; } }
+    if (roots[0] <= 0) roots2f(c2, c1, roots);
+  }
+}
+// one warp per (frame, candidate)
+__global__ void fit_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  const int NP = prm.rows * prm.cols;
+  const int f = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= W.cand_n[f]) return;
+  const int root = W.cand_root[f * kMaxRegions + k];
+  const int *parent = W.parent + (size_t)f * NP;
+  const float4 *pts = W.pts + (size_t)f * NP;
+  const int last = W.maxidx[(size_t)f * NP + root];
+  float acc = 0.0f;   // lanes 0..8 : xx xy xz yy yz zz x y z   (computeMeanAndCovarianceMatrix<float>)
+  for (int base = root & ~31; base <= last; base += 32) {
+    int i = base + lane;
+    bool in = (i >= root && i <= last) && parent[i] == root;
+    unsigned mask = __ballot_sync(0xffffffffu, in);
+    while (mask) {
+      int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      float4 p = pts[base + b];
+      float v;
+      switch (lane) {
+        case 0: v = __fmul_rn(p.x, p.x); break;
+        case 1: v = __fmul_rn(p.x, p.y); break;
+        case 2: v = __fmul_rn(p.x, p.z); break;
+        case 3: v = __fmul_rn(p.y, p.y); break;
+        case 4: v = __fmul_rn(p.y, p.z); break;
+        case 5: v = __fmul_rn(p.z, p.z); break;
+        case 6: v = p.x; break;
+        case 7: v = p.y; break;
+        case 8: v = p.z; break;
+        default: v = 0.0f; break;
+      }
+      acc = __fadd_rn(acc, v);
+    }
+  }
+  float accu[9];
+#pragma unroll
+  for (int j = 0; j < 9; j++) accu[j] = __shfl_sync(0xffffffffu, acc, j);
+  if (lane != 0) return;
+  float cnt = (float)W.count[(size_t)f * NP + root];
+#pragma unroll
+  for (int j = 0; j < 9; j++) accu[j] = __fdiv_rn(accu[j], cnt);
+  float cov[9];
+  cov[0] = __fsub_rn(accu[0], __fmul_rn(accu[6], accu[6])); cov[1] = __fsub_rn(accu[1], __fmul_rn(accu[6], accu[7])); cov[2] = __fsub_rn(accu[2], __fmul_rn(accu[6], accu[8]));
+  cov[4] = __fsub_rn(accu[3], __fmul_rn(accu[7], accu[7])); cov[5] = __fsub_rn(accu[4], __fmul_rn(accu[7], accu[8])); cov[8] = __fsub_rn(accu[5], __fmul_rn(accu[8], accu[8]));
+  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+  // pcl::eigen33(mat, eigenvalue, eigenvector)
+  float scale = 0.0f;
+  for (int j = 0; j < 9; j++) scale = fmaxf(scale, fabsf(cov[j]));
+  if (scale <= 1.17549435e-38f) scale = 1.0f;
+  float sm[9];
+  for (int j = 0; j < 9; j++) sm[j] = __fdiv_rn(cov[j], scale);
+  float ev[3];
+  roots3f(sm, ev);
+  float eigen_value = ev[0] * scale;
+  sm[0] -= ev[0]; sm[4] -= ev[0]; sm[8] -= ev[0];
+  float v1[3] = {sm[1] * sm[5] - sm[2] * sm[4], sm[2] * sm[3] - sm[0] * sm[5], sm[0] * sm[4] - sm[1] * sm[3]};      // row0 x row1
+  float v2[3] = {sm[1] * sm[8] - sm[2] * sm[7], sm[2] * sm[6] - sm[0] * sm[8], sm[0] * sm[7] - sm[1] * sm[6]};      // row0 x row2
+  float v3[3] = {sm[4] * sm[8] - sm[5] * sm[7], sm[5] * sm[6] - sm[3] * sm[8], sm[3] * sm[7] - sm[4] * sm[6]};      // row1 x row2
+  float l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2], l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2], l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+  const float *v; float l;
+  if (l1 >= l2 && l1 >= l3) { v = v1; l = l1; } else if (l2 >= l1 && l2 >= l3) { v = v2; l = l2; } else { v = v3; l = l3; }
+  float s = sqrtf(l);
+  float pp[4] = {__fdiv_rn(v[0], s), __fdiv_rn(v[1], s), __fdiv_rn(v[2], s), 0.0f};
+  pp[3] = -1 * (pp[0] * accu[6] + pp[1] * accu[7] + pp[2] * accu[8] + pp[3] * 1.0f);
+  // (PCL flips the sign towards an accumulated view point here; the reference re-normalises the sign afterwards -- PlaneExtractor.cpp:98-99,176-178)
+  float eig_sum = cov[0] + cov[4] + cov[8];
+  float curvature = (eig_sum != 0) ? fabsf(eigen_value / eig_sum) : 0.0f;
+  W.cand_coef[f * kMaxRegions + k] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+  int valid = curvature < 0.001f;   // maximum_curvature_
+  W.cand_valid[f * kMaxRegions + k] = valid;
+  if (valid) W.count[(size_t)f * NP + root] = -(k + 1);   // marks the root as a model label (refine_labels_)
+}
+
+// ---------------------------------------------------------------------------------------------- P8: refinement
+__device__ __forceinline__ int block_incl_max_scan(int v, BlockScratch &S, bool reverse) {
+  // inclusive max scan in thread order (or reverse thread order)
+  int lane = lane_id(), w = warp_id(), nw = n_warps();
+  int x = v;
+  if (!reverse) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x = max(x, t); }
+    if (lane == 31) S.warp_i[w] = x;
+    __syncthreads();
+    int pre = -0x7fffffff;
+    for (int i = 0; i < w; i++) pre = max(pre, S.warp_i[i]);
+    __syncthreads();
+    return max(x, pre);
+  } else {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_down_sync(0xffffffffu, x, o); if (lane + o < 32) x = max(x, t); }
+    if (lane == 0) S.warp_i[w] = x;
+    __syncthreads();
+    int pre = -0x7fffffff;
+    for (int i = w + 1; i < nw; i++) pre = max(pre, S.warp_i[i]);
+    __syncthreads();
+    return max(x, pre);
+  }
+}
+__device__ __forceinline__ bool refine_ok(const float4 c, const float4 p) {   // PlaneRefinementComparator: |a x + b y + c z + d| < 0.02
+  float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c.x, p.x), __fmul_rn(c.y, p.y)), __fmul_rn(c.z, p.z)), c.w);
+  return fabsf(d) < 0.02f;
+}
+// blockDim.x = cols rounded up to 32 (<= 1024); thread = column
+__global__ void refine_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  __shared__ BlockScratch S;
+  __shared__ int s_m[1024];
+  const int H = prm.rows, Wd = prm.cols, NP = H * Wd;
+  const int f = blockIdx.x, c = threadIdx.x;
+  int *parent = W.parent + (size_t)f * NP;
+  const int *count = W.count + (size_t)f * NP;
+  const float4 *pts = W.pts + (size_t)f * NP;
+  const float4 *coef = W.cand_coef + f * kMaxRegions;
+  const int *croot = W.cand_root + f * kMaxRegions;
+  int *csize = W.cand_size + f * kMaxRegions;
+  auto model_of = [&](int pix) -> int { int r = parent[pix]; int cn = count[r]; return cn < 0 ? (-cn - 1) : -1; };
+  for (int pass = 0; pass < 2; pass++) {
+    const bool fwd = pass == 0;
+    for (int step = 0; step < H - 1; step++) {
+      const int r = fwd ? step : (H - 1 - step);          // current row
+      const int rn = fwd ? r + 1 : r - 1;                 // row hit by the vertical check
+      int m = -1;
+      if (c < Wd) m = model_of(r * Wd + c);
+      // ---- horizontal propagation along the row (scan direction = traversal direction)
+      int src = (c < Wd && m >= 0) ? c : (fwd ? -1 : -(1 << 30));
+      int s;
+      if (fwd) s = block_incl_max_scan(src, S, false);                // nearest source at or left of c
+      else s = -block_incl_max_scan((c < Wd && m >= 0) ? -c : -(1 << 30), S, true);   // nearest source at or right of c
+      if (c < Wd) s_m[c] = m;
+      __syncthreads();
+      bool has_src = fwd ? (s >= 0) : (s < (1 << 29));
+      int L = -1; bool blocked = false;
+      if (c < Wd && m < 0) {
+        if (has_src) { L = s_m[s]; blocked = !refine_ok(coef[L], pts[r * Wd + c]); }
+        else blocked = true;
+      }
+      int bsrc = (c < Wd && m < 0 && blocked) ? c : -1;
+      int b;
+      if (fwd) b = block_incl_max_scan(bsrc, S, false);                // last blocked index <= c
+      else b = -block_incl_max_scan((c < Wd && m < 0 && blocked) ? -c : -(1 << 30), S, true);   // first blocked index >= c
+      bool recv = false;
+      if (c < Wd && m < 0 && has_src) recv = fwd ? (b < s) : (b > s);
+      // the forward pass never uses column W-1 as "current"; every receiver's chain starts at a source that IS a valid current
+      if (recv) { m = L; parent[r * Wd + c] = croot[L]; atomicAdd(&csize[L], 1); }
+      // ---- vertical check from the (updated) current row
+      bool cur_ok = (c < Wd) && m >= 0 && (fwd ? (c <= Wd - 2) : true);
+      if (cur_ok) {
+        int tp = rn * Wd + c;
+        if (model_of(tp) < 0 && refine_ok(coef[m], pts[tp])) { parent[tp] = croot[m]; atomicAdd(&csize[m], 1); }
+      }
+      __syncthreads();
+      if (!fwd && c == 0 && m >= 0) {   // colIdx == 0: "left" neighbour is the last pixel of the previous row (pointer arithmetic in PCL)
+        int tp = r * Wd - 1;
+        if (model_of(tp) < 0 && refine_ok(coef[m], pts[tp])) { parent[tp] = croot[m]; atomicAdd(&csize[m], 1); }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- P9: selection (PlaneExtractor.cpp:89-106,126-183)
+__global__ void select_kernel(PlaneParamsDev prm, PlaneFramePtrs W, int n_frames) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  int K = W.cand_n[f];
+  int best = -1, best_size = -1; double bv[4] = {0, 0, 0, 0};
+  for (int k = 0; k < K; k++) {
+    if (!W.cand_valid[f * kMaxRegions + k]) continue;
+    int size = W.cand_size[f * kMaxRegions + k];
+    if (size < prm.min_size) continue;
+    float4 cf = W.cand_coef[f * kMaxRegions + k];
+    if (cf.w < 0) { cf.x = -cf.x; cf.y = -cf.y; cf.z = -cf.z; cf.w = -cf.w; }
+    double v[4] = {(double)cf.x, (double)cf.y, (double)cf.z, (double)cf.w};
+    double cos_theta = v[0] * 0.0 + v[1] * 1.0 + v[2] * 0.0;
+    cos_theta = cos_theta / sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / 1.0;
+    double theta = acos(cos_theta);
+    if (theta > M_PI / 4 && theta < 3 * M_PI / 4) continue;
+    if (size > best_size) { best_size = size; best = k; for (int j = 0; j < 4; j++) bv[j] = v[j]; }
+  }
+  if (best < 0) { W.out_found[f] = 0; W.out_inl[f] = 0; for (int j = 0; j < 4; j++) W.out_plane[4 * f + j] = 0; return; }
+  double value = (bv[0] * 0.0 + bv[1] * 0.0 + bv[2] * 0.0 + bv[3]) / sqrt(bv[0] * bv[0] + bv[1] * bv[1] + bv[2] * bv[2]);
+  if (value < 0) for (int j = 0; j < 4; j++) bv[j] = -bv[j];
+  for (int j = 0; j < 4; j++) W.out_plane[4 * f + j] = bv[j];
+  W.out_found[f] = 1; W.out_inl[f] = best_size;
+}
+
+// ---------------------------------------------------------------------------------------------- host driver
+// debug_stage: 0 = normal run; 1 = stop after the distance map (out: float[NP]); 2 = after normals (float4[NP]);
+// 3 = after connected components (int[NP] labels = min pixel index); 4 = after refinement (int[NP]).  First frame only.
+int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *depth_dev, size_t pitch, double *plane_cam_host, int *found_host,
+                      int *n_inliers_host, int debug_stage, void *debug_out) {
+  const int H = h->cam.rows, Wd = h->cam.cols;
+  if (H > 1024 || Wd > 1024 || H < 24 || Wd < 24 || pitch < (size_t)Wd) { h->err = "plane_extract: image must be between 24 and 1024 pixels per side"; return ESLAM_ERR_BAD_ARG; }
+  if (!h->pl) h->pl = new PlaneWorkspace();
+  PlaneWorkspace &w = *h->pl;
+  const size_t NP = (size_t)H * Wd, NI = (size_t)(H + 1) * (Wd + 1) * 3;
+  const int chunk = n_frames < 64 ? n_frames : 64;
+  ESLAM_CUDA_OK(h, w.pts.reserve(chunk * NP * 16)); ESLAM_CUDA_OK(h, w.nrm.reserve(chunk * NP * 16));
+  ESLAM_CUDA_OK(h, w.iiX.reserve(chunk * NI * 8)); ESLAM_CUDA_OK(h, w.iiY.reserve(chunk * NI * 8));
+  ESLAM_CUDA_OK(h, w.dm.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.parent.reserve(chunk * NP * 4));
+  ESLAM_CUDA_OK(h, w.count.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.maxidx.reserve(chunk * NP * 4));
+  ESLAM_CUDA_OK(h, w.cand_root.reserve((size_t)chunk * kMaxRegions * 4)); ESLAM_CUDA_OK(h, w.cand_n.reserve((size_t)chunk * 4));
+  ESLAM_CUDA_OK(h, w.cand_coef.reserve((size_t)chunk * kMaxRegions * 16)); ESLAM_CUDA_OK(h, w.cand_valid.reserve((size_t)chunk * kMaxRegions * 4));
+  ESLAM_CUDA_OK(h, w.cand_size.reserve((size_t)chunk * kMaxRegions * 4));
+  ESLAM_CUDA_OK(h, w.out_plane.reserve((size_t)chunk * 32)); ESLAM_CUDA_OK(h, w.out_found.reserve((size_t)chunk * 4)); ESLAM_CUDA_OK(h, w.out_inl.reserve((size_t)chunk * 4));
+  PlaneFramePtrs P;
+  P.pts = w.pts.as<float4>(); P.nrm = w.nrm.as<float4>(); P.iiX = w.iiX.as<double>(); P.iiY = w.iiY.as<double>(); P.dm = w.dm.as<float>();
+  P.parent = w.parent.as<int>(); P.count = w.count.as<int>(); P.maxidx = w.maxidx.as<int>();
+  P.cand_root = w.cand_root.as<int>(); P.cand_n = w.cand_n.as<int>(); P.cand_coef = w.cand_coef.as<float4>(); P.cand_valid = w.cand_valid.as<int>();
+  P.cand_size = w.cand_size.as<int>(); P.out_plane = w.out_plane.as<double>(); P.out_found = w.out_found.as<int>(); P.out_inl = w.out_inl.as<int>();
+  PlaneParamsDev prm;
+  prm.fx = h->cam.fx; prm.fy = h->cam.fy; prm.cx = h->cam.cx; prm.cy = h->cam.cy; prm.scale = h->cam.scale; prm.rows = H; prm.cols = Wd;
+  const float AngTh = (float)h->prm.plane_angle_deg;
+  prm.dis_th = (float)h->prm.plane_dist;
+  prm.ang_cos = cosf((float)(0.017453 * AngTh));   // mps.setAngularThreshold(0.017453 * AngTh) -> PlaneCoefficientComparator: cosf
+  prm.min_size = h->prm.plane_min_size;
+  const size_t ring_bytes = (size_t)H * 4 * 6 * sizeof(double);
+  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+  const int tpr = ((H + 31) / 32) * 32, tpc = ((Wd + 31) / 32) * 32;
+  const size_t frame_stride = (size_t)H * pitch;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+    const int F = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;
+    const uint16_t *d0 = depth_dev + (size_t)f0 * frame_stride;
+    dim3 gpix((unsigned)((NP + 255) / 256), (unsigned)F);
+    points_kernel<<<gpix, 256, 0, s>>>(d0, pitch, frame_stride, prm, P); ESLAM_LAUNCHED(h);
+    integral_kernel<<<F, tpr, ring_bytes, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    distmap_kernel<<<F, tpc, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    if (debug_stage == 1) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.dm, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
+    normals_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    if (debug_stage == 2) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.nrm, NP * 16, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
+    ccl_union_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    ccl_flatten_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    ccl_commit_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    if (debug_stage == 3) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.parent, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
+    candidates_kernel<<<F, 1024, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    dim3 gfit(kMaxRegions / 8, (unsigned)F);
+    fit_kernel<<<gfit, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    refine_kernel<<<F, tpc, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    if (debug_stage == 4) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.parent, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
+    select_kernel<<<(F + 63) / 64, 64, 0, s>>>(prm, P, F); ESLAM_LAUNCHED(h);
+    ESLAM_CUDA_OK(h, cudaGetLastError());
+    ESLAM_CUDA_OK(h, cudaMemcpyAsync(plane_cam_host + 4 * (size_t)f0, P.out_plane, sizeof(double) * 4 * F, cudaMemcpyDeviceToHost, s));
+    ESLAM_CUDA_OK(h, cudaMemcpyAsync(found_host + f0, P.out_found, sizeof(int) * F, cudaMemcpyDeviceToHost, s));
+    if (n_inliers_host) ESLAM_CUDA_OK(h, cudaMemcpyAsync(n_inliers_host + f0, P.out_inl, sizeof(int) * F, cudaMemcpyDeviceToHost, s));
+    ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
+  }
+  return ESLAM_OK;
+}
+
+int plane_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *depth_dev, size_t pitch, double *plane_cam_host, int *found_host,
+                  int *n_inliers_host) {
+  return plane_extract_dbg(h, s, n_frames, depth_dev, pitch, plane_cam_host, found_host, n_inliers_host, 0, nullptr);
+}
+
+void plane_free(EslamHandle *h) {
+  if (!h->pl) return;
+  PlaneWorkspace &w = *h->pl;
+  DevBuf *bufs[] = {&w.pts, &w.nrm, &w.iiX, &w.iiY, &w.dm, &w.parent, &w.count, &w.maxidx, &w.cand_root, &w.cand_n, &w.cand_coef, &w.cand_valid, &w.cand_size,
+                    &w.out_plane, &w.out_found, &w.out_inl};
+  for (DevBuf *b : bufs) b->release();
+  w.pin.release();
+  delete h->pl; h->pl = nullptr;
+}
+
+}  // namespace eslam

@@ -1,0 +1,40 @@
+"""Shared builders for the parity tests (synthetic graphs, comparisons)."""
+import numpy as np
+
+import orc
+from eslam_b200 import synth
+
+K = np.array([[535.4, 0, 320.1], [0, 539.2, 247.6], [0, 0, 1.0]])
+
+
+def make_ba_problem(n_frames=40, n_objects=10, edges_per_frame=10, seed=4242, with_gravity=True):
+    """Config-4 shaped graph (BASELINE.json configs[3]); measurements come from the oracle's own projection."""
+    g = synth.ba_graph(n_frames, n_objects, edges_per_frame, seed)
+    objs, Twc = g["objs"], g["Twc"]
+    Tcw = np.array([orc.se3_inverse(T) for T in Twc])
+    et, fr, ob, meas, info = [], [], [], [], []
+    if with_gravity:
+        for o in range(n_objects):
+            et.append(2); fr.append(0); ob.append(o); meas.append(np.r_[0, 0, 1, 0, np.zeros(6)]); info.append(100.0 ** 2)
+    for f in range(n_frames):
+        for k, o in enumerate(g["pick2d"][f]):
+            bb = orc.ellipsoid_bbox(objs[o], Tcw[f], K) + g["noise2d"][f, k]
+            et.append(0); fr.append(f); ob.append(int(o)); meas.append(np.r_[bb, np.zeros(6)]); info.append(1.0)
+    for f in range(n_frames):
+        for k, o in enumerate(g["pick3d"][f]):
+            local = orc.ellipsoid_transform_from(orc.ellipsoid_exp_update(objs[o], g["noise3d"][f, k]), Tcw[f])
+            et.append(1); fr.append(f); ob.append(int(o)); meas.append(local); info.append(10000.0 * 0.9)
+    init = np.array([orc.ellipsoid_exp_update(objs[o], g["init_noise"][o]) for o in range(n_objects)])
+    return dict(type=et, frame=fr, object=ob, meas=np.array(meas), info=info, Tcw=Tcw, n_objects=n_objects, K=K, init=init, truth=objs)
+
+
+def ellipsoid_close(a, b, rtol=1e-4):
+    """pose/axes within rtol (relative to max(1,|value|)); quaternion sign-normalised."""
+    a, b = np.array(a, dtype=float), np.array(b, dtype=float)
+    if np.dot(a[3:7], b[3:7]) < 0:
+        b = b.copy(); b[3:7] = -b[3:7]
+    return np.all(np.abs(a - b) <= rtol * np.maximum(1.0, np.abs(b)))
+
+
+def dump_points(keep, name, n):
+    return getattr(keep, name)[:n]
