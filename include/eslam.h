@@ -168,6 +168,11 @@ const char *eslam_last_error(EslamHandle *h);
 /* number of kernel launches issued by this handle so far (bench.py "gpu_launches") */
 long long eslam_launch_count(EslamHandle *h);
 
+/* profiling hooks (bench.py): device time of each kernel of the most recent extraction batch, measured with CUDA
+ * events on the launching stream.  ms[0] = extract kernel, ms[1] = symmetry+finalize kernel, ms[2] = both. */
+int eslam_set_profiling(EslamHandle *h, int on);
+int eslam_get_stage_ms(EslamHandle *h, float ms[3]);
+
 /* ------------------------------------------------------------------ ground plane */
 /* replaces PlaneExtractor::extractGroundPlane (PlaneExtractor.cpp:126-183), batched over frames.
  * plane_cam: [n_frames*4] camera-frame plane (oriented so the camera is on the + side, :176-178)

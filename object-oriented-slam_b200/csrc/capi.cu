@@ -109,8 +109,11 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
   if (rc) return rc;
   ExtractParamsDev prm = make_dev_params(h);
   size_t frame_stride = (size_t)h->cam.rows * pitch;
+  if (h->profiling) ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[0], s));
   if ((rc = extract_launch(h, s, depth_dev, pitch, frame_stride, n_obj, prm, P))) return rc;
+  if (h->profiling) ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[1], s));
   if ((rc = symmetry_finalize_launch(h, s, depth_dev, pitch, frame_stride, n_obj, prm, P))) return rc;
+  if (h->profiling) ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[2], s));
   return ESLAM_OK;
 }
 
@@ -196,8 +199,27 @@ void eslam_destroy(EslamHandle *h) {
   }
   graph_free(h);
   plane_free(h);
+  for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+// per-kernel device times of the most recent extraction batch (CUDA events on the launching stream)
+int eslam_set_profiling(EslamHandle *h, int on) {
+  if (!h) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  if (on && !h->ev[0]) for (int i = 0; i < 4; i++) ESLAM_CUDA_OK(h, cudaEventCreate(&h->ev[i]));
+  h->profiling = on != 0;
+  return ESLAM_OK;
+}
+int eslam_get_stage_ms(EslamHandle *h, float ms[3]) {
+  if (!h || !h->profiling || !h->ev[0]) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  ESLAM_CUDA_OK(h, cudaEventSynchronize(h->ev[2]));
+  ESLAM_CUDA_OK(h, cudaEventElapsedTime(&ms[0], h->ev[0], h->ev[1]));
+  ESLAM_CUDA_OK(h, cudaEventElapsedTime(&ms[1], h->ev[1], h->ev[2]));
+  ESLAM_CUDA_OK(h, cudaEventElapsedTime(&ms[2], h->ev[0], h->ev[2]));
+  return ESLAM_OK;
 }
 
 const char *eslam_last_error(EslamHandle *h) { return h ? h->err.c_str() : "null handle"; }

@@ -57,6 +57,9 @@ struct EslamHandle {
   bool plane_set = false;
   double plane_world[4] = {0, 0, 1, 0};
   long long launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float stage_ms[3] = {0, 0, 0};   // extract kernel, symmetry+finalize kernel, total of the last profiled batch
   std::string err;
   eslam::ExtractWorkspace *ex = nullptr;
   eslam::GraphWorkspace *gr = nullptr;

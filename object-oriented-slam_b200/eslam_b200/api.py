@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "eslam_launch_count", "eslam_extract_ground_plane_host", "eslam_extract_ground_plane_dev", "eslam_plane_to_world",
     "eslam_set_supporting_plane", "eslam_calibrate_measurement", "eslam_estimate_ellipsoids_host", "eslam_estimate_ellipsoids_dev",
     "eslam_fetch_ellipsoids", "eslam_init_quadric", "eslam_edges_eval_host", "eslam_edges_upload", "eslam_edges_eval_dev",
-    "eslam_edges_download", "eslam_optimize_objects_host", "eslam_pose_inverse",
+    "eslam_edges_download", "eslam_optimize_objects_host", "eslam_pose_inverse", "eslam_set_profiling", "eslam_get_stage_ms",
 ]
 
 
@@ -106,6 +106,14 @@ class Handle:
     def check(self, rc, what):
         if rc != 0:
             raise EslamError(f"{what} failed ({rc}): {self.lib.eslam_last_error(self._h).decode()}")
+
+    def set_profiling(self, on=True):
+        self.check(self.lib.eslam_set_profiling(self._h, C.c_int(1 if on else 0)), "eslam_set_profiling")
+
+    def stage_ms(self):
+        ms = (C.c_float * 3)()
+        self.check(self.lib.eslam_get_stage_ms(self._h, ms), "eslam_get_stage_ms")
+        return [float(x) for x in ms]
 
     @property
     def launches(self):

@@ -52,10 +52,9 @@ for f in range(3):
     nan_mis = (np.isnan(g_n[..., 0]) != np.isnan(normals[..., 0])).sum()
     ok = ~np.isnan(normals[..., 0]) & ~np.isnan(g_n[..., 0])
     print(f"   normals: nan-mask mismatches {nan_mis}; value mismatches {(g_n[..., :3][ok] != normals[ok]).any(axis=-1).sum()} of {ok.sum()}; max diff {np.abs(g_n[..., :3][ok]-normals[ok]).max():.3e}")
-    from test_gpu_parity import _canon_labels
+    from test_gpu_parity import _same_partition
     g_l3 = h.debug_plane_stage(depth[f], 3); g_l4 = h.debug_plane_stage(depth[f], 4)
-    can = _canon_labels(labels)
-    print(f"   labels after refine: mismatches {(g_l4 != can).sum()}  (pre-refine vs refined differ in {(g_l3 != g_l4).sum()} px)")
+    print(f"   labels after refine: same partition {_same_partition(g_l4, labels)}  (pre-refine vs refined differ in {(g_l3 != g_l4).sum()} px)")
 t = time.time(); pg, fg, ng = h.extract_ground_plane(depth); tg = time.time() - t
 t = time.time(); po, fo_, no = orc.extract_ground_plane(depth); to = time.time() - t
 print(f" planes gpu {tg*1e3:.1f} ms oracle {to*1e3:.1f} ms"); print(pg, fg, ng); print(po, fo_, no); print(" max|d plane|", np.abs(pg - po).max())
