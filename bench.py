@@ -181,8 +181,10 @@ def main():
     n_obj = len(fo)
     h = E.Handle(device=local)
     h.set_supporting_plane(plane)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # explicit non-default stream: kernels AND the timing events live on it
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
     host_depth = torch.from_numpy(depth.view(np.int16)).pin_memory()      # pinned host copy (e2e leg)
     dev_depth = host_depth.to("cuda", non_blocking=True)
     torch.cuda.synchronize()

@@ -24,9 +24,15 @@ __device__ __forceinline__ int lower_bound_u32(const unsigned *a, int n, unsigne
   return lo;
 }
 __device__ __forceinline__ int vload(const int *p) { return *((const volatile int *)p); }
+// find with path halving: parent pointers only ever move towards the root (a smaller index), so the racy
+// parent[i] = grandparent stores are benign (they always write an ancestor of i).
 __device__ int uf_find(int *parent, int i) {
   int p = vload(parent + i);
-  while (p != i) { i = p; p = vload(parent + i); }
+  while (p != i) {
+    int gp = vload(parent + p);
+    if (gp != p) *((volatile int *)(parent + i)) = gp;
+    i = p; p = gp;
+  }
   return i;
 }
 __device__ void uf_union(int *parent, int a, int b) {

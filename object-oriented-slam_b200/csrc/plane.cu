@@ -271,7 +271,15 @@ __global__ void normals_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
 
 // ---------------------------------------------------------------------------------------------- P5: connected components
 __device__ __forceinline__ int pvload(const int *p) { return *((const volatile int *)p); }
-__device__ int p_find(int *parent, int i) { int p = pvload(parent + i); while (p != i) { i = p; p = pvload(parent + i); } return i; }
+__device__ int p_find(int *parent, int i) {   // path halving (benign races: only ancestors are ever written)
+  int p = pvload(parent + i);
+  while (p != i) {
+    int gp = pvload(parent + p);
+    if (gp != p) *((volatile int *)(parent + i)) = gp;
+    i = p; p = gp;
+  }
+  return i;
+}
 __device__ void p_union(int *parent, int a, int b) {
   while (true) {
     a = p_find(parent, a); b = p_find(parent, b);

@@ -46,6 +46,11 @@ __device__ double sym_eval(const SymCtx &c, const dplane &pl) {
   plane_another(pl, p2);
   const int M = c.M;
   const int npts = (c.symtype == 2) ? 2 * M : M;
+  // per-plane constants of GetSymmetryPointOfPlane hoisted out of the point loop (same values, same rounding)
+  const double down1 = sqrt(pl.p[0] * pl.p[0] + pl.p[1] * pl.p[1] + pl.p[2] * pl.p[2]);
+  const double n1x = pl.p[0] / down1, n1y = pl.p[1] / down1, n1z = pl.p[2] / down1;
+  const double down2 = sqrt(p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
+  const double n2x = p2[0] / down2, n2y = p2[1] / down2, n2z = p2[2] / down2;
   double ln_total = 0.0;
   int invalid = 0;
   for (int base = 0; base < npts; base += 32) {
@@ -55,7 +60,11 @@ __device__ double sym_eval(const SymCtx &c, const dplane &pl) {
       int second = idx >= M;
       int j = idx - (second ? M : 0);
       d3 pt = mk3(c.objn[3 * j], c.objn[3 * j + 1], c.objn[3 * j + 2]);
-      d3 pm = mirror_point(pt, second ? p2 : pl.p);
+      const double q0 = second ? p2[0] : pl.p[0], q1 = second ? p2[1] : pl.p[1], q2 = second ? p2[2] : pl.p[2], q3 = second ? p2[3] : pl.p[3];
+      const double val = q0 * pt.x + q1 * pt.y + q2 * pt.z + q3 * 1.0;
+      const double dis_pl = fabs(val) / (second ? down2 : down1);
+      const double kk = 2 * ((val > 0) ? -1.0 : 1.0) * dis_pl;
+      d3 pm = mk3(pt.x + kk * (second ? n2x : n1x), pt.y + kk * (second ? n2y : n1y), pt.z + kk * (second ? n2z : n1z));
       double uvh[3];
 #pragma unroll
       for (int r = 0; r < 3; r++) { double s = c.P[r * 4] * pm.x; s += c.P[r * 4 + 1] * pm.y; s += c.P[r * 4 + 2] * pm.z; s += c.P[r * 4 + 3] * 1.0; uvh[r] = s; }
@@ -192,7 +201,7 @@ __device__ SeedResult sym_optimize(const SymCtx &c, dplane est, int iters) {
 }
 
 // grid = n_obj, block = 288 (9 warps = 9 seeds)
-__global__ void __launch_bounds__(288) symmetry_finalize_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride,
+__global__ void __launch_bounds__(288, 2) symmetry_finalize_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride,
                                                                 const ObjMeta *__restrict__ metas, ObjState *__restrict__ states, ExtractParamsDev prm,
                                                                 ExtractPtrs W, EslamEllipsoidOut *__restrict__ outs) {
   __shared__ BlockScratch S;
