@@ -252,21 +252,38 @@ __global__ void __launch_bounds__(512, 1) extract_kernel(const uint16_t *__restr
     __syncthreads();
     block_radix_sort(k0, v0, k1, v1, n3, bits_for((unsigned)(gx * gy * gz)), RS);
     const float r2 = prm.cluster_r2;
-    for (int pos = tid; pos < n3; pos += blockDim.x) {
-      int i = (int)v0[pos];
-      float4 p = B[i];
-      int cx = (int)((p.x - mn[0]) / cs), cy = (int)((p.y - mn[1]) / cs), cz = (int)((p.z - mn[2]) / cs);
-      int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
-      for (int dz = -1; dz <= 1; dz++) {
-        int zz = cz + dz; if (zz < 0 || zz >= nz) continue;
-        for (int dy = -1; dy <= 1; dy++) {
-          int yy = cy + dy; if (yy < 0 || yy >= ny) continue;
-          unsigned klo = (unsigned)((zz * ny + yy) * nx + xlo), khi = (unsigned)((zz * ny + yy) * nx + xhi);
-          int q = lower_bound_u32(k0, n3, klo);
-          for (; q < n3 && k0[q] <= khi; q++) {
+    int pow2 = 1;
+    while (pow2 < n3) pow2 <<= 1;
+    // Warp-converged neighbour search: every lane walks the same 9 (dz,dy) rows; the data-dependent scan of a row is
+    // re-converged with __any_sync each step, so divergent union-find retries never serialise the rest of the warp.
+    for (int base = 0; base < n3; base += blockDim.x) {
+      const int pos = base + tid;
+      const bool act = pos < n3;
+      int i = 0, cx = 0, cy = 0, cz = 0;
+      float4 p = make_float4(0, 0, 0, 0);
+      if (act) {
+        i = (int)v0[pos]; p = B[i];
+        cx = (int)((p.x - mn[0]) / cs); cy = (int)((p.y - mn[1]) / cs); cz = (int)((p.z - mn[2]) / cs);
+      }
+      const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
+#pragma unroll 1
+      for (int row = 0; row < 9; row++) {
+        const int zz = cz + row / 3 - 1, yy = cy + row % 3 - 1;
+        const bool valid = act && zz >= 0 && zz < nz && yy >= 0 && yy < ny;
+        unsigned khi = 0; int q = n3;
+        if (valid) {
+          unsigned klo = (unsigned)((zz * ny + yy) * nx + xlo);
+          khi = (unsigned)((zz * ny + yy) * nx + xhi);
+          q = 0;
+          for (int st = pow2; st > 0; st >>= 1) { int t = q + st; if (t <= n3 && k0[t - 1] < klo) q = t; }   // lower_bound, uniform trip count
+        }
+        while (true) {
+          const bool more = valid && q < n3 && k0[q] <= khi;
+          if (!__any_sync(0xffffffffu, more)) break;
+          if (more) {
             int j = (int)v0[q];
-            if (j >= i) continue;
-            if (l2_simple(p, B[j]) < r2) uf_union(parent, i, j);   // RadiusResultSet::addPoint: dist < radius^2
+            if (j < i && l2_simple(p, B[j]) < r2) uf_union(parent, i, j);   // RadiusResultSet::addPoint: dist < radius^2
+            q++;
           }
         }
       }

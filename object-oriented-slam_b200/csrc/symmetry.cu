@@ -24,189 +24,288 @@
 
 namespace eslam {
 
-constexpr int kSymSmemPts = 1024;
+constexpr int kSymSmemPts = 512;   // cloud staged in shared memory (SoA) up to this many points
+constexpr int kSymQueue = 256;     // per-warp query queue / distance slots / NN cache (fast path when #mirrored points <= 256)
 
-struct SymCtx {
+struct PlanePair {   // per-evaluation constants of GetSymmetryPointOfPlane for the plane and its dual (hoisted, same rounding)
+  double p1[4], p2[4], down1, down2, n1[3], n2[3];
+};
+// Everything that is uniform across a block (object) or a warp (seed) lives in SHARED memory, not in per-lane registers:
+// the kernel is latency bound (long fp64 div/sqrt chains), so occupancy -- registers per thread -- is what buys throughput.
+struct SymBlock {
   const uint16_t *img; size_t pitch;
-  const double *objn; const float4 *nn;   // nn: float cloud (shared memory when M <= kSymSmemPts)
-  int M, symtype;
-  double P[12];
-  d3 cam_t;
-  int bx0, bx2, by1, by3;
-  int rows, cols;
-  double fx, cx, cy, scale, sinv;
+  const double *objn; const float4 *nn_g;
+  int M, symtype, npts, in_smem;
+  int bx0, bx2, by1, by3, rows, cols;
+  double P[12], cam[3], fx, cx, cy, scale, sinv;
+  float nx[kSymSmemPts], ny[kSymSmemPts], nz[kSymSmemPts];
+};
+struct SeedResult { double prob, init_err, final_err; dplane plane; };
+struct SymWarp {
+  PlanePair pp;
+  dplane est, backup, trial;
+  double H[9], b[3], x[3], J[3];
+  double lambda, ni, currentChi, tempChi, iniChi, rho, e1;
+  int nBad, ok, qmax, again;
+  SeedResult res;
+  unsigned short queue[kSymQueue];
+  unsigned short cache[kSymQueue];   // nearest neighbour found by the previous evaluation of each mirrored point
+  double dis[kSymQueue];
 };
 
 __device__ __forceinline__ int x86_int(double a) { return (a > -2147483649.0 && a < 2147483648.0) ? (int)a : (int)0x80000000; }
 
-// edge error (= -mean ln P) of plane `pl`; warp-collective, every lane returns the same value.
-__device__ double sym_eval(const SymCtx &c, const dplane &pl) {
+__device__ __noinline__ void make_pair(PlanePair &P, const dplane &pl) {
+  for (int k = 0; k < 4; k++) P.p1[k] = pl.p[k];
+  plane_another(pl, P.p2);
+  P.down1 = sqrt(P.p1[0] * P.p1[0] + P.p1[1] * P.p1[1] + P.p1[2] * P.p1[2]);
+  P.down2 = sqrt(P.p2[0] * P.p2[0] + P.p2[1] * P.p2[1] + P.p2[2] * P.p2[2]);
+  for (int k = 0; k < 3; k++) { P.n1[k] = P.p1[k] / P.down1; P.n2[k] = P.p2[k] / P.down2; }
+}
+__device__ __forceinline__ d3 mirrored(const SymBlock &B, const PlanePair &P, int idx) {   // GetSymmetryPointOfPlane :193-214
+  const int second = idx >= B.M;
+  const int j = idx - (second ? B.M : 0);
+  const d3 pt = mk3(B.objn[3 * j], B.objn[3 * j + 1], B.objn[3 * j + 2]);
+  const double *q = second ? P.p2 : P.p1;
+  const double *n = second ? P.n2 : P.n1;
+  const double val = q[0] * pt.x + q[1] * pt.y + q[2] * pt.z + q[3] * 1.0;
+  const double dis_pl = fabs(val) / (second ? P.down2 : P.down1);
+  const double kk = 2 * ((val > 0) ? -1.0 : 1.0) * dis_pl;
+  return mk3(pt.x + kk * n[0], pt.y + kk * n[1], pt.z + kk * n[2]);
+}
+// 0 = cost 0 (occluded / no depth), 1 = needs the nearest-neighbour distance, 2 = invalid (not counted)   SymmetrySolver.cpp:62-116
+__device__ __noinline__ int classify(const SymBlock &B, d3 pm) {
+  double uvh[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) { double s = B.P[r * 4] * pm.x; s += B.P[r * 4 + 1] * pm.y; s += B.P[r * 4 + 2] * pm.z; s += B.P[r * 4 + 3] * 1.0; uvh[r] = s; }
+  const double u = uvh[0] / uvh[2], v = uvh[1] / uvh[2];
+  const int x = x86_int(u), y = x86_int(v);
+  const bool valid = isfinite(pm.x) && isfinite(pm.y) && isfinite(pm.z);
+  bool inrange = (B.bx0 < x && x < B.bx2) && (B.by1 < y && y < B.by3);
+  if (inrange && (x < 0 || y < 0 || x >= B.cols || y >= B.rows)) inrange = false;
+  if (inrange) {
+    const unsigned short d0 = B.img[(size_t)y * B.pitch + x];
+    const double xi = (x - B.cx), yi = (y - B.cy), f = B.fx;
+    const double realz = (double)d0 * sqrt(xi * xi + f * f + yi * yi) / f;   // calculateProjZ, Symmetry.cpp:137-139 (lazy range image)
+    const unsigned short d = (unsigned short)(int)realz;                      // ushort(realz)
+    if (d == 0) return 0;
+    const double depth = d / B.scale;
+    const double ax = B.cam[0] - pm.x, ay = B.cam[1] - pm.y, az = B.cam[2] - pm.z;
+    const double dis_cam = sqrt(ax * ax + ay * ay + az * az);
+    if (dis_cam > depth) return 0;
+  }
+  return valid ? 1 : 2;
+}
+// Exact float NN (flann::L2_Simple operation order; minimum r, first index on ties -- the oracle's linear scan) + fp64 distance to the
+// float neighbour (findMinimalDistanceWithKdTree :140-166).  `hint` (neighbour of the previous evaluation, or 0xffff) only seeds the
+// bound: a candidate with fl(dx^2) > bound has r >= fl(dx^2) > bound (rounding is monotone) and is skipped after 3 instructions.
+__device__ __noinline__ double nn_distance(const SymBlock &B, d3 pm, unsigned short hint, unsigned short *found) {
+  const float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
+  float bd = FLT_MAX; int best = 0x7fffffff;
+  const int M = B.M;
+  float bx, by, bz;
+  if (B.in_smem) {
+    if (hint != 0xffffu) {
+      float dd = __fsub_rn(qx, B.nx[hint]); float r = __fadd_rn(0.0f, __fmul_rn(dd, dd));
+      dd = __fsub_rn(qy, B.ny[hint]); r = __fadd_rn(r, __fmul_rn(dd, dd));
+      dd = __fsub_rn(qz, B.nz[hint]); r = __fadd_rn(r, __fmul_rn(dd, dd));
+      bd = r; best = hint;
+    }
+    for (int k = 0; k < M; k++) {
+      float dd = __fsub_rn(qx, B.nx[k]);
+      const float dx2 = __fmul_rn(dd, dd);
+      if (dx2 > bd) continue;
+      float r = __fadd_rn(0.0f, dx2);
+      dd = __fsub_rn(qy, B.ny[k]); r = __fadd_rn(r, __fmul_rn(dd, dd));
+      dd = __fsub_rn(qz, B.nz[k]); r = __fadd_rn(r, __fmul_rn(dd, dd));
+      if (r < bd || (r == bd && k < best)) { bd = r; best = k; }
+    }
+    bx = B.nx[best]; by = B.ny[best]; bz = B.nz[best];
+  } else {
+    for (int k = 0; k < M; k++) {
+      const float4 q = B.nn_g[k];
+      float r = 0.0f, dd;
+      dd = __fsub_rn(qx, q.x); r = __fadd_rn(r, __fmul_rn(dd, dd));
+      dd = __fsub_rn(qy, q.y); r = __fadd_rn(r, __fmul_rn(dd, dd));
+      dd = __fsub_rn(qz, q.z); r = __fadd_rn(r, __fmul_rn(dd, dd));
+      if (r < bd) { bd = r; best = k; }
+    }
+    const float4 q = B.nn_g[best];
+    bx = q.x; by = q.y; bz = q.z;
+  }
+  if (found) *found = (unsigned short)best;
+  const double dx = pm.x - (double)bx, dy = pm.y - (double)by, dz = pm.z - (double)bz;
+  return sqrt(dx * dx + dy * dy + dz * dz);
+}
+
+// edge error (= -mean ln P) of the plane stored in shared memory at `pl`; warp-collective, every lane returns the same value.
+// Fast path (#points <= kSymQueue): (1) classify all mirrored points, compacting those that need a nearest-neighbour query into a
+// per-warp queue so that (2) the brute-force searches run with full lanes; (3) ln P accumulated in the reference's point order.
+// (__noinline__: the kernel is instruction-fetch bound when the ~1k-instruction evaluation body is replicated at its 5 call sites)
+__device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dplane *pl) {
   const int lane = threadIdx.x & 31;
-  double p2[4];
-  plane_another(pl, p2);
-  const int M = c.M;
-  const int npts = (c.symtype == 2) ? 2 * M : M;
-  // per-plane constants of GetSymmetryPointOfPlane hoisted out of the point loop (same values, same rounding)
-  const double down1 = sqrt(pl.p[0] * pl.p[0] + pl.p[1] * pl.p[1] + pl.p[2] * pl.p[2]);
-  const double n1x = pl.p[0] / down1, n1y = pl.p[1] / down1, n1z = pl.p[2] / down1;
-  const double down2 = sqrt(p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
-  const double n2x = p2[0] / down2, n2y = p2[1] / down2, n2z = p2[2] / down2;
+  if (lane == 0) make_pair(W.pp, *pl);
+  __syncwarp();
+  const PlanePair &PP = W.pp;
+  const int npts = B.npts;
   double ln_total = 0.0;
   int invalid = 0;
-  for (int base = 0; base < npts; base += 32) {
-    int idx = base + lane;
-    double lnP = 0.0; int inv = 0;
-    if (idx < npts) {
-      int second = idx >= M;
-      int j = idx - (second ? M : 0);
-      d3 pt = mk3(c.objn[3 * j], c.objn[3 * j + 1], c.objn[3 * j + 2]);
-      const double q0 = second ? p2[0] : pl.p[0], q1 = second ? p2[1] : pl.p[1], q2 = second ? p2[2] : pl.p[2], q3 = second ? p2[3] : pl.p[3];
-      const double val = q0 * pt.x + q1 * pt.y + q2 * pt.z + q3 * 1.0;
-      const double dis_pl = fabs(val) / (second ? down2 : down1);
-      const double kk = 2 * ((val > 0) ? -1.0 : 1.0) * dis_pl;
-      d3 pm = mk3(pt.x + kk * (second ? n2x : n1x), pt.y + kk * (second ? n2y : n1y), pt.z + kk * (second ? n2z : n1z));
-      double uvh[3];
-#pragma unroll
-      for (int r = 0; r < 3; r++) { double s = c.P[r * 4] * pm.x; s += c.P[r * 4 + 1] * pm.y; s += c.P[r * 4 + 2] * pm.z; s += c.P[r * 4 + 3] * 1.0; uvh[r] = s; }
-      double u = uvh[0] / uvh[2], v = uvh[1] / uvh[2];
-      int x = x86_int(u), y = x86_int(v);
-      bool valid = isfinite(pm.x) && isfinite(pm.y) && isfinite(pm.z);
-      bool inrange = (c.bx0 < x && x < c.bx2) && (c.by1 < y && y < c.by3);
-      if (inrange && (x < 0 || y < 0 || x >= c.cols || y >= c.rows)) inrange = false;
-      bool need_nn = false;
-      if (inrange) {
-        unsigned short d0 = c.img[(size_t)y * c.pitch + x];
-        double xi = (x - c.cx), yi = (y - c.cy), f = c.fx;
-        double realz = (double)d0 * sqrt(xi * xi + f * f + yi * yi) / f;   // calculateProjZ, Symmetry.cpp:137-139
-        unsigned short d = (unsigned short)(int)realz;                      // ushort(realz)
-        if (d != 0) {
-          double depth = d / c.scale;
-          double ax = c.cam_t.x - pm.x, ay = c.cam_t.y - pm.y, az = c.cam_t.z - pm.z;
-          double dis_cam = sqrt(ax * ax + ay * ay + az * az);
-          if (!(dis_cam > depth)) { if (valid) need_nn = true; else inv = 1; }
-        }
-      } else {
-        if (valid) need_nn = true; else inv = 1;
-      }
-      double dis = 0.0;
-      if (need_nn) {
-        float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
-        float bd = FLT_MAX; int best = 0;
-        for (int k = 0; k < M; k++) {
-          float4 q = c.nn[k];
-          float r = 0.0f, dd;
-          dd = __fsub_rn(qx, q.x); r = __fadd_rn(r, __fmul_rn(dd, dd));
-          dd = __fsub_rn(qy, q.y); r = __fadd_rn(r, __fmul_rn(dd, dd));
-          dd = __fsub_rn(qz, q.z); r = __fadd_rn(r, __fmul_rn(dd, dd));
-          if (r < bd) { bd = r; best = k; }
-        }
-        float4 q = c.nn[best];
-        double dx = pm.x - (double)q.x, dy = pm.y - (double)q.y, dz = pm.z - (double)q.z;
-        dis = sqrt(dx * dx + dy * dy + dz * dz);
-      }
-      lnP = -0.5 * c.sinv * c.sinv * dis * dis;
+  if (npts <= kSymQueue && B.in_smem) {
+    int qn = 0;
+    for (int base = 0; base < npts; base += 32) {
+      const int idx = base + lane;
+      int cls = 0;
+      if (idx < npts) { cls = classify(B, mirrored(B, PP, idx)); W.dis[idx] = 0.0; }
+      const unsigned need = __ballot_sync(0xffffffffu, cls == 1);
+      if (cls == 1) W.queue[qn + __popc(need & ((1u << lane) - 1u))] = (unsigned short)idx;
+      qn += __popc(need);
+      invalid += __popc(__ballot_sync(0xffffffffu, cls == 2));
     }
-    int cnt = min(32, npts - base);
-    for (int k = 0; k < cnt; k++) ln_total += __shfl_sync(0xffffffffu, lnP, k);
-    invalid += __popc(__ballot_sync(0xffffffffu, inv != 0));
+    __syncwarp();
+    for (int qb = 0; qb < qn; qb += 32) {
+      if (qb + lane < qn) {
+        const int idx = W.queue[qb + lane];
+        W.dis[idx] = nn_distance(B, mirrored(B, PP, idx), W.cache[idx], &W.cache[idx]);
+      }
+    }
+    __syncwarp();
+    const double sinv = B.sinv;
+    for (int base = 0; base < npts; base += 32) {
+      const int idx = base + lane;
+      const double dis = (idx < npts) ? W.dis[idx] : 0.0;
+      const double lnP = -0.5 * sinv * sinv * dis * dis;
+      const int cnt = min(32, npts - base);
+      for (int k = 0; k < cnt; k++) ln_total += __shfl_sync(0xffffffffu, lnP, k);
+    }
+    __syncwarp();
+  } else {
+    const double sinv = B.sinv;
+    for (int base = 0; base < npts; base += 32) {
+      const int idx = base + lane;
+      double lnP = 0.0; int cls = 0;
+      if (idx < npts) {
+        const d3 pm = mirrored(B, PP, idx);
+        cls = classify(B, pm);
+        const double dis = (cls == 1) ? nn_distance(B, pm, 0xffffu, nullptr) : 0.0;
+        lnP = -0.5 * sinv * sinv * dis * dis;
+      }
+      const int cnt = min(32, npts - base);
+      for (int k = 0; k < cnt; k++) ln_total += __shfl_sync(0xffffffffu, lnP, k);
+      invalid += __popc(__ballot_sync(0xffffffffu, cls == 2));
+    }
   }
-  int num_valid = npts - invalid;
-  double aver = (num_valid > 0) ? (ln_total / (double)num_valid) : -INFINITY;
+  const int num_valid = npts - invalid;
+  const double aver = (num_valid > 0) ? (ln_total / (double)num_valid) : -INFINITY;
   return -aver;
 }
 
-__device__ __forceinline__ void sym_oplus(dplane &p, const double *u, int symtype) {
+__device__ __noinline__ void sym_oplus(dplane &p, const double *u, int symtype) {
   if (symtype == 1) plane_oplus_common(p, u[0], 0.0, u[1]);           // VertexPlane: (yaw, 0, dis)   :527-532, Plane.h:46-59
   else { plane_oplus_common(p, u[0], 0.0, u[1]); p.dual += u[2]; }    // VertexDualPlane             :544-547, Plane.h:62-77
 }
 
 template <int DIM>
-__device__ bool lm_solve_dim(const double *H, const double *b, double lambda, double *x) {
+__device__ __noinline__ bool lm_solve_dim(const double *H, const double *b, double lambda, double *x) {
   double M[DIM * DIM];
   for (int i = 0; i < DIM * DIM; i++) M[i] = H[i];
   for (int i = 0; i < DIM; i++) M[i * DIM + i] += lambda;
   return ldlt_solve_small<DIM>(M, b, x);
 }
 
-struct SeedResult { double prob, init_err, final_err; dplane plane; };
-
-// OptimizeSymmetryPlane / OptimizeSymmetryDualPlane: one vertex, one unary edge (information 1), optimize(iters)
-__device__ SeedResult sym_optimize(const SymCtx &c, dplane est, int iters) {
-  const int dim = (c.symtype == 1) ? 2 : 3;
-  SeedResult R;
-  double err = sym_eval(c, est);
-  R.init_err = err;
-  double lambda = -1, ni = 2; int nBad = 0;
-  double H[9], b[3], x[3] = {0, 0, 0}, J[3];
-  bool ok = true;
-  for (int it = 0; it < iters && ok; it++) {
-    err = sym_eval(c, est);
-    double currentChi = err * (1.0 * err);
-    double tempChi = currentChi;
-    const double iniChi = currentChi;
-    {  // linearizeOplus (numeric) + constructQuadraticForm
-      const double delta = 1e-9, scalar = 1.0 / (2 * delta);
-      double add[3] = {0, 0, 0};
-      for (int d = 0; d < dim; d++) {
-        dplane pp = est; add[d] = delta; sym_oplus(pp, add, c.symtype);
-        double e1 = sym_eval(c, pp);
-        dplane pm = est; add[d] = -delta; sym_oplus(pm, add, c.symtype);
-        double e2 = sym_eval(c, pm);
-        add[d] = 0.0;
-        J[d] = scalar * (e1 - e2);
-      }
+// OptimizeSymmetryPlane / OptimizeSymmetryDualPlane: one vertex, one unary edge (information 1), optimize(iters).
+// Warp-collective: lane 0 runs the scalar Levenberg-Marquardt bookkeeping on the shared-memory state, all lanes evaluate costs.
+__device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
+  const int lane = threadIdx.x & 31;
+  const int symtype = B.symtype;
+  const int dim = (symtype == 1) ? 2 : 3;
+  double err = sym_eval(B, W, &W.est);
+  if (lane == 0) { W.res.init_err = err; W.lambda = -1; W.ni = 2; W.nBad = 0; W.x[0] = W.x[1] = W.x[2] = 0; W.ok = 1; }
+  __syncwarp();
+  for (int it = 0; it < iters; it++) {
+    if (!W.ok) break;
+    err = sym_eval(B, W, &W.est);
+    if (lane == 0) { W.currentChi = err * (1.0 * err); W.tempChi = W.currentChi; W.iniChi = W.currentChi; }
+    // linearizeOplus (numeric, delta 1e-9) + constructQuadraticForm
+    for (int d = 0; d < dim; d++) {
+      if (lane == 0) { double add[3] = {0, 0, 0}; add[d] = 1e-9; W.trial = W.est; sym_oplus(W.trial, add, symtype); }
+      __syncwarp();
+      const double e1 = sym_eval(B, W, &W.trial);
+      if (lane == 0) { double add[3] = {0, 0, 0}; add[d] = -1e-9; W.trial = W.est; sym_oplus(W.trial, add, symtype); }
+      __syncwarp();
+      const double e2 = sym_eval(B, W, &W.trial);
+      if (lane == 0) W.J[d] = (1.0 / (2 * 1e-9)) * (e1 - e2);
+    }
+    if (lane == 0) {
       for (int i = 0; i < dim; i++) {
-        b[i] = 0.0 - (J[i] * 1.0) * err;
-        for (int j = 0; j < dim; j++) H[i * dim + j] = 0.0 + (J[i] * 1.0) * J[j];
+        W.b[i] = 0.0 - (W.J[i] * 1.0) * err;
+        for (int j = 0; j < dim; j++) W.H[i * dim + j] = 0.0 + (W.J[i] * 1.0) * W.J[j];
       }
-    }
-    if (it == 0) {
-      double mx = 0;
-      for (int j = 0; j < dim; j++) mx = fmax(fabs(H[j * dim + j]), mx);
-      lambda = 1e-5 * mx; ni = 2; nBad = 0;
-    }
-    double rho = 0; int qmax = 0;
-    do {
-      dplane backup = est;
-      bool ok2 = (dim == 2) ? lm_solve_dim<2>(H, b, lambda, x) : lm_solve_dim<3>(H, b, lambda, x);
-      sym_oplus(est, x, c.symtype);
-      err = sym_eval(c, est);
-      tempChi = err * (1.0 * err);
-      if (!ok2) tempChi = DBL_MAX;
-      rho = (currentChi - tempChi);
-      double scale = 0;
-      for (int j = 0; j < dim; j++) scale += x[j] * (lambda * x[j] + b[j]);
-      scale += 1e-3;
-      rho /= scale;
-      if (rho > 0 && isfinite(tempChi)) {
-        double alpha = 1. - pow((2 * rho - 1), 3.0);
-        alpha = fmin(alpha, 2. / 3.);
-        double sf = fmax(1. / 3., alpha);
-        lambda *= sf; ni = 2; currentChi = tempChi;
-      } else {
-        lambda *= ni; ni *= 2; est = backup;
+      if (it == 0) {
+        double mx = 0;
+        for (int j = 0; j < dim; j++) mx = fmax(fabs(W.H[j * dim + j]), mx);
+        W.lambda = 1e-5 * mx; W.ni = 2; W.nBad = 0;
       }
-      qmax++;
-    } while (rho < 0 && qmax < 10);
-    if (qmax == 10 || rho == 0) ok = false;
-    else {
-      if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
-      if (nBad >= 3) ok = false;
+      W.rho = 0; W.qmax = 0;
+    }
+    __syncwarp();
+    while (true) {
+      if (lane == 0) {
+        W.backup = W.est;
+        double x[3] = {W.x[0], W.x[1], W.x[2]};
+        bool ok2 = (dim == 2) ? lm_solve_dim<2>(W.H, W.b, W.lambda, x) : lm_solve_dim<3>(W.H, W.b, W.lambda, x);
+        W.x[0] = x[0]; W.x[1] = x[1]; W.x[2] = x[2];
+        W.again = ok2 ? 1 : 0;   // reused as "ok2" until the decision below
+        sym_oplus(W.est, x, symtype);
+      }
+      __syncwarp();
+      err = sym_eval(B, W, &W.est);
+      if (lane == 0) {
+        const bool ok2 = W.again != 0;
+        double tempChi = err * (1.0 * err);
+        if (!ok2) tempChi = DBL_MAX;
+        double rho = (W.currentChi - tempChi);
+        double scale = 0;
+        for (int j = 0; j < dim; j++) scale += W.x[j] * (W.lambda * W.x[j] + W.b[j]);
+        scale += 1e-3;
+        rho /= scale;
+        if (rho > 0 && isfinite(tempChi)) {
+          double alpha = 1. - pow((2 * rho - 1), 3.0);
+          alpha = fmin(alpha, 2. / 3.);
+          const double sf = fmax(1. / 3., alpha);
+          W.lambda *= sf; W.ni = 2; W.currentChi = tempChi;
+        } else {
+          W.lambda *= W.ni; W.ni *= 2; W.est = W.backup;
+        }
+        W.tempChi = tempChi; W.rho = rho; W.qmax++;
+        W.again = (rho < 0 && W.qmax < 10) ? 1 : 0;
+        if (!W.again) {
+          if (W.qmax == 10 || rho == 0) W.ok = 0;
+          else {
+            if ((W.iniChi - W.currentChi) * 1e3 < W.iniChi) W.nBad++; else W.nBad = 0;
+            if (W.nBad >= 3) W.ok = 0;
+          }
+        }
+      }
+      __syncwarp();
+      if (!W.again) break;
     }
   }
-  R.final_err = err;          // e->error() after optimize(): value of the LAST computeError call (possibly a rejected trial)
-  R.prob = exp(-err);
-  R.plane = est;
-  return R;
+  if (lane == 0) {
+    W.res.final_err = err;          // e->error() after optimize(): value of the LAST computeError call (possibly a rejected trial)
+    W.res.prob = exp(-err);
+    W.res.plane = W.est;
+  }
+  __syncwarp();
 }
 
 // grid = n_obj, block = 288 (9 warps = 9 seeds)
-__global__ void __launch_bounds__(288, 2) symmetry_finalize_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride,
+__global__ void __launch_bounds__(288, 3) symmetry_finalize_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride,
                                                                 const ObjMeta *__restrict__ metas, ObjState *__restrict__ states, ExtractParamsDev prm,
                                                                 ExtractPtrs W, EslamEllipsoidOut *__restrict__ outs) {
   __shared__ BlockScratch S;
-  __shared__ float4 s_nn[kSymSmemPts];
-  __shared__ SeedResult s_seed[9];
+  extern __shared__ __align__(16) unsigned char sym_smem[];
+  SymBlock &B = *reinterpret_cast<SymBlock *>(sym_smem);
+  SymWarp *Ws = reinterpret_cast<SymWarp *>(sym_smem + ((sizeof(SymBlock) + 15) & ~(size_t)15));
   __shared__ int s_best;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ObjMeta m = metas[blockIdx.x];
@@ -234,39 +333,42 @@ __global__ void __launch_bounds__(288, 2) symmetry_finalize_kernel(const uint16_
 
   if (run_sym) {
     const bool in_smem = M <= kSymSmemPts;
-    if (in_smem) for (int i = tid; i < M; i += blockDim.x) s_nn[i] = objnf[i];
-    __syncthreads();
-    SymCtx c;
-    c.img = depth + (size_t)m.frame * frame_stride; c.pitch = pitch;
-    c.objn = objn; c.nn = in_smem ? s_nn : objnf; c.M = M; c.symtype = m.symtype;
-    for (int i = 0; i < 12; i++) c.P[i] = st.P[i];
-    c.cam_t = mk3(st.T_oc[0], st.T_oc[1], st.T_oc[2]);
-    c.bx0 = st.bbox_i[0]; c.by1 = st.bbox_i[1]; c.bx2 = st.bbox_i[2]; c.by3 = st.bbox_i[3];
-    c.rows = prm.rows; c.cols = prm.cols; c.fx = prm.fx; c.cx = prm.cx; c.cy = prm.cy; c.scale = prm.scale;
-    c.sinv = 1.0 / prm.sigma;
-    // GenerateInitPlanes (Symmetry.cpp:44-86): seed = i*3+m, dis = -0.2 + 0.2 i, angle = -5deg + 5deg m
-    {
+    if (in_smem) for (int i = tid; i < M; i += blockDim.x) { float4 q = objnf[i]; B.nx[i] = q.x; B.ny[i] = q.y; B.nz[i] = q.z; }
+    if (tid == 0) {
+      B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch;
+      B.objn = objn; B.nn_g = objnf; B.M = M; B.symtype = m.symtype; B.npts = (m.symtype == 2) ? 2 * M : M; B.in_smem = in_smem ? 1 : 0;
+      for (int i = 0; i < 12; i++) B.P[i] = st.P[i];
+      B.cam[0] = st.T_oc[0]; B.cam[1] = st.T_oc[1]; B.cam[2] = st.T_oc[2];
+      B.bx0 = st.bbox_i[0]; B.by1 = st.bbox_i[1]; B.bx2 = st.bbox_i[2]; B.by3 = st.bbox_i[3];
+      B.rows = prm.rows; B.cols = prm.cols; B.fx = prm.fx; B.cx = prm.cx; B.cy = prm.cy; B.scale = prm.scale;
+      B.sinv = 1.0 / prm.sigma;
+    }
+    SymWarp &Wp = Ws[warp];
+    for (int i = lane; i < kSymQueue; i += 32) Wp.cache[i] = 0xffffu;
+    if (lane == 0) {
+      // GenerateInitPlanes (Symmetry.cpp:44-86): seed = i*3+m, dis = -0.2 + 0.2 i, angle = -5deg + 5deg m
       const double diff_dis = 0.2, diff_angle = M_PI / 180.0 * 5;
       const double start_dis = -diff_dis * 1, start_angle = -diff_angle * 1;
-      int si = warp / 3, sm = warp % 3;
-      double dis = start_dis + diff_dis * si, angle = start_angle + diff_angle * sm;
-      dplane init; init.p[0] = sin(angle); init.p[1] = -cos(angle); init.p[2] = 0; init.p[3] = -dis; init.dual = 0;   // fromDisAngleTrans
-      SeedResult r = sym_optimize(c, init, prm.symmetry_iters);
-      if (lane == 0) {
-        s_seed[warp] = r;
-        st.seed_prob[warp] = r.prob; st.seed_init[warp] = r.init_err; st.seed_final[warp] = r.final_err; st.seed_dual[warp] = r.plane.dual;
-        for (int k = 0; k < 4; k++) st.seed_plane[warp][k] = r.plane.p[k];
-      }
+      const int si = warp / 3, sm = warp % 3;
+      const double dis = start_dis + diff_dis * si, angle = start_angle + diff_angle * sm;
+      Wp.est.p[0] = sin(angle); Wp.est.p[1] = -cos(angle); Wp.est.p[2] = 0; Wp.est.p[3] = -dis; Wp.est.dual = 0;   // fromDisAngleTrans
+    }
+    __syncthreads();
+    sym_optimize(B, Wp, prm.symmetry_iters);
+    if (lane == 0) {
+      const SeedResult &r = Wp.res;
+      st.seed_prob[warp] = r.prob; st.seed_init[warp] = r.init_err; st.seed_final[warp] = r.final_err; st.seed_dual[warp] = r.plane.dual;
+      for (int k = 0; k < 4; k++) st.seed_plane[warp][k] = r.plane.p[k];
     }
     __syncthreads();
     if (tid == 0) {  // sort(desc by prob) of 9 entries == insertion sort == stable: first maximum wins (Symmetry.cpp:122-126)
       int best = 0;
-      for (int s = 1; s < 9; s++) if (s_seed[s].prob > s_seed[best].prob) best = s;
+      for (int s = 1; s < 9; s++) if (Ws[s].res.prob > Ws[best].res.prob) best = s;
       s_best = best; st.best_seed = best;
     }
     __syncthreads();
-    bestp = s_seed[s_best].plane;
-    sym_prob = s_seed[s_best].prob;
+    bestp = Ws[s_best].res.plane;
+    sym_prob = Ws[s_best].res.prob;
   }
 
   // ---- completion :399-446 (mirrored points generated on the fly, never stored) ----
@@ -333,7 +435,10 @@ __global__ void __launch_bounds__(288, 2) symmetry_finalize_kernel(const uint16_
 int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int n_obj,
                              const ExtractParamsDev &prm, const ExtractPtrs &ptrs) {
   ExtractWorkspace &w = *h->ex;
-  symmetry_finalize_kernel<<<n_obj, 288, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>(), w.state.as<ObjState>(), prm, ptrs,
+  const size_t smem = ((sizeof(SymBlock) + 15) & ~(size_t)15) + 9 * sizeof(SymWarp);
+  static bool attr_set = false;
+  if (!attr_set) { ESLAM_CUDA_OK(h, cudaFuncSetAttribute(symmetry_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  symmetry_finalize_kernel<<<n_obj, 288, smem, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>(), w.state.as<ObjState>(), prm, ptrs,
                                                  w.out.as<EslamEllipsoidOut>());
   ESLAM_LAUNCHED(h);
   ESLAM_CUDA_OK(h, cudaGetLastError());
