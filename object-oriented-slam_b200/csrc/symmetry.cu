@@ -38,7 +38,7 @@ struct SymBlock {
   int M, symtype, npts, in_smem;
   int bx0, bx2, by1, by3, rows, cols;
   double P[12], cam[3], fx, cx, cy, scale, sinv;
-  float nx[kSymSmemPts], ny[kSymSmemPts], nz[kSymSmemPts];
+  float4 nn4[kSymSmemPts];
 };
 struct SeedResult { double prob, init_err, final_err; dplane plane; };
 struct SymWarp {
@@ -49,7 +49,6 @@ struct SymWarp {
   int nBad, ok, qmax, again;
   SeedResult res;
   unsigned short queue[kSymQueue];
-  unsigned short cache[kSymQueue];   // nearest neighbour found by the previous evaluation of each mirrored point
   double dis[kSymQueue];
 };
 
@@ -97,44 +96,24 @@ __device__ __noinline__ int classify(const SymBlock &B, d3 pm) {
   return valid ? 1 : 2;
 }
 // Exact float NN (flann::L2_Simple operation order; minimum r, first index on ties -- the oracle's linear scan) + fp64 distance to the
-// float neighbour (findMinimalDistanceWithKdTree :140-166).  `hint` (neighbour of the previous evaluation, or 0xffff) only seeds the
-// bound: a candidate with fl(dx^2) > bound has r >= fl(dx^2) > bound (rounding is monotone) and is skipped after 3 instructions.
-__device__ __noinline__ double nn_distance(const SymBlock &B, d3 pm, unsigned short hint, unsigned short *found) {
+// float neighbour (findMinimalDistanceWithKdTree :140-166).  All lanes scan the same cloud point at the same time (one broadcast
+// LDS.128 per point); a per-lane early reject would only add divergence, so the loop body is branch free.
+__device__ __noinline__ double nn_distance(const SymBlock &B, d3 pm) {
   const float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
-  float bd = FLT_MAX; int best = 0x7fffffff;
+  float bd = FLT_MAX; int best = 0;
   const int M = B.M;
-  float bx, by, bz;
-  if (B.in_smem) {
-    if (hint != 0xffffu) {
-      float dd = __fsub_rn(qx, B.nx[hint]); float r = __fadd_rn(0.0f, __fmul_rn(dd, dd));
-      dd = __fsub_rn(qy, B.ny[hint]); r = __fadd_rn(r, __fmul_rn(dd, dd));
-      dd = __fsub_rn(qz, B.nz[hint]); r = __fadd_rn(r, __fmul_rn(dd, dd));
-      bd = r; best = hint;
-    }
-    for (int k = 0; k < M; k++) {
-      float dd = __fsub_rn(qx, B.nx[k]);
-      const float dx2 = __fmul_rn(dd, dd);
-      if (dx2 > bd) continue;
-      float r = __fadd_rn(0.0f, dx2);
-      dd = __fsub_rn(qy, B.ny[k]); r = __fadd_rn(r, __fmul_rn(dd, dd));
-      dd = __fsub_rn(qz, B.nz[k]); r = __fadd_rn(r, __fmul_rn(dd, dd));
-      if (r < bd || (r == bd && k < best)) { bd = r; best = k; }
-    }
-    bx = B.nx[best]; by = B.ny[best]; bz = B.nz[best];
-  } else {
-    for (int k = 0; k < M; k++) {
-      const float4 q = B.nn_g[k];
-      float r = 0.0f, dd;
-      dd = __fsub_rn(qx, q.x); r = __fadd_rn(r, __fmul_rn(dd, dd));
-      dd = __fsub_rn(qy, q.y); r = __fadd_rn(r, __fmul_rn(dd, dd));
-      dd = __fsub_rn(qz, q.z); r = __fadd_rn(r, __fmul_rn(dd, dd));
-      if (r < bd) { bd = r; best = k; }
-    }
-    const float4 q = B.nn_g[best];
-    bx = q.x; by = q.y; bz = q.z;
+  const float4 *nn = B.in_smem ? B.nn4 : B.nn_g;
+#pragma unroll 4
+  for (int k = 0; k < M; k++) {
+    const float4 q = nn[k];
+    float dd = __fsub_rn(qx, q.x);
+    float r = __fmul_rn(dd, dd);                 // 0 + dx^2 is exact
+    dd = __fsub_rn(qy, q.y); r = __fadd_rn(r, __fmul_rn(dd, dd));
+    dd = __fsub_rn(qz, q.z); r = __fadd_rn(r, __fmul_rn(dd, dd));
+    if (r < bd) { bd = r; best = k; }
   }
-  if (found) *found = (unsigned short)best;
-  const double dx = pm.x - (double)bx, dy = pm.y - (double)by, dz = pm.z - (double)bz;
+  const float4 q = nn[best];
+  const double dx = pm.x - (double)q.x, dy = pm.y - (double)q.y, dz = pm.z - (double)q.z;
   return sqrt(dx * dx + dy * dy + dz * dz);
 }
 
@@ -150,7 +129,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
   const int npts = B.npts;
   double ln_total = 0.0;
   int invalid = 0;
-  if (npts <= kSymQueue && B.in_smem) {
+  if (npts <= kSymQueue) {
     int qn = 0;
     for (int base = 0; base < npts; base += 32) {
       const int idx = base + lane;
@@ -165,7 +144,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
     for (int qb = 0; qb < qn; qb += 32) {
       if (qb + lane < qn) {
         const int idx = W.queue[qb + lane];
-        W.dis[idx] = nn_distance(B, mirrored(B, PP, idx), W.cache[idx], &W.cache[idx]);
+        W.dis[idx] = nn_distance(B, mirrored(B, PP, idx));
       }
     }
     __syncwarp();
@@ -186,7 +165,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
       if (idx < npts) {
         const d3 pm = mirrored(B, PP, idx);
         cls = classify(B, pm);
-        const double dis = (cls == 1) ? nn_distance(B, pm, 0xffffu, nullptr) : 0.0;
+        const double dis = (cls == 1) ? nn_distance(B, pm) : 0.0;
         lnP = -0.5 * sinv * sinv * dis * dis;
       }
       const int cnt = min(32, npts - base);
@@ -333,7 +312,7 @@ __global__ void __launch_bounds__(288, 3) symmetry_finalize_kernel(const uint16_
 
   if (run_sym) {
     const bool in_smem = M <= kSymSmemPts;
-    if (in_smem) for (int i = tid; i < M; i += blockDim.x) { float4 q = objnf[i]; B.nx[i] = q.x; B.ny[i] = q.y; B.nz[i] = q.z; }
+    if (in_smem) for (int i = tid; i < M; i += blockDim.x) B.nn4[i] = objnf[i];
     if (tid == 0) {
       B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch;
       B.objn = objn; B.nn_g = objnf; B.M = M; B.symtype = m.symtype; B.npts = (m.symtype == 2) ? 2 * M : M; B.in_smem = in_smem ? 1 : 0;
@@ -344,7 +323,6 @@ __global__ void __launch_bounds__(288, 3) symmetry_finalize_kernel(const uint16_
       B.sinv = 1.0 / prm.sigma;
     }
     SymWarp &Wp = Ws[warp];
-    for (int i = lane; i < kSymQueue; i += 32) Wp.cache[i] = 0xffffu;
     if (lane == 0) {
       // GenerateInitPlanes (Symmetry.cpp:44-86): seed = i*3+m, dis = -0.2 + 0.2 i, angle = -5deg + 5deg m
       const double diff_dis = 0.2, diff_angle = M_PI / 180.0 * 5;
