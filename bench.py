@@ -239,12 +239,13 @@ def main():
     t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
     gather_ms = None
     if world > 1:
+        from eslam_b200 import shard
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        rec = torch.from_numpy(np.frombuffer(bytes(out), dtype=np.uint8).copy()).cuda()
-        allrec = torch.empty(world * rec.numel(), dtype=torch.uint8, device="cuda")
         torch.cuda.synchronize(); g0 = time.perf_counter()
-        dist.all_gather_into_tensor(allrec, rec)
+        # the one exchange step of the path: fixed-size per-(frame,bbox) records, all-gathered over NCCL ("gather of map")
+        allrec = shard.gather_records(out, np.arange(n_obj) + rank * n_obj, n_obj * world, device="cuda")
         torch.cuda.synchronize(); gather_ms = (time.perf_counter() - g0) * 1e3
+        assert sum(1 for o in allrec if o.n_crop > 0) >= n_obj
     ms, e2e_ms = float(t[0]), float(t[1])
     if rank != 0:
         if world > 1:

@@ -107,7 +107,8 @@ __device__ __forceinline__ float4 voxel_centroid(const float4 *pts, const unsign
   return make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 0.0f);
 }
 
-__global__ void __launch_bounds__(512, 1) extract_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride, const ObjMeta *__restrict__ metas,
+constexpr int kExtractThreads = 256;   // 3 CTAs/SM: different objects sit in different phases, hiding the many block barriers
+__global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride, const ObjMeta *__restrict__ metas,
                                                       ObjState *__restrict__ states, ExtractParamsDev prm, ExtractPtrs W) {
   __shared__ BlockScratch S;
   __shared__ RadixScratch RS;
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(512, 1) extract_kernel(const uint16_t *__restr
 int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int n_obj, const ExtractParamsDev &prm,
                    const ExtractPtrs &ptrs) {
   ExtractWorkspace &w = *h->ex;
-  extract_kernel<<<n_obj, 512, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>(), w.state.as<ObjState>(), prm, ptrs);
+  extract_kernel<<<n_obj, kExtractThreads, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>(), w.state.as<ObjState>(), prm, ptrs);
   ESLAM_LAUNCHED(h);
   ESLAM_CUDA_OK(h, cudaGetLastError());
   return ESLAM_OK;

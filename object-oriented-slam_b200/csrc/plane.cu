@@ -389,29 +389,27 @@ __global__ void fit_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   const int *parent = W.parent + (size_t)f * NP;
   const float4 *pts = W.pts + (size_t)f * NP;
   const int last = W.maxidx[(size_t)f * NP + root];
-  float acc = 0.0f;   // lanes 0..8 : xx xy xz yy yz zz x y z   (computeMeanAndCovarianceMatrix<float>)
-  for (int base = root & ~31; base <= last; base += 32) {
-    int i = base + lane;
-    bool in = (i >= root && i <= last) && parent[i] == root;
-    unsigned mask = __ballot_sync(0xffffffffu, in);
-    while (mask) {
-      int b = __ffs(mask) - 1;
-      mask &= mask - 1;
-      float4 p = pts[base + b];
-      float v;
-      switch (lane) {
-        case 0: v = __fmul_rn(p.x, p.x); break;
-        case 1: v = __fmul_rn(p.x, p.y); break;
-        case 2: v = __fmul_rn(p.x, p.z); break;
-        case 3: v = __fmul_rn(p.y, p.y); break;
-        case 4: v = __fmul_rn(p.y, p.z); break;
-        case 5: v = __fmul_rn(p.z, p.z); break;
-        case 6: v = p.x; break;
-        case 7: v = p.y; break;
-        case 8: v = p.z; break;
-        default: v = 0.0f; break;
-      }
-      acc = __fadd_rn(acc, v);
+  // lanes 0..8 own one accumulator each: xx xy xz yy yz zz x y z (computeMeanAndCovarianceMatrix<float>).  The region's pixels are
+  // consumed in raster order; the only dependent chain is the 4-cycle FADD: every group of 32 pixels is fetched coalesced one
+  // group ahead (software prefetch) and broadcast with shuffles, products are formed branch-free (x*1.0f is exact for lanes 6..8).
+  float acc = 0.0f;
+  const int ia = (lane < 3) ? 0 : (lane < 5 ? 1 : (lane == 5 ? 2 : lane - 6));        // first factor:  x x x y y z x y z
+  const int ib = (lane < 3) ? lane : (lane < 5 ? lane - 2 : (lane == 5 ? 2 : 3));     // second factor: x y z y z z 1 1 1
+  int base = root & ~31;
+  float4 nxt = make_float4(0, 0, 0, 0); bool nin = false;
+  { int i = base + lane; nin = (i >= root && i <= last) && parent[i] == root; if (nin) nxt = pts[i]; }
+  for (; base <= last; base += 32) {
+    const float4 mine = nxt; const bool in = nin;
+    { int i = base + 32 + lane; nin = (i <= last) && parent[i] == root; nxt = nin ? pts[i] : make_float4(0, 0, 0, 0); }
+    const unsigned mask = __ballot_sync(0xffffffffu, in);
+    if (mask == 0) continue;
+#pragma unroll
+    for (int b = 0; b < 32; b++) {
+      const float x = __shfl_sync(0xffffffffu, mine.x, b), y = __shfl_sync(0xffffffffu, mine.y, b), z = __shfl_sync(0xffffffffu, mine.z, b);
+      const float a = (ia == 0) ? x : (ia == 1 ? y : z);
+      const float c = (ib == 0) ? x : (ib == 1 ? y : (ib == 2 ? z : 1.0f));
+      const float v = __fmul_rn(a, c);
+      if ((mask >> b) & 1u) acc = __fadd_rn(acc, v);
     }
   }
   float accu[9];
@@ -575,7 +573,7 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   if (!h->pl) h->pl = new PlaneWorkspace();
   PlaneWorkspace &w = *h->pl;
   const size_t NP = (size_t)H * Wd, NI = (size_t)(H + 1) * (Wd + 1) * 3;
-  const int chunk = n_frames < 64 ? n_frames : 64;
+  const int chunk = n_frames < 256 ? n_frames : 256;   // per-frame CTAs (integral / distmap / refine) need >= 148 frames in flight
   ESLAM_CUDA_OK(h, w.pts.reserve(chunk * NP * 16)); ESLAM_CUDA_OK(h, w.nrm.reserve(chunk * NP * 16));
   ESLAM_CUDA_OK(h, w.iiX.reserve(chunk * NI * 8)); ESLAM_CUDA_OK(h, w.iiY.reserve(chunk * NI * 8));
   ESLAM_CUDA_OK(h, w.dm.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.parent.reserve(chunk * NP * 4));
