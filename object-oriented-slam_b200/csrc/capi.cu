@@ -100,20 +100,56 @@ int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const
   return ESLAM_OK;
 }
 
+// host_depth != nullptr: pipelined host entry -- the depth batch is uploaded in chunks on copy_stream while the kernels of the
+// previous chunk run on `s` (objects must be ordered by frame, which is how a frame stream arrives; otherwise one chunk).
 int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *depth_dev, size_t pitch, int n_obj, const int *frame_of_obj, const double *bbox4,
-                const int *label, const double *Twc7, bool want_dump, ExtractPtrs &P) {
+                const int *label, const double *Twc7, bool want_dump, ExtractPtrs &P, const uint16_t *host_depth = nullptr) {
   if (!h->plane_set) { h->err = "supporting plane not set (eslam_set_supporting_plane)"; return ESLAM_ERR_NO_PLANE; }
   if (n_obj <= 0 || n_frames <= 0 || !depth_dev || !frame_of_obj || !bbox4 || !label || !Twc7) return ESLAM_ERR_BAD_ARG;
   if (pitch < (size_t)h->cam.cols) return ESLAM_ERR_BAD_ARG;
   int rc = prepare_batch(h, s, n_frames, n_obj, frame_of_obj, bbox4, label, Twc7, want_dump, P);
   if (rc) return rc;
   ExtractParamsDev prm = make_dev_params(h);
-  size_t frame_stride = (size_t)h->cam.rows * pitch;
+  const size_t frame_stride = (size_t)h->cam.rows * pitch;
   if (h->profiling) ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[0], s));
-  if ((rc = extract_launch(h, s, depth_dev, pitch, frame_stride, n_obj, prm, P))) return rc;
-  if (h->profiling) ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[1], s));
-  if ((rc = symmetry_finalize_launch(h, s, depth_dev, pitch, frame_stride, n_obj, prm, P))) return rc;
-  if (h->profiling) ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[2], s));
+  if (!host_depth) {
+    if ((rc = extract_launch(h, s, depth_dev, pitch, frame_stride, 0, n_obj, prm, P))) return rc;
+    if (h->profiling) ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[1], s));
+    if ((rc = symmetry_finalize_launch(h, s, depth_dev, pitch, frame_stride, 0, n_obj, prm, P))) return rc;
+    if (h->profiling) ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[2], s));
+    return ESLAM_OK;
+  }
+  bool sorted = true;
+  for (int i = 1; i < n_obj; i++) if (frame_of_obj[i] < frame_of_obj[i - 1]) { sorted = false; break; }
+  // Each CTA is latency bound, so a chunk must not run alone: every chunk gets its own compute stream and the chunks overlap each
+  // other (and the uploads still in flight); the caller's stream joins them at the end.
+  const int n_chunks = (sorted && n_frames >= 64) ? 4 : 1;
+  if (!h->copy_stream) ESLAM_CUDA_OK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int c = 0; c < n_chunks; c++) {
+    if (!h->chunk_ev[c]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
+    if (!h->chunk_done[c]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
+    if (!h->chunk_stream[c]) ESLAM_CUDA_OK(h, cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
+  }
+  if (!h->chunk_ev[15]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->chunk_ev[15], cudaEventDisableTiming));
+  ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_ev[15], s));   // metadata upload (prepare_batch) happened on s
+  int o = 0;
+  for (int c = 0; c < n_chunks; c++) {
+    const int f0 = (int)((long long)n_frames * c / n_chunks), f1 = (int)((long long)n_frames * (c + 1) / n_chunks);
+    if (f1 > f0) ESLAM_CUDA_OK(h, cudaMemcpyAsync(const_cast<uint16_t *>(depth_dev) + (size_t)f0 * frame_stride, host_depth + (size_t)f0 * frame_stride,
+                                                   (size_t)(f1 - f0) * frame_stride * sizeof(uint16_t), cudaMemcpyHostToDevice, h->copy_stream));
+    ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_ev[c], h->copy_stream));
+    cudaStream_t cs = (n_chunks == 1) ? s : h->chunk_stream[c];
+    ESLAM_CUDA_OK(h, cudaStreamWaitEvent(cs, h->chunk_ev[c], 0));
+    if (cs != s) ESLAM_CUDA_OK(h, cudaStreamWaitEvent(cs, h->chunk_ev[15], 0));
+    int o1 = o;
+    if (sorted) { while (o1 < n_obj && frame_of_obj[o1] < f1) o1++; } else o1 = n_obj;
+    if (c == n_chunks - 1) o1 = n_obj;
+    if ((rc = extract_launch(h, cs, depth_dev, pitch, frame_stride, o, o1 - o, prm, P))) return rc;
+    if ((rc = symmetry_finalize_launch(h, cs, depth_dev, pitch, frame_stride, o, o1 - o, prm, P))) return rc;
+    if (cs != s) { ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_done[c], cs)); ESLAM_CUDA_OK(h, cudaStreamWaitEvent(s, h->chunk_done[c], 0)); }
+    o = o1;
+  }
+  if (h->profiling) { ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[1], s)); ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[2], s)); }
   return ESLAM_OK;
 }
 
@@ -200,6 +236,9 @@ void eslam_destroy(EslamHandle *h) {
   graph_free(h);
   plane_free(h);
   for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 16; i++) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < 4; i++) { if (h->chunk_stream[i]) cudaStreamDestroy(h->chunk_stream[i]); if (h->chunk_done[i]) cudaEventDestroy(h->chunk_done[i]); }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -328,9 +367,8 @@ int eslam_estimate_ellipsoids_host(EslamHandle *h, int n_frames, const uint16_t 
   if (!h->ex) h->ex = new ExtractWorkspace();
   size_t bytes = (size_t)n_frames * h->cam.rows * pitch * sizeof(uint16_t);
   ESLAM_CUDA_OK(h, h->ex->depth.reserve(bytes));
-  ESLAM_CUDA_OK(h, cudaMemcpyAsync(h->ex->depth.p, depth, bytes, cudaMemcpyHostToDevice, s));
   ExtractPtrs P;
-  int rc = run_extract(h, s, n_frames, h->ex->depth.as<uint16_t>(), pitch, n_obj, frame_of_obj, bbox4, label, Twc7, dump != nullptr, P);
+  int rc = run_extract(h, s, n_frames, h->ex->depth.as<uint16_t>(), pitch, n_obj, frame_of_obj, bbox4, label, Twc7, dump != nullptr, P, depth);
   if (rc) return rc;
   ESLAM_CUDA_OK(h, cudaMemcpyAsync(out, h->ex->out.p, sizeof(EslamEllipsoidOut) * (size_t)n_obj, cudaMemcpyDeviceToHost, s));
   ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));

@@ -54,6 +54,10 @@ struct EslamHandle {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;  // owned stream used by the *_host entry points
+  cudaStream_t copy_stream = nullptr;  // H2D stream of the pipelined *_host extraction
+  cudaEvent_t chunk_ev[16] = {};
+  cudaStream_t chunk_stream[4] = {};   // per-chunk compute streams: chunks overlap each other and the remaining uploads
+  cudaEvent_t chunk_done[4] = {};
   bool plane_set = false;
   double plane_world[4] = {0, 0, 1, 0};
   long long launches = 0;

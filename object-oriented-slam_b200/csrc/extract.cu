@@ -452,10 +452,11 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
   }
 }
 
-int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int n_obj, const ExtractParamsDev &prm,
+int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj, const ExtractParamsDev &prm,
                    const ExtractPtrs &ptrs) {
   ExtractWorkspace &w = *h->ex;
-  extract_kernel<<<n_obj, kExtractThreads, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>(), w.state.as<ObjState>(), prm, ptrs);
+  if (n_obj <= 0) return ESLAM_OK;
+  extract_kernel<<<n_obj, kExtractThreads, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs);
   ESLAM_LAUNCHED(h);
   ESLAM_CUDA_OK(h, cudaGetLastError());
   return ESLAM_OK;

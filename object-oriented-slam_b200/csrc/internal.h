@@ -16,9 +16,9 @@ int graph_optimize(EslamHandle *h, int iters, double *ell_inout, EslamLmStats *s
 void graph_free(EslamHandle *h);
 
 // extract.cu / symmetry.cu
-int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int n_obj, const ExtractParamsDev &prm,
+int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj, const ExtractParamsDev &prm,
                    const ExtractPtrs &ptrs);
-int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int n_obj,
+int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj,
                              const ExtractParamsDev &prm, const ExtractPtrs &ptrs);
 
 // plane.cu

@@ -38,7 +38,7 @@ struct SymBlock {
   int M, symtype, npts, in_smem;
   int bx0, bx2, by1, by3, rows, cols;
   double P[12], cam[3], fx, cx, cy, scale, sinv;
-  float4 nn4[kSymSmemPts];
+  unsigned long long X2[kSymSmemPts / 2], Y2[kSymSmemPts / 2], Z2[kSymSmemPts / 2];   // pair-interleaved SoA float cloud (odd tail padded far away)
 };
 struct SeedResult { double prob, init_err, final_err; dplane plane; };
 struct SymWarp {
@@ -95,25 +95,50 @@ __device__ __noinline__ int classify(const SymBlock &B, d3 pm) {
   }
   return valid ? 1 : 2;
 }
-// Exact float NN (flann::L2_Simple operation order; minimum r, first index on ties -- the oracle's linear scan) + fp64 distance to the
-// float neighbour (findMinimalDistanceWithKdTree :140-166).  All lanes scan the same cloud point at the same time (one broadcast
-// LDS.128 per point); a per-lane early reject would only add divergence, so the loop body is branch free.
+// packed fp32x2 arithmetic (Blackwell FADD2/FMUL2): two cloud points per instruction, each half rounded (rn) exactly like the scalar op
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) { return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32); }
+
+// Exact float NN (flann::L2_Simple operation order; minimum r = ((dx^2 + dy^2) + dz^2), first index on ties -- the oracle's linear
+// scan) + fp64 distance to the float neighbour (findMinimalDistanceWithKdTree :140-166).  All lanes scan the same pair of cloud
+// points at the same time (broadcast LDS.64 of the pair-interleaved SoA copy); the loop body is branch free.
 __device__ __noinline__ double nn_distance(const SymBlock &B, d3 pm) {
   const float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
   float bd = FLT_MAX; int best = 0;
   const int M = B.M;
-  const float4 *nn = B.in_smem ? B.nn4 : B.nn_g;
-#pragma unroll 4
-  for (int k = 0; k < M; k++) {
-    const float4 q = nn[k];
-    float dd = __fsub_rn(qx, q.x);
-    float r = __fmul_rn(dd, dd);                 // 0 + dx^2 is exact
-    dd = __fsub_rn(qy, q.y); r = __fadd_rn(r, __fmul_rn(dd, dd));
-    dd = __fsub_rn(qz, q.z); r = __fadd_rn(r, __fmul_rn(dd, dd));
-    if (r < bd) { bd = r; best = k; }
+  float bx, by, bz;
+  if (B.in_smem) {
+    const unsigned long long qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
+    const int pairs = (M + 1) >> 1;
+#pragma unroll 2
+    for (int j = 0; j < pairs; j++) {
+      unsigned long long dx = f2_sub(qx2, B.X2[j]), dy = f2_sub(qy2, B.Y2[j]), dz = f2_sub(qz2, B.Z2[j]);
+      // products packed (FMUL2), sums scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false,
+      // which would change the rounding; scalar add.rn.f32 is never contracted.
+      const unsigned long long sx = f2_mul(dx, dx), sy = f2_mul(dy, dy), sz = f2_mul(dz, dz);
+      const float r0 = __fadd_rn(__fadd_rn(__uint_as_float((unsigned)sx), __uint_as_float((unsigned)sy)), __uint_as_float((unsigned)sz));
+      const float r1 = __fadd_rn(__fadd_rn(__uint_as_float((unsigned)(sx >> 32)), __uint_as_float((unsigned)(sy >> 32))), __uint_as_float((unsigned)(sz >> 32)));
+      if (r0 < bd) { bd = r0; best = 2 * j; }
+      if (r1 < bd) { bd = r1; best = 2 * j + 1; }
+    }
+    const unsigned long long X = B.X2[best >> 1], Y = B.Y2[best >> 1], Z = B.Z2[best >> 1];
+    const int sh = (best & 1) * 32;
+    bx = __uint_as_float((unsigned)(X >> sh)); by = __uint_as_float((unsigned)(Y >> sh)); bz = __uint_as_float((unsigned)(Z >> sh));
+  } else {
+    for (int k = 0; k < M; k++) {
+      const float4 q = B.nn_g[k];
+      float dd = __fsub_rn(qx, q.x);
+      float r = __fmul_rn(dd, dd);
+      dd = __fsub_rn(qy, q.y); r = __fadd_rn(r, __fmul_rn(dd, dd));
+      dd = __fsub_rn(qz, q.z); r = __fadd_rn(r, __fmul_rn(dd, dd));
+      if (r < bd) { bd = r; best = k; }
+    }
+    const float4 q = B.nn_g[best];
+    bx = q.x; by = q.y; bz = q.z;
   }
-  const float4 q = nn[best];
-  const double dx = pm.x - (double)q.x, dy = pm.y - (double)q.y, dz = pm.z - (double)q.z;
+  const double dx = pm.x - (double)bx, dy = pm.y - (double)by, dz = pm.z - (double)bz;
   return sqrt(dx * dx + dy * dy + dz * dz);
 }
 
@@ -312,7 +337,12 @@ __global__ void __launch_bounds__(288, 3) symmetry_finalize_kernel(const uint16_
 
   if (run_sym) {
     const bool in_smem = M <= kSymSmemPts;
-    if (in_smem) for (int i = tid; i < M; i += blockDim.x) B.nn4[i] = objnf[i];
+    if (in_smem) for (int j = tid; j < (M + 1) / 2; j += blockDim.x) {
+      const float4 a = objnf[2 * j];
+      const float far_ = 1.0e30f;   // (q - 1e30)^2 overflows to +inf: never < FLT_MAX, so the pad can never win
+      const float4 b = (2 * j + 1 < M) ? objnf[2 * j + 1] : make_float4(far_, far_, far_, 0.0f);
+      B.X2[j] = f2_pack(a.x, b.x); B.Y2[j] = f2_pack(a.y, b.y); B.Z2[j] = f2_pack(a.z, b.z);
+    }
     if (tid == 0) {
       B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch;
       B.objn = objn; B.nn_g = objnf; B.M = M; B.symtype = m.symtype; B.npts = (m.symtype == 2) ? 2 * M : M; B.in_smem = in_smem ? 1 : 0;
@@ -410,14 +440,15 @@ __global__ void __launch_bounds__(288, 3) symmetry_finalize_kernel(const uint16_
   }
 }
 
-int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int n_obj,
+int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj,
                              const ExtractParamsDev &prm, const ExtractPtrs &ptrs) {
   ExtractWorkspace &w = *h->ex;
+  if (n_obj <= 0) return ESLAM_OK;
   const size_t smem = ((sizeof(SymBlock) + 15) & ~(size_t)15) + 9 * sizeof(SymWarp);
   static bool attr_set = false;
   if (!attr_set) { ESLAM_CUDA_OK(h, cudaFuncSetAttribute(symmetry_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-  symmetry_finalize_kernel<<<n_obj, 288, smem, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>(), w.state.as<ObjState>(), prm, ptrs,
-                                                 w.out.as<EslamEllipsoidOut>());
+  symmetry_finalize_kernel<<<n_obj, 288, smem, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs,
+                                                    w.out.as<EslamEllipsoidOut>() + obj0);
   ESLAM_LAUNCHED(h);
   ESLAM_CUDA_OK(h, cudaGetLastError());
   return ESLAM_OK;
