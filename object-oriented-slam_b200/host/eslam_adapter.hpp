@@ -1,0 +1,213 @@
+// eslam_adapter.hpp -- C++ host-side mirror of the reference's operator classes over the C-ABI (include/eslam.h).
+//
+// The classes keep the reference's names and call shapes so that src/core/Tracking.cpp can be pointed at them:
+//   EllipsoidSLAM::PlaneExtractor     src/plane/PlaneExtractor.h:41-70
+//   EllipsoidSLAM::EllipsoidExtractor src/pca/EllipsoidExtractor.h:37-131
+//   EllipsoidSLAM::Initializer        include/core/Initializer.h:36-80
+//   EllipsoidSLAM::Optimizer          include/core/Optimizer.h:14-32
+//   EllipsoidSLAM::Frame              include/core/Frame.h:12-41
+// Two layers: (1) POD signatures (always available -- this is what is compiled and link-checked in this repository, which has no
+// Eigen/OpenCV); (2) Eigen / cv::Mat overloads with the reference's exact signatures, enabled when those headers exist
+// (compile-verified elsewhere).  No compute happens here: every method forwards to libeslam_b200.so (CUDA only, no CPU fallback).
+#pragma once
+#include <array>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/eslam.h"
+
+#if defined(__has_include)
+#if __has_include(<Eigen/Core>) && __has_include(<opencv2/core.hpp>)
+#define ESLAM_HAVE_EIGEN_OPENCV 1
+#include <Eigen/Core>
+#include <opencv2/core.hpp>
+#endif
+#endif
+
+namespace EllipsoidSLAM {
+
+using Pose7 = std::array<double, 7>;        // x y z qx qy qz qw
+using Ellipsoid10 = std::array<double, 10>; // pose7 + a b c
+using Plane4 = std::array<double, 4>;
+
+struct camera_intrinsic { double fx, fy, cx, cy, scale; };   // include/core/Geometry.h:27-33
+
+struct ellipsoid_pod {   // the fields of g2o::ellipsoid the path reads/writes (include/core/Ellipsoid.h:26-136)
+  Ellipsoid10 vec{};
+  double prob = 1.0;
+  int miLabel = -1, miInstanceID = -1;
+};
+
+struct SymmetryOutputData {  // src/symmetry/Symmetry.h
+  bool result = false; double prob = 0; int symmetryType = 0; Plane4 planeVec{}, planeVec2{}; std::array<double, 3> center{};
+};
+
+class Context {   // owns the EslamHandle shared by the extractor / optimizer objects (one per GPU)
+ public:
+  Context(const EslamParams &p, const EslamCamera &c, int device = 0) {
+    if (eslam_create(&p, &c, device, &h_) != ESLAM_OK) throw std::runtime_error("eslam_create failed: a CUDA device is required (no CPU fallback)");
+    cam_ = c; prm_ = p;
+  }
+  ~Context() { eslam_destroy(h_); }
+  Context(const Context &) = delete;
+  EslamHandle *get() const { return h_; }
+  const EslamCamera &camera() const { return cam_; }
+  const EslamParams &params() const { return prm_; }
+  void check(int rc, const char *what) const { if (rc != ESLAM_OK) throw std::runtime_error(std::string(what) + ": " + eslam_last_error(h_)); }
+ private:
+  EslamHandle *h_ = nullptr; EslamCamera cam_{}; EslamParams prm_{};
+};
+
+class Frame {   // src/core/Frame.cpp:7-27
+ public:
+  static int total_frame;
+  Frame(double timestamp_, const double *pose_tail7, const std::vector<std::array<double, 8>> &bboxMat, const uint16_t *depth, int rows, int cols)
+      : timestamp(timestamp_), mmObservations(bboxMat), frame_img(depth, depth + (size_t)rows * cols) {
+    for (int i = 0; i < 7; i++) cam_pose_Twc[i] = pose_tail7[i];
+    eslam_pose_inverse(cam_pose_Twc.data(), cam_pose_Tcw.data());
+    frame_seq_id = total_frame++;
+    mvbOutlier.assign(bboxMat.size(), false);
+  }
+  double timestamp; int frame_seq_id;
+  Pose7 cam_pose_Twc{}, cam_pose_Tcw{};
+  std::vector<std::array<double, 8>> mmObservations;   // id x1 y1 x2 y2 label rate instanceID
+  std::vector<uint16_t> frame_img;
+  std::vector<bool> mvbOutlier;
+  std::vector<ellipsoid_pod *> mpLocalObjects;
+};
+inline int Frame::total_frame = 0;
+
+class PlaneExtractor {
+ public:
+  explicit PlaneExtractor(Context &c) : ctx_(c) {}
+  // bool extractGroundPlane(const cv::Mat &depth, g2o::plane &plane)   (PlaneExtractor.cpp:126-183)
+  bool extractGroundPlane(const uint16_t *depth, size_t pitch, Plane4 &plane) {
+    int found = 0, inl = 0;
+    ctx_.check(eslam_extract_ground_plane_host(ctx_.get(), 1, depth, pitch, plane.data(), &found, &inl), "extractGroundPlane");
+    n_inliers_ = inl;
+    return found != 0;
+  }
+  int inliers() const { return n_inliers_; }
+#ifdef ESLAM_HAVE_EIGEN_OPENCV
+  bool extractGroundPlane(const cv::Mat &depth, Eigen::Vector4d &plane_param) {
+    Plane4 p; bool ok = extractGroundPlane(depth.ptr<uint16_t>(0), depth.step / sizeof(uint16_t), p);
+    for (int i = 0; i < 4; i++) plane_param[i] = p[i];
+    return ok;
+  }
+#endif
+ private:
+  Context &ctx_; int n_inliers_ = 0;
+};
+
+class EllipsoidExtractor {
+ public:
+  explicit EllipsoidExtractor(Context &c) : ctx_(c) {}
+  void OpenSymmetry() { if (!ctx_.params().symmetry_open) throw std::runtime_error("symmetry is a creation-time parameter (EslamParams.symmetry_open)"); }
+  void SetSupportingPlane(const Plane4 &plane_world) { ctx_.check(eslam_set_supporting_plane(ctx_.get(), plane_world.data()), "SetSupportingPlane"); }
+  // g2o::ellipsoid EstimateLocalEllipsoid(cv::Mat& depth, Vector4d& bbox, int label, VectorXd& pose, camera_intrinsic&)  (EllipsoidExtractor.cpp:292-493)
+  ellipsoid_pod EstimateLocalEllipsoid(const uint16_t *depth, size_t pitch, const std::array<double, 4> &bbox, int label, const Pose7 &pose) {
+    const int frame_of_obj = 0;
+    EslamEllipsoidOut o;
+    ctx_.check(eslam_estimate_ellipsoids_host(ctx_.get(), 1, depth, pitch, 1, &frame_of_obj, bbox.data(), &label, pose.data(), &o, nullptr), "EstimateLocalEllipsoid");
+    miSystemState = o.status; mResult = (o.status == ESLAM_OBJ_OK);
+    mSym.result = o.symmetry_result != 0; mSym.prob = o.prob; mSym.symmetryType = o.symmetry_type;
+    for (int i = 0; i < 4; i++) { mSym.planeVec[i] = o.sym_plane_world[i]; mSym.planeVec2[i] = o.sym_plane2_world[i]; }
+    for (int i = 0; i < 3; i++) mSym.center[i] = o.sym_center_world[i];
+    ellipsoid_pod e; for (int i = 0; i < 10; i++) e.vec[i] = o.ellipsoid[i];
+    e.prob = o.prob; e.miLabel = label;
+    return e;
+  }
+  // batched form: every bbox of a batch of frames in one call
+  std::vector<EslamEllipsoidOut> EstimateLocalEllipsoids(int n_frames, const uint16_t *depth, size_t pitch, const std::vector<int> &frame_of_obj,
+                                                         const std::vector<double> &bbox4, const std::vector<int> &label, const std::vector<double> &Twc7) {
+    std::vector<EslamEllipsoidOut> out(frame_of_obj.size());
+    ctx_.check(eslam_estimate_ellipsoids_host(ctx_.get(), n_frames, depth, pitch, (int)frame_of_obj.size(), frame_of_obj.data(), bbox4.data(), label.data(), Twc7.data(),
+                                              out.data(), nullptr), "EstimateLocalEllipsoids");
+    return out;
+  }
+  bool GetResult() const { return mResult; }
+  SymmetryOutputData GetSymmetryOutputData() const { return mSym; }
+  int miSystemState = 0;
+ private:
+  Context &ctx_; bool mResult = false; SymmetryOutputData mSym;
+};
+
+struct Observation { int label; std::array<double, 4> bbox; double rate; Frame *pFrame; };   // include/core/Initializer.h:14-24
+using Observations = std::vector<Observation *>;
+
+class Initializer {
+ public:
+  Initializer(Context &c, int rows, int cols) : ctx_(c), rows_(rows), cols_(cols) {}
+  // g2o::ellipsoid initializeQuadric(Observations&, Matrix3d& calib)   (Initializer.cpp:290-305)
+  ellipsoid_pod initializeQuadric(const Observations &obs, const double K[9]) {
+    std::vector<double> tw, det;
+    for (const Observation *o : obs) { tw.insert(tw.end(), o->pFrame->cam_pose_Twc.begin(), o->pFrame->cam_pose_Twc.end()); det.insert(det.end(), o->bbox.begin(), o->bbox.end()); det.push_back(o->rate); }
+    ellipsoid_pod e; int ok = 0;
+    ctx_.check(eslam_init_quadric(ctx_.get(), (int)obs.size(), tw.data(), det.data(), K, rows_, cols_, e.vec.data(), &ok), "initializeQuadric");
+    mbResult = ok != 0;
+    if (mbResult && !obs.empty()) e.miLabel = obs[0]->label;
+    return e;
+  }
+  bool getInitializeResult() const { return mbResult; }
+ private:
+  Context &ctx_; int rows_, cols_; bool mbResult = false;
+};
+
+class Optimizer {
+ public:
+  explicit Optimizer(Context &c) : ctx_(c) {}
+  void SetGroundPlane(const Plane4 &normal) { mbGroundPlaneSet = true; mGroundPlaneNormal = normal; }
+  // void GlobalObjectGraphOptimization(std::vector<Frame*>&, Map*, rows, cols, Matrix3d& K, std::map<int,Observations>&, ...)  (Optimizer.cpp:83-317)
+  // `ellipsoids` plays the role of Map::GetAllEllipsoidsMap(): instance id -> ellipsoid, updated in place.
+  EslamLmStats GlobalObjectGraphOptimization(const std::vector<Frame *> &pFrames, std::map<int, ellipsoid_pod *> &ellipsoids, const double K[9],
+                                             const std::map<int, Observations> &objectObservations, int iters = 10) {
+    const EslamParams &prm = ctx_.params();
+    std::vector<int> inst; std::map<int, int> vid;
+    for (const auto &kv : objectObservations) if (ellipsoids.count(kv.first)) { vid[kv.first] = (int)inst.size(); inst.push_back(kv.first); }
+    std::vector<int> type, frame, object; std::vector<double> meas, info, Tcw, ell;
+    auto push_meas = [&](const double *m, int n) { for (int i = 0; i < 10; i++) meas.push_back(i < n ? m[i] : 0.0); };
+    for (int id : inst) {
+      if (mbGroundPlaneSet && prm.gravity_prior_open == 1) {   // :183-196
+        type.push_back(ESLAM_EDGE_GRAVITY); frame.push_back(0); object.push_back(vid[id]); push_meas(mGroundPlaneNormal.data(), 4);
+        const double s = 1 * prm.gravity_prior_scale; info.push_back(s * s);
+      }
+      const Observations &obs = objectObservations.at(id);
+      if (obs.size() > 2) for (const Observation *o : obs) {     // :201-245 (the NaN gate is applied below)
+        type.push_back(ESLAM_EDGE_PROJ); frame.push_back(o->pFrame->frame_seq_id); object.push_back(vid[id]); push_meas(o->bbox.data(), 4); info.push_back((1.0 * 1.0) * o->rate);
+      }
+    }
+    for (size_t f = 0; f < pFrames.size(); f++) for (const ellipsoid_pod *obj : pFrames[f]->mpLocalObjects) {   // :249-279
+      if (!obj || !vid.count(obj->miInstanceID)) continue;
+      type.push_back(ESLAM_EDGE_9DOF); frame.push_back((int)f); object.push_back(vid[obj->miInstanceID]); push_meas(obj->vec.data(), 10);
+      const double s = 1.0 * std::sqrt(obj->prob); info.push_back((s * s) * prm.edge3d_scale);
+    }
+    for (const Frame *f : pFrames) Tcw.insert(Tcw.end(), f->cam_pose_Tcw.begin(), f->cam_pose_Tcw.end());
+    for (int id : inst) ell.insert(ell.end(), ellipsoids[id]->vec.begin(), ellipsoids[id]->vec.end());
+    EslamLmStats st{};
+    if (inst.empty() || type.empty()) return st;
+    auto make_batch = [&](EslamEdgeBatch &g) {
+      g.n_edges = (int)type.size(); g.type = type.data(); g.frame = frame.data(); g.object = object.data(); g.meas = meas.data(); g.info = info.data();
+      g.n_frames = (int)pFrames.size(); g.Tcw = Tcw.data(); g.n_objects = (int)inst.size(); for (int i = 0; i < 9; i++) g.K[i] = K[i];
+    };
+    EslamEdgeBatch g; make_batch(g);
+    {  // NaN gate of the 2-D edges before insertion (:234-243)
+      std::vector<double> res((size_t)g.n_edges * 9), chi((size_t)g.n_edges);
+      ctx_.check(eslam_edges_eval_host(ctx_.get(), &g, ell.data(), res.data(), nullptr, chi.data()), "edges_eval");
+      size_t w = 0;
+      for (size_t k = 0; k < type.size(); k++) {
+        if (type[k] == ESLAM_EDGE_PROJ && chi[k] != chi[k]) continue;
+        type[w] = type[k]; frame[w] = frame[k]; object[w] = object[k]; info[w] = info[k]; for (int i = 0; i < 10; i++) meas[w * 10 + i] = meas[k * 10 + i]; w++;
+      }
+      type.resize(w); frame.resize(w); object.resize(w); info.resize(w); meas.resize(w * 10);
+      make_batch(g);
+    }
+    ctx_.check(eslam_optimize_objects_host(ctx_.get(), &g, iters, ell.data(), &st), "optimize");
+    for (size_t k = 0; k < inst.size(); k++) for (int i = 0; i < 10; i++) ellipsoids[inst[k]]->vec[i] = ell[k * 10 + i];
+    return st;
+  }
+ private:
+  Context &ctx_; bool mbGroundPlaneSet = false; Plane4 mGroundPlaneNormal{};
+};
+
+}  // namespace EllipsoidSLAM

@@ -1,0 +1,16 @@
+"""The C++ host adapter (reference-named classes over the C-ABI) must compile with plain g++ and link against libeslam_b200.so."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_adapter_compiles_links_and_runs(tmp_path):
+    exe = str(tmp_path / "host_adapter_check")
+    libdir = os.path.join(ROOT, "object-oriented-slam_b200")
+    cuda_lib = "/usr/local/cuda/lib64"
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "host_adapter_check.cpp"), "-L" + libdir, "-leslam_b200",
+                           "-L" + cuda_lib, "-Wl,-rpath," + libdir, "-Wl,-rpath," + cuda_lib])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "adapter ok" in out.stdout
