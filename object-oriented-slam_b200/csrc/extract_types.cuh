@@ -16,7 +16,7 @@ struct ObjMeta {  // built on the host per batch (tiny), uploaded once
 struct ObjState {  // device resident, one per object
   int status;
   int n_crop, n_voxel, n_plane, n_clusters, n_cluster, n_sym, n_final;
-  int run_sym, symtype, best_seed, pad;
+  int run_sym, symtype, best_seed, done;   // done: #seeds finished (last arriver finalises)
   int bbox_i[4];            // (int)bbox[k] as used by isInRange (SymmetrySolver.cpp:75)
   double center[3];
   double pca_center[3], pca_rot[9], pca_eval[3];

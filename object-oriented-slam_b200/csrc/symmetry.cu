@@ -24,7 +24,7 @@
 
 namespace eslam {
 
-constexpr int kSymSmemPts = 512;   // cloud staged in shared memory (SoA) up to this many points
+constexpr int kSymSmemPts = 256;   // cloud staged in shared memory (pair-interleaved SoA) up to this many points
 constexpr int kSymQueue = 256;     // per-warp query queue / distance slots / NN cache (fast path when #mirrored points <= 256)
 
 struct PlanePair {   // per-evaluation constants of GetSymmetryPointOfPlane for the plane and its dual (hoisted, same rounding)
@@ -302,135 +302,86 @@ __device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
   __syncwarp();
 }
 
-// grid = n_obj, block = 288 (9 warps = 9 seeds)
-__global__ void __launch_bounds__(288, 3) symmetry_finalize_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride,
-                                                                const ObjMeta *__restrict__ metas, ObjState *__restrict__ states, ExtractParamsDev prm,
-                                                                ExtractPtrs W, EslamEllipsoidOut *__restrict__ outs) {
-  __shared__ BlockScratch S;
-  extern __shared__ __align__(16) unsigned char sym_smem[];
-  SymBlock &B = *reinterpret_cast<SymBlock *>(sym_smem);
-  SymWarp *Ws = reinterpret_cast<SymWarp *>(sym_smem + ((sizeof(SymBlock) + 15) & ~(size_t)15));
-  __shared__ int s_best;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const ObjMeta m = metas[blockIdx.x];
-  ObjState &st = states[blockIdx.x];
-  EslamEllipsoidOut &out = outs[blockIdx.x];
-  const int status = st.status;
-  if (tid == 0) {
-    for (int i = 0; i < 10; i++) out.ellipsoid[i] = 0;
-    out.prob = 0; out.status = status; out.symmetry_type = m.symtype > 0 ? m.symtype : 0; out.symmetry_result = 0; out.best_seed = -1;
-    for (int i = 0; i < 4; i++) { out.sym_plane_world[i] = 0; out.sym_plane2_world[i] = 0; }
-    for (int i = 0; i < 3; i++) out.sym_center_world[i] = 0;
-    out.n_crop = st.n_crop; out.n_voxel = st.n_voxel; out.n_plane = st.n_plane; out.n_clusters = st.n_clusters; out.n_cluster = st.n_cluster;
-    out.n_sym = st.n_sym; out.n_final = 0; out.reserved = 0;
-    if (!prm.symmetry_open) out.symmetry_type = 0;
-  }
-  if (status != 0) return;
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// completion (EllipsoidExtractor.cpp:399-446), extents (:495-531) and ellipsoid assembly (:461-492) by ONE warp
+__device__ __noinline__ void finalize_object(const ObjMeta &m, ObjState &st, const ExtractParamsDev &prm, const ExtractPtrs &W, EslamEllipsoidOut &out) {
+  const int lane = threadIdx.x & 31;
   const int M = st.n_sym;
   const int run_sym = st.run_sym;
   const double *objn = W.objn + 3 * (size_t)m.off;
-  const float4 *objnf = W.objnf + m.off;
   se3 Two = se3_load(st.T_wo);
   const se3 Twc = se3_load(m.Twc);
   double sym_prob = 1.0;
   dplane bestp; bestp.p[0] = 1; bestp.p[1] = 0; bestp.p[2] = 0; bestp.p[3] = 0; bestp.dual = 0;
-
-  if (run_sym) {
-    const bool in_smem = M <= kSymSmemPts;
-    if (in_smem) for (int j = tid; j < (M + 1) / 2; j += blockDim.x) {
-      const float4 a = objnf[2 * j];
-      const float far_ = 1.0e30f;   // (q - 1e30)^2 overflows to +inf: never < FLT_MAX, so the pad can never win
-      const float4 b = (2 * j + 1 < M) ? objnf[2 * j + 1] : make_float4(far_, far_, far_, 0.0f);
-      B.X2[j] = f2_pack(a.x, b.x); B.Y2[j] = f2_pack(a.y, b.y); B.Z2[j] = f2_pack(a.z, b.z);
-    }
-    if (tid == 0) {
-      B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch;
-      B.objn = objn; B.nn_g = objnf; B.M = M; B.symtype = m.symtype; B.npts = (m.symtype == 2) ? 2 * M : M; B.in_smem = in_smem ? 1 : 0;
-      for (int i = 0; i < 12; i++) B.P[i] = st.P[i];
-      B.cam[0] = st.T_oc[0]; B.cam[1] = st.T_oc[1]; B.cam[2] = st.T_oc[2];
-      B.bx0 = st.bbox_i[0]; B.by1 = st.bbox_i[1]; B.bx2 = st.bbox_i[2]; B.by3 = st.bbox_i[3];
-      B.rows = prm.rows; B.cols = prm.cols; B.fx = prm.fx; B.cx = prm.cx; B.cy = prm.cy; B.scale = prm.scale;
-      B.sinv = 1.0 / prm.sigma;
-    }
-    SymWarp &Wp = Ws[warp];
-    if (lane == 0) {
-      // GenerateInitPlanes (Symmetry.cpp:44-86): seed = i*3+m, dis = -0.2 + 0.2 i, angle = -5deg + 5deg m
-      const double diff_dis = 0.2, diff_angle = M_PI / 180.0 * 5;
-      const double start_dis = -diff_dis * 1, start_angle = -diff_angle * 1;
-      const int si = warp / 3, sm = warp % 3;
-      const double dis = start_dis + diff_dis * si, angle = start_angle + diff_angle * sm;
-      Wp.est.p[0] = sin(angle); Wp.est.p[1] = -cos(angle); Wp.est.p[2] = 0; Wp.est.p[3] = -dis; Wp.est.dual = 0;   // fromDisAngleTrans
-    }
-    __syncthreads();
-    sym_optimize(B, Wp, prm.symmetry_iters);
-    if (lane == 0) {
-      const SeedResult &r = Wp.res;
-      st.seed_prob[warp] = r.prob; st.seed_init[warp] = r.init_err; st.seed_final[warp] = r.final_err; st.seed_dual[warp] = r.plane.dual;
-      for (int k = 0; k < 4; k++) st.seed_plane[warp][k] = r.plane.p[k];
-    }
-    __syncthreads();
-    if (tid == 0) {  // sort(desc by prob) of 9 entries == insertion sort == stable: first maximum wins (Symmetry.cpp:122-126)
-      int best = 0;
-      for (int s = 1; s < 9; s++) if (Ws[s].res.prob > Ws[best].res.prob) best = s;
-      s_best = best; st.best_seed = best;
-    }
-    __syncthreads();
-    bestp = Ws[s_best].res.plane;
-    sym_prob = Ws[s_best].res.prob;
+  int best = -1;
+  if (run_sym) {   // sort(desc by prob) of 9 entries == insertion sort == stable: first maximum wins (Symmetry.cpp:122-126)
+    const volatile double *sp = st.seed_prob;
+    best = 0;
+    for (int s = 1; s < 9; s++) if (sp[s] > sp[best]) best = s;
+    for (int k = 0; k < 4; k++) bestp.p[k] = ((const volatile double *)st.seed_plane[best])[k];
+    bestp.dual = ((const volatile double *)st.seed_dual)[best];
+    sym_prob = sp[best];
   }
-
-  // ---- completion :399-446 (mirrored points generated on the fly, never stored) ----
   double p1[4] = {bestp.p[0], bestp.p[1], bestp.p[2], bestp.p[3]}, p2[4];
   plane_another(bestp, p2);
   const int copies = run_sym ? ((m.symtype == 2) ? 4 : 2) : 1;
   const int nfin = copies * M;
-  auto gen_point = [&](int idx) -> d3 {
+  auto gen_point = [&](int idx) -> d3 {   // mirrored points generated on the fly, never stored
     int part = idx / M, j = idx - part * M;
     d3 p = mk3(objn[3 * j], objn[3 * j + 1], objn[3 * j + 2]);
-    if (part == 1) p = mirror_point(p, p1);                       // pSymCloudNormalized
-    else if (part == 2) p = mirror_point(p, p2);                  // pSymCloudNormalized2_1
+    if (part == 1) p = mirror_point(p, p1);                         // pSymCloudNormalized
+    else if (part == 2) p = mirror_point(p, p2);                    // pSymCloudNormalized2_1
     else if (part == 3) p = mirror_point(mirror_point(p, p1), p2);  // pSymCloudNormalized2_2
     return p;
   };
   hom34 Tmo_h;
   bool retransform = false;
   if (run_sym) {
-    double s3[3] = {0, 0, 0};
-    for (int i = tid; i < nfin; i += blockDim.x) { d3 p = gen_point(i); s3[0] += p.x; s3[1] += p.y; s3[2] += p.z; }
-    block_sum_double<3>(s3, S);
-    double nn = (double)nfin;
-    d3 cc = mk3(s3[0] / nn, s3[1] / nn, s3[2] / nn);   // GetPointcloudCenter
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int i = lane; i < nfin; i += 32) { d3 p = gen_point(i); s0 += p.x; s1 += p.y; s2 += p.z; }
+    s0 = warp_sum_d(s0); s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+    const double nn = (double)nfin;
+    d3 cc = mk3(s0 / nn, s1 / nn, s2 / nn);   // GetPointcloudCenter
     d3 c0 = mk3(p1[0], p1[1], p1[2]);
-    double n0 = norm3(c0);
+    const double n0 = norm3(c0);
     c0 = mk3(c0.x / n0, c0.y / n0, c0.z / n0);
     mat3 Rom; m3_setcol(Rom, 0, c0); m3_setcol(Rom, 2, mk3(0, 0, 1)); m3_setcol(Rom, 1, cross3(mk3(0, 0, 1), c0));
     se3 Tom; Tom.t = cc; Tom.r = q_from_R(Rom);
     Tmo_h = se3_hom(se3_inv(Tom));
     retransform = true;
-    if (tid == 0) {
+    if (lane == 0) {
       d3 cw = hom_apply(se3_hom(Two), cc);
       out.sym_center_world[0] = cw.x; out.sym_center_world[1] = cw.y; out.sym_center_world[2] = cw.z;
       double w1[4]; plane_transform_rigid(Two, p1, w1);
       for (int k = 0; k < 4; k++) out.sym_plane_world[k] = w1[k];
       if (m.symtype == 2) { double w2[4]; plane_transform_rigid(Two, p2, w2); for (int k = 0; k < 4; k++) out.sym_plane2_world[k] = w2[k]; }
-      out.symmetry_result = 1; out.best_seed = s_best;
+      out.symmetry_result = 1; out.best_seed = best; st.best_seed = best;
     }
     Two = se3_mul(Two, Tom);
   }
-  // ---- ProcessPCANormalized :495-531 : axis-aligned extents
-  double ext[3] = {0, 0, 0};
-  for (int i = tid; i < nfin; i += blockDim.x) {
+  double e0x = 0, e0y = 0, e0z = 0;   // ProcessPCANormalized: axis-aligned extents
+  for (int i = lane; i < nfin; i += 32) {
     d3 p = gen_point(i);
     if (retransform) p = hom_apply(Tmo_h, p);
-    ext[0] = fmax(ext[0], fabs(p.x)); ext[1] = fmax(ext[1], fabs(p.y)); ext[2] = fmax(ext[2], fabs(p.z));
+    e0x = fmax(e0x, fabs(p.x)); e0y = fmax(e0y, fabs(p.y)); e0z = fmax(e0z, fabs(p.z));
     if (W.d_final) { double *q = W.d_final + 3 * ((size_t)4 * m.off + i); q[0] = p.x; q[1] = p.y; q[2] = p.z; }
   }
-  for (int k = 0; k < 3; k++) ext[k] = -block_min_double(-ext[k], S);
-  if (tid == 0) {
+  e0x = warp_max_d(e0x); e0y = warp_max_d(e0y); e0z = warp_max_d(e0z);
+  if (lane == 0) {
     ellipsoid e0;
     mat3 I = m3_eye();
     e0.pose.r = q_from_R(I); e0.pose.t = mk3(0, 0, 0);
-    e0.s[0] = ext[0]; e0.s[1] = ext[1]; e0.s[2] = ext[2];
+    e0.s[0] = e0x; e0.s[1] = e0y; e0.s[2] = e0z;
     ellipsoid eg = e0; eg.pose = se3_mul(Two, e0.pose);                 // transform_from(*pSE3Two)       :465
     ellipsoid el = eg; el.pose = se3_mul(se3_inv(Twc), eg.pose);        // transform_from(campose_wc.inverse()) :468-469
     ell_store(el, out.ellipsoid);
@@ -440,14 +391,86 @@ __global__ void __launch_bounds__(288, 3) symmetry_finalize_kernel(const uint16_
   }
 }
 
+// grid = 9 * n_obj one-warp CTAs: CTA b handles seed (b % 9) of object (b / 9).  Seeds are independent until the very end; the warp
+// that finishes LAST for an object (atomic counter) performs the completion/finalisation, so no warp ever waits at a barrier for a
+// slower seed and the SM keeps ~28 independent warps in flight (the kernel is latency / issue bound, not bandwidth bound).
+__global__ void __launch_bounds__(32, 28) symmetry_finalize_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride,
+                                                                   const ObjMeta *__restrict__ metas, ObjState *__restrict__ states, ExtractParamsDev prm,
+                                                                   ExtractPtrs W, EslamEllipsoidOut *__restrict__ outs) {
+  __shared__ SymBlock B;
+  __shared__ SymWarp Wp;
+  const int lane = threadIdx.x & 31;
+  const int obj = blockIdx.x / 9, seed = blockIdx.x - obj * 9;
+  const ObjMeta &m = metas[obj];
+  ObjState &st = states[obj];
+  EslamEllipsoidOut &out = outs[obj];
+  const int status = st.status;
+  const int run_sym = st.run_sym;
+  if (seed == 0 && lane == 0) {
+    for (int i = 0; i < 10; i++) out.ellipsoid[i] = 0;
+    out.prob = 0; out.status = status; out.symmetry_type = m.symtype > 0 ? m.symtype : 0; out.symmetry_result = 0; out.best_seed = -1;
+    for (int i = 0; i < 4; i++) { out.sym_plane_world[i] = 0; out.sym_plane2_world[i] = 0; }
+    for (int i = 0; i < 3; i++) out.sym_center_world[i] = 0;
+    out.n_crop = st.n_crop; out.n_voxel = st.n_voxel; out.n_plane = st.n_plane; out.n_clusters = st.n_clusters; out.n_cluster = st.n_cluster;
+    out.n_sym = st.n_sym; out.n_final = 0; out.reserved = 0;
+    if (!prm.symmetry_open) out.symmetry_type = 0;
+  }
+  if (status != 0) return;
+  if (!run_sym) {   // no symmetry for this label: seed 0 finalises directly
+    if (seed == 0) { __syncwarp(); finalize_object(m, st, prm, W, out); }
+    return;
+  }
+  const int M = st.n_sym;
+  const double *objn = W.objn + 3 * (size_t)m.off;
+  const float4 *objnf = W.objnf + m.off;
+  {
+    const bool in_smem = M <= kSymSmemPts;
+    if (in_smem) for (int j = lane; j < (M + 1) / 2; j += 32) {
+      const float4 a = objnf[2 * j];
+      const float far_ = 1.0e30f;   // (q - 1e30)^2 overflows to +inf: never < FLT_MAX, so the pad can never win
+      const float4 b = (2 * j + 1 < M) ? objnf[2 * j + 1] : make_float4(far_, far_, far_, 0.0f);
+      B.X2[j] = f2_pack(a.x, b.x); B.Y2[j] = f2_pack(a.y, b.y); B.Z2[j] = f2_pack(a.z, b.z);
+    }
+    if (lane == 0) {
+      B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch;
+      B.objn = objn; B.nn_g = objnf; B.M = M; B.symtype = m.symtype; B.npts = (m.symtype == 2) ? 2 * M : M; B.in_smem = in_smem ? 1 : 0;
+      for (int i = 0; i < 12; i++) B.P[i] = st.P[i];
+      B.cam[0] = st.T_oc[0]; B.cam[1] = st.T_oc[1]; B.cam[2] = st.T_oc[2];
+      B.bx0 = st.bbox_i[0]; B.by1 = st.bbox_i[1]; B.bx2 = st.bbox_i[2]; B.by3 = st.bbox_i[3];
+      B.rows = prm.rows; B.cols = prm.cols; B.fx = prm.fx; B.cx = prm.cx; B.cy = prm.cy; B.scale = prm.scale;
+      B.sinv = 1.0 / prm.sigma;
+      // GenerateInitPlanes (Symmetry.cpp:44-86): seed = i*3+m, dis = -0.2 + 0.2 i, angle = -5deg + 5deg m
+      const double diff_dis = 0.2, diff_angle = M_PI / 180.0 * 5;
+      const double start_dis = -diff_dis * 1, start_angle = -diff_angle * 1;
+      const int si = seed / 3, sm = seed % 3;
+      const double dis = start_dis + diff_dis * si, angle = start_angle + diff_angle * sm;
+      Wp.est.p[0] = sin(angle); Wp.est.p[1] = -cos(angle); Wp.est.p[2] = 0; Wp.est.p[3] = -dis; Wp.est.dual = 0;   // fromDisAngleTrans
+    }
+    __syncwarp();
+  }
+  sym_optimize(B, Wp, prm.symmetry_iters);
+  int prev = 0;
+  if (lane == 0) {
+    const SeedResult &r = Wp.res;
+    st.seed_prob[seed] = r.prob; st.seed_init[seed] = r.init_err; st.seed_final[seed] = r.final_err; st.seed_dual[seed] = r.plane.dual;
+    for (int k = 0; k < 4; k++) st.seed_plane[seed][k] = r.plane.p[k];
+    __threadfence();
+    prev = atomicAdd(&st.done, 1);
+  }
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  if (prev == 8) {   // last seed of this object: every other seed's results are visible (fence + atomic)
+    __threadfence();
+    finalize_object(m, st, prm, W, out);
+  }
+}
+
 int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj,
                              const ExtractParamsDev &prm, const ExtractPtrs &ptrs) {
   ExtractWorkspace &w = *h->ex;
   if (n_obj <= 0) return ESLAM_OK;
-  const size_t smem = ((sizeof(SymBlock) + 15) & ~(size_t)15) + 9 * sizeof(SymWarp);
   static bool attr_set = false;
-  if (!attr_set) { ESLAM_CUDA_OK(h, cudaFuncSetAttribute(symmetry_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-  symmetry_finalize_kernel<<<n_obj, 288, smem, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs,
+  if (!attr_set) { ESLAM_CUDA_OK(h, cudaFuncSetAttribute(symmetry_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); attr_set = true; }
+  symmetry_finalize_kernel<<<9 * n_obj, 32, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs,
                                                     w.out.as<EslamEllipsoidOut>() + obj0);
   ESLAM_LAUNCHED(h);
   ESLAM_CUDA_OK(h, cudaGetLastError());
