@@ -281,7 +281,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config, objects_per_step_per_gpu=n_obj, ok_fraction=ok_frac, gather_ms=gather_ms),
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(depth.nbytes) * world, "d2h_bytes_per_step": int(C.sizeof(EslamEllipsoidOut) * n_obj) * world},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
                              "sample": f"{min(args.cpu_sample, args.frames)} frames of the same batch, {cpu_dt:.1f} s, oracle/liboracle.so single thread"}}
     print(json.dumps(line))

@@ -40,7 +40,7 @@ struct PlaneFramePtrs {
   float4 *pts, *nrm;
   double *iiX, *iiY;
   float *dm;
-  int *parent, *count, *maxidx;
+  int *parent, *count, *maxidx, *cmin, *cmax;   // per-root size, last pixel, column range (bounding box of the region)
   int *cand_root;      // [F * kMaxRegions]
   int *cand_n;         // [F]
   float4 *cand_coef;   // [F * kMaxRegions]
@@ -51,7 +51,7 @@ struct PlaneFramePtrs {
 };
 
 struct PlaneWorkspace {
-  DevBuf pts, nrm, iiX, iiY, dm, parent, count, maxidx, cand_root, cand_n, cand_coef, cand_valid, cand_size, out_plane, out_found, out_inl;
+  DevBuf pts, nrm, iiX, iiY, dm, parent, count, maxidx, cmin, cmax, cand_root, cand_n, cand_coef, cand_valid, cand_size, out_plane, out_found, out_inl;
   PinBuf pin;
   int chunk = 0;
 };
@@ -72,6 +72,8 @@ __global__ void points_kernel(const uint16_t *__restrict__ depth, size_t pitch, 
   W.parent[(size_t)f * NP + idx] = idx;
   W.count[(size_t)f * NP + idx] = 0;
   W.maxidx[(size_t)f * NP + idx] = 0;
+  W.cmin[(size_t)f * NP + idx] = 0x7fffffff;
+  W.cmax[(size_t)f * NP + idx] = -1;
 }
 
 // ---------------------------------------------------------------------------------------------- P2: integral images (exact recurrence)
@@ -310,12 +312,32 @@ __global__ void ccl_flatten_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   const int NP = prm.rows * prm.cols;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int f = blockIdx.y;
-  if (idx >= NP) return;
+  const bool act = idx < NP;
   int *parent = W.parent + (size_t)f * NP;
-  int r = p_find(parent, idx);
-  atomicAdd(W.count + (size_t)f * NP + r, 1);
-  atomicMax(W.maxidx + (size_t)f * NP + r, idx);
-  W.dm[(size_t)f * NP + idx] = __int_as_float(r);   // dm is free now: stash the flattened label (written back below)
+  int r = act ? p_find(parent, idx) : -1 - (int)(threadIdx.x & 31);
+  // warp-aggregated statistics: consecutive pixels mostly share a root, so one lane per distinct root issues the atomics
+  const unsigned peers = __match_any_sync(0xffffffffu, r);
+  if (act) {
+    const int lane = threadIdx.x & 31;
+    const int lo = __ffs(peers) - 1, hi = 31 - __clz(peers);
+    const int col = idx % prm.cols;
+    const int col_lo = __shfl_sync(peers, col, lo), col_hi = __shfl_sync(peers, col, hi);
+    const int row_lo = __shfl_sync(peers, idx / prm.cols, lo), row_hi = __shfl_sync(peers, idx / prm.cols, hi);
+    if (row_lo == row_hi) {
+      if (lane == lo) {
+        atomicAdd(W.count + (size_t)f * NP + r, __popc(peers));
+        atomicMax(W.maxidx + (size_t)f * NP + r, idx + (hi - lo));
+        atomicMin(W.cmin + (size_t)f * NP + r, col_lo);
+        atomicMax(W.cmax + (size_t)f * NP + r, col_hi);
+      }
+    } else {   // the warp straddles an image row (cols not a multiple of 32): per-lane atomics
+      atomicAdd(W.count + (size_t)f * NP + r, 1);
+      atomicMax(W.maxidx + (size_t)f * NP + r, idx);
+      atomicMin(W.cmin + (size_t)f * NP + r, col);
+      atomicMax(W.cmax + (size_t)f * NP + r, col);
+    }
+    W.dm[(size_t)f * NP + idx] = __int_as_float(r);   // dm is free now: stash the flattened label (written back below)
+  }
 }
 __global__ void ccl_commit_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   const int NP = prm.rows * prm.cols;
@@ -378,44 +400,91 @@ __device__ void roots3f(const float *m /*3x3*/, float *roots) {   // pcl::comput
     if (roots[0] <= 0) roots2f(c2, c1, roots);
   }
 }
-// one warp per (frame, candidate)
-__global__ void fit_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
-  const int NP = prm.rows * prm.cols;
+// One 128-thread CTA per (frame, candidate) at a time (CTAs of a frame stride over its candidates).  The float moment sums must be
+// formed in raster order (bit parity with pcl::computeMeanAndCovarianceMatrix<float>), so the dependent FADD chain is the critical
+// path; everything else is taken off it with a producer/consumer split:
+//   warps 1..3 (producers) walk the region's bounding box in raster order, test membership with coalesced loads + ballots and
+//                          write the member points, order preserved, into one half of a double-buffered shared-memory tile;
+//   warp 0 (consumer)      lanes 0..8 own one accumulator each (xx xy xz yy yz zz x y z): per point one broadcast LDS.128, two
+//                          selects, one FMUL (x*1.0f is exact for lanes 6..8) and the FADD.
+constexpr int kFitThreads = 128;
+constexpr int kFitGroupsPerWarp = 5;                                   // 32-pixel groups per producer warp per tile
+constexpr int kFitTilePts = 3 * kFitGroupsPerWarp * 32;                // 480 points per tile
+__global__ void __launch_bounds__(kFitThreads) fit_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  __shared__ float s_v[2][kFitTilePts * 9];    // the 9 addends of every member point (products formed by the producers)
+  __shared__ int s_cnt[2][4];
+  const int NP = prm.rows * prm.cols, Wd = prm.cols;
   const int f = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (k >= W.cand_n[f]) return;
-  const int root = W.cand_root[f * kMaxRegions + k];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int *parent = W.parent + (size_t)f * NP;
   const float4 *pts = W.pts + (size_t)f * NP;
+  const int ncand = W.cand_n[f];
+  for (int k = blockIdx.x; k < ncand; k += gridDim.x) {
+  const int root = W.cand_root[f * kMaxRegions + k];
   const int last = W.maxidx[(size_t)f * NP + root];
-  // lanes 0..8 own one accumulator each: xx xy xz yy yz zz x y z (computeMeanAndCovarianceMatrix<float>).  The region's pixels are
-  // consumed in raster order; the only dependent chain is the 4-cycle FADD: every group of 32 pixels is fetched coalesced one
-  // group ahead (software prefetch) and broadcast with shuffles, products are formed branch-free (x*1.0f is exact for lanes 6..8).
+  const int r0 = root / Wd, r1 = last / Wd;                       // bounding box rows / columns (32-aligned)
+  const int c0 = W.cmin[(size_t)f * NP + root] & ~31, c1 = W.cmax[(size_t)f * NP + root];
+  const int gpr = (c1 - c0) / 32 + 1;                             // groups per row
+  const int ngroups = (r1 - r0 + 1) * gpr;
+  const int gpt = 3 * kFitGroupsPerWarp;                          // groups per tile
+  const int ntiles = (ngroups + gpt - 1) / gpt;
   float acc = 0.0f;
-  const int ia = (lane < 3) ? 0 : (lane < 5 ? 1 : (lane == 5 ? 2 : lane - 6));        // first factor:  x x x y y z x y z
-  const int ib = (lane < 3) ? lane : (lane < 5 ? lane - 2 : (lane == 5 ? 2 : 3));     // second factor: x y z y z z 1 1 1
-  int base = root & ~31;
-  float4 nxt = make_float4(0, 0, 0, 0); bool nin = false;
-  { int i = base + lane; nin = (i >= root && i <= last) && parent[i] == root; if (nin) nxt = pts[i]; }
-  for (; base <= last; base += 32) {
-    const float4 mine = nxt; const bool in = nin;
-    { int i = base + 32 + lane; nin = (i <= last) && parent[i] == root; nxt = nin ? pts[i] : make_float4(0, 0, 0, 0); }
-    const unsigned mask = __ballot_sync(0xffffffffu, in);
-    if (mask == 0) continue;
+  __syncthreads();
+  // tile t is produced during iteration t (into buffer t&1) and consumed during iteration t+1
+  for (int t = 0; t <= ntiles; t++) {
+    if (warp >= 1 && t < ntiles) {
+      const int pw = warp - 1;
+      float4 mine[kFitGroupsPerWarp]; unsigned masks[kFitGroupsPerWarp];
+      int total = 0;
 #pragma unroll
-    for (int b = 0; b < 32; b++) {
-      const float x = __shfl_sync(0xffffffffu, mine.x, b), y = __shfl_sync(0xffffffffu, mine.y, b), z = __shfl_sync(0xffffffffu, mine.z, b);
-      const float a = (ia == 0) ? x : (ia == 1 ? y : z);
-      const float c = (ib == 0) ? x : (ib == 1 ? y : (ib == 2 ? z : 1.0f));
-      const float v = __fmul_rn(a, c);
-      if ((mask >> b) & 1u) acc = __fadd_rn(acc, v);
+      for (int q = 0; q < kFitGroupsPerWarp; q++) {
+        const int g = t * gpt + pw * kFitGroupsPerWarp + q;
+        bool in = false; mine[q] = make_float4(0, 0, 0, 0);
+        if (g < ngroups) {
+          const int rr = r0 + g / gpr, cc = c0 + (g % gpr) * 32 + lane;
+          if (cc < Wd) { const int i = rr * Wd + cc; const int lab = parent[i]; mine[q] = pts[i]; in = lab == root; }
+        }
+        masks[q] = __ballot_sync(0xffffffffu, in);
+        total += __popc(masks[q]);
+      }
+      if (lane == 0) s_cnt[t & 1][warp] = total;
+      // producers only: named barrier 1 (96 threads) orders the per-warp totals before the offsets are formed
+      asm volatile("bar.sync 1, 96;");
+      int off = 0;
+      for (int w2 = 1; w2 < warp; w2++) off += s_cnt[t & 1][w2];
+#pragma unroll
+      for (int q = 0; q < kFitGroupsPerWarp; q++) {
+        if ((masks[q] >> lane) & 1u) {
+          float *o = &s_v[t & 1][(off + __popc(masks[q] & ((1u << lane) - 1u))) * 9];
+          const float4 p = mine[q];
+          o[0] = __fmul_rn(p.x, p.x); o[1] = __fmul_rn(p.x, p.y); o[2] = __fmul_rn(p.x, p.z);
+          o[3] = __fmul_rn(p.y, p.y); o[4] = __fmul_rn(p.y, p.z); o[5] = __fmul_rn(p.z, p.z);
+          o[6] = p.x; o[7] = p.y; o[8] = p.z;
+        }
+        off += __popc(masks[q]);
+      }
     }
+    if (warp == 0 && t >= 1) {
+      const int b = (t - 1) & 1;
+      const int n = s_cnt[b][1] + s_cnt[b][2] + s_cnt[b][3];
+      const float *buf = s_v[b] + (lane < 9 ? lane : 0);
+      int j = 0;
+      for (; j + 8 <= n; j += 8) {   // 8 independent LDS, then the 8-long dependent FADD chain
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = buf[(j + u) * 9];
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc = __fadd_rn(acc, v[u]);
+      }
+      for (; j < n; j++) acc = __fadd_rn(acc, buf[j * 9]);
+    }
+    __syncthreads();
   }
+  if (warp == 0) {
   float accu[9];
 #pragma unroll
   for (int j = 0; j < 9; j++) accu[j] = __shfl_sync(0xffffffffu, acc, j);
-  if (lane != 0) return;
+  if (lane == 0) {
   float cnt = (float)W.count[(size_t)f * NP + root];
 #pragma unroll
   for (int j = 0; j < 9; j++) accu[j] = __fdiv_rn(accu[j], cnt);
@@ -449,6 +518,9 @@ __global__ void fit_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   int valid = curvature < 0.001f;   // maximum_curvature_
   W.cand_valid[f * kMaxRegions + k] = valid;
   if (valid) W.count[(size_t)f * NP + root] = -(k + 1);   // marks the root as a model label (refine_labels_)
+  }
+  }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- P8: refinement
@@ -578,13 +650,14 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   ESLAM_CUDA_OK(h, w.iiX.reserve(chunk * NI * 8)); ESLAM_CUDA_OK(h, w.iiY.reserve(chunk * NI * 8));
   ESLAM_CUDA_OK(h, w.dm.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.parent.reserve(chunk * NP * 4));
   ESLAM_CUDA_OK(h, w.count.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.maxidx.reserve(chunk * NP * 4));
+  ESLAM_CUDA_OK(h, w.cmin.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.cmax.reserve(chunk * NP * 4));
   ESLAM_CUDA_OK(h, w.cand_root.reserve((size_t)chunk * kMaxRegions * 4)); ESLAM_CUDA_OK(h, w.cand_n.reserve((size_t)chunk * 4));
   ESLAM_CUDA_OK(h, w.cand_coef.reserve((size_t)chunk * kMaxRegions * 16)); ESLAM_CUDA_OK(h, w.cand_valid.reserve((size_t)chunk * kMaxRegions * 4));
   ESLAM_CUDA_OK(h, w.cand_size.reserve((size_t)chunk * kMaxRegions * 4));
   ESLAM_CUDA_OK(h, w.out_plane.reserve((size_t)chunk * 32)); ESLAM_CUDA_OK(h, w.out_found.reserve((size_t)chunk * 4)); ESLAM_CUDA_OK(h, w.out_inl.reserve((size_t)chunk * 4));
   PlaneFramePtrs P;
   P.pts = w.pts.as<float4>(); P.nrm = w.nrm.as<float4>(); P.iiX = w.iiX.as<double>(); P.iiY = w.iiY.as<double>(); P.dm = w.dm.as<float>();
-  P.parent = w.parent.as<int>(); P.count = w.count.as<int>(); P.maxidx = w.maxidx.as<int>();
+  P.parent = w.parent.as<int>(); P.count = w.count.as<int>(); P.maxidx = w.maxidx.as<int>(); P.cmin = w.cmin.as<int>(); P.cmax = w.cmax.as<int>();
   P.cand_root = w.cand_root.as<int>(); P.cand_n = w.cand_n.as<int>(); P.cand_coef = w.cand_coef.as<float4>(); P.cand_valid = w.cand_valid.as<int>();
   P.cand_size = w.cand_size.as<int>(); P.out_plane = w.out_plane.as<double>(); P.out_found = w.out_found.as<int>(); P.out_inl = w.out_inl.as<int>();
   PlaneParamsDev prm;
@@ -595,6 +668,7 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   prm.min_size = h->prm.plane_min_size;
   const size_t ring_bytes = (size_t)H * 4 * 6 * sizeof(double);
   ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // 2 CTAs (2 x 92 KB) per SM
   const int tpr = ((H + 31) / 32) * 32, tpc = ((Wd + 31) / 32) * 32;
   const size_t frame_stride = (size_t)H * pitch;
   for (int f0 = 0; f0 < n_frames; f0 += chunk) {
@@ -612,8 +686,8 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
     ccl_commit_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     if (debug_stage == 3) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.parent, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
     candidates_kernel<<<F, 1024, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
-    dim3 gfit(kMaxRegions / 8, (unsigned)F);
-    fit_kernel<<<gfit, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    dim3 gfit(8, (unsigned)F);    // 8 CTAs per frame stride over that frame's candidate regions
+    fit_kernel<<<gfit, kFitThreads, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     refine_kernel<<<F, tpc, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     if (debug_stage == 4) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.parent, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
     select_kernel<<<(F + 63) / 64, 64, 0, s>>>(prm, P, F); ESLAM_LAUNCHED(h);
@@ -634,7 +708,7 @@ int plane_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *
 void plane_free(EslamHandle *h) {
   if (!h->pl) return;
   PlaneWorkspace &w = *h->pl;
-  DevBuf *bufs[] = {&w.pts, &w.nrm, &w.iiX, &w.iiY, &w.dm, &w.parent, &w.count, &w.maxidx, &w.cand_root, &w.cand_n, &w.cand_coef, &w.cand_valid, &w.cand_size,
+  DevBuf *bufs[] = {&w.pts, &w.nrm, &w.iiX, &w.iiY, &w.dm, &w.parent, &w.count, &w.maxidx, &w.cmin, &w.cmax, &w.cand_root, &w.cand_n, &w.cand_coef, &w.cand_valid, &w.cand_size,
                     &w.out_plane, &w.out_found, &w.out_inl};
   for (DevBuf *b : bufs) b->release();
   w.pin.release();
