@@ -140,7 +140,7 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     from eslam_b200 import synth
     plane = synth.GROUND_PLANE_WORLD
-    workload_name = ("synthetic 640x480 depth, 1 bbox/frame, ~6-7k stride-3 samples per box, label 28 (dual symmetry)" if args.workload == "one_box"
+    workload_name = ("synthetic 640x480 depth, 1 bbox/frame, ~10k stride-3 points segmented per box, label 28 (dual symmetry)" if args.workload == "one_box"
                      else "synthetic 640x480 depth, 8 bbox/frame, labels 28/41/62")
     config = {"workload": workload_name, "frames_per_step_per_gpu": args.frames, "image": "640x480 uint16", "l2_policy": "inputs larger than L2 (batch >= 600 MB of depth)",
               "symmetry": "on", "plane": "supporting plane given (extraction path); ground-plane kernels benchmarked separately in profiles/"}
