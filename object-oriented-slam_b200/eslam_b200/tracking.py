@@ -1,0 +1,157 @@
+"""N1: per-frame orchestration of the hot path -- a thin host-side driver over the C-ABI that follows
+src/core/Tracking.cpp (GrabPoseAndObjects :170-204, UpdateObjectObservation :493-564, UpdateDepthEllipsoidEstimation :290-381,
+Update3DObservationDataAssociation :383-417, checkKeyFrameForInstances :421-475, JudgeInitialization :567-638,
+ProcessGroundPlaneEstimation :716-799) and the result writer of System::SaveObjectsToFile (src/core/System.cpp:75-91).
+All compute (plane, ellipsoids, initialiser, BA) goes through a `backend` with the Handle interface (eslam_b200.api.Handle on the GPU;
+the tests plug in an oracle-backed object with the same methods to exercise this host logic without a GPU).  No viewer, no Map
+visualisation lists, no interactive prompts."""
+import numpy as np
+
+from .api import Frame, Observation, calibrate_measurement, plane_to_world
+
+MINIMUM_INITIALIZATION_FRAME = 15   # Tracking_MINIMUM_INITIALIZATION_FRAME (src/config/Config.cpp:29)
+
+
+def se3_mul(a, b):
+    """g2o::SE3Quat::operator* (se3quat.h:110-116) on 7-vectors x y z qx qy qz qw (normalises, w >= 0)."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    qa, qb = a[3:], b[3:]
+    qv = qa[:3]
+    uv = 2.0 * np.cross(qv, b[:3])
+    t = a[:3] + (b[:3] + qa[3] * uv + np.cross(qv, uv))
+    x = qa[3] * qb[0] + qa[0] * qb[3] + qa[1] * qb[2] - qa[2] * qb[1]
+    y = qa[3] * qb[1] + qa[1] * qb[3] + qa[2] * qb[0] - qa[0] * qb[2]
+    z = qa[3] * qb[2] + qa[2] * qb[3] + qa[0] * qb[1] - qa[1] * qb[0]
+    w = qa[3] * qb[3] - qa[0] * qb[0] - qa[1] * qb[1] - qa[2] * qb[2]
+    q = np.array([x, y, z, w])
+    if q[3] < 0:
+        q = -q
+    return np.concatenate([t, q / np.linalg.norm(q)])
+
+
+def pose_inverse_np(T):
+    T = np.asarray(T, float)
+    qc = np.array([-T[3], -T[4], -T[5], T[6]])
+    v = -T[:3]
+    uv = 2.0 * np.cross(qc[:3], v)
+    return np.concatenate([v + qc[3] * uv + np.cross(qc[:3], uv), qc])
+
+
+class Tracking:
+    def __init__(self, backend, optimizer_cls, K, rows=480, cols=640, keyframe_check_close=True, min_init_frames=MINIMUM_INITIALIZATION_FRAME):
+        self.h = backend
+        self.optimizer = optimizer_cls(backend)
+        self.K = np.asarray(K, float)
+        self.rows, self.cols = rows, cols
+        self.keyframe_check_close = keyframe_check_close
+        self.min_init_frames = min_init_frames
+        self.miGroundPlaneState = 1          # OpenGroundPlaneEstimation (:690)
+        self.mGroundPlane = None
+        self.mvpFrames = []
+        self.mmObjectObservations = {}       # instance -> [Observation]
+        self.mmObjectObservations3D = {}     # instance -> [(frame, ellipsoid dict)]
+        self.map_ellipsoids = {}             # instance -> ellipsoid dict (world frame)  == Map::GetAllEllipsoidsMap()
+
+    # ---- :716-799
+    def ProcessGroundPlaneEstimation(self, frame):
+        pl, found, _ = self.h.extract_ground_plane(frame.frame_img)
+        if not found[0]:
+            return False
+        self.mGroundPlane = plane_to_world(pl[0], frame.cam_pose_Twc)
+        self.miGroundPlaneState = 2
+        self.h.set_supporting_plane(self.mGroundPlane)
+        self.optimizer.SetGroundPlane(self.mGroundPlane)
+        return True
+
+    # ---- :421-475
+    def checkKeyFrameForInstances(self, frame, associations):
+        dis_th, ang_th = (0.0, 0.0) if self.keyframe_check_close else (0.4, np.pi / 180.0 * 15)
+        checks = []
+        for inst in associations:
+            if inst < 0:
+                checks.append(False)
+            elif inst not in self.mmObjectObservations:
+                checks.append(True)
+            else:
+                last = self.mmObjectObservations[inst][-1].pFrame.cam_pose_Twc
+                diff = se3_mul(pose_inverse_np(frame.cam_pose_Twc), last)
+                dis = np.linalg.norm(diff[:3])
+                n = np.linalg.norm(diff[3:6])
+                angle = 2.0 * np.arctan2(n, abs(diff[6]))      # Eigen::AngleAxisd(quat).angle()
+                checks.append(bool(dis > dis_th or angle > ang_th))
+        return checks
+
+    # ---- :170-204
+    def GrabPoseAndObjects(self, timestamp, pose, bboxMat, imDepth, withAssociation=True, iters=10):
+        frame = Frame(timestamp, pose, bboxMat, imDepth)
+        frame.frame_seq_id = len(self.mvpFrames)        # Frame::total_frame is per-process in the reference; per-tracker here
+        self.mvpFrames.append(frame)
+        obs_mat = frame.mmObservations
+        if self.miGroundPlaneState == 1:
+            self.ProcessGroundPlaneEstimation(frame)
+        # ---- UpdateDepthEllipsoidEstimation :290-381 (all eligible boxes of the frame in ONE batched call)
+        frame.mpLocalObjects = [None] * len(obs_mat)
+        eligible = []
+        for i, det in enumerate(obs_mat):
+            is_border = calibrate_measurement(det[1:5], self.h.params, self.h.camera)
+            c2 = self.miGroundPlaneState == 2
+            c3 = withAssociation and int(round(det[7])) < 0
+            if (not is_border) and c2 and not c3:
+                eligible.append(i)
+        if eligible:
+            out, _, _ = self.h.estimate_ellipsoids(frame.frame_img, [0] * len(eligible), obs_mat[eligible, 1:5], [int(round(obs_mat[i, 5])) for i in eligible],
+                                                   frame.cam_pose_Twc[None])
+            for k, i in enumerate(eligible):
+                if out[k].status == 0:
+                    frame.mpLocalObjects[i] = dict(vec=np.array(out[k].ellipsoid), prob=float(out[k].prob), miLabel=int(round(obs_mat[i, 5])), miInstanceID=-1)
+        if not withAssociation:
+            raise NotImplementedError("automatic data association (DataAssociationSolver) is row N4; the demo uses manual association")
+        associations = [int(round(det[7])) for det in obs_mat]          # GetMannualAssociation :477-490
+        key = self.checkKeyFrameForInstances(frame, associations)
+        # ---- Update3DObservationDataAssociation :383-417
+        for i, inst in enumerate(associations):
+            obj = frame.mpLocalObjects[i]
+            if obj is None or inst < 0:
+                continue
+            if not key[i]:
+                frame.mpLocalObjects[i] = None
+                continue
+            obj["miInstanceID"] = inst
+            self.mmObjectObservations3D.setdefault(inst, []).append((frame, obj))
+        # ---- 2-D observations :532-563
+        for i, det in enumerate(obs_mat):
+            inst = associations[i]
+            if inst < 0 or not key[i]:
+                continue
+            if calibrate_measurement(det[1:5], self.h.params, self.h.camera):
+                continue
+            self.mmObjectObservations.setdefault(inst, []).append(Observation(int(det[5]), det[1:5], det[6], frame))
+        self.JudgeInitialization()
+        # ---- ProcessCurrentFrame :219-226
+        if self.map_ellipsoids:
+            self.optimizer.GlobalObjectGraphOptimization(self.mvpFrames, self.map_ellipsoids, self.rows, self.cols, self.K, self.mmObjectObservations, iters=iters)
+        return frame
+
+    # ---- :567-638
+    def JudgeInitialization(self):
+        for inst, obs in self.mmObjectObservations.items():
+            if inst in self.map_ellipsoids or len(obs) < self.min_init_frames:
+                continue
+            Twc = np.array([o.pFrame.cam_pose_Twc for o in obs]); det = np.array([np.r_[o.bbox, o.rate] for o in obs])
+            e, ok = self.h.init_quadric(Twc, det, self.K, self.rows, self.cols)
+            if ok:
+                self.map_ellipsoids[inst] = dict(vec=e, prob=1.0, miLabel=obs[0].label, miInstanceID=inst)
+        for inst, lst in self.mmObjectObservations3D.items():
+            if inst in self.map_ellipsoids:
+                continue
+            frame, obj = lst[-1]
+            vec = np.array(obj["vec"], float)
+            vec[:7] = se3_mul(frame.cam_pose_Twc, vec[:7])             # pE->transform_from(cam_pose_Twc)
+            self.map_ellipsoids[inst] = dict(vec=vec, prob=obj["prob"], miLabel=obj["miLabel"], miInstanceID=inst)
+
+    # ---- System::SaveObjectsToFile (System.cpp:75-91, dataprocess_utils.cpp:105-127): "instance x y z qx qy qz qw a b c", 12 significant digits
+    def SaveObjectsToFile(self, path):
+        with open(path, "w") as f:
+            for inst in sorted(self.map_ellipsoids):
+                row = [float(inst)] + [float(v) for v in self.map_ellipsoids[inst]["vec"]]
+                f.write(" ".join(f"{v:.12g}" for v in row) + "\n")
