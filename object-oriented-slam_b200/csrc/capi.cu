@@ -289,6 +289,16 @@ int eslam_extract_ground_plane_host(EslamHandle *h, int n_frames, const uint16_t
   return plane_extract(h, h->stream, n_frames, h->ex->depth.as<uint16_t>(), pitch, plane_cam, found, n_inliers);
 }
 
+// test/bench hook: symmetry work counters of object `obj` of the last batch: out = {cost evaluations, NN queries, mirrored points, n_sym}
+int eslam_debug_counters(EslamHandle *h, int obj, unsigned long long out[4]) {
+  if (!h || !h->ex || obj < 0 || obj >= h->ex->n_obj) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  ObjState st;
+  ESLAM_CUDA_OK(h, cudaMemcpy(&st, h->ex->state.as<ObjState>() + obj, sizeof(ObjState), cudaMemcpyDeviceToHost));
+  out[0] = st.n_evals; out[1] = st.n_queries; out[2] = st.n_points; out[3] = (unsigned long long)st.n_sym;
+  return ESLAM_OK;
+}
+
 // test-only hook (not in include/eslam.h): intermediate buffers of the plane pipeline for stage-isolated parity tests
 int eslam_debug_plane_stage(EslamHandle *h, const uint16_t *depth, size_t pitch, int stage, void *out) {
   if (!h || !depth || !out || stage < 1 || stage > 4) return ESLAM_ERR_BAD_ARG;

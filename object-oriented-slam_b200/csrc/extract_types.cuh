@@ -24,6 +24,7 @@ struct ObjState {  // device resident, one per object
   double T_oc[7];           // camera pose in the object-normalised frame
   double P[12];             // K[I|0] hom(T_oc^-1)
   double seed_prob[9], seed_init[9], seed_final[9], seed_plane[9][4], seed_dual[9];
+  unsigned long long n_evals, n_queries, n_points;   // symmetry work counters (cost evaluations, NN queries, mirrored points)
 };
 
 struct ExtractParamsDev {

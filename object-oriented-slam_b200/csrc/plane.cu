@@ -93,39 +93,56 @@ __global__ void integral_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   double left[6] = {0, 0, 0, 0, 0, 0};
   const bool inner_row = (r >= 1 && r <= H - 2);
   const int steps = Wd + 2 * (H - 1);
-  float4 pl = make_float4(0, 0, 0, 0), pc = make_float4(0, 0, 0, 0), pr = make_float4(0, 0, 0, 0);  // P(r,c-1), P(r,c), P(r,c+1)
-  if (r < H) { pc = pts[(size_t)r * Wd]; if (Wd > 1) pr = pts[(size_t)r * Wd + 1]; }
-  for (int t = 0; t < steps; t++) {
-    int c = t - 2 * r;
+  // Thread r handles column c = t - 2r at step t.  The three point streams it needs (row above, row below, own row one column
+  // ahead) are prefetched FOUR steps ahead into register queues whose slot index is the position inside the 4x unrolled step loop
+  // (static indexing), so the L2/DRAM latency of the strided reads is off the 1 598-step critical path.
+  float4 Uq[4], Dq[4], Rq[4];
+  float4 pl = make_float4(0, 0, 0, 0), pc = make_float4(0, 0, 0, 0);
+  const float4 zero4 = make_float4(0, 0, 0, 0);
+  auto prefetch = [&](int c, float4 &u, float4 &d, float4 &rw) {
+    u = zero4; d = zero4; rw = zero4;
     if (r < H && c >= 0 && c < Wd) {
-      float v[6] = {0, 0, 0, 0, 0, 0};
-      if (inner_row && c >= 1 && c <= Wd - 2) {
-        float4 up = pts[(size_t)(r - 1) * Wd + c], dn = pts[(size_t)(r + 1) * Wd + c];
-        v[0] = __fsub_rn(pr.x, pl.x); v[1] = __fsub_rn(pr.y, pl.y); v[2] = __fsub_rn(pr.z, pl.z);
-        v[3] = __fsub_rn(dn.x, up.x); v[4] = __fsub_rn(dn.y, up.y); v[5] = __fsub_rn(dn.z, up.z);
-      }
-      double up1[6], ul[6];
-      if (r == 0) { for (int k = 0; k < 6; k++) { up1[k] = 0.0; ul[k] = 0.0; } }
-      else {
-        const double *a = &ring[((size_t)(r - 1) * 4 + (c & 3)) * 6];
-        for (int k = 0; k < 6; k++) up1[k] = a[k];
-        if (c == 0) { for (int k = 0; k < 6; k++) ul[k] = 0.0; }
-        else { const double *b = &ring[((size_t)(r - 1) * 4 + ((c - 1) & 3)) * 6]; for (int k = 0; k < 6; k++) ul[k] = b[k]; }
-      }
-      double *mine = &ring[((size_t)r * 4 + (c & 3)) * 6];
-      size_t o = ((size_t)(r + 1) * IW + (c + 1)) * 3;
-#pragma unroll
-      for (int k = 0; k < 6; k++) {
-        double val = __dadd_rn(__dsub_rn(__dadd_rn(up1[k], left[k]), ul[k]), (double)v[k]);
-        left[k] = val; mine[k] = val;
-      }
-      iiX[o] = left[0]; iiX[o + 1] = left[1]; iiX[o + 2] = left[2];
-      iiY[o] = left[3]; iiY[o + 1] = left[4]; iiY[o + 2] = left[5];
-      // slide the row window
-      pl = pc; pc = pr;
-      if (c + 2 < Wd) pr = pts[(size_t)r * Wd + c + 2];
+      if (inner_row) { u = pts[(size_t)(r - 1) * Wd + c]; d = pts[(size_t)(r + 1) * Wd + c]; }
+      if (c + 1 < Wd) rw = pts[(size_t)r * Wd + c + 1];
     }
-    __syncthreads();
+  };
+  if (r < H) pc = pts[(size_t)r * Wd];
+#pragma unroll
+  for (int u = 0; u < 4; u++) prefetch(u - 2 * r, Uq[u], Dq[u], Rq[u]);
+  for (int t0 = 0; t0 < steps; t0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int t = t0 + u;
+      const int c = t - 2 * r;
+      const float4 up = Uq[u], dn = Dq[u], pr = Rq[u];
+      prefetch(c + 4, Uq[u], Dq[u], Rq[u]);
+      if (t < steps && r < H && c >= 0 && c < Wd) {
+        float v[6] = {0, 0, 0, 0, 0, 0};
+        if (inner_row && c >= 1 && c <= Wd - 2) {
+          v[0] = __fsub_rn(pr.x, pl.x); v[1] = __fsub_rn(pr.y, pl.y); v[2] = __fsub_rn(pr.z, pl.z);
+          v[3] = __fsub_rn(dn.x, up.x); v[4] = __fsub_rn(dn.y, up.y); v[5] = __fsub_rn(dn.z, up.z);
+        }
+        double up1[6], ul[6];
+        if (r == 0) { for (int k = 0; k < 6; k++) { up1[k] = 0.0; ul[k] = 0.0; } }
+        else {
+          const double *a = &ring[((size_t)(r - 1) * 4 + (c & 3)) * 6];
+          for (int k = 0; k < 6; k++) up1[k] = a[k];
+          if (c == 0) { for (int k = 0; k < 6; k++) ul[k] = 0.0; }
+          else { const double *b = &ring[((size_t)(r - 1) * 4 + ((c - 1) & 3)) * 6]; for (int k = 0; k < 6; k++) ul[k] = b[k]; }
+        }
+        double *mine = &ring[((size_t)r * 4 + (c & 3)) * 6];
+        size_t o = ((size_t)(r + 1) * IW + (c + 1)) * 3;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          double val = __dadd_rn(__dsub_rn(__dadd_rn(up1[k], left[k]), ul[k]), (double)v[k]);
+          left[k] = val; mine[k] = val;
+        }
+        iiX[o] = left[0]; iiX[o + 1] = left[1]; iiX[o + 2] = left[2];
+        iiY[o] = left[3]; iiY[o + 1] = left[4]; iiY[o + 2] = left[5];
+        pl = pc; pc = pr;   // slide the row window
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -297,16 +314,41 @@ __device__ __forceinline__ bool plane_compare(const float4 *pts, const float4 *n
   float dotn = __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
   return (fabsf(__fsub_rn(a.w, b.w)) < threshold) && (dotn > ang_cos);
 }
+// Pass 1: horizontal runs inside each warp's 32 consecutive pixels get their first pixel as parent (plain stores, no atomics).
+__global__ void ccl_runs_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  const int Wd = prm.cols, NP = prm.rows * prm.cols;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y, lane = threadIdx.x & 31;
+  const bool act = idx < NP;
+  const float4 *pts = W.pts + (size_t)f * NP, *nrm = W.nrm + (size_t)f * NP;
+  const int ci = act ? idx % Wd : 0;
+  const bool h = act && ci >= 1 && plane_compare(pts, nrm, idx, idx - 1, prm.dis_th, prm.ang_cos);
+  const unsigned starts = __ballot_sync(0xffffffffu, !h || lane == 0);
+  if (act) {
+    const int head_lane = 31 - __clz(starts & (0xffffffffu >> (31 - lane)));
+    W.parent[(size_t)f * NP + idx] = idx - (lane - head_lane);
+  }
+}
+// Pass 2: the remaining links.  A vertical link is redundant when the pixel and its left neighbour are in the same run, both link
+// upwards and the two upper pixels are linked to each other; only the non-redundant ones (run heads, seams) touch the union-find.
 __global__ void ccl_union_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   const int Wd = prm.cols, NP = prm.rows * prm.cols;
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  int f = blockIdx.y;
-  if (idx >= NP) return;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y, lane = threadIdx.x & 31;
+  const bool act = idx < NP;
   const float4 *pts = W.pts + (size_t)f * NP, *nrm = W.nrm + (size_t)f * NP;
   int *parent = W.parent + (size_t)f * NP;
-  int ri = idx / Wd, ci = idx - ri * Wd;
-  if (ci >= 1 && plane_compare(pts, nrm, idx, idx - 1, prm.dis_th, prm.ang_cos)) p_union(parent, idx, idx - 1);
-  if (ri >= 1 && plane_compare(pts, nrm, idx, idx - Wd, prm.dis_th, prm.ang_cos)) p_union(parent, idx, idx - Wd);
+  const int ri = act ? idx / Wd : 0, ci = act ? idx - ri * Wd : 0;
+  const bool h = act && ci >= 1 && plane_compare(pts, nrm, idx, idx - 1, prm.dis_th, prm.ang_cos);
+  const bool v = act && ri >= 1 && plane_compare(pts, nrm, idx, idx - Wd, prm.dis_th, prm.ang_cos);
+  const bool v_left = __shfl_up_sync(0xffffffffu, v ? 1 : 0, 1) != 0;
+  bool need_v = v;
+  if (v && h && lane >= 1 && v_left && ci >= 1) {
+    const bool h_up = plane_compare(pts, nrm, idx - Wd, idx - Wd - 1, prm.dis_th, prm.ang_cos);   // the upper pixels' own horizontal link
+    if (h_up) need_v = false;
+  }
+  if (h && lane == 0) p_union(parent, idx, idx - 1);   // run continues across the warp seam
+  if (need_v) p_union(parent, idx, idx - Wd);
 }
 __global__ void ccl_flatten_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   const int NP = prm.rows * prm.cols;
@@ -681,6 +723,7 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
     if (debug_stage == 1) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.dm, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
     normals_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     if (debug_stage == 2) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.nrm, NP * 16, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
+    ccl_runs_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     ccl_union_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     ccl_flatten_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     ccl_commit_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);

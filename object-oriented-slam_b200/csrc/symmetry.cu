@@ -37,6 +37,7 @@ struct SymBlock {
   const double *objn; const float4 *nn_g;
   int M, symtype, npts, in_smem;
   int bx0, bx2, by1, by3, rows, cols;
+  ObjState *st;
   double P[12], cam[3], fx, cx, cy, scale, sinv;
   unsigned long long X2[kSymSmemPts / 2], Y2[kSymSmemPts / 2], Z2[kSymSmemPts / 2];   // pair-interleaved SoA float cloud (odd tail padded far away)
 };
@@ -142,6 +143,41 @@ __device__ __noinline__ double nn_distance(const SymBlock &B, d3 pm) {
   return sqrt(dx * dx + dy * dy + dz * dz);
 }
 
+// Warp-cooperative variant for a PARTIAL chunk of cq <= 16 queries (shared-memory cloud): the 32 lanes are split into
+// L = 32 / pow2ceil(cq) parts, part p scans the p-th slice of the cloud for query (lane % slots); the parts are merged with an
+// (r, index) lexicographic butterfly -- slices are index-ordered, so "smallest r, then smallest index" is exactly the linear scan's
+// first-minimum rule.  Returns the distance for lanes with part == 0 && q < cq (other lanes: 0).
+__device__ __noinline__ double nn_distance_split(const SymBlock &B, d3 pm, int slots, bool active) {
+  const int lane = threadIdx.x & 31;
+  const int L = 32 / slots;
+  const int part = lane / slots;
+  const float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
+  const unsigned long long qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
+  const int pairs = (B.M + 1) >> 1;
+  const int pp = (pairs + L - 1) / L;
+  const int j0 = part * pp, j1 = min(pairs, j0 + pp);
+  float bd = FLT_MAX; int best = 0x7fffffff;
+  for (int j = j0; j < j1; j++) {
+    unsigned long long dx = f2_sub(qx2, B.X2[j]), dy = f2_sub(qy2, B.Y2[j]), dz = f2_sub(qz2, B.Z2[j]);
+    const unsigned long long sx = f2_mul(dx, dx), sy = f2_mul(dy, dy), sz = f2_mul(dz, dz);
+    const float r0 = __fadd_rn(__fadd_rn(__uint_as_float((unsigned)sx), __uint_as_float((unsigned)sy)), __uint_as_float((unsigned)sz));
+    const float r1 = __fadd_rn(__fadd_rn(__uint_as_float((unsigned)(sx >> 32)), __uint_as_float((unsigned)(sy >> 32))), __uint_as_float((unsigned)(sz >> 32)));
+    if (r0 < bd) { bd = r0; best = 2 * j; }
+    if (r1 < bd) { bd = r1; best = 2 * j + 1; }
+  }
+  for (int o = slots; o < 32; o <<= 1) {   // merge the parts of the same query (lanes q, q+slots, q+2*slots, ...)
+    const float obd = __shfl_xor_sync(0xffffffffu, bd, o);
+    const int obest = __shfl_xor_sync(0xffffffffu, best, o);
+    if (obd < bd || (obd == bd && obest < best)) { bd = obd; best = obest; }
+  }
+  if (!active || part != 0 || best == 0x7fffffff) return 0.0;
+  const unsigned long long X = B.X2[best >> 1], Y = B.Y2[best >> 1], Z = B.Z2[best >> 1];
+  const int sh = (best & 1) * 32;
+  const double bx = (double)__uint_as_float((unsigned)(X >> sh)), by = (double)__uint_as_float((unsigned)(Y >> sh)), bz = (double)__uint_as_float((unsigned)(Z >> sh));
+  const double dx = pm.x - bx, dy = pm.y - by, dz = pm.z - bz;
+  return sqrt(dx * dx + dy * dy + dz * dz);
+}
+
 // edge error (= -mean ln P) of the plane stored in shared memory at `pl`; warp-collective, every lane returns the same value.
 // Fast path (#points <= kSymQueue): (1) classify all mirrored points, compacting those that need a nearest-neighbour query into a
 // per-warp queue so that (2) the brute-force searches run with full lanes; (3) ln P accumulated in the reference's point order.
@@ -166,10 +202,22 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
       invalid += __popc(__ballot_sync(0xffffffffu, cls == 2));
     }
     __syncwarp();
+    if (lane == 0) { atomicAdd(&B.st->n_evals, 1ULL); atomicAdd(&B.st->n_queries, (unsigned long long)qn); atomicAdd(&B.st->n_points, (unsigned long long)npts); }
     for (int qb = 0; qb < qn; qb += 32) {
-      if (qb + lane < qn) {
-        const int idx = W.queue[qb + lane];
-        W.dis[idx] = nn_distance(B, mirrored(B, PP, idx));
+      const int cq = min(32, qn - qb);
+      if (cq > 16 || !B.in_smem) {
+        if (lane < cq) {
+          const int idx = W.queue[qb + lane];
+          W.dis[idx] = nn_distance(B, mirrored(B, PP, idx));
+        }
+      } else {   // partial chunk: split every query's scan over several lanes
+        int slots = 1;
+        while (slots < cq) slots <<= 1;
+        const int q = lane % slots;
+        const bool active = q < cq;
+        const int idx = W.queue[qb + (active ? q : 0)];
+        const double dis = nn_distance_split(B, mirrored(B, PP, idx), slots, active);
+        if (active && lane < slots) W.dis[idx] = dis;
       }
     }
     __syncwarp();
@@ -432,7 +480,7 @@ __global__ void __launch_bounds__(32, 28) symmetry_finalize_kernel(const uint16_
       B.X2[j] = f2_pack(a.x, b.x); B.Y2[j] = f2_pack(a.y, b.y); B.Z2[j] = f2_pack(a.z, b.z);
     }
     if (lane == 0) {
-      B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch;
+      B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch; B.st = &st;
       B.objn = objn; B.nn_g = objnf; B.M = M; B.symtype = m.symtype; B.npts = (m.symtype == 2) ? 2 * M : M; B.in_smem = in_smem ? 1 : 0;
       for (int i = 0; i < 12; i++) B.P[i] = st.P[i];
       B.cam[0] = st.T_oc[0]; B.cam[1] = st.T_oc[1]; B.cam[2] = st.T_oc[2];

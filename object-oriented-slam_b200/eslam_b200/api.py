@@ -140,6 +140,11 @@ class Handle:
                                                            _ip(found), _ip(ninl)), "eslam_extract_ground_plane_dev")
         return pl, found, ninl
 
+    def debug_counters(self, obj):
+        out = (C.c_ulonglong * 4)()
+        self.check(self.lib.eslam_debug_counters(self._h, C.c_int(obj), out), "eslam_debug_counters")
+        return [int(v) for v in out]
+
     def debug_plane_stage(self, depth, stage):
         """test hook: 1 distance map (float), 2 normals+plane_d (float4), 3 labels after CCL, 4 labels after refinement."""
         depth = np.ascontiguousarray(depth, dtype=np.uint16)

@@ -37,6 +37,43 @@ def pose_inverse_np(T):
     return np.concatenate([v + qc[3] * uv + np.cross(qc[:3], uv), qc])
 
 
+class DataAssociationSolver:
+    """N4: src/core/DataAssociation.cpp:16-135 -- greedy nearest-centre association (threshold 1 m) of the frame's single-frame
+    ellipsoids with the map, used when withAssociation=False ("not steady" per Tracking.cpp:505-518).  Quirks kept: the value returned
+    for a match is the COLUMN index in the instance-ordered map (DataAssociation.cpp:113-114), new instances count from 0."""
+
+    def __init__(self):
+        self.miInstanceNum = 0
+
+    def CreateInstance(self):
+        self.miInstanceNum += 1
+        return self.miInstanceNum - 1
+
+    def Solve(self, frame, map_ellipsoids):
+        n = len(frame.mmObservations)
+        assoc = [-1] * n
+        valid = [i for i in range(n) if frame.mpLocalObjects[i] is not None]
+        if not valid:
+            return assoc
+        insts = sorted(map_ellipsoids)
+        cost = np.zeros((len(valid), len(insts)))
+        for a, i in enumerate(valid):
+            world = se3_mul(frame.cam_pose_Twc, np.asarray(frame.mpLocalObjects[i]["vec"], float)[:7])
+            for b, inst in enumerate(insts):
+                cost[a, b] = np.linalg.norm(np.asarray(map_ellipsoids[inst]["vec"])[:3] - world[:3])
+        for a, i in enumerate(valid):                       # SolveCostMat :90-135
+            if cost.shape[1] < 1:
+                assoc[i] = self.CreateInstance()
+                continue
+            j = int(np.argmin(cost[a]))
+            if cost[a, j] < 1.0:
+                assoc[i] = j
+                cost[:, j] = 999
+            else:
+                assoc[i] = self.CreateInstance()
+        return assoc
+
+
 class Tracking:
     def __init__(self, backend, optimizer_cls, K, rows=480, cols=640, keyframe_check_close=True, min_init_frames=MINIMUM_INITIALIZATION_FRAME):
         self.h = backend
@@ -51,6 +88,7 @@ class Tracking:
         self.mmObjectObservations = {}       # instance -> [Observation]
         self.mmObjectObservations3D = {}     # instance -> [(frame, ellipsoid dict)]
         self.map_ellipsoids = {}             # instance -> ellipsoid dict (world frame)  == Map::GetAllEllipsoidsMap()
+        self.pDASolver = DataAssociationSolver()
 
     # ---- :716-799
     def ProcessGroundPlaneEstimation(self, frame):
@@ -104,9 +142,10 @@ class Tracking:
             for k, i in enumerate(eligible):
                 if out[k].status == 0:
                     frame.mpLocalObjects[i] = dict(vec=np.array(out[k].ellipsoid), prob=float(out[k].prob), miLabel=int(round(obs_mat[i, 5])), miInstanceID=-1)
-        if not withAssociation:
-            raise NotImplementedError("automatic data association (DataAssociationSolver) is row N4; the demo uses manual association")
-        associations = [int(round(det[7])) for det in obs_mat]          # GetMannualAssociation :477-490
+        if withAssociation:
+            associations = [int(round(det[7])) for det in obs_mat]      # GetMannualAssociation :477-490
+        else:
+            associations = self.pDASolver.Solve(frame, self.map_ellipsoids)   # :515-518
         key = self.checkKeyFrameForInstances(frame, associations)
         # ---- Update3DObservationDataAssociation :383-417
         for i, inst in enumerate(associations):

@@ -202,3 +202,55 @@ def test_ground_plane_matches_oracle(handle):
     ok, pl = pe.extractGroundPlane(frames[0])
     assert ok and np.array_equal(pl, pg[0])
     assert np.allclose(E.plane_to_world(pl, tw[0]), orc.plane_to_world(pl, tw[0]), atol=1e-12)
+
+
+# ------------------------------------------------------------------ full-size, size-independent properties (BASELINE.json sizes)
+def test_full_batch_properties(handle):
+    """256 frames x 1 bbox (configs[1] shape): monotone stage counts, run-to-run bit determinism, batch == single-object results,
+    permutation equivariance, and agreement with the oracle on a random sample (the oracle is too slow for the whole batch)."""
+    import bench
+    depth, fo, bb, lb, tw = bench.make_frames("one_box", 256, 777000)
+    handle.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+    a, _, _ = handle.estimate_ellipsoids(depth, fo, bb, lb, tw)
+    b, _, _ = handle.estimate_ellipsoids(depth, fo, bb, lb, tw)
+    assert bytes(a) == bytes(b)                                   # idempotent / deterministic to the bit
+    ok = 0
+    for o in a:
+        assert o.n_crop >= o.n_voxel >= o.n_plane >= o.n_cluster >= 0 and o.n_sym <= max(o.n_cluster, 0)
+        if o.status == 0:
+            ok += 1
+            assert o.n_cluster >= 100 and o.n_final in (o.n_sym, 2 * o.n_sym, 4 * o.n_sym)
+            assert 0.0 < o.prob <= 1.0 and np.isfinite(np.array(o.ellipsoid)).all() and min(o.ellipsoid[7:10]) > 0
+            assert abs(np.linalg.norm(np.array(o.ellipsoid[3:7])) - 1.0) < 1e-12 and o.ellipsoid[6] >= 0
+    assert ok >= 250
+    perm = np.random.default_rng(0).permutation(256)
+    c, _, _ = handle.estimate_ellipsoids(depth, fo[perm], bb[perm], lb[perm], tw)
+    for k, i in enumerate(perm):
+        assert bytes(c[k]) == bytes(a[int(i)])
+    for i in (3, 77, 200):
+        s, _, _ = handle.estimate_ellipsoids(depth[i], [0], bb[i:i + 1], lb[i:i + 1], tw[i:i + 1])
+        assert bytes(s[0]) == bytes(a[i])
+    for i in (5, 123, 255):
+        o, _, _, _ = orc.estimate_ellipsoids(depth[i], [0], bb[i:i + 1], lb[i:i + 1], tw[i:i + 1], synth.GROUND_PLANE_WORLD)
+        assert (o[0].status, o[0].n_crop, o[0].n_voxel, o[0].n_plane, o[0].n_cluster, o[0].n_sym) == (a[i].status, a[i].n_crop, a[i].n_voxel, a[i].n_plane, a[i].n_cluster, a[i].n_sym)
+        assert ellipsoid_close(a[i].ellipsoid, o[0].ellipsoid, 1e-4)
+
+
+def test_full_size_graph_properties(handle):
+    """configs[3] shape: 500 keyframes x 50 edges (+50 gravity priors).  chi2 is the weighted residual norm; Jacobian rows of unused
+    dimensions are zero; scale columns of the 3-D edge are the identity up to the yaw permutation; sample agrees with the oracle."""
+    p = make_ba_problem(500, 50, 50)
+    gg = EdgeGraph(p["type"], p["frame"], p["object"], p["meas"], p["info"], p["Tcw"], p["n_objects"], K)
+    r, J, chi = handle.edges_eval(gg, p["init"])
+    t = np.array(p["type"]); info = np.array(p["info"])
+    assert len(t) == 25050 and np.isfinite(r).all() and np.isfinite(J).all()
+    assert np.allclose(chi, info * (r ** 2).sum(axis=1), rtol=1e-12)
+    assert not r[t == 0][:, 4:].any() and not r[t == 2][:, 1:].any() and not J[t == 0][:, 4:, :].any() and not J[t == 2][:, 1:, :].any()
+    S = np.abs(J[t == 1][:, 6:9, 6:9])                               # d(scale residual)/d(scale) = I
+    assert np.allclose(S, np.eye(3)[None], atol=1e-6)
+    assert np.abs(J[t == 2][:, 0, 6:9]).max() < 1e-6                  # gravity prior does not see the scale
+    go = orc.Graph(np.array(p["type"])[::97], np.array(p["frame"])[::97], np.array(p["object"])[::97], p["meas"][::97], info[::97], p["Tcw"], p["n_objects"], K)
+    r0, J0, _ = orc.edges_eval(go, p["init"])
+    assert np.abs(r[::97] - r0).max() < 1e-9 and np.abs(J[::97] - J0).max() < 2e-3
+    e1, s1 = handle.optimize_objects(gg, p["init"], 10)
+    assert s1.chi2_final < 0.5 * s1.chi2_initial and np.isfinite(e1).all()

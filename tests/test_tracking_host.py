@@ -72,3 +72,17 @@ def test_full_cabinet_sequence_smoke():
         n_extracted += sum(o is not None for o in f.mpLocalObjects)
     assert tr.miGroundPlaneState == 2 and list(tr.map_ellipsoids) == [0] and n_extracted >= 15
     assert np.isfinite(tr.map_ellipsoids[0]["vec"]).all()
+
+
+def test_automatic_data_association_rules():
+    from eslam_b200.tracking import DataAssociationSolver
+
+    class F:
+        pass
+    f = F(); f.cam_pose_Twc = np.array([0, 0, 0, 0, 0, 0, 1.0]); f.mmObservations = np.zeros((3, 8))
+    mk = lambda x: dict(vec=np.array([x, 0, 2, 0, 0, 0, 1, .3, .3, .3]), prob=1.0, miLabel=1, miInstanceID=-1)
+    f.mpLocalObjects = [mk(0.1), None, mk(5.0)]
+    s = DataAssociationSolver()
+    assert s.Solve(f, {}) == [0, -1, 1]                                   # empty map: every valid observation creates an instance
+    m = {7: mk(0.0), 9: mk(3.0)}
+    assert DataAssociationSolver().Solve(f, m) == [0, -1, 0]              # match -> column index 0; 5.0 is > 1 m from both -> new instance 0

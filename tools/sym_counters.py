@@ -1,0 +1,13 @@
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "object-oriented-slam_b200")]
+import numpy as np
+import eslam_b200 as E
+from eslam_b200 import synth
+import bench
+depth, fo, bb, lb, tw = bench.make_frames("one_box", 64, 1000)
+h = E.Handle(); h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+out, _, _ = h.estimate_ellipsoids(depth, fo, bb, lb, tw)
+c = np.array([h.debug_counters(i) for i in range(64)], float)
+print("per object: evals %.0f  queries/eval %.1f  points/eval %.1f  n_sym %.1f  n_crop %.0f n_cluster %.0f" % (c[:,0].mean(), (c[:,1]/c[:,0]).mean(), (c[:,2]/c[:,0]).mean(), c[:,3].mean(), np.mean([o.n_crop for o in out]), np.mean([o.n_cluster for o in out])))
+print("evals min/max", c[:,0].min(), c[:,0].max())
