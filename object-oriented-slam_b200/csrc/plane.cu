@@ -80,7 +80,8 @@ __global__ void points_kernel(const uint16_t *__restrict__ depth, size_t pitch, 
 // II(r+1,c+1) = ((II(r,c+1) + II(r+1,c)) - II(r,c)) + x(r,c)   in double, IntegralImage2D<float,3>::computeIntegralImages.
 // blockDim.x = rows rounded up to 32 (<= 1024); dynamic smem = rows * 4 * 6 doubles.
 __global__ void integral_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
-  extern __shared__ double ring[];   // [rows][4][6]
+  extern __shared__ double ring[];   // [4 slots][6 channels][RH rows]: row is the fastest index -> conflict-free (thread = row)
+  const int RH = blockDim.x;
   const int H = prm.rows, Wd = prm.cols, NP = H * Wd, IW = Wd + 1;
   const int f = blockIdx.x;
   const int r = threadIdx.x;
@@ -125,17 +126,17 @@ __global__ void integral_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
         double up1[6], ul[6];
         if (r == 0) { for (int k = 0; k < 6; k++) { up1[k] = 0.0; ul[k] = 0.0; } }
         else {
-          const double *a = &ring[((size_t)(r - 1) * 4 + (c & 3)) * 6];
-          for (int k = 0; k < 6; k++) up1[k] = a[k];
+          const double *a = &ring[(size_t)((c & 3) * 6) * RH + (r - 1)];
+          for (int k = 0; k < 6; k++) up1[k] = a[(size_t)k * RH];
           if (c == 0) { for (int k = 0; k < 6; k++) ul[k] = 0.0; }
-          else { const double *b = &ring[((size_t)(r - 1) * 4 + ((c - 1) & 3)) * 6]; for (int k = 0; k < 6; k++) ul[k] = b[k]; }
+          else { const double *b = &ring[(size_t)(((c - 1) & 3) * 6) * RH + (r - 1)]; for (int k = 0; k < 6; k++) ul[k] = b[(size_t)k * RH]; }
         }
-        double *mine = &ring[((size_t)r * 4 + (c & 3)) * 6];
+        double *mine = &ring[(size_t)((c & 3) * 6) * RH + r];
         size_t o = ((size_t)(r + 1) * IW + (c + 1)) * 3;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
           double val = __dadd_rn(__dsub_rn(__dadd_rn(up1[k], left[k]), ul[k]), (double)v[k]);
-          left[k] = val; mine[k] = val;
+          left[k] = val; mine[(size_t)k * RH] = val;
         }
         iiX[o] = left[0]; iiX[o + 1] = left[1]; iiX[o + 2] = left[2];
         iiY[o] = left[3]; iiY[o + 1] = left[4]; iiY[o + 2] = left[5];
@@ -614,27 +615,33 @@ __global__ void refine_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
       const int rn = fwd ? r + 1 : r - 1;                 // row hit by the vertical check
       int m = -1;
       if (c < Wd) m = model_of(r * Wd + c);
-      // ---- horizontal propagation along the row (scan direction = traversal direction)
-      int src = (c < Wd && m >= 0) ? c : (fwd ? -1 : -(1 << 30));
-      int s;
-      if (fwd) s = block_incl_max_scan(src, S, false);                // nearest source at or left of c
-      else s = -block_incl_max_scan((c < Wd && m >= 0) ? -c : -(1 << 30), S, true);   // nearest source at or right of c
+      // a row without any model pixel can neither propagate sideways nor vertically: one barrier instead of eight
+      if (!__syncthreads_or((c < Wd && m >= 0) ? 1 : 0)) continue;
       if (c < Wd) s_m[c] = m;
       __syncthreads();
-      bool has_src = fwd ? (s >= 0) : (s < (1 << 29));
-      int L = -1; bool blocked = false;
-      if (c < Wd && m < 0) {
-        if (has_src) { L = s_m[s]; blocked = !refine_ok(coef[L], pts[r * Wd + c]); }
-        else blocked = true;
+      // ---- horizontal propagation along the row (scan direction = traversal direction); skipped when no non-model pixel has a
+      //      model pixel as its upstream neighbour (then nothing can be relabelled in this row)
+      bool cand = false;
+      if (c < Wd && m < 0) cand = fwd ? (c >= 1 && s_m[c - 1] >= 0) : (c + 1 < Wd && s_m[c + 1] >= 0);
+      int L = -1;
+      if (__syncthreads_or(cand ? 1 : 0)) {
+        int s;
+        if (fwd) s = block_incl_max_scan((c < Wd && m >= 0) ? c : -1, S, false);                 // nearest source at or left of c
+        else s = -block_incl_max_scan((c < Wd && m >= 0) ? -c : -(1 << 30), S, true);            // nearest source at or right of c
+        const bool has_src = fwd ? (s >= 0) : (s < (1 << 29));
+        bool blocked = false;
+        if (c < Wd && m < 0) {
+          if (has_src) { L = s_m[s]; blocked = !refine_ok(coef[L], pts[r * Wd + c]); }
+          else blocked = true;
+        }
+        int b;
+        if (fwd) b = block_incl_max_scan((c < Wd && m < 0 && blocked) ? c : -1, S, false);       // last blocked index <= c
+        else b = -block_incl_max_scan((c < Wd && m < 0 && blocked) ? -c : -(1 << 30), S, true);  // first blocked index >= c
+        bool recv = false;
+        if (c < Wd && m < 0 && has_src) recv = fwd ? (b < s) : (b > s);
+        // the forward pass never uses column W-1 as "current"; every receiver's chain starts at a source that IS a valid current
+        if (recv) { m = L; parent[r * Wd + c] = croot[L]; atomicAdd(&csize[L], 1); }
       }
-      int bsrc = (c < Wd && m < 0 && blocked) ? c : -1;
-      int b;
-      if (fwd) b = block_incl_max_scan(bsrc, S, false);                // last blocked index <= c
-      else b = -block_incl_max_scan((c < Wd && m < 0 && blocked) ? -c : -(1 << 30), S, true);   // first blocked index >= c
-      bool recv = false;
-      if (c < Wd && m < 0 && has_src) recv = fwd ? (b < s) : (b > s);
-      // the forward pass never uses column W-1 as "current"; every receiver's chain starts at a source that IS a valid current
-      if (recv) { m = L; parent[r * Wd + c] = croot[L]; atomicAdd(&csize[L], 1); }
       // ---- vertical check from the (updated) current row
       bool cur_ok = (c < Wd) && m >= 0 && (fwd ? (c <= Wd - 2) : true);
       if (cur_ok) {
@@ -708,7 +715,7 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   prm.dis_th = (float)h->prm.plane_dist;
   prm.ang_cos = cosf((float)(0.017453 * AngTh));   // mps.setAngularThreshold(0.017453 * AngTh) -> PlaneCoefficientComparator: cosf
   prm.min_size = h->prm.plane_min_size;
-  const size_t ring_bytes = (size_t)H * 4 * 6 * sizeof(double);
+  const size_t ring_bytes = (size_t)(((H + 31) / 32) * 32) * 4 * 6 * sizeof(double);
   ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
   ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // 2 CTAs (2 x 92 KB) per SM
   const int tpr = ((H + 31) / 32) * 32, tpc = ((Wd + 31) / 32) * 32;
