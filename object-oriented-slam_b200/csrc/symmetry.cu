@@ -190,46 +190,51 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
   const int npts = B.npts;
   double ln_total = 0.0;
   int invalid = 0;
-  if (npts <= kSymQueue) {
-    int qn = 0;
-    for (int base = 0; base < npts; base += 32) {
-      const int idx = base + lane;
-      int cls = 0;
-      if (idx < npts) { cls = classify(B, mirrored(B, PP, idx)); W.dis[idx] = 0.0; }
-      const unsigned need = __ballot_sync(0xffffffffu, cls == 1);
-      if (cls == 1) W.queue[qn + __popc(need & ((1u << lane) - 1u))] = (unsigned short)idx;
-      qn += __popc(need);
-      invalid += __popc(__ballot_sync(0xffffffffu, cls == 2));
-    }
-    __syncwarp();
-    if (lane == 0) { atomicAdd(&B.st->n_evals, 1ULL); atomicAdd(&B.st->n_queries, (unsigned long long)qn); atomicAdd(&B.st->n_points, (unsigned long long)npts); }
-    for (int qb = 0; qb < qn; qb += 32) {
-      const int cq = min(32, qn - qb);
-      if (cq > 16 || !B.in_smem) {
-        if (lane < cq) {
-          const int idx = W.queue[qb + lane];
-          W.dis[idx] = nn_distance(B, mirrored(B, PP, idx));
-        }
-      } else {   // partial chunk: split every query's scan over several lanes
-        int slots = 1;
-        while (slots < cq) slots <<= 1;
-        const int q = lane % slots;
-        const bool active = q < cq;
-        const int idx = W.queue[qb + (active ? q : 0)];
-        const double dis = nn_distance_split(B, mirrored(B, PP, idx), slots, active);
-        if (active && lane < slots) W.dis[idx] = dis;
-      }
-    }
-    __syncwarp();
+  if (B.M <= kSymQueue) {
+    // the mirrored cloud is processed in halves of M points (plane 1, then the dual plane), so the per-warp queue / distance slots
+    // only need M entries; ln P keeps accumulating in the reference's point order across the halves
     const double sinv = B.sinv;
-    for (int base = 0; base < npts; base += 32) {
-      const int idx = base + lane;
-      const double dis = (idx < npts) ? W.dis[idx] : 0.0;
-      const double lnP = -0.5 * sinv * sinv * dis * dis;
-      const int cnt = min(32, npts - base);
-      for (int k = 0; k < cnt; k++) ln_total += __shfl_sync(0xffffffffu, lnP, k);
+    for (int h0 = 0; h0 < npts; h0 += B.M) {
+      const int cntp = min(B.M, npts - h0);
+      int qn = 0;
+      for (int base = 0; base < cntp; base += 32) {
+        const int li = base + lane;
+        int cls = 0;
+        if (li < cntp) { cls = classify(B, mirrored(B, PP, h0 + li)); W.dis[li] = 0.0; }
+        const unsigned need = __ballot_sync(0xffffffffu, cls == 1);
+        if (cls == 1) W.queue[qn + __popc(need & ((1u << lane) - 1u))] = (unsigned short)li;
+        qn += __popc(need);
+        invalid += __popc(__ballot_sync(0xffffffffu, cls == 2));
+      }
+      __syncwarp();
+      if (lane == 0) { atomicAdd(&B.st->n_evals, 1ULL); atomicAdd(&B.st->n_queries, (unsigned long long)qn); atomicAdd(&B.st->n_points, (unsigned long long)cntp); }
+      for (int qb = 0; qb < qn; qb += 32) {
+        const int cq = min(32, qn - qb);
+        if (cq > 16 || !B.in_smem) {
+          if (lane < cq) {
+            const int li = W.queue[qb + lane];
+            W.dis[li] = nn_distance(B, mirrored(B, PP, h0 + li));
+          }
+        } else {   // partial chunk: split every query's scan over several lanes
+          int slots = 1;
+          while (slots < cq) slots <<= 1;
+          const int q = lane % slots;
+          const bool active = q < cq;
+          const int li = W.queue[qb + (active ? q : 0)];
+          const double dis = nn_distance_split(B, mirrored(B, PP, h0 + li), slots, active);
+          if (active && lane < slots) W.dis[li] = dis;
+        }
+      }
+      __syncwarp();
+      for (int base = 0; base < cntp; base += 32) {
+        const int li = base + lane;
+        const double dis = (li < cntp) ? W.dis[li] : 0.0;
+        const double lnP = -0.5 * sinv * sinv * dis * dis;
+        const int cnt = min(32, cntp - base);
+        for (int k = 0; k < cnt; k++) ln_total += __shfl_sync(0xffffffffu, lnP, k);
+      }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const double sinv = B.sinv;
     for (int base = 0; base < npts; base += 32) {

@@ -9,5 +9,8 @@ depth, fo, bb, lb, tw = bench.make_frames("one_box", 64, 1000)
 h = E.Handle(); h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
 out, _, _ = h.estimate_ellipsoids(depth, fo, bb, lb, tw)
 c = np.array([h.debug_counters(i) for i in range(64)], float)
-print("per object: evals %.0f  queries/eval %.1f  points/eval %.1f  n_sym %.1f  n_crop %.0f n_cluster %.0f" % (c[:,0].mean(), (c[:,1]/c[:,0]).mean(), (c[:,2]/c[:,0]).mean(), c[:,3].mean(), np.mean([o.n_crop for o in out]), np.mean([o.n_cluster for o in out])))
-print("evals min/max", c[:,0].min(), c[:,0].max())
+ok = c[:, 0] > 0
+print("objects with evals:", ok.sum(), "status", [o.status for o in out][:16])
+c = c[ok]
+print("per object: evals %.0f  queries/eval %.1f  points/eval %.1f  n_sym %.1f" % (c[:,0].mean(), (c[:,1]/c[:,0]).mean(), (c[:,2]/c[:,0]).mean(), c[:,3].mean()))
+print("evals min/max", c[:,0].min(), c[:,0].max(), " first rows", c[:4])
