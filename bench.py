@@ -59,12 +59,52 @@ def make_frames(kind, n_frames, seed_base):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle-reason samples DURING the timed region (B200_PROFILING.md clocks line).
+
+    NVML is polled from a thread every 10 ms (the timed region of a default run is only a few hundred ms, shorter than
+    nvidia-smi's start-up); if NVML cannot be opened the recipe's nvidia-smi loop is used instead."""
+
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.sm, self.mx, self.reasons, self.stop_flag, self.thread, self.nv = [], 0, set(), False, None, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll(self):
+        nv, hd = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(hd)
+                for name, const in self.REASONS:
+                    if mask & getattr(nv, const):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        try:
+            self.nv = self._nvml_handle()
+            self.mx = float(self.nv[0].nvmlDeviceGetMaxClockInfo(self.nv[1], self.nv[0].NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
@@ -78,13 +118,16 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
-        sm, mx, reasons = [], 0, set()
+        sm, mx, reasons = list(self.sm), self.mx, set(self.reasons)
         for ln in self.lines:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 8:
@@ -96,7 +139,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 def oracle_fps(depth, fo, bb, lb, tw, plane, n_frames, threads):
@@ -128,7 +172,7 @@ def oracle_fps(depth, fo, bb, lb, tw, plane, n_frames, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=1024, help="frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
