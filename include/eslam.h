@@ -226,9 +226,24 @@ int eslam_edges_download(EslamHandle *h, double *residuals, double *jacobians, d
 int eslam_optimize_objects_host(EslamHandle *h, const EslamEdgeBatch *g, int iters, double *ellipsoids10,
                                 EslamLmStats *stats);
 
+/* SLAM mode of the same optimisation: Optimizer.cpp:126-159 with bSLAM_mode = true.  Every pose
+ * g->Tcw[f], f >= 1, becomes a free VertexSE3Expmap (frame 0 stays fixed, :137), consecutive frames are tied by
+ * EdgeSE3Expmap odometry edges (types_six_dof_expmap.h:83-99) inserted BEFORE the ellipsoid edges (they are created in
+ * the pose loop), information = odom_info * I6 (:149-152, 1.0 in the reference).
+ *   odom_meas7 [(n_frames-1)*7]: measurement of edge k between frames k and k+1 (Tcw_{k+1} * Tcw_k^-1, :141-143);
+ *                                NULL = computed from g->Tcw like the reference does.
+ *   ellipsoids10 updated in place; Tcw_out7 [n_frames*7] receives the optimised poses (may be NULL: the reference
+ *   itself only writes the ellipsoids back, :293-306).
+ * The linear system is solved exactly (block-tridiagonal pose chain + dense reduced object system) instead of the
+ * reference's dense LDLT of the full matrix (linear_solver_dense.h:65-113). */
+int eslam_optimize_slam_host(EslamHandle *h, const EslamEdgeBatch *g, const double *odom_meas7, double odom_info, int iters,
+                             double *ellipsoids10, double *Tcw_out7, EslamLmStats *stats);
+
 /* ------------------------------------------------------------------ Frame helper */
 /* Frame::Frame pose handling (Frame.cpp:13-14): Twc7 -> Tcw7 = Twc.inverse() */
 void eslam_pose_inverse(const double T7[7], double Tinv7[7]);
+/* g2o::SE3Quat::operator* (se3quat.h:110-116, incl. normalizeRotation): out = A * B */
+void eslam_pose_mul(const double A7[7], const double B7[7], double out7[7]);
 
 #ifdef __cplusplus
 }

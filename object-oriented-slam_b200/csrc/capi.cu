@@ -233,6 +233,7 @@ void eslam_destroy(EslamHandle *h) {
     w.pin_meta.release(); w.pin_out.release(); w.pin_depth.release();
     delete h->ex;
   }
+  slam_free(h);
   graph_free(h);
   plane_free(h);
   for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -426,6 +427,24 @@ void eslam_pose_inverse(const double T[7], double Ti[7]) {  // SE3Quat::inverse,
   double mt[3] = {T[0] * -1., T[1] * -1., T[2] * -1.}, o[3];
   h_rot(qc, mt, o);
   Ti[0] = o[0]; Ti[1] = o[1]; Ti[2] = o[2]; Ti[3] = qc.x; Ti[4] = qc.y; Ti[5] = qc.z; Ti[6] = qc.w;
+}
+
+void eslam_pose_mul(const double A[7], const double B[7], double out[7]) {  // SE3Quat::operator*, se3quat.h:110-116
+  HQ a{A[3], A[4], A[5], A[6]}, b{B[3], B[4], B[5], B[6]};
+  double o[3];
+  h_rot(a, B, o);
+  HQ r{a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x,
+       a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+  if (r.w < 0) { r.x *= -1; r.y *= -1; r.z *= -1; r.w *= -1; }   // normalizeRotation, se3quat.h:345-350
+  double n = sqrt(r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w);
+  out[0] = A[0] + o[0]; out[1] = A[1] + o[1]; out[2] = A[2] + o[2];
+  out[3] = r.x / n; out[4] = r.y / n; out[5] = r.z / n; out[6] = r.w / n;
+}
+
+int eslam_optimize_slam_host(EslamHandle *h, const EslamEdgeBatch *g, const double *odom_meas7, double odom_info, int iters, double *ell, double *Tcw_out7,
+                             EslamLmStats *stats) {
+  if (!h || !g || !ell) return ESLAM_ERR_BAD_ARG;
+  return slam_optimize(h, g, odom_meas7, odom_info, iters, ell, Tcw_out7, stats, h->stream);
 }
 
 }  // extern "C"

@@ -44,6 +44,7 @@ struct PinBuf {
 
 struct ExtractWorkspace;  // extract.cu
 struct GraphWorkspace;    // edges.cu
+struct SlamWorkspace;     // slam.cu
 struct PlaneWorkspace;    // plane.cu
 
 }  // namespace eslam
@@ -67,6 +68,7 @@ struct EslamHandle {
   std::string err;
   eslam::ExtractWorkspace *ex = nullptr;
   eslam::GraphWorkspace *gr = nullptr;
+  eslam::SlamWorkspace *sl = nullptr;
   eslam::PlaneWorkspace *pl = nullptr;
 };
 

@@ -15,6 +15,11 @@ int graph_download(EslamHandle *h, double *res, double *jac, double *chi2, cudaS
 int graph_optimize(EslamHandle *h, int iters, double *ell_inout, EslamLmStats *stats, cudaStream_t s);
 void graph_free(EslamHandle *h);
 
+// slam.cu (SLAM mode: free poses + odometry edges)
+int slam_optimize(EslamHandle *h, const EslamEdgeBatch *g, const double *odom_meas7, double odom_info, int iters, double *ell_inout, double *Tcw_out,
+                  EslamLmStats *stats, cudaStream_t s);
+void slam_free(EslamHandle *h);
+
 // extract.cu / symmetry.cu
 int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj, const ExtractParamsDev &prm,
                    const ExtractPtrs &ptrs);

@@ -4,4 +4,4 @@ works without a GPU (symbols are checked), creating a handle does not."""
 from ._structs import (EDGE_9DOF, EDGE_GRAVITY, EDGE_PROJ, EslamCamera, EslamEdgeBatch, EslamEllipsoidOut, EslamLmStats,  # noqa: F401
                        EslamParams, EslamStageDump, default_camera, default_params)
 from .api import (EllipsoidExtractor, EslamError, Frame, Handle, Initializer, Observation, Optimizer, PlaneExtractor, load_library,  # noqa: F401
-                  calibrate_measurement, plane_to_world, pose_inverse)
+                  calibrate_measurement, plane_to_world, pose_inverse, pose_mul)

@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "eslam_launch_count", "eslam_extract_ground_plane_host", "eslam_extract_ground_plane_dev", "eslam_plane_to_world",
     "eslam_set_supporting_plane", "eslam_calibrate_measurement", "eslam_estimate_ellipsoids_host", "eslam_estimate_ellipsoids_dev",
     "eslam_fetch_ellipsoids", "eslam_init_quadric", "eslam_edges_eval_host", "eslam_edges_upload", "eslam_edges_eval_dev",
-    "eslam_edges_download", "eslam_optimize_objects_host", "eslam_pose_inverse", "eslam_set_profiling", "eslam_get_stage_ms",
+    "eslam_edges_download", "eslam_optimize_objects_host", "eslam_optimize_slam_host", "eslam_pose_inverse", "eslam_pose_mul", "eslam_set_profiling", "eslam_get_stage_ms",
 ]
 
 
@@ -47,6 +47,7 @@ def load_library(path=None):
             getattr(lib, n).restype = C.c_size_t
         lib.eslam_plane_to_world.restype = None
         lib.eslam_pose_inverse.restype = None
+        lib.eslam_pose_mul.restype = None
         _LIB = lib
     return _LIB
 
@@ -69,6 +70,11 @@ def _u16p(a):
 
 def pose_inverse(T7):
     out = np.zeros(7); t = _d(T7); load_library().eslam_pose_inverse(_dp(t), _dp(out)); return out
+
+
+def pose_mul(A7, B7):
+    """g2o::SE3Quat::operator* (se3quat.h:110-116)."""
+    out = np.zeros(7); load_library().eslam_pose_mul(_dp(_d(A7)), _dp(_d(B7)), _dp(out)); return out
 
 
 def plane_to_world(plane_cam, Twc7):
@@ -206,6 +212,15 @@ class Handle:
         e = _d(ellipsoids).copy(); st = EslamLmStats()
         self.check(self.lib.eslam_optimize_objects_host(self._h, C.byref(graph.c), C.c_int(iters), _dp(e), C.byref(st)), "eslam_optimize_objects_host")
         return e, st
+
+
+    def optimize_slam(self, graph, ellipsoids, iters=10, odom_meas=None, odom_info=1.0):
+        """SLAM mode (Optimizer.cpp:126-159, bSLAM_mode = true): free poses + odometry edges.  Returns (ellipsoids, Tcw, stats)."""
+        e = _d(ellipsoids).copy(); st = EslamLmStats(); T = np.zeros((graph.c.n_frames, 7))
+        om = _d(odom_meas).reshape(-1, 7) if odom_meas is not None else None
+        self.check(self.lib.eslam_optimize_slam_host(self._h, C.byref(graph.c), _dp(om) if om is not None else None, C.c_double(odom_info), C.c_int(iters),
+                                                     _dp(e), _dp(T), C.byref(st)), "eslam_optimize_slam_host")
+        return e, T, st
 
 
 class _DumpArrays:
@@ -385,7 +400,7 @@ class Optimizer:
         ell = np.array([ellipsoids_by_instance[i]["vec"] for i in inst_ids])
         return inst_ids, et, fr, ob, meas, info, is2d, Tcw, ell
 
-    def GlobalObjectGraphOptimization(self, pFrames, ellipsoids_by_instance, rows, cols, K, objectObservations, iters=10):
+    def GlobalObjectGraphOptimization(self, pFrames, ellipsoids_by_instance, rows, cols, K, objectObservations, iters=10, bSLAM_mode=False):
         inst_ids, et, fr, ob, meas, info, is2d, Tcw, ell = self.build_graph(pFrames, ellipsoids_by_instance, K, objectObservations)
         if not inst_ids or not et:
             return ellipsoids_by_instance
@@ -396,7 +411,14 @@ class Optimizer:
             if not all(keep):
                 sel = np.nonzero(keep)[0]
                 g = EdgeGraph(np.array(et)[sel], np.array(fr)[sel], np.array(ob)[sel], np.array(meas)[sel], np.array(info)[sel], Tcw, len(inst_ids), K)
-        out, st = self.h.optimize_objects(g, ell, iters)
+        if bSLAM_mode:   # Optimizer.cpp:139-158: odometry measurement from the frames' Twc, information = I
+            odo = []
+            for k in range(1, len(pFrames)):
+                prev_Tcw = pose_inverse(pFrames[k - 1].cam_pose_Twc); curr_Tcw = pose_inverse(pFrames[k].cam_pose_Twc)
+                odo.append(pose_mul(curr_Tcw, pose_inverse(prev_Tcw)))
+            out, self.last_Tcw, st = self.h.optimize_slam(g, ell, iters, odom_meas=np.array(odo) if odo else None, odom_info=1.0)
+        else:
+            out, st = self.h.optimize_objects(g, ell, iters)
         self.last_stats = st
         for k, inst in enumerate(inst_ids):
             ellipsoids_by_instance[inst]["vec"] = out[k].copy()

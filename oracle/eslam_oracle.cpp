@@ -119,6 +119,17 @@ int orc_optimize_objects(const EslamEdgeBatch *g, int iters, double *ellipsoids1
   return 0;
 }
 
+int orc_optimize_slam(const EslamEdgeBatch *g, const double *odom_meas7, double odom_info, int iters, double *ellipsoids10, double *Tcw_out7, EslamLmStats *stats) {
+  EdgeBatch b{g->n_edges, g->type, g->frame, g->object, g->meas, g->info, g->n_frames, g->Tcw, g->n_objects, g->K};
+  LmStats st = optimize_slam(b, odom_meas7, odom_info, iters, ellipsoids10, Tcw_out7);
+  if (stats) { stats->iterations = st.iterations; stats->trials_total = st.trials_total; stats->terminated = st.terminated; stats->chi2_initial = st.chi2_initial; stats->chi2_final = st.chi2_final; stats->lambda_final = st.lambda_final; }
+  return 0;
+}
+// odometry residual (for tests): err6 = log(meas * v1 * v2^-1)
+void orc_odom_error(const double meas7[7], const double v1[7], const double v2[7], double err6[6]) {
+  odom_error(se3_from_vector(meas7), se3_from_vector(v1), se3_from_vector(v2), err6);
+}
+
 // ---- extraction
 int orc_calibrate_measurement(const EslamParams *p, const EslamCamera *c, const double m[4]) {  // dataprocess_utils.cpp:150-190
   int x_length = m[2] - m[0], y_length = m[3] - m[1];

@@ -290,4 +290,139 @@ inline LmStats optimize_objects(const EdgeBatch &g, int iters, double *ellipsoid
   return st;
 }
 
+// ---- SLAM mode (Optimizer.cpp:126-159 with bSLAM_mode = true): camera poses are free 6-DoF vertices (frame 0 fixed),
+// consecutive frames are tied by EdgeSE3Expmap odometry edges (types_six_dof_expmap.h:83-99), every Jacobian is numeric
+// (base_binary_edge.hpp:131-205), the system is solved densely (LinearSolverDense, no marginalisation).
+// Hessian order = vertex id order (sparse_optimizer.cpp sortVectorContainers): poses 1..F-1 then ellipsoids.
+// Edge order = insertion order: F-1 odometry edges first (added inside the pose loop), then the ellipsoid edges of `g`.
+inline SE3 pose_oplus(const SE3 &T, const double u[6]) { return se3_mul(se3_exp(u), T); }  // VertexSE3Expmap::oplusImpl, types_six_dof_expmap.h:73-76
+inline void odom_error(const SE3 &meas, const SE3 &v1, const SE3 &v2, double err[6]) {       // EdgeSE3Expmap::computeError :89-98
+  SE3 e = se3_mul(se3_mul(meas, v1), se3_inverse(v2));
+  se3_log(e, err);
+}
+inline LmStats optimize_slam(const EdgeBatch &g, const double *odom_meas7, double odom_info, int iters, double *ellipsoids10, double *Tcw_out7) {
+  const int No = g.n_objects, F = g.n_frames, NP = F - 1;
+  std::vector<Ellipsoid> est(No);
+  for (int i = 0; i < No; i++) est[i] = ell_from_vector(ellipsoids10 + 10 * i);
+  std::vector<SE3> Tcw(F), odo(NP > 0 ? NP : 0);
+  for (int f = 0; f < F; f++) Tcw[f] = se3_from_vector(g.Tcw + 7 * f);
+  for (int k = 0; k < NP; k++)
+    odo[k] = odom_meas7 ? se3_from_vector(odom_meas7 + 7 * k) : se3_mul(Tcw[k + 1], se3_inverse(Tcw[k]));  // Optimizer.cpp:141-143
+  const int n = 6 * NP + 9 * No;
+  auto pidx = [&](int f) { return 6 * (f - 1); };          // f >= 1
+  auto oidx = [&](int o) { return 6 * NP + 9 * o; };
+  std::vector<double> err((size_t)g.n_edges * 9, 0.0), oerr((size_t)(NP > 0 ? NP : 0) * 6, 0.0);
+  struct Snap { std::vector<Ellipsoid> e; std::vector<SE3> T; };
+  std::vector<Snap> stack;
+  LmProblem P;
+  P.dim = n;
+  P.compute_errors = [&]() {
+    double chi = 0;
+    for (int k = 0; k < NP; k++) {
+      odom_error(odo[k], Tcw[k], Tcw[k + 1], &oerr[(size_t)k * 6]);
+      double c = 0;
+      for (int r = 0; r < 6; r++) c += oerr[(size_t)k * 6 + r] * (odom_info * oerr[(size_t)k * 6 + r]);
+      chi += c;
+    }
+    for (int k = 0; k < g.n_edges; k++) {
+      int t = g.type[k]; int D = edge_dim(t);
+      const SE3 &T = (t == EDGE_GRAVITY) ? Tcw[0] : Tcw[g.frame[k]];
+      edge_compute_error(t, T, est[g.object[k]], g.meas + 10 * k, g.K, &err[(size_t)k * 9]);
+      double c = 0;
+      for (int r = 0; r < D; r++) c += err[(size_t)k * 9 + r] * (g.info[k] * err[(size_t)k * 9 + r]);
+      chi += c;
+    }
+    return chi;
+  };
+  // H(ia.., ib..) += A^T (w I) B with the reference's association (A(r,i)*w)*B(r,j)
+  auto add_block = [&](std::vector<double> &H, int ia, int da, const double *A, int ib, int db, const double *B, int D, double w, int lda, int ldb) {
+    for (int i = 0; i < da; i++)
+      for (int j = 0; j < db; j++) {
+        double h = 0;
+        for (int r = 0; r < D; r++) { double pr = (A[r * lda + i] * w) * B[r * ldb + j]; if (r == 0) h = pr; else h += pr; }
+        H[(size_t)(ia + i) * n + ib + j] += h;
+        if (ia != ib) H[(size_t)(ib + j) * n + ia + i] += h;   // off-diagonal block: the lower copy is the transpose (linear_solver_dense.h:88-91)
+      }
+  };
+  auto add_b = [&](std::vector<double> &b, int ia, int da, const double *A, const double *e, int D, double w, int lda) {
+    for (int i = 0; i < da; i++) {
+      double bi = 0;
+      for (int r = 0; r < D; r++) { double pr = A[r * lda + i] * (-(w * e[r])); if (r == 0) bi = pr; else bi += pr; }
+      b[ia + i] += bi;
+    }
+  };
+  P.build_system = [&](std::vector<double> &H, std::vector<double> &b) {
+    H.assign((size_t)n * n, 0.0); b.assign(n, 0.0);
+    const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+    for (int k = 0; k < NP; k++) {  // odometry edges: vertex i = frame k, vertex j = frame k+1
+      double Ji[36], Jj[36], e1[6], e2[6], add[6] = {0, 0, 0, 0, 0, 0};
+      bool iFree = k >= 1;
+      if (iFree) for (int d = 0; d < 6; d++) {
+        add[d] = delta; odom_error(odo[k], pose_oplus(Tcw[k], add), Tcw[k + 1], e1);
+        add[d] = -delta; odom_error(odo[k], pose_oplus(Tcw[k], add), Tcw[k + 1], e2);
+        add[d] = 0.0;
+        for (int r = 0; r < 6; r++) Ji[r * 6 + d] = scalar * (e1[r] - e2[r]);
+      }
+      for (int d = 0; d < 6; d++) {
+        add[d] = delta; odom_error(odo[k], Tcw[k], pose_oplus(Tcw[k + 1], add), e1);
+        add[d] = -delta; odom_error(odo[k], Tcw[k], pose_oplus(Tcw[k + 1], add), e2);
+        add[d] = 0.0;
+        for (int r = 0; r < 6; r++) Jj[r * 6 + d] = scalar * (e1[r] - e2[r]);
+      }
+      const double *e = &oerr[(size_t)k * 6];
+      if (iFree) {
+        add_b(b, pidx(k), 6, Ji, e, 6, odom_info, 6);
+        add_block(H, pidx(k), 6, Ji, pidx(k), 6, Ji, 6, odom_info, 6, 6);
+        add_block(H, pidx(k), 6, Ji, pidx(k + 1), 6, Jj, 6, odom_info, 6, 6);
+      }
+      add_b(b, pidx(k + 1), 6, Jj, e, 6, odom_info, 6);
+      add_block(H, pidx(k + 1), 6, Jj, pidx(k + 1), 6, Jj, 6, odom_info, 6, 6);
+    }
+    double Jo[81], Jp[54];
+    for (int k = 0; k < g.n_edges; k++) {
+      int t = g.type[k]; int D = edge_dim(t); int o = g.object[k];
+      int f = (t == EDGE_GRAVITY) ? 0 : g.frame[k];
+      const SE3 &T = Tcw[f];
+      const double *e = &err[(size_t)k * 9];
+      double w = g.info[k];
+      edge_numeric_jacobian(t, T, est[o], g.meas + 10 * k, g.K, Jo);
+      if (t == EDGE_GRAVITY) {  // unary (base_unary_edge.hpp:65-66)
+        for (int i = 0; i < 9; i++) {
+          double bi = 0;
+          for (int r = 0; r < D; r++) { double pr = (Jo[r * 9 + i] * w) * e[r]; if (r == 0) bi = pr; else bi += pr; }
+          b[oidx(o) + i] -= bi;
+        }
+        add_block(H, oidx(o), 9, Jo, oidx(o), 9, Jo, D, w, 9, 9);
+        continue;
+      }
+      bool pFree = f >= 1;
+      if (pFree) {
+        double add[6] = {0, 0, 0, 0, 0, 0}, e1[9], e2[9];
+        for (int d = 0; d < 6; d++) {
+          add[d] = delta; edge_compute_error(t, pose_oplus(T, add), est[o], g.meas + 10 * k, g.K, e1);
+          add[d] = -delta; edge_compute_error(t, pose_oplus(T, add), est[o], g.meas + 10 * k, g.K, e2);
+          add[d] = 0.0;
+          for (int r = 0; r < D; r++) Jp[r * 6 + d] = scalar * (e1[r] - e2[r]);
+        }
+        add_b(b, pidx(f), 6, Jp, e, D, w, 6);
+        add_block(H, pidx(f), 6, Jp, pidx(f), 6, Jp, D, w, 6, 6);
+        add_block(H, pidx(f), 6, Jp, oidx(o), 9, Jo, D, w, 6, 9);
+      }
+      add_b(b, oidx(o), 9, Jo, e, D, w, 9);
+      add_block(H, oidx(o), 9, Jo, oidx(o), 9, Jo, D, w, 9, 9);
+    }
+  };
+  P.push = [&]() { stack.push_back(Snap{est, Tcw}); };
+  P.pop = [&]() { est = stack.back().e; Tcw = stack.back().T; stack.pop_back(); };
+  P.discard_top = [&]() { stack.pop_back(); };
+  P.update = [&](const double *x) {
+    for (int f = 1; f < F; f++) Tcw[f] = pose_oplus(Tcw[f], x + pidx(f));
+    for (int i = 0; i < No; i++) est[i] = ell_exp_update(est[i], x + oidx(i));
+  };
+  LmStats st = lm_optimize(P, iters);
+  for (int i = 0; i < No; i++) ell_to_vector(est[i], ellipsoids10 + 10 * i);
+  if (Tcw_out7) for (int f = 0; f < F; f++) se3_to_vector(Tcw[f], Tcw_out7 + 7 * f);
+  return st;
+}
+
 }  // namespace orc

@@ -140,6 +140,18 @@ def optimize_objects(g, ellipsoids, iters=10):
     return e, st
 
 
+def optimize_slam(g, ellipsoids, iters=10, odom_meas=None, odom_info=1.0):
+    """SLAM mode (free poses, odometry edges); returns (ellipsoids, Tcw, stats)."""
+    e = _d(ellipsoids).copy(); st = EslamLmStats(); T = np.zeros((g.c.n_frames, 7))
+    om = _d(odom_meas).reshape(-1, 7) if odom_meas is not None else None
+    lib().orc_optimize_slam(C.byref(g.c), _dp(om) if om is not None else None, C.c_double(odom_info), C.c_int(iters), _dp(e), _dp(T), C.byref(st))
+    return e, T, st
+
+
+def odom_error(meas7, v1, v2):
+    out = np.zeros(6); lib().orc_odom_error(_dp(_d(meas7)), _dp(_d(v1)), _dp(_d(v2)), _dp(out)); return out
+
+
 class Dump:
     def __init__(self, cap):
         self.cap = cap

@@ -245,3 +245,53 @@ def test_calibrate_measurement():
     assert orc.calibrate_measurement([50, 50, 300, 300]) == 0
     assert orc.calibrate_measurement([5, 50, 300, 300]) == 1
     assert orc.calibrate_measurement([50, 50, 630, 300]) == 1
+
+
+# ---- SLAM mode: free poses + odometry edges ----
+def test_odometry_edge_is_zero_at_the_measured_relative_pose():
+    rng = np.random.default_rng(3)
+    v1 = orc.se3_exp(rng.normal(0, 0.5, 6)); v2 = orc.se3_exp(rng.normal(0, 0.5, 6))
+    meas = orc.se3_mul(v2, orc.se3_inverse(v1))                      # Optimizer.cpp:141-143
+    assert np.abs(orc.odom_error(meas, v1, v2)).max() < 1e-12        # log(C v1 v2^-1) = 0, types_six_dof_expmap.h:89-98
+    xi = np.array([0.01, -0.02, 0.03, 0.1, 0.0, -0.05])
+    e = orc.odom_error(orc.se3_mul(orc.se3_exp(xi), meas), v1, v2)   # left-perturbed measurement -> error = xi
+    assert np.abs(e - xi).max() < 1e-9
+
+
+def test_slam_mode_recovers_perturbed_poses():
+    from helpers import make_slam_problem
+    p = make_slam_problem(16, 5, 4, seed=11, pose_noise=0.01, noise=0.0)   # noise-free measurements: the truth is the optimum
+    g = orc.Graph(p["type"], p["frame"], p["object"], p["meas"], p["info"], p["Tcw"], p["n_objects"], p["K"])
+    e, T, st = orc.optimize_slam(g, p["init"], 10, odom_meas=p["odom"])
+    assert st.chi2_final < 1e-9 * st.chi2_initial
+    d1 = max(np.abs(orc.se3_log(orc.se3_mul(a, orc.se3_inverse(b)))).max() for a, b in zip(T[1:], p["Tcw_true"][1:]))
+    assert d1 < 1e-7 and np.abs(e - p["truth"]).max() < 1e-7, d1
+    assert np.array_equal(T[0], p["Tcw"][0])                         # first pose is fixed (Optimizer.cpp:137)
+
+
+def test_slam_mode_with_fixed_poses_limit_equals_mapping_mode():
+    """With a single frame there is no free pose and no odometry edge: SLAM mode must reproduce mapping mode exactly."""
+    from helpers import make_ba_problem
+    p = make_ba_problem(1, 3, 6, seed=5)
+    g = orc.Graph(p["type"], p["frame"], p["object"], p["meas"], p["info"], p["Tcw"], p["n_objects"], p["K"])
+    e0, s0 = orc.optimize_objects(g, p["init"], 5)
+    e1, T, s1 = orc.optimize_slam(g, p["init"], 5)
+    assert np.array_equal(e0, e1) and (s0.iterations, s0.trials_total) == (s1.iterations, s1.trials_total)
+
+
+def test_slam_mode_noise_floor():
+    """Documents why SLAM-mode state parity is asserted at 1e-3 (not 1e-4) on noisy graphs: the reference algorithm (numeric Jacobians
+    with delta = 1e-9, weak odometry information) amplifies a 1e-13 measurement change -- the size of a libm ulp difference -- to
+    ~1e-4 in the state after two iterations, while chi2 stays put.  Mapping mode is an order of magnitude better conditioned."""
+    from helpers import make_slam_problem, K
+    p = make_slam_problem(30, 6, 8, seed=7, pose_noise=0.01)
+    g0 = orc.Graph(p["type"], p["frame"], p["object"], p["meas"], p["info"], p["Tcw"], p["n_objects"], K)
+    m2 = p["meas"].copy(); m2[:, :4] += 1e-13 * np.sign(m2[:, :4])
+    g1 = orc.Graph(p["type"], p["frame"], p["object"], m2, p["info"], p["Tcw"], p["n_objects"], K)
+    e0, T0, s0 = orc.optimize_slam(g0, p["init"], 2, odom_meas=p["odom"])
+    e1, T1, s1 = orc.optimize_slam(g1, p["init"], 2, odom_meas=p["odom"])
+    assert abs(s1.chi2_final - s0.chi2_final) <= 1e-5 * s0.chi2_final
+    assert np.abs(e1 - e0).max() < 1e-3 and np.abs(T1 - T0).max() < 1e-3        # bounded ...
+    assert np.abs(e1 - e0).max() > 1e-6                                          # ... but far above the 1e-13 input change
+    m0, _ = orc.optimize_objects(g0, p["init"], 2); m1, _ = orc.optimize_objects(g1, p["init"], 2)
+    assert np.abs(m1 - m0).max() < np.abs(e1 - e0).max()

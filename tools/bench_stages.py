@@ -88,3 +88,24 @@ if args.only in ("all", "edges"):
         line["cpu_lm_iterations"] = so.iterations; line["cpu_chi2_final"] = so.chi2_final
         line["max_rel_ellipsoid_diff"] = float(np.max(np.abs(eg - eo) / np.maximum(1.0, np.abs(eo))))
     print(json.dumps(line))
+
+if args.only in ("all", "slam"):
+    # SLAM mode on the configs[3] graph: 499 free poses + 50 ellipsoids = 3444 unknowns, 25 050 + 499 edges
+    import orc
+    from helpers import make_slam_problem, K
+    p = make_slam_problem(500, 50, 50, pose_noise=0.005)
+    gg = EdgeGraph(p["type"], p["frame"], p["object"], p["meas"], p["info"], p["Tcw"], p["n_objects"], K)
+    h.optimize_slam(gg, p["init"], 2, odom_meas=p["odom"])          # allocations + first launches
+    l0 = h.launches
+    t0 = time.perf_counter(); eg, Tg, sg = h.optimize_slam(gg, p["init"], 10, odom_meas=p["odom"]); ms = (time.perf_counter() - t0) * 1e3
+    line = {"stage": "slam_mode optimize(10) (free poses + odometry edges)", "unknowns": 6 * 499 + 9 * 50, "edges": int(gg.c.n_edges) + 499, "ms": ms,
+            "iterations": sg.iterations, "trials": sg.trials_total, "chi2": [sg.chi2_initial, sg.chi2_final], "launches": int(h.launches - l0)}
+    if not args.skip_cpu:
+        go = orc.Graph(p["type"], p["frame"], p["object"], p["meas"], p["info"], p["Tcw"], p["n_objects"], K)
+        t0 = time.perf_counter(); eo, To, so = orc.optimize_slam(go, p["init"], 10, odom_meas=p["odom"]); line["cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
+        line["cpu_iterations"] = so.iterations; line["cpu_trials"] = so.trials_total; line["cpu_chi2_final"] = so.chi2_final
+        line["max_rel_ellipsoid_diff"] = float(np.max(np.abs(eg - eo) / np.maximum(1.0, np.abs(eo))))
+        sgn = np.sign(np.sum(Tg[:, 3:] * To[:, 3:], axis=1))[:, None]
+        Tg2 = Tg.copy(); Tg2[:, 3:] *= sgn
+        line["max_rel_pose_diff"] = float(np.max(np.abs(Tg2 - To) / np.maximum(1.0, np.abs(To))))
+    print(json.dumps(line))
