@@ -44,60 +44,75 @@ static __device__ void edge_error(int type, const se3 &Tcw, const ellipsoid &obj
   }
 }
 
-// sequential (graph-order) sum of the per-edge chi2 by one warp: lanes fetch 32 values, lane 0 adds them in order.
-static __device__ double warp_ordered_sum(const double *v, int n) {
+// sequential (graph-order) sum acc + v[0] + v[1] + ... by one warp: the lanes stage 256 values in shared memory (coalesced, the
+// next chunk already in flight), lane 0 adds them strictly in order.  Every lane returns the same value.
+static __device__ double warp_ordered_sum(const double *v, int n, double acc = 0.0) {
+  __shared__ double stage[256];
   int lane = threadIdx.x & 31;
-  double acc = 0.0;
-  for (int base = 0; base < n; base += 32) {
-    double x = (base + lane < n) ? v[base + lane] : 0.0;
-    int cnt = min(32, n - base);
-    for (int k = 0; k < cnt; k++) {
-      double xk = __shfl_sync(0xffffffffu, x, k);
-      acc += xk;
+  double nxt[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) nxt[j] = (j * 32 + lane < n) ? v[j * 32 + lane] : 0.0;
+  for (int base = 0; base < n; base += 256) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) stage[j * 32 + lane] = nxt[j];
+    __syncwarp();
+    int nb = base + 256;
+#pragma unroll
+    for (int j = 0; j < 8; j++) nxt[j] = (nb + j * 32 + lane < n) ? v[nb + j * 32 + lane] : 0.0;
+    if (lane == 0) {
+      int cnt = min(256, n - base);
+      for (int k = 0; k < cnt; k++) acc += stage[k];
     }
+    __syncwarp();
   }
-  return acc;  // every lane holds the same value
+  return __shfl_sync(0xffffffffu, acc, 0);
 }
 
 // one CTA (96 threads) per object: thread t < 81 owns H(i,j), t in [81,90) owns b(i); edges visited in graph order so the
-// fp64 accumulation order equals g2o's (activeEdges sorted by internalId, optimizable_graph.cpp:273).
+// fp64 accumulation order equals g2o's (activeEdges sorted by internalId, optimizable_graph.cpp:273).  The Jacobians / residuals of
+// 16 edges at a time are staged in shared memory with coalesced, independent loads (the scattered per-edge reads were the whole cost);
+// rows >= dim of every Jacobian are stored as zeros, so all 9 rows are summed (adding +0.0 is exact).
 static __global__ void __launch_bounds__(96) build_system_kernel(const int *__restrict__ obj_start, const int *__restrict__ obj_edges, const int *__restrict__ type,
                                                           const double *__restrict__ info, const double *__restrict__ res, const double *__restrict__ jac,
                                                           double *__restrict__ H, double *__restrict__ b) {
+  constexpr int CH = 16;
+  __shared__ double Js[CH][81], rs[CH][9], ws[CH];
+  __shared__ int ts[CH];
   int o = blockIdx.x, t = threadIdx.x;
-  if (t >= 90) return;
   int s = obj_start[o], epos = obj_start[o + 1];
   double acc = 0.0;
-  if (t < 81) {
-    int i = t / 9, j = t % 9;
-    for (int k = s; k < epos; k++) {
-      int e = obj_edges[k];
-      int D = edge_dim(type[e]);
-      double w = info[e];
-      const double *J = jac + (size_t)e * 81;
-      double h = 0;
-      for (int r = 0; r < D; r++) { double pr = (J[r * 9 + i] * w) * J[r * 9 + j]; h = (r == 0) ? pr : h + pr; }
-      acc += h;
-    }
-    H[(size_t)o * 81 + t] = acc;
-  } else {
-    int i = t - 81;
-    for (int k = s; k < epos; k++) {
-      int e = obj_edges[k];
-      int ty = type[e];
-      int D = edge_dim(ty);
-      double w = info[e];
-      const double *J = jac + (size_t)e * 81;
-      const double *r_ = res + (size_t)e * 9;
-      double bi = 0;
-      for (int r = 0; r < D; r++) {
-        double pr = (ty == ESLAM_EDGE_GRAVITY) ? ((J[r * 9 + i] * w) * r_[r]) : (J[r * 9 + i] * (-(w * r_[r])));
-        bi = (r == 0) ? pr : bi + pr;
+  const int i = (t < 81) ? t / 9 : t - 81, j = t % 9;
+  for (int c0 = s; c0 < epos; c0 += CH) {
+    int cnt = min(CH, epos - c0);
+    for (int q = t; q < cnt * 81; q += 96) { int k = q / 81, m = q % 81; Js[k][m] = jac[(size_t)obj_edges[c0 + k] * 81 + m]; }
+    for (int q = t; q < cnt * 9; q += 96) { int k = q / 9, m = q % 9; rs[k][m] = res[(size_t)obj_edges[c0 + k] * 9 + m]; }
+    if (t < cnt) { int e = obj_edges[c0 + t]; ws[t] = info[e]; ts[t] = type[e]; }
+    __syncthreads();
+    if (t < 81) {
+      for (int k = 0; k < cnt; k++) {
+        double w = ws[k];
+        double h = 0;
+#pragma unroll
+        for (int r = 0; r < 9; r++) { double pr = (Js[k][r * 9 + i] * w) * Js[k][r * 9 + j]; h = (r == 0) ? pr : h + pr; }
+        acc += h;
       }
-      if (ty == ESLAM_EDGE_GRAVITY) acc -= bi; else acc += bi;
+    } else if (t < 90) {
+      for (int k = 0; k < cnt; k++) {
+        double w = ws[k];
+        bool grav = ts[k] == ESLAM_EDGE_GRAVITY;
+        double bi = 0;
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          double pr = grav ? ((Js[k][r * 9 + i] * w) * rs[k][r]) : (Js[k][r * 9 + i] * (-(w * rs[k][r])));
+          bi = (r == 0) ? pr : bi + pr;
+        }
+        if (grav) acc -= bi; else acc += bi;
+      }
     }
-    b[(size_t)o * 9 + i] = acc;
+    __syncthreads();
   }
+  if (t < 81) H[(size_t)o * 81 + t] = acc;
+  else if (t < 90) b[(size_t)o * 9 + i] = acc;
 }
 
 }  // namespace eslam

@@ -214,19 +214,9 @@ __global__ void __launch_bounds__(64) slam_build_pose_kernel(int NP, int ncols, 
   }
 }
 
-// ordered sum of two arrays (odometry edges first, then the ellipsoid edges: g2o's active edge order), one warp
+// ordered sum of two arrays (odometry edges first, then the ellipsoid edges: g2o's active edge order)
 __device__ double warp_ordered_sum2(const double *v1, int n1, const double *v2, int n2) {
-  int lane = threadIdx.x & 31;
-  double acc = 0.0;
-  for (int pass = 0; pass < 2; pass++) {
-    const double *v = pass ? v2 : v1; int n = pass ? n2 : n1;
-    for (int base = 0; base < n; base += 32) {
-      double x = (base + lane < n) ? v[base + lane] : 0.0;
-      int cnt = min(32, n - base);
-      for (int k = 0; k < cnt; k++) acc += __shfl_sync(0xffffffffu, x, k);
-    }
-  }
-  return acc;
+  return warp_ordered_sum(v2, n2, warp_ordered_sum(v1, n1));
 }
 
 __global__ void slam_lm_begin_kernel(LmState *st, const double *ochi2, int NP, const double *chi2, int n_edges, const double *Dp, const double *Hoo, int n_obj,
@@ -246,68 +236,115 @@ __global__ void slam_lm_begin_kernel(LmState *st, const double *ochi2, int NP, c
 
 // ---------------------------------------------------------------------------------------------------------------- solver
 // block-tridiagonal Cholesky of Hpp + lambda I, one warp.  L_k L_k^T = A_k - M_k M_k^T,  M_k = C_k L_{k-1}^-T,
-// C_k = block(k, k-1) = Op[k-1]^T.
+// C_k = block(k, k-1) = Op[k-1]^T.  The chain is sequential by nature (499 dependent 6x6 steps): the next step's blocks are
+// prefetched into registers while the current one is factorised, the 6x6 Cholesky runs in registers of lane 0.
 __global__ void __launch_bounds__(32) slam_factor_kernel(LmState *st, int NP, const double *__restrict__ Dp, const double *__restrict__ Op,
                                                          double *__restrict__ Lf, double *__restrict__ Mf) {
   __shared__ double L[36], M[36], A[36];
-  __shared__ int bad;
   int lane = threadIdx.x;
   double lambda = st->lambda;
-  if (lane == 0) bad = 0;
+  int bad = 0;
   for (int t = lane; t < 36; t += 32) { L[t] = 0; M[t] = 0; }
+  // lane t holds entries t and t+32 (t < 4) of the diagonal block, and of the transposed off-diagonal block, of the next step
+  int t0 = lane, t1 = lane + 32;
+  double d0 = Dp[t0], d1 = (t1 < 36) ? Dp[t1] : 0.0, c0 = 0, c1 = 0;
   __syncwarp();
   for (int k = 0; k < NP; k++) {
-    if (k > 0 && lane < 6) {  // row `lane` of M: solve  m L_{k-1}^T = c  with c = C_k(lane,:) = Op[k-1](:,lane)
-      double y[6];
-      for (int j = 0; j < 6; j++) {
-        double v = Op[(size_t)(k - 1) * 36 + j * 6 + lane];
-        for (int m = 0; m < j; m++) v -= L[j * 6 + m] * y[m];
-        y[j] = v / L[j * 6 + j];
+    double a0 = d0, a1 = d1, cc0 = c0, cc1 = c1;
+    if (k + 1 < NP) {  // prefetch step k+1: D_{k+1} and C_{k+1} = Op[k]^T  (C(i,j) = Op[k](j,i))
+      d0 = Dp[(size_t)(k + 1) * 36 + t0]; if (t1 < 36) d1 = Dp[(size_t)(k + 1) * 36 + t1];
+      c0 = Op[(size_t)k * 36 + (t0 % 6) * 6 + t0 / 6]; if (t1 < 36) c1 = Op[(size_t)k * 36 + (t1 % 6) * 6 + t1 / 6];
+    }
+    if (k > 0) {  // stage C_k in A[], then rows of M = C L^-T by lanes 0..5
+      A[t0] = cc0; if (t1 < 36) A[t1] = cc1;
+      __syncwarp();
+      if (lane < 6) {
+        double y[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          double v = A[lane * 6 + j];
+#pragma unroll
+          for (int m = 0; m < j; m++) v -= L[j * 6 + m] * y[m];
+          y[j] = v / L[j * 6 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 6; j++) M[lane * 6 + j] = y[j];
       }
-      for (int j = 0; j < 6; j++) M[lane * 6 + j] = y[j];
+      __syncwarp();
+    }
+    {
+      int i = t0 / 6, j = t0 % 6;
+      double v = a0; if (i == j) v += lambda;
+      if (k > 0) {
+#pragma unroll
+        for (int m = 0; m < 6; m++) v -= M[i * 6 + m] * M[j * 6 + m];
+      }
+      A[t0] = v;
+      if (t1 < 36) {
+        i = t1 / 6; j = t1 % 6;
+        v = a1; if (i == j) v += lambda;
+        if (k > 0) {
+#pragma unroll
+          for (int m = 0; m < 6; m++) v -= M[i * 6 + m] * M[j * 6 + m];
+        }
+        A[t1] = v;
+      }
     }
     __syncwarp();
-    for (int t = lane; t < 36; t += 32) {
-      int i = t / 6, j = t % 6;
-      double v = Dp[(size_t)k * 36 + t];
-      if (i == j) v += lambda;
-      if (k > 0) for (int m = 0; m < 6; m++) v -= M[i * 6 + m] * M[j * 6 + m];
-      A[t] = v;
-    }
-    __syncwarp();
-    if (lane == 0) {  // dense 6x6 Cholesky (lower), sequential
+    if (lane == 0) {  // 6x6 Cholesky (lower) in registers
+      double l[6][6];
+#pragma unroll
       for (int j = 0; j < 6; j++) {
         double d = A[j * 6 + j];
-        for (int m = 0; m < j; m++) d -= L[j * 6 + m] * L[j * 6 + m];
+#pragma unroll
+        for (int m = 0; m < j; m++) d -= l[j][m] * l[j][m];
         if (!(d > 0)) { bad = 1; d = 1; }
         double ljj = sqrt(d);
-        L[j * 6 + j] = ljj;
+        l[j][j] = ljj;
+#pragma unroll
         for (int i = j + 1; i < 6; i++) {
           double v = A[i * 6 + j];
-          for (int m = 0; m < j; m++) v -= L[i * 6 + m] * L[j * 6 + m];
-          L[i * 6 + j] = v / ljj;
+#pragma unroll
+          for (int m = 0; m < j; m++) v -= l[i][m] * l[j][m];
+          l[i][j] = v / ljj;
         }
-        for (int i = 0; i < j; i++) L[i * 6 + j] = 0;
       }
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j < 6; j++) L[i * 6 + j] = (j <= i) ? l[i][j] : 0.0;
     }
     __syncwarp();
-    for (int t = lane; t < 36; t += 32) { Lf[(size_t)k * 36 + t] = L[t]; Mf[(size_t)k * 36 + t] = M[t]; }
+    Lf[(size_t)k * 36 + t0] = L[t0]; Mf[(size_t)k * 36 + t0] = M[t0];
+    if (t1 < 36) { Lf[(size_t)k * 36 + t1] = L[t1]; Mf[(size_t)k * 36 + t1] = M[t1]; }
     __syncwarp();
   }
   if (lane == 0 && bad) st->all_ok = 0;
 }
 
-// X = (Hpp + lambda I)^-1 W, one thread per column (coalesced across columns), sequential along the chain
+// X = (Hpp + lambda I)^-1 W, one thread per column (coalesced across columns), sequential along the chain.  The factor blocks of
+// the next step are staged in shared memory (double buffer) and the next W/X rows are prefetched while the current step computes.
 __global__ void __launch_bounds__(64) slam_subst_kernel(int NP, int ncols, const double *__restrict__ Lf, const double *__restrict__ Mf,
                                                         const double *__restrict__ W, double *__restrict__ X) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncols) return;
-  double y[6], prev[6];
-  for (int k = 0; k < NP; k++) {
-    const double *L = Lf + (size_t)k * 36, *M = Mf + (size_t)k * 36;
-    double w[6];
+  __shared__ double Ls[2][36], Ms[2][36];
+  int tid = threadIdx.x;
+  int c = blockIdx.x * blockDim.x + tid;
+  bool act = c < ncols;
+  int cc = act ? c : ncols - 1;
+  double y[6], prev[6], w[6], wn[6];
+  if (tid < 36) { Ls[0][tid] = Lf[tid]; Ms[0][tid] = Mf[tid]; }
 #pragma unroll
-    for (int i = 0; i < 6; i++) w[i] = W[(size_t)(6 * k + i) * ncols + c];
+  for (int i = 0; i < 6; i++) wn[i] = W[(size_t)i * ncols + cc];
+  __syncthreads();
+  for (int k = 0; k < NP; k++) {
+    const double *L = Ls[k & 1], *M = Ms[k & 1];
+#pragma unroll
+    for (int i = 0; i < 6; i++) w[i] = wn[i];
+    if (k + 1 < NP) {
+      if (tid < 36) { Ls[(k + 1) & 1][tid] = Lf[(size_t)(k + 1) * 36 + tid]; Ms[(k + 1) & 1][tid] = Mf[(size_t)(k + 1) * 36 + tid]; }
+#pragma unroll
+      for (int i = 0; i < 6; i++) wn[i] = W[(size_t)(6 * (k + 1) + i) * ncols + cc];
+    }
     if (k > 0) {
 #pragma unroll
       for (int i = 0; i < 6; i++) {
@@ -322,39 +359,56 @@ __global__ void __launch_bounds__(64) slam_subst_kernel(int NP, int ncols, const
       for (int m = 0; m < i; m++) v -= L[i * 6 + m] * y[m];
       y[i] = v / L[i * 6 + i];
     }
+    if (act) {
 #pragma unroll
-    for (int i = 0; i < 6; i++) { X[(size_t)(6 * k + i) * ncols + c] = y[i]; prev[i] = y[i]; }
+      for (int i = 0; i < 6; i++) X[(size_t)(6 * k + i) * ncols + c] = y[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) prev[i] = y[i];
+    __syncthreads();
+  }
+  // backward sweep; buffers: L_k in Ls[k&1], M_{k+1} in Ms[(k+1)&1] (left there by the forward sweep for k = NP-1)
+  if (NP > 0) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) wn[i] = prev[i];   // y_{NP-1} is still in registers
   }
   for (int k = NP - 1; k >= 0; k--) {
-    const double *L = Lf + (size_t)k * 36;
-    double v6[6];
+    const double *L = Ls[k & 1], *M = Ms[(k + 1) & 1];
 #pragma unroll
-    for (int i = 0; i < 6; i++) v6[i] = X[(size_t)(6 * k + i) * ncols + c];
+    for (int i = 0; i < 6; i++) w[i] = wn[i];
+    if (k > 0) {  // stage what step k-1 needs: L_{k-1} (slot of L_{k+1}) and M_k (slot of M_{k+2}); neither slot is read by step k
+      if (tid < 36) { Ls[(k - 1) & 1][tid] = Lf[(size_t)(k - 1) * 36 + tid]; Ms[k & 1][tid] = Mf[(size_t)k * 36 + tid]; }
+#pragma unroll
+      for (int i = 0; i < 6; i++) wn[i] = X[(size_t)(6 * (k - 1) + i) * ncols + cc];
+    }
     if (k < NP - 1) {
-      const double *M = Mf + (size_t)(k + 1) * 36;  // M_{k+1}^T x_{k+1}
 #pragma unroll
       for (int i = 0; i < 6; i++) {
 #pragma unroll
-        for (int m = 0; m < 6; m++) v6[i] -= M[m * 6 + i] * prev[m];
+        for (int m = 0; m < 6; m++) w[i] -= M[m * 6 + i] * prev[m];
       }
     }
 #pragma unroll
     for (int i = 5; i >= 0; i--) {
-      double v = v6[i];
+      double v = w[i];
 #pragma unroll
       for (int m = i + 1; m < 6; m++) v -= L[m * 6 + i] * y[m];
       y[i] = v / L[i * 6 + i];
     }
+    if (act) {
 #pragma unroll
-    for (int i = 0; i < 6; i++) { X[(size_t)(6 * k + i) * ncols + c] = y[i]; prev[i] = y[i]; }
+      for (int i = 0; i < 6; i++) X[(size_t)(6 * k + i) * ncols + c] = y[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) prev[i] = y[i];
+    __syncthreads();
   }
 }
 
-// S = Hoo + lambda I - W^T X (n_o x n_o, stored column-major == row-major of the transposed, lower triangle used) and
-// rhs = b_o - W^T X[:, last].  32x32 tile per CTA, 2x2 per thread, K swept in order (deterministic).
+// S = Hoo + lambda I - W^T X (n_o x n_o, column-major with leading dimension n_o+1, lower triangle used) and
+// rhs = b_o - W^T X[:, last], stored as row n_o of S.  32x32 tile per CTA, 2x2 per thread, K swept in order (deterministic).
 __global__ void __launch_bounds__(256) slam_schur_kernel(const LmState *st, int rows, int n_o, int ncols, const double *__restrict__ W, const double *__restrict__ X,
-                                                         const double *__restrict__ Hoo, const double *__restrict__ bo, double *__restrict__ S,
-                                                         double *__restrict__ rhs) {
+                                                         const double *__restrict__ Hoo, const double *__restrict__ bo, double *__restrict__ S) {
   __shared__ double Ws[16][33], Xs[16][33];
   int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
@@ -378,63 +432,81 @@ __global__ void __launch_bounds__(256) slam_schur_kernel(const LmState *st, int 
     for (int v = 0; v < 2; v++) {
       int a = a0 + ty + 16 * u, b = b0 + tx + 16 * v;
       if (a >= n_o || b >= ncols) continue;
-      if (b == n_o) { rhs[a] = bo[a] - acc[u][v]; continue; }
+      if (b == n_o) { S[(size_t)a * (n_o + 1) + n_o] = bo[a] - acc[u][v]; continue; }
       double hv = 0.0;
       if (a / 9 == b / 9) hv = Hoo[(size_t)(a / 9) * 81 + (a % 9) * 9 + (b % 9)];
       if (a == b) hv += lambda;
-      S[(size_t)b * n_o + a] = hv - acc[u][v];   // element (a, b) of S, column-major
+      S[(size_t)b * (n_o + 1) + a] = hv - acc[u][v];   // element (a, b) of S, column-major
     }
 }
 
-// in-place Cholesky of the lower triangle of S (column-major) + solve S x = rhs, one CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) slam_dense_solve_kernel(LmState *st, int n, double *__restrict__ S, double *__restrict__ rhs, double *__restrict__ x) {
+// in-place LDL^T of the lower triangle of S + solve S x = rhs, one CTA of 1024 threads.  S is column-major with leading dimension
+// n+1: row n of every column is the right-hand side, so the forward substitution happens inside the elimination.  Columns are left
+// unscaled (c_ik = L_ik d_k).  Panels of 8 columns are factorised in shared memory, then applied to the trailing matrix as ONE
+// rank-8 update (8 FMAs per global read-modify-write instead of 1; same operation order as eight rank-1 updates).  The backward
+// substitution x_k = (w_k - sum_{i>k} c_ik x_i) / d_k is done by a single warp with shuffles.
+__global__ void __launch_bounds__(1024) slam_dense_solve_kernel(LmState *st, int n, double *__restrict__ S, double *__restrict__ x) {
+  extern __shared__ double sm[];
+  const int ld = n + 1, ldp = n + 1;
+  double *P = sm, *F = sm + 8 * ldp, *xs = sm + 16 * ldp;
   __shared__ int bad;
-  __shared__ double piv;
   int tid = threadIdx.x;
   int tx = tid % 32, ty = tid / 32;
   if (tid == 0) bad = 0;
   __syncthreads();
-  for (int k = 0; k < n; k++) {
-    if (tid == 0) {
-      double d = S[(size_t)k * n + k];
-      if (!(d > 0)) { bad = 1; d = 1; }
-      piv = sqrt(d);
-      S[(size_t)k * n + k] = piv;
+  for (int kb = 0; kb < n; kb += 8) {
+    const int nb = min(8, n - kb);
+    const int m = n + 1 - kb;  // rows kb..n of the panel
+    for (int t = tid; t < nb * m; t += 1024) { int kk = t / m, r = t % m; P[kk * ldp + r] = S[(size_t)(kb + kk) * ld + kb + r]; }
+    __syncthreads();
+    for (int kk = 0; kk < nb; kk++) {
+      double d = P[kk * ldp + kk];
+      if (!(d > 0)) { if (tid == 0) bad = 1; d = 1; }
+      int ncol = nb - 1 - kk;
+      for (int t = tid; t < ncol * m; t += 1024) {
+        int jj = kk + 1 + t / m, r = t % m;
+        if (r >= jj) P[jj * ldp + r] -= P[kk * ldp + r] * (P[kk * ldp + jj] / d);
+      }
+      __syncthreads();
+    }
+    for (int t = tid; t < nb * m; t += 1024) {
+      int kk = t / m, r = t % m;
+      double c = P[kk * ldp + r], d = P[kk * ldp + kk];
+      if (!(d > 0)) d = 1;
+      if (r >= kk) S[(size_t)(kb + kk) * ld + kb + r] = c;
+      F[kk * ldp + r] = c / d;
     }
     __syncthreads();
-    double pk = piv;
-    for (int i = k + 1 + tid; i < n; i += 1024) S[(size_t)k * n + i] /= pk;
-    __syncthreads();
-    // trailing update of columns j > k: S(i,j) -= L(i,k) L(j,k), i >= j
-    for (int j = k + 1 + ty; j < n; j += 32) {
-      double ljk = S[(size_t)k * n + j];
-      for (int i = j + tx; i < n; i += 32) S[(size_t)j * n + i] -= S[(size_t)k * n + i] * ljk;
-    }
-    __syncthreads();
-  }
-  // forward: L y = rhs (column oriented)
-  for (int k = 0; k < n; k++) {
-    if (tid == 0) { piv = rhs[k] / S[(size_t)k * n + k]; rhs[k] = piv; }
-    __syncthreads();
-    double yk = piv;
-    for (int i = k + 1 + tid; i < n; i += 1024) rhs[i] -= S[(size_t)k * n + i] * yk;
-    __syncthreads();
-  }
-  // backward: L^T x = y  (x_k = (y_k - sum_{i>k} L(i,k) x_i) / L(k,k)); column k of L is contiguous
-  for (int k = n - 1; k >= 0; k--) {
-    __shared__ double part[32];
-    double s = 0;
-    for (int i = k + 1 + tid; i < n; i += 1024) s += S[(size_t)k * n + i] * x[i];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (tx == 0) part[ty] = s;
-    __syncthreads();
-    if (tid == 0) {
-      double tot = 0;
-      for (int w = 0; w < 32; w++) tot += part[w];
-      x[k] = (rhs[k] - tot) / S[(size_t)k * n + k];
+    for (int j = kb + nb + ty; j < n; j += 32) {
+      double f[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++) f[kk] = (kk < nb) ? F[kk * ldp + (j - kb)] : 0.0;
+      double *cj = S + (size_t)j * ld;
+      for (int i = j + tx; i <= n; i += 32) {
+        double acc = cj[i];
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) if (kk < nb) acc -= P[kk * ldp + (i - kb)] * f[kk];
+        cj[i] = acc;
+      }
     }
     __syncthreads();
   }
+  if (ty == 0) {
+    for (int k = n - 1; k >= 0; k--) {
+      const double *ck = S + (size_t)k * ld;
+      double s = 0;
+      for (int i = k + 1 + tx; i < n; i += 32) s += ck[i] * xs[i];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (tx == 0) {
+        double d = ck[k];
+        if (!(d > 0)) d = 1;
+        xs[k] = (ck[n] - s) / d;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += 1024) x[i] = xs[i];
   if (tid == 0 && bad) st->all_ok = 0;
 }
 
@@ -535,6 +607,9 @@ int slam_optimize(EslamHandle *h, const EslamEdgeBatch *g, const double *odom_me
   SlamWorkspace &q = *h->sl;
   const int F = g->n_frames, NP = F - 1, No = g->n_objects, E = g->n_edges;
   const int n_o = 9 * No, ncols = n_o + 1, rows = 6 * NP;
+  const size_t solve_smem = (size_t)(17 * (n_o + 1)) * 8;   // panel P[8][n_o+1], F[8][n_o+1], x[n_o]
+  if (solve_smem > 220 * 1024) { h->err = "slam mode: more than 183 ellipsoids are not supported by the single-CTA reduced solve"; return ESLAM_ERR_BAD_ARG; }
+  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(slam_dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
   q.NP = NP; q.No = No; q.E = E; q.F = F; q.ncols = ncols; q.odom_info = odom_info;
   // odometry measurements: given, or Tcw[k+1] * Tcw[k]^-1 (Optimizer.cpp:141-143)
   std::vector<double> odo((size_t)(NP > 0 ? NP : 1) * 7, 0.0);
@@ -563,7 +638,7 @@ int slam_optimize(EslamHandle *h, const EslamEdgeBatch *g, const double *odom_me
   ESLAM_CUDA_OK(h, q.Dp.reserve((size_t)NP * 288 + 8)); ESLAM_CUDA_OK(h, q.Op.reserve((size_t)NP * 288 + 8)); ESLAM_CUDA_OK(h, q.bp.reserve((size_t)NP * 48 + 8));
   ESLAM_CUDA_OK(h, q.W.reserve((size_t)rows * ncols * 8 + 8)); ESLAM_CUDA_OK(h, q.X.reserve((size_t)rows * ncols * 8 + 8));
   ESLAM_CUDA_OK(h, q.Lf.reserve((size_t)NP * 288 + 8)); ESLAM_CUDA_OK(h, q.Mf.reserve((size_t)NP * 288 + 8));
-  ESLAM_CUDA_OK(h, q.S.reserve((size_t)n_o * n_o * 8)); ESLAM_CUDA_OK(h, q.rhs.reserve((size_t)n_o * 8));
+  ESLAM_CUDA_OK(h, q.S.reserve((size_t)(n_o + 1) * n_o * 8)); ESLAM_CUDA_OK(h, q.rhs.reserve((size_t)n_o * 8));
   ESLAM_CUDA_OK(h, q.xo_tmp.reserve((size_t)n_o * 8)); ESLAM_CUDA_OK(h, q.xo.reserve((size_t)n_o * 8));
   ESLAM_CUDA_OK(h, q.xp_tmp.reserve((size_t)rows * 8 + 8)); ESLAM_CUDA_OK(h, q.xp.reserve((size_t)rows * 8 + 8));
   ESLAM_CUDA_OK(h, cudaMemcpyAsync(q.T.p, g->Tcw, (size_t)F * 56, cudaMemcpyHostToDevice, s));
@@ -603,10 +678,9 @@ int slam_optimize(EslamHandle *h, const EslamEdgeBatch *g, const double *odom_me
         ESLAM_LAUNCHED(h);
       }
       dim3 grid((ncols + 31) / 32, (n_o + 31) / 32);
-      slam_schur_kernel<<<grid, 256, 0, s>>>(st, rows, n_o, ncols, q.W.as<double>(), q.X.as<double>(), w.H.as<double>(), w.b.as<double>(), q.S.as<double>(),
-                                             q.rhs.as<double>());
+      slam_schur_kernel<<<grid, 256, 0, s>>>(st, rows, n_o, ncols, q.W.as<double>(), q.X.as<double>(), w.H.as<double>(), w.b.as<double>(), q.S.as<double>());
       ESLAM_LAUNCHED(h);
-      slam_dense_solve_kernel<<<1, 1024, 0, s>>>(st, n_o, q.S.as<double>(), q.rhs.as<double>(), q.xo_tmp.as<double>());
+      slam_dense_solve_kernel<<<1, 1024, solve_smem, s>>>(st, n_o, q.S.as<double>(), q.xo_tmp.as<double>());
       ESLAM_LAUNCHED(h);
       if (NP > 0) {
         slam_xp_kernel<<<(rows + 3) / 4, 128, 0, s>>>(rows, n_o, ncols, q.X.as<double>(), q.xo_tmp.as<double>(), q.xp_tmp.as<double>());
