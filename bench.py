@@ -8,8 +8,8 @@ filter -> clustering -> PCA -> 9-seed symmetry LM -> completion -> ellipsoid) ov
 (BASELINE.json configs[1]: 1 bbox/frame, label 28 => dual-reflection symmetry).  The batch (B x 614 400 B of depth) is larger than
 the 126 MB L2, so every step re-reads its input from HBM.
   value          frames/s with the depth batch already resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e            frames/s through the reference-facing C-ABI call with HOST (pinned) buffers: H2D of the depth batch, kernels and
-                 D2H of the EslamEllipsoidOut records inside the timed region
+  e2e            frames/s through the reference-facing C-ABI call with HOST (pinned) buffers: H2D of the depth pixels the path reads
+                 (the union rectangle of each frame's boxes), kernels and D2H of the EslamEllipsoidOut records inside the timed region
   roofline       dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline   the CPU oracle (oracle/liboracle.so, a single-threaded restatement of the reference: kind "port") on a bounded sample
 --impl reference times the same oracle on all host threads (the reference cannot be built in this image: no Eigen/PCL/OpenCV).
@@ -275,11 +275,13 @@ def main():
     for _ in range(2):
         step_e2e()
     barrier()
+    h2d0 = h.h2d_bytes
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    h2d_per_step = (h.h2d_bytes - h2d0) // args.steps    # counted by the library from the copies it issued
     t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
     gather_ms = None
     if world > 1:
@@ -324,7 +326,7 @@ def main():
     line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config, objects_per_step_per_gpu=n_obj, ok_fraction=ok_frac, gather_ms=gather_ms),
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(depth.nbytes) * world, "d2h_bytes_per_step": int(C.sizeof(EslamEllipsoidOut) * n_obj) * world},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_per_step) * world, "d2h_bytes_per_step": int(C.sizeof(EslamEllipsoidOut) * n_obj) * world},
             "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
                              "sample": f"{min(args.cpu_sample, args.frames)} frames of the same batch, {cpu_dt:.1f} s, oracle/liboracle.so single thread"}}

@@ -167,6 +167,10 @@ void eslam_destroy(EslamHandle *h);
 const char *eslam_last_error(EslamHandle *h);
 /* number of kernel launches issued by this handle so far (bench.py "gpu_launches") */
 long long eslam_launch_count(EslamHandle *h);
+/* depth bytes the *_host extraction entry has uploaded so far (running total; bench.py "h2d_bytes_per_step"): only the union
+ * rectangle of each frame's boxes travels -- the path never reads a pixel outside a box (PointCloudFilter.cpp:31-52,
+ * EllipsoidExtractor.cpp:583-643, SymmetrySolver.cpp:75-84) */
+unsigned long long eslam_h2d_bytes(EslamHandle *h);
 
 /* profiling hooks (bench.py): device time of each kernel of the most recent extraction batch, measured with CUDA
  * events on the launching stream.  ms[0] = extract kernel, ms[1] = symmetry+finalize kernel, ms[2] = both. */

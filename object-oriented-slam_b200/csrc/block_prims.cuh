@@ -51,6 +51,55 @@ __device__ __forceinline__ int block_excl_scan(int v, BlockScratch &S, int &tota
   return res;
 }
 
+// ---- one-barrier ordered compaction scans for CTAs of exactly 256 threads (8 warps) ----
+// Flags are ranked with ballots; the per-(item, warp) counts go through a double-buffered shared table, so one __syncthreads()
+// per call suffices (call k+2 reuses the buffer of call k only after every warp has passed the barrier of call k+1).
+// `phase` is a per-thread register that all threads of the CTA flip together.  Every thread of the CTA must call.
+struct ScanScratch { int cnt[2][32]; };
+
+// ITEMS flags per thread in item-major order: item k of thread t has rank position k*256 + t.  ITEMS <= 4.
+template <int ITEMS>
+__device__ __forceinline__ void block_flag_scan(const bool (&f)[ITEMS], int (&ex)[ITEMS], int &total, ScanScratch &S, int &phase) {
+  static_assert(ITEMS >= 1 && ITEMS <= 4, "8 warps x ITEMS counters must fit one warp-wide scan");
+  const int lane = lane_id(), w = warp_id();
+  unsigned bal[ITEMS];
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    bal[k] = __ballot_sync(0xffffffffu, f[k]);
+    if (lane == k) S.cnt[phase][k * 8 + w] = __popc(bal[k]);
+  }
+  __syncthreads();
+  const int c = (lane < ITEMS * 8) ? S.cnt[phase][lane] : 0;
+  int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  total = __shfl_sync(0xffffffffu, inc, 31);
+  const int excl = inc - c;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) ex[k] = __shfl_sync(0xffffffffu, excl, k * 8 + w) + __popc(bal[k] & lt);
+  phase ^= 1;
+}
+// two independent flag streams (a, b) ranked separately in thread order
+__device__ __forceinline__ void block_flag_scan2(bool a, bool b, int &exa, int &exb, int &tota, int &totb, ScanScratch &S, int &phase) {
+  const int lane = lane_id(), w = warp_id();
+  const unsigned ba = __ballot_sync(0xffffffffu, a), bb = __ballot_sync(0xffffffffu, b);
+  if (lane == 0) S.cnt[phase][w] = __popc(ba);
+  if (lane == 1) S.cnt[phase][8 + w] = __popc(bb);
+  __syncthreads();
+  const int c = (lane < 16) ? S.cnt[phase][lane] : 0;
+  int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  tota = __shfl_sync(0xffffffffu, inc, 7);
+  totb = __shfl_sync(0xffffffffu, inc, 15) - tota;
+  const int excl = inc - c;
+  const unsigned lt = (1u << lane) - 1u;
+  exa = __shfl_sync(0xffffffffu, excl, w) + __popc(ba & lt);
+  exb = __shfl_sync(0xffffffffu, excl, 8 + w) - tota + __popc(bb & lt);
+  phase ^= 1;
+}
+
 __device__ __forceinline__ int block_sum_int(int v, BlockScratch &S) { int tot; block_excl_scan(v, S, tot); return tot; }
 
 // K-wide deterministic fp64 sum (fixed butterfly + fixed warp order): every thread gets the result in out[]

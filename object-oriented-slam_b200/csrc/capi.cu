@@ -87,6 +87,8 @@ int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const
   P.k0 = w.k0.as<unsigned>(); P.k1 = w.k1.as<unsigned>(); P.v0 = w.v0.as<unsigned>(); P.v1 = w.v1.as<unsigned>();
   P.parent = w.parent.as<int>(); P.count = w.count.as<int>();
   P.objn = w.objn.as<double>(); P.objnf = w.objnf.as<float4>();
+  ESLAM_CUDA_OK(h, w.symscratch.reserve((size_t)n_obj * 9 * 2 * 256 * sizeof(float4)));   // 2 * kSymQueue slots per seed warp
+  P.nncache = w.symscratch.as<float4>();
   P.d_crop = P.d_voxel = P.d_world = P.d_sym = P.d_final = nullptr; P.d_label = nullptr;
   if (want_dump) {
     ESLAM_CUDA_OK(h, w.d_crop.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_voxel.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_world.reserve(CAP * 24));
@@ -112,7 +114,7 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
   ExtractParamsDev prm = make_dev_params(h);
   const size_t frame_stride = (size_t)h->cam.rows * pitch;
   if (h->profiling) ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[0], s));
-  if (!host_depth) {
+  if (!host_depth && (h->profiling || n_obj < 128)) {   // one stream, kernels back to back (per-kernel event times are meaningful)
     if ((rc = extract_launch(h, s, depth_dev, pitch, frame_stride, 0, n_obj, prm, P))) return rc;
     if (h->profiling) ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[1], s));
     if ((rc = symmetry_finalize_launch(h, s, depth_dev, pitch, frame_stride, 0, n_obj, prm, P))) return rc;
@@ -121,29 +123,68 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
   }
   bool sorted = true;
   for (int i = 1; i < n_obj; i++) if (frame_of_obj[i] < frame_of_obj[i - 1]) { sorted = false; break; }
-  // Each CTA is latency bound, so a chunk must not run alone: every chunk gets its own compute stream and the chunks overlap each
-  // other (and the uploads still in flight); the caller's stream joins them at the end.
-  const int n_chunks = (sorted && n_frames >= 64) ? 4 : 1;
-  if (!h->copy_stream) ESLAM_CUDA_OK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  // Both kernels are latency / issue bound per CTA, so a chunk must not run alone: every chunk gets its own compute stream and the
+  // extraction of one chunk overlaps the symmetry search of another (and, for the host entry, the uploads still in flight); the
+  // caller's stream joins them at the end.  Device-resident input: chunks of objects.  Host input: chunks of frames (objects must be
+  // ordered by frame, which is how a frame stream arrives; otherwise one chunk).
+  int n_chunks = 1;
+  if (!host_depth) n_chunks = n_obj >= 512 ? kMaxChunks : (n_obj >= 256 ? 4 : 2);
+  else if (sorted && n_frames >= 64) n_chunks = 4;
+  if (host_depth && !h->copy_stream) ESLAM_CUDA_OK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (int c = 0; c < n_chunks; c++) {
     if (!h->chunk_ev[c]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
     if (!h->chunk_done[c]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
     if (!h->chunk_stream[c]) ESLAM_CUDA_OK(h, cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
   }
   if (!h->chunk_ev[15]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->chunk_ev[15], cudaEventDisableTiming));
-  ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_ev[15], s));   // metadata upload (prepare_batch) happened on s
+  ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_ev[15], s));   // metadata upload (prepare_batch) happened on s; earlier work on s is ordered too
+  const ExtractWorkspace &w = *h->ex;
+  const int rows = h->cam.rows, cols = h->cam.cols;
   int o = 0;
   for (int c = 0; c < n_chunks; c++) {
-    const int f0 = (int)((long long)n_frames * c / n_chunks), f1 = (int)((long long)n_frames * (c + 1) / n_chunks);
-    if (f1 > f0) ESLAM_CUDA_OK(h, cudaMemcpyAsync(const_cast<uint16_t *>(depth_dev) + (size_t)f0 * frame_stride, host_depth + (size_t)f0 * frame_stride,
-                                                   (size_t)(f1 - f0) * frame_stride * sizeof(uint16_t), cudaMemcpyHostToDevice, h->copy_stream));
-    ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_ev[c], h->copy_stream));
     cudaStream_t cs = (n_chunks == 1) ? s : h->chunk_stream[c];
-    ESLAM_CUDA_OK(h, cudaStreamWaitEvent(cs, h->chunk_ev[c], 0));
+    int o1;
+    if (host_depth) {
+      const int f0 = (int)((long long)n_frames * c / n_chunks), f1 = (int)((long long)n_frames * (c + 1) / n_chunks);
+      o1 = o;
+      if (sorted) { while (o1 < n_obj && frame_of_obj[o1] < f1) o1++; } else o1 = n_obj;
+      if (c == n_chunks - 1) o1 = n_obj;
+      if (sorted) {
+        // The kernels only ever read pixels inside the (int-truncated) boxes: crop and GetCenter sample inside the box, the lazy range
+        // image is read where isInRange holds.  Upload the union rectangle of each frame's boxes (64-byte aligned columns) instead
+        // of the whole 614 400-byte frame; frames without a valid box are not uploaded at all.
+        int k = o;
+        while (k < o1) {
+          const int f = frame_of_obj[k];
+          int x0 = cols, y0 = rows, x1 = -1, y1 = -1;
+          for (; k < o1 && frame_of_obj[k] == f; k++) {
+            const ObjMeta &m = w.meta_host[k];
+            if (m.pre_status != 0) continue;
+            x0 = m.x1 < x0 ? m.x1 : x0; y0 = m.y1 < y0 ? m.y1 : y0; x1 = m.x2 > x1 ? m.x2 : x1; y1 = m.y2 > y1 ? m.y2 : y1;
+          }
+          if (x1 < 0) continue;
+          x0 &= ~31; x1 = (x1 + 32) & ~31; if (x1 > cols) x1 = cols;
+          y1 = y1 + 1 < rows ? y1 + 1 : rows;
+          const size_t offp = (size_t)f * frame_stride + (size_t)y0 * pitch + x0;
+          if ((long long)(x1 - x0) * 4 >= (long long)pitch * 3)   // nearly full rows: one contiguous copy
+            ESLAM_CUDA_OK(h, cudaMemcpyAsync(const_cast<uint16_t *>(depth_dev) + (size_t)f * frame_stride + (size_t)y0 * pitch, host_depth + (size_t)f * frame_stride + (size_t)y0 * pitch,
+                                             (size_t)(y1 - y0) * pitch * sizeof(uint16_t), cudaMemcpyHostToDevice, h->copy_stream));
+          else
+            ESLAM_CUDA_OK(h, cudaMemcpy2DAsync(const_cast<uint16_t *>(depth_dev) + offp, pitch * sizeof(uint16_t), host_depth + offp, pitch * sizeof(uint16_t),
+                                               (size_t)(x1 - x0) * sizeof(uint16_t), (size_t)(y1 - y0), cudaMemcpyHostToDevice, h->copy_stream));
+          h->h2d_bytes += (size_t)(x1 - x0) * (size_t)(y1 - y0) * sizeof(uint16_t);
+        }
+      } else if (f1 > f0) {
+        ESLAM_CUDA_OK(h, cudaMemcpyAsync(const_cast<uint16_t *>(depth_dev) + (size_t)f0 * frame_stride, host_depth + (size_t)f0 * frame_stride,
+                                         (size_t)(f1 - f0) * frame_stride * sizeof(uint16_t), cudaMemcpyHostToDevice, h->copy_stream));
+        h->h2d_bytes += (size_t)(f1 - f0) * frame_stride * sizeof(uint16_t);
+      }
+      ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_ev[c], h->copy_stream));
+      ESLAM_CUDA_OK(h, cudaStreamWaitEvent(cs, h->chunk_ev[c], 0));
+    } else {
+      o1 = (int)((long long)n_obj * (c + 1) / n_chunks);
+    }
     if (cs != s) ESLAM_CUDA_OK(h, cudaStreamWaitEvent(cs, h->chunk_ev[15], 0));
-    int o1 = o;
-    if (sorted) { while (o1 < n_obj && frame_of_obj[o1] < f1) o1++; } else o1 = n_obj;
-    if (c == n_chunks - 1) o1 = n_obj;
     if ((rc = extract_launch(h, cs, depth_dev, pitch, frame_stride, o, o1 - o, prm, P))) return rc;
     if ((rc = symmetry_finalize_launch(h, cs, depth_dev, pitch, frame_stride, o, o1 - o, prm, P))) return rc;
     if (cs != s) { ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_done[c], cs)); ESLAM_CUDA_OK(h, cudaStreamWaitEvent(s, h->chunk_done[c], 0)); }
@@ -239,7 +280,7 @@ void eslam_destroy(EslamHandle *h) {
   for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (int i = 0; i < 16; i++) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  for (int i = 0; i < 4; i++) { if (h->chunk_stream[i]) cudaStreamDestroy(h->chunk_stream[i]); if (h->chunk_done[i]) cudaEventDestroy(h->chunk_done[i]); }
+  for (int i = 0; i < kMaxChunks; i++) { if (h->chunk_stream[i]) cudaStreamDestroy(h->chunk_stream[i]); if (h->chunk_done[i]) cudaEventDestroy(h->chunk_done[i]); }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -264,6 +305,7 @@ int eslam_get_stage_ms(EslamHandle *h, float ms[3]) {
 
 const char *eslam_last_error(EslamHandle *h) { return h ? h->err.c_str() : "null handle"; }
 long long eslam_launch_count(EslamHandle *h) { return h ? h->launches : 0; }
+unsigned long long eslam_h2d_bytes(EslamHandle *h) { return h ? h->h2d_bytes : 0; }
 
 size_t eslam_sizeof_params(void) { return sizeof(EslamParams); }
 size_t eslam_sizeof_camera(void) { return sizeof(EslamCamera); }
@@ -290,13 +332,13 @@ int eslam_extract_ground_plane_host(EslamHandle *h, int n_frames, const uint16_t
   return plane_extract(h, h->stream, n_frames, h->ex->depth.as<uint16_t>(), pitch, plane_cam, found, n_inliers);
 }
 
-// test/bench hook: symmetry work counters of object `obj` of the last batch: out = {cost evaluations, NN queries, mirrored points, n_sym}
-int eslam_debug_counters(EslamHandle *h, int obj, unsigned long long out[4]) {
+// test/bench hook: symmetry work counters of object `obj` of the last batch: out = {cost evaluations (per half), NN scans, mirrored points, n_sym, NN cache hits}
+int eslam_debug_counters(EslamHandle *h, int obj, unsigned long long out[5]) {
   if (!h || !h->ex || obj < 0 || obj >= h->ex->n_obj) return ESLAM_ERR_BAD_ARG;
   cudaSetDevice(h->device);
   ObjState st;
   ESLAM_CUDA_OK(h, cudaMemcpy(&st, h->ex->state.as<ObjState>() + obj, sizeof(ObjState), cudaMemcpyDeviceToHost));
-  out[0] = st.n_evals; out[1] = st.n_queries; out[2] = st.n_points; out[3] = (unsigned long long)st.n_sym;
+  out[0] = st.n_evals; out[1] = st.n_queries; out[2] = st.n_points; out[3] = (unsigned long long)st.n_sym; out[4] = st.n_hits;
   return ESLAM_OK;
 }
 

@@ -42,6 +42,7 @@ struct PinBuf {
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+constexpr int kMaxChunks = 8;
 struct ExtractWorkspace;  // extract.cu
 struct GraphWorkspace;    // edges.cu
 struct SlamWorkspace;     // slam.cu
@@ -57,8 +58,9 @@ struct EslamHandle {
   cudaStream_t stream = nullptr;  // owned stream used by the *_host entry points
   cudaStream_t copy_stream = nullptr;  // H2D stream of the pipelined *_host extraction
   cudaEvent_t chunk_ev[16] = {};
-  cudaStream_t chunk_stream[4] = {};   // per-chunk compute streams: chunks overlap each other and the remaining uploads
-  cudaEvent_t chunk_done[4] = {};
+  cudaStream_t chunk_stream[8] = {};   // per-chunk compute streams: chunks overlap each other and the remaining uploads
+  cudaEvent_t chunk_done[8] = {};
+  unsigned long long h2d_bytes = 0;    // depth bytes uploaded by the *_host extraction entry (running total)
   bool plane_set = false;
   double plane_world[4] = {0, 0, 1, 0};
   long long launches = 0;

@@ -108,25 +108,29 @@ __device__ __forceinline__ float4 voxel_centroid(const float4 *pts, const unsign
 }
 
 constexpr int kExtractThreads = 256;   // 3 CTAs/SM: different objects sit in different phases, hiding the many block barriers
+constexpr int kSmemParents = 12288;    // 48 KB of dynamic shared memory per CTA (3 CTAs/SM still fit in 227 KB)
 __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride, const ObjMeta *__restrict__ metas,
                                                       ObjState *__restrict__ states, ExtractParamsDev prm, ExtractPtrs W) {
   __shared__ BlockScratch S;
   __shared__ RadixScratch RS;
-  __shared__ int s_sel, s_K;
+  __shared__ ScanScratch SS;
+  __shared__ int s_sel;
+  extern __shared__ int s_parent[];   // union-find parents / cluster labels when the filtered cloud fits (kSmemParents), else HBM
+  int phase = 0;
   const int tid = threadIdx.x;
   const ObjMeta m = metas[blockIdx.x];
   ObjState &st = states[blockIdx.x];
   if (tid == 0) {
     st.status = m.pre_status;
     st.n_crop = st.n_voxel = st.n_plane = st.n_clusters = st.n_cluster = st.n_sym = st.n_final = 0;
-    st.run_sym = 0; st.symtype = m.symtype; st.best_seed = -1; st.done = 0; st.n_evals = 0; st.n_queries = 0; st.n_points = 0;
+    st.run_sym = 0; st.symtype = m.symtype; st.best_seed = -1; st.done = 0; st.n_evals = 0; st.n_queries = 0; st.n_points = 0; st.n_hits = 0;
     for (int k = 0; k < 4; k++) st.bbox_i[k] = (int)m.bbox[k];
     for (int s = 0; s < 9; s++) { st.seed_prob[s] = st.seed_init[s] = st.seed_final[s] = st.seed_dual[s] = 0; for (int k = 0; k < 4; k++) st.seed_plane[s][k] = 0; }
   }
   if (m.pre_status != 0) return;
   float4 *A = W.ptsA + m.off, *B = W.ptsB + m.off, *Cc = W.ptsC + m.off;
   unsigned *k0 = W.k0 + m.off, *k1 = W.k1 + m.off, *v0 = W.v0 + m.off, *v1 = W.v1 + m.off;
-  int *parent = W.parent + m.off, *count = W.count + m.off;
+  int *parent = W.parent + m.off, *count = W.count + m.off;   // parent is re-pointed to shared memory once n3 is known
   const uint16_t *img = depth + (size_t)m.frame * frame_stride;
   const se3 Twc = se3_load(m.Twc);
   const hom34 Twc_h = se3_hom(Twc);
@@ -135,26 +139,32 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
   int n1 = 0;
   {
     const int total = m.nx * m.ny;
-    for (int tile = 0; tile < total; tile += blockDim.x) {
-      int i = tile + tid;
-      bool keep = false;
-      double X = 0, Y = 0, Z = 0;
-      if (i < total) {
-        int iy = i / m.nx, ix = i - iy * m.nx;
-        int x = m.x1 + 3 * ix, y = m.y1 + 3 * iy;
-        unsigned short d = img[(size_t)y * pitch + x];
-        Z = d / prm.scale;
-        if (!(Z <= 0.1 || Z > prm.depth_range)) {
-          keep = true;
-          X = (x - prm.cx) * Z / prm.fx;
-          Y = (y - prm.cy) * Z / prm.fy;
+    for (int tile = 0; tile < total; tile += 4 * kExtractThreads) {
+      unsigned short d[4]; int px[4], py[4]; bool keep[4]; int ex[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {   // four independent strided loads in flight per thread
+        const int i = tile + k * kExtractThreads + tid;
+        d[k] = 0; px[k] = 0; py[k] = 0;
+        if (i < total) {
+          const int iy = i / m.nx, ix = i - iy * m.nx;
+          px[k] = m.x1 + 3 * ix; py[k] = m.y1 + 3 * iy;
+          d[k] = img[(size_t)py[k] * pitch + px[k]];
         }
       }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const double Z = d[k] / prm.scale;
+        keep[k] = (tile + k * kExtractThreads + tid < total) && !(Z <= 0.1 || Z > prm.depth_range);
+      }
       int tot;
-      int ex = block_excl_scan(keep ? 1 : 0, S, tot);
-      if (keep) {
-        A[n1 + ex] = make_float4((float)X, (float)Y, (float)Z, 0.0f);   // QuadricPointCloudToPcl: double -> float
-        if (W.d_crop) { double *q = W.d_crop + 3 * (size_t)(m.off + n1 + ex); q[0] = X; q[1] = Y; q[2] = Z; }
+      block_flag_scan<4>(keep, ex, tot, SS, phase);
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (keep[k]) {
+        const double Z = d[k] / prm.scale;
+        const double X = (px[k] - prm.cx) * Z / prm.fx;
+        const double Y = (py[k] - prm.cy) * Z / prm.fy;
+        A[n1 + ex[k]] = make_float4((float)X, (float)Y, (float)Z, 0.0f);   // QuadricPointCloudToPcl: double -> float
+        if (W.d_crop) { double *q = W.d_crop + 3 * (size_t)(m.off + n1 + ex[k]); q[0] = X; q[1] = Y; q[2] = Z; }
       }
       n1 += tot;
     }
@@ -177,21 +187,20 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
           keep = plane_signed_dist(prm.plane, pw) > prm.plane_margin;  // ApplySupportingPlaneFilter
         }
       }
-      int tot;
-      int packed = (head ? 1 : 0) | (keep ? 0x10000 : 0);
-      int ex = block_excl_scan(packed, S, tot);
-      int hr = ex & 0xffff, kr = ex >> 16;
+      int hr, kr, toth, totk;
+      block_flag_scan2(head, keep, hr, kr, toth, totk, SS, phase);
       if (head && W.d_voxel) { double *q = W.d_voxel + 3 * (size_t)(m.off + n2 + hr); q[0] = pc.x; q[1] = pc.y; q[2] = pc.z; }
       if (keep) {
         B[n3 + kr] = make_float4((float)pw.x, (float)pw.y, (float)pw.z, 0.0f);   // QuadricPointCloudToPclXYZ
         if (W.d_world) { double *q = W.d_world + 3 * (size_t)(m.off + n3 + kr); q[0] = pw.x; q[1] = pw.y; q[2] = pw.z; }
       }
-      n2 += tot & 0xffff; n3 += tot >> 16;
+      n2 += toth; n3 += totk;
     }
   }
   __syncthreads();
   if (tid == 0) { st.n_crop = n1; st.n_voxel = n2; st.n_plane = n3; }
   if (n3 < 1) { if (tid == 0) st.status = ESLAM_OBJ_NO_POINTS_AFTER_PLANE; return; }
+  if (n3 <= kSmemParents) parent = s_parent;   // block-uniform: pointer chasing at shared-memory instead of L2 latency
 
   // ---------------- S5: GetCenter (EllipsoidExtractor.cpp:583-643) ----------------
   if (tid == 0) {
@@ -255,8 +264,11 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
     const float r2 = prm.cluster_r2;
     int pow2 = 1;
     while (pow2 < n3) pow2 <<= 1;
-    // Warp-converged neighbour search: every lane walks the same 9 (dz,dy) rows; the data-dependent scan of a row is
-    // re-converged with __any_sync each step, so divergent union-find retries never serialise the rest of the warp.
+    // Warp-converged neighbour search over the FORWARD half of the 27-cell neighbourhood (each unordered pair is tested exactly once,
+    // from the point that comes first in (z, y, x) cell order; l2_simple is symmetric to the last bit): the rest of the own cell and
+    // cell x+1 by walking on from the point's own sorted position, then rows (dz,dy) = (0,+1), (+1,-1), (+1,0), (+1,+1) over x-1..x+1.
+    // The data-dependent scan of a row is re-converged with __any_sync each step, so divergent union-find retries never serialise
+    // the rest of the warp.
     for (int base = 0; base < n3; base += blockDim.x) {
       const int pos = base + tid;
       const bool act = pos < n3;
@@ -268,11 +280,13 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
       }
       const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
 #pragma unroll 1
-      for (int row = 0; row < 9; row++) {
-        const int zz = cz + row / 3 - 1, yy = cy + row % 3 - 1;
-        const bool valid = act && zz >= 0 && zz < nz && yy >= 0 && yy < ny;
+      for (int row = 0; row < 5; row++) {
+        const int zz = cz + (row >= 2 ? 1 : 0), yy = cy + (row == 0 ? 0 : (row == 1 ? 1 : row - 3));
+        const bool valid = act && zz < nz && yy >= 0 && yy < ny;
         unsigned khi = 0; int q = n3;
-        if (valid) {
+        if (row == 0) {
+          if (valid) { khi = (unsigned)((zz * ny + yy) * nx + xhi); q = pos + 1; }
+        } else if (valid) {
           unsigned klo = (unsigned)((zz * ny + yy) * nx + xlo);
           khi = (unsigned)((zz * ny + yy) * nx + xhi);
           q = 0;
@@ -283,14 +297,24 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
           if (!__any_sync(0xffffffffu, more)) break;
           if (more) {
             int j = (int)v0[q];
-            if (j < i && l2_simple(p, B[j]) < r2) uf_union(parent, i, j);   // RadiusResultSet::addPoint: dist < radius^2
+            if (l2_simple(p, B[j]) < r2) uf_union(parent, i, j);   // RadiusResultSet::addPoint: dist < radius^2
             q++;
           }
         }
       }
     }
     __syncthreads();
-    for (int i = tid; i < n3; i += blockDim.x) { int r = uf_find(parent, i); k1[i] = (unsigned)r; atomicAdd(count + r, 1); }
+    // flatten; cluster sizes with one atomic per (warp, root)
+    for (int base = 0; base < n3; base += blockDim.x) {
+      const int i = base + tid;
+      const bool act = i < n3;
+      const int r = act ? uf_find(parent, i) : -1 - (tid & 31);
+      const unsigned peers = __match_any_sync(0xffffffffu, r);
+      if (act) {
+        k1[i] = (unsigned)r;
+        if ((__ffs(peers) - 1) == (tid & 31)) atomicAdd(count + r, __popc(peers));
+      }
+    }
     __syncthreads();
     for (int i = tid; i < n3; i += blockDim.x) parent[i] = (int)k1[i];   // flattened labels (root = min index of the component)
     __syncthreads();
@@ -298,10 +322,10 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
     int K = 0;
     for (int tile = 0; tile < n3; tile += blockDim.x) {
       int i = tile + tid;
-      bool acc = (i < n3) && (parent[i] == i) && (count[i] >= prm.min_cluster);
-      int tot;
-      int ex = block_excl_scan(acc ? 1 : 0, S, tot);
-      if (acc) v1[K + ex] = (unsigned)i;
+      const bool acc[1] = {(i < n3) && (parent[i] == i) && (count[i] >= prm.min_cluster)};
+      int tot, ex[1];
+      block_flag_scan<1>(acc, ex, tot, SS, phase);
+      if (acc[0]) v1[K + ex[0]] = (unsigned)i;
       K += tot;
     }
     __syncthreads();
@@ -311,7 +335,7 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
         while (b >= 0 && count[v1[b]] < c) { v1[b + 1] = v1[b]; b--; }
         v1[b + 1] = r;
       }
-      st.n_clusters = K; s_K = K; s_sel = -1;
+      st.n_clusters = K; s_sel = -1;
     }
     __syncthreads();
     // first cluster whose minimum distance to the centre is < CenterDis (or the only cluster)  :696-714
@@ -347,10 +371,10 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
     const int root = (int)v1[sel];
     for (int tile = 0; tile < n3; tile += blockDim.x) {
       int i = tile + tid;
-      bool in = (i < n3) && (parent[i] == root);
-      int tot;
-      int ex = block_excl_scan(in ? 1 : 0, S, tot);
-      if (in) Cc[nc + ex] = B[i];
+      const bool in[1] = {(i < n3) && (parent[i] == root)};
+      int tot, ex[1];
+      block_flag_scan<1>(in, ex, tot, SS, phase);
+      if (in[0]) Cc[nc + ex[0]] = B[i];
       nc += tot;
     }
   }
@@ -437,12 +461,13 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
       head = (j == 0) || (k0[j - 1] != k0[j]);
       if (head) { float4 c = voxel_centroid(Cc, k0, v0, j, nc); po = hom_apply(Tow_h, mk3((double)c.x, (double)c.y, (double)c.z)); }
     }
-    int tot;
-    int ex = block_excl_scan(head ? 1 : 0, S, tot);
+    const bool hd[1] = {head};
+    int tot, ex[1];
+    block_flag_scan<1>(hd, ex, tot, SS, phase);
     if (head) {
-      double *q = objn + 3 * (size_t)(M + ex); q[0] = po.x; q[1] = po.y; q[2] = po.z;
-      objnf[M + ex] = make_float4((float)po.x, (float)po.y, (float)po.z, 0.0f);   // initializeKDTree: double -> float
-      if (W.d_sym) { double *qq = W.d_sym + 3 * (size_t)(m.off + M + ex); qq[0] = po.x; qq[1] = po.y; qq[2] = po.z; }
+      double *q = objn + 3 * (size_t)(M + ex[0]); q[0] = po.x; q[1] = po.y; q[2] = po.z;
+      objnf[M + ex[0]] = make_float4((float)po.x, (float)po.y, (float)po.z, 0.0f);   // initializeKDTree: double -> float
+      if (W.d_sym) { double *qq = W.d_sym + 3 * (size_t)(m.off + M + ex[0]); qq[0] = po.x; qq[1] = po.y; qq[2] = po.z; }
     }
     M += tot;
   }
@@ -456,7 +481,13 @@ int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, si
                    const ExtractPtrs &ptrs) {
   ExtractWorkspace &w = *h->ex;
   if (n_obj <= 0) return ESLAM_OK;
-  extract_kernel<<<n_obj, kExtractThreads, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemParents * (int)sizeof(int)));
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(extract_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set = true;
+  }
+  extract_kernel<<<n_obj, kExtractThreads, kSmemParents * sizeof(int), s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs);
   ESLAM_LAUNCHED(h);
   ESLAM_CUDA_OK(h, cudaGetLastError());
   return ESLAM_OK;

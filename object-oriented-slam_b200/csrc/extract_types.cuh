@@ -24,7 +24,7 @@ struct ObjState {  // device resident, one per object
   double T_oc[7];           // camera pose in the object-normalised frame
   double P[12];             // K[I|0] hom(T_oc^-1)
   double seed_prob[9], seed_init[9], seed_final[9], seed_plane[9][4], seed_dual[9];
-  unsigned long long n_evals, n_queries, n_points;   // symmetry work counters (cost evaluations, NN queries, mirrored points)
+  unsigned long long n_evals, n_queries, n_points, n_hits;   // symmetry work counters (cost evaluations, NN scans, mirrored points, NN cache hits)
 };
 
 struct ExtractParamsDev {
@@ -50,13 +50,14 @@ struct ExtractPtrs {  // device pointers of the per-point workspace (total capac
   int *parent, *count;
   double *objn;     // [cap*3] object-normalised cloud (double)
   float4 *objnf;    // float copy for the NN search
+  float4 *nncache;  // [n_obj*9][2*kSymQueue] per-seed NN cache of the symmetry kernel (query float3 + neighbour index)
   // optional stage dump (device mirrors, NULL when no dump requested)
   double *d_crop, *d_voxel, *d_world, *d_sym, *d_final;  // d_final has 4x capacity
   int *d_label;
 };
 
 struct ExtractWorkspace {
-  DevBuf meta, state, out, ptsA, ptsB, ptsC, k0, k1, v0, v1, parent, count, objn, objnf, symscratch;
+  DevBuf meta, state, out, ptsA, ptsB, ptsC, k0, k1, v0, v1, parent, count, objn, objnf, symscratch;   // symscratch = NN cache
   DevBuf d_crop, d_voxel, d_world, d_sym, d_final, d_label;
   DevBuf depth;   // staging for the *_host entry point
   PinBuf pin_meta, pin_out, pin_depth;

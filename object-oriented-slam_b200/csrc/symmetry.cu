@@ -35,6 +35,7 @@ struct PlanePair {   // per-evaluation constants of GetSymmetryPointOfPlane for 
 struct SymBlock {
   const uint16_t *img; size_t pitch;
   const double *objn; const float4 *nn_g;
+  float4 *cache;   // per-warp NN cache in HBM/L2: slot i = (float query x, y, z, nearest index) of mirrored point i at its last full scan
   int M, symtype, npts, in_smem;
   int bx0, bx2, by1, by3, rows, cols;
   ObjState *st;
@@ -102,10 +103,19 @@ __device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsig
 __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) { return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32); }
 
+struct NNRes { double dis; int best; };
+// fp64 distance from the query to the FLOAT neighbour `best` of the shared-memory cloud (findMinimalDistanceWithKdTree :159-163)
+__device__ __forceinline__ double dist_to_neighbour(const SymBlock &B, d3 pm, int best) {
+  const unsigned long long X = B.X2[best >> 1], Y = B.Y2[best >> 1], Z = B.Z2[best >> 1];
+  const int sh = (best & 1) * 32;
+  const double bx = (double)__uint_as_float((unsigned)(X >> sh)), by = (double)__uint_as_float((unsigned)(Y >> sh)), bz = (double)__uint_as_float((unsigned)(Z >> sh));
+  const double dx = pm.x - bx, dy = pm.y - by, dz = pm.z - bz;
+  return sqrt(dx * dx + dy * dy + dz * dz);
+}
 // Exact float NN (flann::L2_Simple operation order; minimum r = ((dx^2 + dy^2) + dz^2), first index on ties -- the oracle's linear
 // scan) + fp64 distance to the float neighbour (findMinimalDistanceWithKdTree :140-166).  All lanes scan the same pair of cloud
 // points at the same time (broadcast LDS.64 of the pair-interleaved SoA copy); the loop body is branch free.
-__device__ __noinline__ double nn_distance(const SymBlock &B, d3 pm) {
+__device__ __noinline__ NNRes nn_distance(const SymBlock &B, d3 pm) {
   const float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
   float bd = FLT_MAX; int best = 0;
   const int M = B.M;
@@ -140,14 +150,15 @@ __device__ __noinline__ double nn_distance(const SymBlock &B, d3 pm) {
     bx = q.x; by = q.y; bz = q.z;
   }
   const double dx = pm.x - (double)bx, dy = pm.y - (double)by, dz = pm.z - (double)bz;
-  return sqrt(dx * dx + dy * dy + dz * dz);
+  NNRes r; r.dis = sqrt(dx * dx + dy * dy + dz * dz); r.best = best;
+  return r;
 }
 
 // Warp-cooperative variant for a PARTIAL chunk of cq <= 16 queries (shared-memory cloud): the 32 lanes are split into
 // L = 32 / pow2ceil(cq) parts, part p scans the p-th slice of the cloud for query (lane % slots); the parts are merged with an
 // (r, index) lexicographic butterfly -- slices are index-ordered, so "smallest r, then smallest index" is exactly the linear scan's
 // first-minimum rule.  Returns the distance for lanes with part == 0 && q < cq (other lanes: 0).
-__device__ __noinline__ double nn_distance_split(const SymBlock &B, d3 pm, int slots, bool active) {
+__device__ __noinline__ NNRes nn_distance_split(const SymBlock &B, d3 pm, int slots, bool active) {
   const int lane = threadIdx.x & 31;
   const int L = 32 / slots;
   const int part = lane / slots;
@@ -170,12 +181,10 @@ __device__ __noinline__ double nn_distance_split(const SymBlock &B, d3 pm, int s
     const int obest = __shfl_xor_sync(0xffffffffu, best, o);
     if (obd < bd || (obd == bd && obest < best)) { bd = obd; best = obest; }
   }
-  if (!active || part != 0 || best == 0x7fffffff) return 0.0;
-  const unsigned long long X = B.X2[best >> 1], Y = B.Y2[best >> 1], Z = B.Z2[best >> 1];
-  const int sh = (best & 1) * 32;
-  const double bx = (double)__uint_as_float((unsigned)(X >> sh)), by = (double)__uint_as_float((unsigned)(Y >> sh)), bz = (double)__uint_as_float((unsigned)(Z >> sh));
-  const double dx = pm.x - bx, dy = pm.y - by, dz = pm.z - bz;
-  return sqrt(dx * dx + dy * dy + dz * dz);
+  NNRes r; r.dis = 0.0; r.best = -1;
+  if (!active || part != 0 || best == 0x7fffffff) return r;
+  r.dis = dist_to_neighbour(B, pm, best); r.best = best;
+  return r;
 }
 
 // edge error (= -mean ln P) of the plane stored in shared memory at `pl`; warp-collective, every lane returns the same value.
@@ -196,24 +205,44 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
     const double sinv = B.sinv;
     for (int h0 = 0; h0 < npts; h0 += B.M) {
       const int cntp = min(B.M, npts - h0);
-      int qn = 0;
+      int qn = 0, hits = 0;
       for (int base = 0; base < cntp; base += 32) {
         const int li = base + lane;
         int cls = 0;
-        if (li < cntp) { cls = classify(B, mirrored(B, PP, h0 + li)); W.dis[li] = 0.0; }
+        if (li < cntp) {
+          const float4 c = B.cache[h0 + li];   // issued before the fp64 classification chain
+          const d3 pm = mirrored(B, PP, h0 + li);
+          cls = classify(B, pm);
+          double dis = 0.0;
+          // NN cache: a bit-identical float query has the same exact nearest neighbour (the +-1e-9 finite-difference perturbations
+          // of the plane almost never change the float-rounded mirrored point), so the brute-force scan is skipped.
+          if (cls == 1 && __float_as_uint(c.x) == __float_as_uint((float)pm.x) && __float_as_uint(c.y) == __float_as_uint((float)pm.y) &&
+              __float_as_uint(c.z) == __float_as_uint((float)pm.z)) {
+            dis = dist_to_neighbour(B, pm, __float_as_int(c.w));
+            cls = 3;
+          }
+          W.dis[li] = dis;
+        }
         const unsigned need = __ballot_sync(0xffffffffu, cls == 1);
         if (cls == 1) W.queue[qn + __popc(need & ((1u << lane) - 1u))] = (unsigned short)li;
         qn += __popc(need);
+        hits += __popc(__ballot_sync(0xffffffffu, cls == 3));
         invalid += __popc(__ballot_sync(0xffffffffu, cls == 2));
       }
       __syncwarp();
-      if (lane == 0) { atomicAdd(&B.st->n_evals, 1ULL); atomicAdd(&B.st->n_queries, (unsigned long long)qn); atomicAdd(&B.st->n_points, (unsigned long long)cntp); }
+      if (lane == 0) {
+        atomicAdd(&B.st->n_evals, 1ULL); atomicAdd(&B.st->n_queries, (unsigned long long)qn); atomicAdd(&B.st->n_points, (unsigned long long)cntp);
+        atomicAdd(&B.st->n_hits, (unsigned long long)hits);
+      }
       for (int qb = 0; qb < qn; qb += 32) {
         const int cq = min(32, qn - qb);
-        if (cq > 16 || !B.in_smem) {
+        if (cq > 16) {
           if (lane < cq) {
             const int li = W.queue[qb + lane];
-            W.dis[li] = nn_distance(B, mirrored(B, PP, h0 + li));
+            const d3 pm = mirrored(B, PP, h0 + li);
+            const NNRes r = nn_distance(B, pm);
+            W.dis[li] = r.dis;
+            B.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
           }
         } else {   // partial chunk: split every query's scan over several lanes
           int slots = 1;
@@ -221,8 +250,12 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
           const int q = lane % slots;
           const bool active = q < cq;
           const int li = W.queue[qb + (active ? q : 0)];
-          const double dis = nn_distance_split(B, mirrored(B, PP, h0 + li), slots, active);
-          if (active && lane < slots) W.dis[li] = dis;
+          const d3 pm = mirrored(B, PP, h0 + li);
+          const NNRes r = nn_distance_split(B, pm, slots, active);
+          if (active && lane < slots) {
+            W.dis[li] = r.dis;
+            B.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
+          }
         }
       }
       __syncwarp();
@@ -243,7 +276,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
       if (idx < npts) {
         const d3 pm = mirrored(B, PP, idx);
         cls = classify(B, pm);
-        const double dis = (cls == 1) ? nn_distance(B, pm) : 0.0;
+        const double dis = (cls == 1) ? nn_distance(B, pm).dis : 0.0;
         lnP = -0.5 * sinv * sinv * dis * dis;
       }
       const int cnt = min(32, npts - base);
@@ -449,7 +482,7 @@ __device__ __noinline__ void finalize_object(const ObjMeta &m, ObjState &st, con
 // slower seed and the SM keeps ~28 independent warps in flight (the kernel is latency / issue bound, not bandwidth bound).
 __global__ void __launch_bounds__(32, 28) symmetry_finalize_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride,
                                                                    const ObjMeta *__restrict__ metas, ObjState *__restrict__ states, ExtractParamsDev prm,
-                                                                   ExtractPtrs W, EslamEllipsoidOut *__restrict__ outs) {
+                                                                   ExtractPtrs W, EslamEllipsoidOut *__restrict__ outs, int obj0) {
   __shared__ SymBlock B;
   __shared__ SymWarp Wp;
   const int lane = threadIdx.x & 31;
@@ -476,8 +509,11 @@ __global__ void __launch_bounds__(32, 28) symmetry_finalize_kernel(const uint16_
   const int M = st.n_sym;
   const double *objn = W.objn + 3 * (size_t)m.off;
   const float4 *objnf = W.objnf + m.off;
+  float4 *cache = W.nncache + (size_t)(obj0 * 9 + blockIdx.x) * (2 * kSymQueue);
   {
     const bool in_smem = M <= kSymSmemPts;
+    // invalidate this warp's NN cache: a NaN x never equals a float-converted finite query
+    if (M <= kSymQueue) for (int j = lane; j < 2 * M; j += 32) cache[j] = make_float4(__uint_as_float(0x7fffffffu), 0.0f, 0.0f, 0.0f);
     if (in_smem) for (int j = lane; j < (M + 1) / 2; j += 32) {
       const float4 a = objnf[2 * j];
       const float far_ = 1.0e30f;   // (q - 1e30)^2 overflows to +inf: never < FLT_MAX, so the pad can never win
@@ -486,6 +522,7 @@ __global__ void __launch_bounds__(32, 28) symmetry_finalize_kernel(const uint16_
     }
     if (lane == 0) {
       B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch; B.st = &st;
+      B.cache = cache;
       B.objn = objn; B.nn_g = objnf; B.M = M; B.symtype = m.symtype; B.npts = (m.symtype == 2) ? 2 * M : M; B.in_smem = in_smem ? 1 : 0;
       for (int i = 0; i < 12; i++) B.P[i] = st.P[i];
       B.cam[0] = st.T_oc[0]; B.cam[1] = st.T_oc[1]; B.cam[2] = st.T_oc[2];
@@ -524,7 +561,7 @@ int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *dep
   static bool attr_set = false;
   if (!attr_set) { ESLAM_CUDA_OK(h, cudaFuncSetAttribute(symmetry_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); attr_set = true; }
   symmetry_finalize_kernel<<<9 * n_obj, 32, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs,
-                                                    w.out.as<EslamEllipsoidOut>() + obj0);
+                                                    w.out.as<EslamEllipsoidOut>() + obj0, obj0);
   ESLAM_LAUNCHED(h);
   ESLAM_CUDA_OK(h, cudaGetLastError());
   return ESLAM_OK;

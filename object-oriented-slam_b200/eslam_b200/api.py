@@ -22,7 +22,7 @@ _LIB = None
 
 ABI_SYMBOLS = [
     "eslam_abi_version", "eslam_default_params", "eslam_default_camera", "eslam_create", "eslam_destroy", "eslam_last_error",
-    "eslam_launch_count", "eslam_extract_ground_plane_host", "eslam_extract_ground_plane_dev", "eslam_plane_to_world",
+    "eslam_launch_count", "eslam_h2d_bytes", "eslam_extract_ground_plane_host", "eslam_extract_ground_plane_dev", "eslam_plane_to_world",
     "eslam_set_supporting_plane", "eslam_calibrate_measurement", "eslam_estimate_ellipsoids_host", "eslam_estimate_ellipsoids_dev",
     "eslam_fetch_ellipsoids", "eslam_init_quadric", "eslam_edges_eval_host", "eslam_edges_upload", "eslam_edges_eval_dev",
     "eslam_edges_download", "eslam_optimize_objects_host", "eslam_optimize_slam_host", "eslam_pose_inverse", "eslam_pose_mul", "eslam_set_profiling", "eslam_get_stage_ms",
@@ -43,6 +43,7 @@ def load_library(path=None):
         lib = C.CDLL(p)
         lib.eslam_last_error.restype = C.c_char_p
         lib.eslam_launch_count.restype = C.c_longlong
+        lib.eslam_h2d_bytes.restype = C.c_ulonglong
         for n in ("eslam_sizeof_params", "eslam_sizeof_camera", "eslam_sizeof_ellipsoid_out", "eslam_sizeof_stage_dump", "eslam_sizeof_edge_batch", "eslam_sizeof_lm_stats"):
             getattr(lib, n).restype = C.c_size_t
         lib.eslam_plane_to_world.restype = None
@@ -125,6 +126,10 @@ class Handle:
     def launches(self):
         return int(self.lib.eslam_launch_count(self._h))
 
+    @property
+    def h2d_bytes(self):
+        return int(self.lib.eslam_h2d_bytes(self._h))
+
     # ---- batched entry points (host buffers) ----
     def set_supporting_plane(self, plane_world):
         p = _d(plane_world)
@@ -147,7 +152,7 @@ class Handle:
         return pl, found, ninl
 
     def debug_counters(self, obj):
-        out = (C.c_ulonglong * 4)()
+        out = (C.c_ulonglong * 5)()
         self.check(self.lib.eslam_debug_counters(self._h, C.c_int(obj), out), "eslam_debug_counters")
         return [int(v) for v in out]
 

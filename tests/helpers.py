@@ -60,3 +60,16 @@ def ellipsoid_close(a, b, rtol=1e-4):
 
 def dump_points(keep, name, n):
     return getattr(keep, name)[:n]
+
+
+def poison_outside_boxes(depth, frame_of_obj, bbox, seed=7):
+    """Copy of the depth batch with every pixel OUTSIDE the int-truncated boxes of its frame replaced by noise.  The path only reads
+    pixels inside a box (PointCloudFilter.cpp:31-52 crop, EllipsoidExtractor.cpp:583-643 centre samples, SymmetrySolver.cpp:75-84
+    isInRange before the range-image read), so results must not change -- the property the rectangle-only upload relies on."""
+    rng = np.random.default_rng(seed)
+    noisy = rng.integers(0, 30000, size=depth.shape, dtype=np.uint16)
+    keep = np.zeros(depth.shape, dtype=bool)
+    for f, b in zip(frame_of_obj, bbox):
+        x1, y1, x2, y2 = (int(v) for v in b)
+        keep[int(f), max(y1, 0):max(y2, 0), max(x1, 0):max(x2, 0)] = True
+    return np.where(keep, depth, noisy)

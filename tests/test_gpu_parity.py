@@ -9,7 +9,7 @@ import orc
 import eslam_b200 as E
 from eslam_b200 import synth
 from eslam_b200.api import EdgeGraph
-from helpers import K, ellipsoid_close, make_ba_problem
+from helpers import K, ellipsoid_close, make_ba_problem, poison_outside_boxes
 
 pytestmark = pytest.mark.gpu
 
@@ -141,6 +141,23 @@ def test_extraction_no_symmetry_and_edge_cases(handle):
     assert og[0].prob == 1.0 and og[3].status == 5 and og[2].status != 0
 
 
+@pytest.mark.parametrize("kind,n_frames", [("one_box", 4), ("multi_box", 2)])
+def test_pixels_outside_boxes_are_never_read(handle, kind, n_frames):
+    """The host entry uploads only the union rectangle of each frame's boxes: noise outside the boxes must not change one bit."""
+    depth, fo, bb, lb, tw = synth.make_batch(n_frames, kind)
+    handle.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+    a, _, _ = handle.estimate_ellipsoids(depth, fo, bb, lb, tw)
+    b, _, _ = handle.estimate_ellipsoids(poison_outside_boxes(depth, fo, bb), fo, bb, lb, tw)
+    assert bytes(a) == bytes(b)
+    assert sum(o.status == 0 for o in a) >= len(a) // 2
+    # device-resident entry with the full frames resident (chunked over streams when the batch is large) gives the same records
+    import torch
+    d = torch.from_numpy(np.ascontiguousarray(depth).view(np.int16)).cuda()
+    handle.estimate_ellipsoids_dev(d.data_ptr(), depth.shape[0], depth.shape[2], fo, bb, lb, tw)
+    c = handle.fetch_ellipsoids(len(fo))
+    assert bytes(c) == bytes(a)
+
+
 def test_missing_plane_is_an_error():
     h = E.Handle()
     depth, fo, bb, lb, tw = synth.make_batch(1)
@@ -214,6 +231,11 @@ def test_full_batch_properties(handle):
     a, _, _ = handle.estimate_ellipsoids(depth, fo, bb, lb, tw)
     b, _, _ = handle.estimate_ellipsoids(depth, fo, bb, lb, tw)
     assert bytes(a) == bytes(b)                                   # idempotent / deterministic to the bit
+    import torch
+    dres = torch.from_numpy(np.ascontiguousarray(depth).view(np.int16)).cuda()   # device-resident entry: object chunks on 4 streams
+    handle.estimate_ellipsoids_dev(dres.data_ptr(), depth.shape[0], depth.shape[2], fo, bb, lb, tw)
+    assert bytes(handle.fetch_ellipsoids(len(fo))) == bytes(a)
+    del dres
     ok = 0
     for o in a:
         assert o.n_crop >= o.n_voxel >= o.n_plane >= o.n_cluster >= 0 and o.n_sym <= max(o.n_cluster, 0)

@@ -295,3 +295,14 @@ def test_slam_mode_noise_floor():
     assert np.abs(e1 - e0).max() > 1e-6                                          # ... but far above the 1e-13 input change
     m0, _ = orc.optimize_objects(g0, p["init"], 2); m1, _ = orc.optimize_objects(g1, p["init"], 2)
     assert np.abs(m1 - m0).max() < np.abs(e1 - e0).max()
+
+
+def test_oracle_never_reads_pixels_outside_the_boxes():
+    """Restated reference behaviour the CUDA host entry relies on (it uploads only the boxes' union rectangle per frame): crop,
+    centre samples and the range-image reads of the symmetry cost all stay inside the int-truncated bbox."""
+    from eslam_b200 import synth
+    from helpers import poison_outside_boxes
+    depth, fo, bb, lb, tw = synth.make_batch(2, "one_box")
+    a, _, _, _ = orc.estimate_ellipsoids(depth, fo, bb, lb, tw, synth.GROUND_PLANE_WORLD)
+    b, _, _, _ = orc.estimate_ellipsoids(poison_outside_boxes(depth, fo, bb), fo, bb, lb, tw, synth.GROUND_PLANE_WORLD)
+    assert bytes(a) == bytes(b) and all(o.status == 0 for o in a)

@@ -12,5 +12,6 @@ c = np.array([h.debug_counters(i) for i in range(64)], float)
 ok = c[:, 0] > 0
 print("objects with evals:", ok.sum(), "status", [o.status for o in out][:16])
 c = c[ok]
-print("per object: evals %.0f  queries/eval %.1f  points/eval %.1f  n_sym %.1f" % (c[:,0].mean(), (c[:,1]/c[:,0]).mean(), (c[:,2]/c[:,0]).mean(), c[:,3].mean()))
+print("per object: half-evals %.0f  NN scans/half-eval %.1f  cache hits/half-eval %.1f  points/half-eval %.1f  n_sym %.1f  hit rate %.3f" % (
+    c[:,0].mean(), (c[:,1]/c[:,0]).mean(), (c[:,4]/c[:,0]).mean(), (c[:,2]/c[:,0]).mean(), c[:,3].mean(), (c[:,4].sum()/(c[:,4].sum()+c[:,1].sum()))))
 print("evals min/max", c[:,0].min(), c[:,0].max(), " first rows", c[:4])
