@@ -2,6 +2,8 @@
 // tiny per-object metadata, moves bulk data H2D/D2H for the *_host entry points and launches the kernels.
 // There is no CPU implementation of any hot-path stage in this library.
 #include <math.h>
+#include <stdlib.h>
+#include <chrono>
 #include <new>
 #include "common.cuh"
 #include "extract_types.cuh"
@@ -89,6 +91,8 @@ int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const
   P.objn = w.objn.as<double>(); P.objnf = w.objnf.as<float4>();
   ESLAM_CUDA_OK(h, w.symscratch.reserve((size_t)n_obj * 9 * 2 * 256 * sizeof(float4)));   // 2 * kSymQueue slots per seed warp
   P.nncache = w.symscratch.as<float4>();
+  ESLAM_CUDA_OK(h, w.symscratch2.reserve((size_t)n_obj * 9 * 2 * 256 * sizeof(uint4)));
+  P.pixcache = w.symscratch2.as<uint4>();
   P.d_crop = P.d_voxel = P.d_world = P.d_sym = P.d_final = nullptr; P.d_label = nullptr;
   if (want_dump) {
     ESLAM_CUDA_OK(h, w.d_crop.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_voxel.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_world.reserve(CAP * 24));
@@ -129,8 +133,21 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
   // ordered by frame, which is how a frame stream arrives; otherwise one chunk).
   int n_chunks = 1;
   if (!host_depth) n_chunks = n_obj >= 512 ? kMaxChunks : (n_obj >= 256 ? 4 : 2);
-  else if (sorted && n_frames >= 64) n_chunks = 4;
-  if (host_depth && !h->copy_stream) ESLAM_CUDA_OK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  else if (sorted && n_frames >= 64) n_chunks = h->host_chunks;
+  if (host_depth && !h->copy_stream) {
+    int lo = 0, hi = 0;
+    ESLAM_CUDA_OK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    ESLAM_CUDA_OK(h, cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, hi));   // pull kernels go ahead of queued compute CTAs
+  }
+  // pinned + mapped host input (cudaHostAlloc / cudaHostRegister; torch pin_memory()): the SMs pull the rectangles themselves
+  const uint16_t *host_mapped = nullptr;
+  if (host_depth && h->h2d_mode == 4 && (pitch % 8) == 0 && (h->cam.cols % 8) == 0 && ((uintptr_t)depth_dev % 16) == 0) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host_depth) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer && ((uintptr_t)attr.devicePointer % 16) == 0)
+      host_mapped = reinterpret_cast<const uint16_t *>(attr.devicePointer);
+    else
+      cudaGetLastError();
+  }
   for (int c = 0; c < n_chunks; c++) {
     if (!h->chunk_ev[c]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
     if (!h->chunk_done[c]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
@@ -140,6 +157,8 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
   ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_ev[15], s));   // metadata upload (prepare_batch) happened on s; earlier work on s is ordered too
   const ExtractWorkspace &w = *h->ex;
   const int rows = h->cam.rows, cols = h->cam.cols;
+  const bool trace = getenv("ESLAM_TRACE") != nullptr;
+  const auto t_issue0 = std::chrono::steady_clock::now();
   int o = 0;
   for (int c = 0; c < n_chunks; c++) {
     cudaStream_t cs = (n_chunks == 1) ? s : h->chunk_stream[c];
@@ -149,11 +168,22 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
       o1 = o;
       if (sorted) { while (o1 < n_obj && frame_of_obj[o1] < f1) o1++; } else o1 = n_obj;
       if (c == n_chunks - 1) o1 = n_obj;
-      if (sorted) {
+      if (host_mapped) {
+        ESLAM_CUDA_OK(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[15], 0));   // needs the ObjMeta table
+        if ((rc = pull_rects_launch(h, h->copy_stream, host_mapped, const_cast<uint16_t *>(depth_dev), pitch, frame_stride, o, o1 - o))) return rc;
+        for (int k = o; k < o1; k++) {
+          const ObjMeta &m = w.meta_host[k];
+          if (m.pre_status != 0) continue;
+          const int x0 = m.x1 & ~7, x1 = (m.x2 + 8) & ~7, y1 = m.y2 + 1;
+          h->h2d_bytes += (size_t)((x1 < cols ? x1 : cols) - x0) * (size_t)((y1 < rows ? y1 : rows) - m.y1) * sizeof(uint16_t);
+        }
+      } else if (sorted && h->h2d_mode != 0) {
         // The kernels only ever read pixels inside the (int-truncated) boxes: crop and GetCenter sample inside the box, the lazy range
         // image is read where isInRange holds.  Upload the union rectangle of each frame's boxes (64-byte aligned columns) instead
         // of the whole 614 400-byte frame; frames without a valid box are not uploaded at all.
         int k = o;
+        std::vector<cudaMemcpy3DBatchOp> &ops = h->ex->copy_ops;
+        ops.clear();
         while (k < o1) {
           const int f = frame_of_obj[k];
           int x0 = cols, y0 = rows, x1 = -1, y1 = -1;
@@ -165,14 +195,38 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
           if (x1 < 0) continue;
           x0 &= ~31; x1 = (x1 + 32) & ~31; if (x1 > cols) x1 = cols;
           y1 = y1 + 1 < rows ? y1 + 1 : rows;
+          if (h->h2d_mode == 1) { x0 = 0; x1 = cols; }
           const size_t offp = (size_t)f * frame_stride + (size_t)y0 * pitch + x0;
-          if ((long long)(x1 - x0) * 4 >= (long long)pitch * 3)   // nearly full rows: one contiguous copy
-            ESLAM_CUDA_OK(h, cudaMemcpyAsync(const_cast<uint16_t *>(depth_dev) + (size_t)f * frame_stride + (size_t)y0 * pitch, host_depth + (size_t)f * frame_stride + (size_t)y0 * pitch,
-                                             (size_t)(y1 - y0) * pitch * sizeof(uint16_t), cudaMemcpyHostToDevice, h->copy_stream));
-          else
-            ESLAM_CUDA_OK(h, cudaMemcpy2DAsync(const_cast<uint16_t *>(depth_dev) + offp, pitch * sizeof(uint16_t), host_depth + offp, pitch * sizeof(uint16_t),
-                                               (size_t)(x1 - x0) * sizeof(uint16_t), (size_t)(y1 - y0), cudaMemcpyHostToDevice, h->copy_stream));
-          h->h2d_bytes += (size_t)(x1 - x0) * (size_t)(y1 - y0) * sizeof(uint16_t);
+          uint16_t *dst = const_cast<uint16_t *>(depth_dev) + offp;
+          const uint16_t *src = host_depth + offp;
+          const size_t wbytes = (size_t)(x1 - x0) * sizeof(uint16_t), nrows = (size_t)(y1 - y0);
+          h->h2d_bytes += wbytes * nrows;
+          if (h->h2d_mode >= 3) {   // one batched call per chunk: the per-frame rectangles as pointer-to-pointer 3-D ops (element = 1 byte)
+            cudaMemcpy3DBatchOp op;
+            memset(&op, 0, sizeof(op));
+            op.src.type = cudaMemcpyOperandTypePointer; op.src.op.ptr.ptr = const_cast<uint16_t *>(src);
+            op.src.op.ptr.rowLength = pitch * sizeof(uint16_t); op.src.op.ptr.layerHeight = nrows;
+            op.dst.type = cudaMemcpyOperandTypePointer; op.dst.op.ptr.ptr = dst;
+            op.dst.op.ptr.rowLength = pitch * sizeof(uint16_t); op.dst.op.ptr.layerHeight = nrows;
+            op.extent.width = wbytes; op.extent.height = nrows; op.extent.depth = 1;
+            op.srcAccessOrder = cudaMemcpySrcAccessOrderStream; op.flags = 0;
+            ops.push_back(op);
+          } else if (h->h2d_mode == 1 || (long long)(x1 - x0) * 4 >= (long long)pitch * 3) {   // (nearly) full rows: one contiguous copy
+            ESLAM_CUDA_OK(h, cudaMemcpyAsync(dst - x0, src - x0, nrows * pitch * sizeof(uint16_t), cudaMemcpyHostToDevice, h->copy_stream));
+          } else {
+            ESLAM_CUDA_OK(h, cudaMemcpy2DAsync(dst, pitch * sizeof(uint16_t), src, pitch * sizeof(uint16_t), wbytes, nrows, cudaMemcpyHostToDevice, h->copy_stream));
+          }
+        }
+        if (!ops.empty()) {
+          size_t fail = 0;
+          cudaError_t e = cudaMemcpy3DBatchAsync(ops.size(), ops.data(), &fail, 0, h->copy_stream);
+          if (e != cudaSuccess) {   // driver without batched copies: issue them one by one, and stay in that mode
+            cudaGetLastError();
+            h->h2d_mode = 2;
+            for (const cudaMemcpy3DBatchOp &op : ops)
+              ESLAM_CUDA_OK(h, cudaMemcpy2DAsync(op.dst.op.ptr.ptr, op.dst.op.ptr.rowLength, op.src.op.ptr.ptr, op.src.op.ptr.rowLength, op.extent.width, op.extent.height,
+                                                 cudaMemcpyHostToDevice, h->copy_stream));
+          }
         }
       } else if (f1 > f0) {
         ESLAM_CUDA_OK(h, cudaMemcpyAsync(const_cast<uint16_t *>(depth_dev) + (size_t)f0 * frame_stride, host_depth + (size_t)f0 * frame_stride,
@@ -191,6 +245,8 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
     o = o1;
   }
   if (h->profiling) { ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[1], s)); ESLAM_CUDA_OK(h, cudaEventRecord(h->ev[2], s)); }
+  if (trace) fprintf(stderr, "[eslam] run_extract: %d chunks, host issue %.3f ms (h2d_mode %d%s)\n", n_chunks,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_issue0).count(), h->h2d_mode, host_mapped ? ", SM pull" : "");
   return ESLAM_OK;
 }
 
@@ -258,6 +314,8 @@ int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHa
   EslamHandle *h = new (std::nothrow) EslamHandle();
   if (!h) return ESLAM_ERR_CUDA;
   h->prm = *p; h->cam = *c; h->device = device; h->sm_count = prop.multiProcessorCount;
+  if (const char *e = getenv("ESLAM_H2D_MODE")) { int v = atoi(e); if (v >= 0 && v <= 4) h->h2d_mode = v; }
+  if (const char *e = getenv("ESLAM_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= kMaxChunks) h->host_chunks = v; }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return ESLAM_ERR_CUDA; }
   *out = h;
   return ESLAM_OK;
@@ -268,7 +326,7 @@ void eslam_destroy(EslamHandle *h) {
   cudaSetDevice(h->device);
   if (h->ex) {
     ExtractWorkspace &w = *h->ex;
-    DevBuf *bufs[] = {&w.meta, &w.state, &w.out, &w.ptsA, &w.ptsB, &w.ptsC, &w.k0, &w.k1, &w.v0, &w.v1, &w.parent, &w.count, &w.objn, &w.objnf, &w.symscratch,
+    DevBuf *bufs[] = {&w.meta, &w.state, &w.out, &w.ptsA, &w.ptsB, &w.ptsC, &w.k0, &w.k1, &w.v0, &w.v1, &w.parent, &w.count, &w.objn, &w.objnf, &w.symscratch, &w.symscratch2,
                       &w.d_crop, &w.d_voxel, &w.d_world, &w.d_sym, &w.d_final, &w.d_label, &w.depth};
     for (DevBuf *b : bufs) b->release();
     w.pin_meta.release(); w.pin_out.release(); w.pin_depth.release();

@@ -60,6 +60,10 @@ struct EslamHandle {
   cudaEvent_t chunk_ev[16] = {};
   cudaStream_t chunk_stream[8] = {};   // per-chunk compute streams: chunks overlap each other and the remaining uploads
   cudaEvent_t chunk_done[8] = {};
+  int h2d_mode = 4;      // upload: 4 = SMs pull each box rectangle from pinned host memory (falls back to 3 for pageable input);
+                         // 3 = union rectangle of each frame's boxes, one batched DMA call per chunk; 2 = same, one call per frame;
+                         // 1 = the boxes' rows (contiguous), 0 = whole frames (env ESLAM_H2D_MODE)
+  int host_chunks = 8;   // pipeline depth of the host entry (env ESLAM_HOST_CHUNKS, 1..8)
   unsigned long long h2d_bytes = 0;    // depth bytes uploaded by the *_host extraction entry (running total)
   bool plane_set = false;
   double plane_world[4] = {0, 0, 1, 0};

@@ -93,28 +93,48 @@ __device__ void voxel_sort(const float4 *pts, int n, float leaf, unsigned *k0, u
   block_radix_sort(k0, v0, k1, v1, n, bits, RS);
 }
 
-// float centroid of the voxel whose first sorted position is j (members in ascending original index)
-__device__ __forceinline__ float4 voxel_centroid(const float4 *pts, const unsigned *k0, const unsigned *v0, int j, int n) {
-  unsigned key = k0[j];
-  float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-  int jj = j;
-  do {
-    float4 p = pts[v0[jj]];
-    sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z);
-    jj++;
-  } while (jj < n && k0[jj] == key);
-  float cnt = (float)(jj - j);
-  return make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 0.0f);
-}
-
 constexpr int kExtractThreads = 256;   // 3 CTAs/SM: different objects sit in different phases, hiding the many block barriers
 constexpr int kSmemParents = 12288;    // 48 KB of dynamic shared memory per CTA (3 CTAs/SM still fit in 227 KB)
+
+// One tile (kExtractThreads sorted positions) of (voxel key, point) staged in shared memory -- every thread issues its own
+// independent gather -- after which the first position of each voxel sums its members from shared memory.  Aliases RadixScratch
+// (idle between sorts).
+struct VoxelTile { unsigned key[kExtractThreads + 1]; float x[kExtractThreads], y[kExtractThreads], z[kExtractThreads]; };
+static_assert(sizeof(VoxelTile) <= sizeof(RadixScratch), "VoxelTile aliases RadixScratch");
+// Returns whether this thread's position is the head of a voxel; if so `c` is the voxel's float centroid (members added in
+// ascending sorted position == ascending original index, PCL's centroid order).  Contains one __syncthreads(); the caller's next
+// block-wide barrier (its compaction scan) separates this tile's reads from the next tile's staging.
+__device__ __forceinline__ bool voxel_tile_centroid(const float4 *pts, const unsigned *k0, const unsigned *v0, int tile, int n, VoxelTile &T, float4 &c) {
+  const int tid = threadIdx.x, j = tile + tid;
+  unsigned key = 0; float4 p = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (j < n) { key = k0[j]; p = pts[v0[j]]; }
+  T.key[tid + 1] = key; T.x[tid] = p.x; T.y[tid] = p.y; T.z[tid] = p.z;
+  if (tid == 0) T.key[0] = (tile > 0) ? k0[tile - 1] : 0u;
+  __syncthreads();
+  const bool head = (j < n) && (j == 0 || T.key[tid] != key);
+  if (head) {
+    float sx = __fadd_rn(0.0f, p.x), sy = __fadd_rn(0.0f, p.y), sz = __fadd_rn(0.0f, p.z);
+    const int lim = min(kExtractThreads, n - tile);
+    int jj = tid + 1;
+    while (jj < lim && T.key[jj + 1] == key) { sx = __fadd_rn(sx, T.x[jj]); sy = __fadd_rn(sy, T.y[jj]); sz = __fadd_rn(sz, T.z[jj]); jj++; }
+    int members = jj - tid;
+    if (jj == kExtractThreads) {   // the voxel continues past the tile: finish from global memory
+      int g = tile + kExtractThreads;
+      while (g < n && k0[g] == key) { const float4 q = pts[v0[g]]; sx = __fadd_rn(sx, q.x); sy = __fadd_rn(sy, q.y); sz = __fadd_rn(sz, q.z); g++; members++; }
+    }
+    const float cnt = (float)members;
+    c = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 0.0f);
+  }
+  return head;
+}
+
 __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride, const ObjMeta *__restrict__ metas,
                                                       ObjState *__restrict__ states, ExtractParamsDev prm, ExtractPtrs W) {
   __shared__ BlockScratch S;
   __shared__ RadixScratch RS;
   __shared__ ScanScratch SS;
   __shared__ int s_sel;
+  VoxelTile &VT = *reinterpret_cast<VoxelTile *>(&RS);
   extern __shared__ int s_parent[];   // union-find parents / cluster labels when the filtered cloud fits (kSmemParents), else HBM
   int phase = 0;
   const int tid = threadIdx.x;
@@ -178,14 +198,12 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
       int j = tile + tid;
       bool head = false, keep = false;
       d3 pc = mk3(0, 0, 0), pw = mk3(0, 0, 0);
-      if (j < n1) {
-        head = (j == 0) || (k0[j - 1] != k0[j]);
-        if (head) {
-          float4 c = voxel_centroid(A, k0, v0, j, n1);
-          pc = mk3((double)c.x, (double)c.y, (double)c.z);      // pclToQuadricPointCloud: float -> double
-          pw = hom_apply(Twc_h, pc);                               // transformPointCloud
-          keep = plane_signed_dist(prm.plane, pw) > prm.plane_margin;  // ApplySupportingPlaneFilter
-        }
+      float4 c;
+      head = voxel_tile_centroid(A, k0, v0, tile, n1, VT, c);
+      if (head) {
+        pc = mk3((double)c.x, (double)c.y, (double)c.z);      // pclToQuadricPointCloud: float -> double
+        pw = hom_apply(Twc_h, pc);                               // transformPointCloud
+        keep = plane_signed_dist(prm.plane, pw) > prm.plane_margin;  // ApplySupportingPlaneFilter
       }
       int hr, kr, toth, totk;
       block_flag_scan2(head, keep, hr, kr, toth, totk, SS, phase);
@@ -264,6 +282,15 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
     const float r2 = prm.cluster_r2;
     int pow2 = 1;
     while (pow2 < n3) pow2 <<= 1;
+    // two-level lower bound: the first key of every 16-key block lives in shared memory (RadixScratch is idle now), so a search costs
+    // ~log2(n/16) shared-memory steps plus 4 global steps inside one 64-byte block instead of ~log2(n) dependent global loads
+    unsigned *coarse = RS.radix;
+    const int ncoarse = (n3 + 15) >> 4;
+    const bool use_coarse = ncoarse <= kRadixWarps * 256;
+    int pow2c = 1;
+    while (pow2c < ncoarse) pow2c <<= 1;
+    if (use_coarse) for (int b = tid; b < ncoarse; b += blockDim.x) coarse[b] = k0[b << 4];
+    __syncthreads();
     // Warp-converged neighbour search over the FORWARD half of the 27-cell neighbourhood (each unordered pair is tested exactly once,
     // from the point that comes first in (z, y, x) cell order; l2_simple is symmetric to the last bit): the rest of the own cell and
     // cell x+1 by walking on from the point's own sorted position, then rows (dz,dy) = (0,+1), (+1,-1), (+1,0), (+1,+1) over x-1..x+1.
@@ -290,7 +317,18 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
           unsigned klo = (unsigned)((zz * ny + yy) * nx + xlo);
           khi = (unsigned)((zz * ny + yy) * nx + xhi);
           q = 0;
-          for (int st = pow2; st > 0; st >>= 1) { int t = q + st; if (t <= n3 && k0[t - 1] < klo) q = t; }   // lower_bound, uniform trip count
+          if (use_coarse) {
+            int cb = 0;   // number of 16-key blocks whose first key is < klo
+            for (int st = pow2c; st > 0; st >>= 1) { int t = cb + st; if (t <= ncoarse && coarse[t - 1] < klo) cb = t; }
+            if (cb > 0) {
+              q = ((cb - 1) << 4) + 1;                     // k0[(cb-1)*16] < klo; the bound lies in ((cb-1)*16, cb*16]
+              const int hi = min(n3, cb << 4);
+#pragma unroll
+              for (int st = 8; st > 0; st >>= 1) { int t = q + st; if (t <= hi && k0[t - 1] < klo) q = t; }
+            }
+          } else {
+            for (int st = pow2; st > 0; st >>= 1) { int t = q + st; if (t <= n3 && k0[t - 1] < klo) q = t; }   // lower_bound, uniform trip count
+          }
         }
         while (true) {
           const bool more = valid && q < n3 && k0[q] <= khi;
@@ -455,12 +493,10 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
   float4 *objnf = W.objnf + m.off;
   for (int tile = 0; tile < nc; tile += blockDim.x) {
     int j = tile + tid;
-    bool head = false;
     d3 po = mk3(0, 0, 0);
-    if (j < nc) {
-      head = (j == 0) || (k0[j - 1] != k0[j]);
-      if (head) { float4 c = voxel_centroid(Cc, k0, v0, j, nc); po = hom_apply(Tow_h, mk3((double)c.x, (double)c.y, (double)c.z)); }
-    }
+    float4 c;
+    const bool head = voxel_tile_centroid(Cc, k0, v0, tile, nc, VT, c);
+    if (head) po = hom_apply(Tow_h, mk3((double)c.x, (double)c.y, (double)c.z));
     const bool hd[1] = {head};
     int tot, ex[1];
     block_flag_scan<1>(hd, ex, tot, SS, phase);
@@ -475,6 +511,44 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
     st.n_sym = M;
     st.run_sym = (prm.symmetry_open && m.symtype > 0 && M >= 1) ? 1 : 0;
   }
+}
+
+// Host entry, pinned (mapped) input: the SMs pull each object's box rectangle straight out of host memory over PCIe (16-byte
+// loads, 4 in flight per thread) into the device-side frame buffer the extraction kernels read.  One launch per chunk replaces one
+// DMA submission per frame (each costs ~5 us on the copy engine, more than moving a 200 KB rectangle), and only the pixels the path
+// can read cross the bus.  Runs on the high-priority copy stream next to the compute kernels of the previous chunks.
+__global__ void __launch_bounds__(256) pull_rects_kernel(const uint16_t *__restrict__ host_src, uint16_t *__restrict__ dst, size_t pitch, size_t frame_stride,
+                                                         const ObjMeta *__restrict__ metas, int n_obj, int rows, int cols) {
+  for (int k = blockIdx.x; k < n_obj; k += gridDim.x) {
+    const ObjMeta &m = metas[k];
+    if (m.pre_status != 0) continue;
+    const int x0 = m.x1 & ~7, x1 = min(cols, (m.x2 + 8) & ~7);
+    const int y0 = m.y1, y1 = min(rows, m.y2 + 1);
+    const int upr = (x1 - x0) >> 3;               // 16-byte units per row
+    const int total = upr * (y1 - y0);
+    const size_t base = (size_t)m.frame * frame_stride + (size_t)y0 * pitch + x0;
+    for (int u0 = threadIdx.x; u0 < total; u0 += 4 * 256) {
+      uint4 v[4]; size_t off[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int u = u0 + j * 256;
+        const int r = u / upr, c = u - r * upr;
+        off[j] = base + (size_t)r * pitch + (size_t)c * 8;
+        if (u < total) v[j] = __ldcs(reinterpret_cast<const uint4 *>(host_src + off[j]));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) if (u0 + j * 256 < total) *reinterpret_cast<uint4 *>(dst + off[j]) = v[j];
+    }
+  }
+}
+int pull_rects_launch(EslamHandle *h, cudaStream_t s, const uint16_t *host_mapped, uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj) {
+  ExtractWorkspace &w = *h->ex;
+  if (n_obj <= 0) return ESLAM_OK;
+  const int grid = n_obj < 96 ? n_obj : 96;
+  pull_rects_kernel<<<grid, 256, 0, s>>>(host_mapped, depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, n_obj, h->cam.rows, h->cam.cols);
+  ESLAM_LAUNCHED(h);
+  ESLAM_CUDA_OK(h, cudaGetLastError());
+  return ESLAM_OK;
 }
 
 int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj, const ExtractParamsDev &prm,

@@ -51,17 +51,19 @@ struct ExtractPtrs {  // device pointers of the per-point workspace (total capac
   double *objn;     // [cap*3] object-normalised cloud (double)
   float4 *objnf;    // float copy for the NN search
   float4 *nncache;  // [n_obj*9][2*kSymQueue] per-seed NN cache of the symmetry kernel (query float3 + neighbour index)
+  uint4 *pixcache;  // same shape: per-point pixel cache (pixel key, range value, depth)
   // optional stage dump (device mirrors, NULL when no dump requested)
   double *d_crop, *d_voxel, *d_world, *d_sym, *d_final;  // d_final has 4x capacity
   int *d_label;
 };
 
 struct ExtractWorkspace {
-  DevBuf meta, state, out, ptsA, ptsB, ptsC, k0, k1, v0, v1, parent, count, objn, objnf, symscratch;   // symscratch = NN cache
+  DevBuf meta, state, out, ptsA, ptsB, ptsC, k0, k1, v0, v1, parent, count, objn, objnf, symscratch, symscratch2;   // symscratch = NN cache, symscratch2 = pixel cache
   DevBuf d_crop, d_voxel, d_world, d_sym, d_final, d_label;
   DevBuf depth;   // staging for the *_host entry point
   PinBuf pin_meta, pin_out, pin_depth;
   std::vector<ObjMeta> meta_host;
+  std::vector<cudaMemcpy3DBatchOp> copy_ops;   // per-chunk upload list of the host entry
   long long cap_total = 0;
   int n_obj = 0;
 };

@@ -36,6 +36,7 @@ struct SymBlock {
   const uint16_t *img; size_t pitch;
   const double *objn; const float4 *nn_g;
   float4 *cache;   // per-warp NN cache in HBM/L2: slot i = (float query x, y, z, nearest index) of mirrored point i at its last full scan
+  uint4 *pcache;   // per-warp pixel cache: slot i = (x | y << 16, ushort range value, depth = value / scale as a double) of the last pixel it read
   int M, symtype, npts, in_smem;
   int bx0, bx2, by1, by3, rows, cols;
   ObjState *st;
@@ -45,10 +46,12 @@ struct SymBlock {
 struct SeedResult { double prob, init_err, final_err; dplane plane; };
 struct SymWarp {
   PlanePair pp;
+  PlanePair fd[6];   // the 2*dim finite-difference planes of one linearisation, prepared by 2*dim lanes in parallel
   dplane est, backup, trial;
   double H[9], b[3], x[3], J[3];
   double lambda, ni, currentChi, tempChi, iniChi, rho, e1;
-  int nBad, ok, qmax, again;
+  int nBad, ok, qmax, again, accepted;
+  unsigned n_evals, n_queries, n_points, n_hits;   // work counters, flushed once per seed
   SeedResult res;
   unsigned short queue[kSymQueue];
   double dis[kSymQueue];
@@ -75,7 +78,10 @@ __device__ __forceinline__ d3 mirrored(const SymBlock &B, const PlanePair &P, in
   return mk3(pt.x + kk * n[0], pt.y + kk * n[1], pt.z + kk * n[2]);
 }
 // 0 = cost 0 (occluded / no depth), 1 = needs the nearest-neighbour distance, 2 = invalid (not counted)   SymmetrySolver.cpp:62-116
-__device__ __noinline__ int classify(const SymBlock &B, d3 pm) {
+// `pc` is the point's pixel-cache entry: when the mirrored point projects to the same pixel as last time (always, for the 1e-9
+// finite-difference perturbations) the range value of that pixel -- a function of the pixel alone -- is reused instead of being
+// reloaded and recomputed (1 gather, 1 sqrt, 2 divisions).
+__device__ __noinline__ int classify(const SymBlock &B, d3 pm, uint4 pc, uint4 *slot) {
   double uvh[3];
 #pragma unroll
   for (int r = 0; r < 3; r++) { double s = B.P[r * 4] * pm.x; s += B.P[r * 4 + 1] * pm.y; s += B.P[r * 4 + 2] * pm.z; s += B.P[r * 4 + 3] * 1.0; uvh[r] = s; }
@@ -85,12 +91,19 @@ __device__ __noinline__ int classify(const SymBlock &B, d3 pm) {
   bool inrange = (B.bx0 < x && x < B.bx2) && (B.by1 < y && y < B.by3);
   if (inrange && (x < 0 || y < 0 || x >= B.cols || y >= B.rows)) inrange = false;
   if (inrange) {
-    const unsigned short d0 = B.img[(size_t)y * B.pitch + x];
-    const double xi = (x - B.cx), yi = (y - B.cy), f = B.fx;
-    const double realz = (double)d0 * sqrt(xi * xi + f * f + yi * yi) / f;   // calculateProjZ, Symmetry.cpp:137-139 (lazy range image)
-    const unsigned short d = (unsigned short)(int)realz;                      // ushort(realz)
+    const unsigned key = (unsigned)x | ((unsigned)y << 16);
+    unsigned d; double depth;
+    if (pc.x == key) {
+      d = pc.y; depth = __hiloint2double((int)pc.w, (int)pc.z);
+    } else {
+      const unsigned short d0 = B.img[(size_t)y * B.pitch + x];
+      const double xi = (x - B.cx), yi = (y - B.cy), f = B.fx;
+      const double realz = (double)d0 * sqrt(xi * xi + f * f + yi * yi) / f;   // calculateProjZ, Symmetry.cpp:137-139 (lazy range image)
+      d = (unsigned short)(int)realz;                                            // ushort(realz)
+      depth = d / B.scale;
+      *slot = make_uint4(key, d, (unsigned)__double2loint(depth), (unsigned)__double2hiint(depth));
+    }
     if (d == 0) return 0;
-    const double depth = d / B.scale;
     const double ax = B.cam[0] - pm.x, ay = B.cam[1] - pm.y, az = B.cam[2] - pm.z;
     const double dis_cam = sqrt(ax * ax + ay * ay + az * az);
     if (dis_cam > depth) return 0;
@@ -187,15 +200,14 @@ __device__ __noinline__ NNRes nn_distance_split(const SymBlock &B, d3 pm, int sl
   return r;
 }
 
-// edge error (= -mean ln P) of the plane stored in shared memory at `pl`; warp-collective, every lane returns the same value.
-// Fast path (#points <= kSymQueue): (1) classify all mirrored points, compacting those that need a nearest-neighbour query into a
-// per-warp queue so that (2) the brute-force searches run with full lanes; (3) ln P accumulated in the reference's point order.
-// (__noinline__: the kernel is instruction-fetch bound when the ~1k-instruction evaluation body is replicated at its 5 call sites)
-__device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dplane *pl) {
+// edge error (= -mean ln P) for the prepared plane pair PP (shared memory); warp-collective, every lane returns the same value.
+// Fast path (#points <= kSymQueue): (1) classify all mirrored points; points that need a nearest-neighbour distance either hit the
+// NN cache or are compacted into a per-warp queue so that (2) the brute-force searches run with full lanes; (3) ln P accumulated in
+// the reference's point order -- over the points with a distance only: every other point contributes -0.0, which never changes the sum.
+// (__noinline__: the kernel is instruction-fetch bound when the ~1k-instruction evaluation body is replicated at its call sites)
+__device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const PlanePair &PP) {
   const int lane = threadIdx.x & 31;
-  if (lane == 0) make_pair(W.pp, *pl);
-  __syncwarp();
-  const PlanePair &PP = W.pp;
+  const unsigned lt = (1u << lane) - 1u;
   const int npts = B.npts;
   double ln_total = 0.0;
   int invalid = 0;
@@ -205,43 +217,42 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
     const double sinv = B.sinv;
     for (int h0 = 0; h0 < npts; h0 += B.M) {
       const int cntp = min(B.M, npts - h0);
-      int qn = 0, hits = 0;
+      int qn = 0, nzn = 0, hits = 0;
       for (int base = 0; base < cntp; base += 32) {
         const int li = base + lane;
         int cls = 0;
+        double dis = 0.0;
         if (li < cntp) {
-          const float4 c = B.cache[h0 + li];   // issued before the fp64 classification chain
+          const float4 c = B.cache[h0 + li];   // both cache entries are requested before the fp64 classification chain
+          const uint4 pc = B.pcache[h0 + li];
           const d3 pm = mirrored(B, PP, h0 + li);
-          cls = classify(B, pm);
-          double dis = 0.0;
+          cls = classify(B, pm, pc, B.pcache + h0 + li);
           // NN cache: a bit-identical float query has the same exact nearest neighbour (the +-1e-9 finite-difference perturbations
-          // of the plane almost never change the float-rounded mirrored point), so the brute-force scan is skipped.
+          // of the plane often leave the float-rounded mirrored point unchanged), so the brute-force scan is skipped.
           if (cls == 1 && __float_as_uint(c.x) == __float_as_uint((float)pm.x) && __float_as_uint(c.y) == __float_as_uint((float)pm.y) &&
               __float_as_uint(c.z) == __float_as_uint((float)pm.z)) {
             dis = dist_to_neighbour(B, pm, __float_as_int(c.w));
             cls = 3;
           }
-          W.dis[li] = dis;
         }
         const unsigned need = __ballot_sync(0xffffffffu, cls == 1);
-        if (cls == 1) W.queue[qn + __popc(need & ((1u << lane) - 1u))] = (unsigned short)li;
-        qn += __popc(need);
-        hits += __popc(__ballot_sync(0xffffffffu, cls == 3));
+        const unsigned hit = __ballot_sync(0xffffffffu, cls == 3);
+        const int pos = nzn + __popc((need | hit) & lt);    // slot in the ordered list of points that carry a distance
+        if (cls == 3) W.dis[pos] = dis;
+        if (cls == 1) W.queue[qn + __popc(need & lt)] = (unsigned short)(li | (pos << 8));   // li, pos < 256
+        qn += __popc(need); nzn += __popc(need | hit); hits += __popc(hit);
         invalid += __popc(__ballot_sync(0xffffffffu, cls == 2));
       }
       __syncwarp();
-      if (lane == 0) {
-        atomicAdd(&B.st->n_evals, 1ULL); atomicAdd(&B.st->n_queries, (unsigned long long)qn); atomicAdd(&B.st->n_points, (unsigned long long)cntp);
-        atomicAdd(&B.st->n_hits, (unsigned long long)hits);
-      }
+      if (lane == 0) { W.n_evals++; W.n_queries += qn; W.n_points += cntp; W.n_hits += hits; }
       for (int qb = 0; qb < qn; qb += 32) {
         const int cq = min(32, qn - qb);
         if (cq > 16) {
           if (lane < cq) {
-            const int li = W.queue[qb + lane];
+            const int e = W.queue[qb + lane], li = e & 255;
             const d3 pm = mirrored(B, PP, h0 + li);
             const NNRes r = nn_distance(B, pm);
-            W.dis[li] = r.dis;
+            W.dis[e >> 8] = r.dis;
             B.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
           }
         } else {   // partial chunk: split every query's scan over several lanes
@@ -249,21 +260,20 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
           while (slots < cq) slots <<= 1;
           const int q = lane % slots;
           const bool active = q < cq;
-          const int li = W.queue[qb + (active ? q : 0)];
+          const int e = W.queue[qb + (active ? q : 0)], li = e & 255;
           const d3 pm = mirrored(B, PP, h0 + li);
           const NNRes r = nn_distance_split(B, pm, slots, active);
           if (active && lane < slots) {
-            W.dis[li] = r.dis;
+            W.dis[e >> 8] = r.dis;
             B.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
           }
         }
       }
       __syncwarp();
-      for (int base = 0; base < cntp; base += 32) {
-        const int li = base + lane;
-        const double dis = (li < cntp) ? W.dis[li] : 0.0;
+      for (int base = 0; base < nzn; base += 32) {
+        const double dis = (base + lane < nzn) ? W.dis[base + lane] : 0.0;
         const double lnP = -0.5 * sinv * sinv * dis * dis;
-        const int cnt = min(32, cntp - base);
+        const int cnt = min(32, nzn - base);
         for (int k = 0; k < cnt; k++) ln_total += __shfl_sync(0xffffffffu, lnP, k);
       }
       __syncwarp();
@@ -275,7 +285,8 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
       double lnP = 0.0; int cls = 0;
       if (idx < npts) {
         const d3 pm = mirrored(B, PP, idx);
-        cls = classify(B, pm);
+        uint4 scratch;
+        cls = classify(B, pm, make_uint4(0xffffffffu, 0u, 0u, 0u), &scratch);
         const double dis = (cls == 1) ? nn_distance(B, pm).dis : 0.0;
         lnP = -0.5 * sinv * sinv * dis * dis;
       }
@@ -287,6 +298,12 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const dpl
   const int num_valid = npts - invalid;
   const double aver = (num_valid > 0) ? (ln_total / (double)num_valid) : -INFINITY;
   return -aver;
+}
+// evaluation of a single plane: lane 0 prepares the pair
+__device__ __forceinline__ double sym_eval_plane(const SymBlock &B, SymWarp &W, const dplane *pl) {
+  if ((threadIdx.x & 31) == 0) make_pair(W.pp, *pl);
+  __syncwarp();
+  return sym_eval(B, W, W.pp);
 }
 
 __device__ __noinline__ void sym_oplus(dplane &p, const double *u, int symtype) {
@@ -304,25 +321,35 @@ __device__ __noinline__ bool lm_solve_dim(const double *H, const double *b, doub
 
 // OptimizeSymmetryPlane / OptimizeSymmetryDualPlane: one vertex, one unary edge (information 1), optimize(iters).
 // Warp-collective: lane 0 runs the scalar Levenberg-Marquardt bookkeeping on the shared-memory state, all lanes evaluate costs.
+// Two exact economies over the literal g2o call sequence: (1) computeActiveErrors() at the top of an iteration re-evaluates the plane
+// whose error is already known (the accepted trial, or the restored backup) -- the cost is a pure function, so the value is reused;
+// (2) the 2*dim finite-difference planes of a linearisation are prepared (oplus + mirror constants) by 2*dim lanes at once.
 __device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
   const int lane = threadIdx.x & 31;
   const int symtype = B.symtype;
   const int dim = (symtype == 1) ? 2 : 3;
-  double err = sym_eval(B, W, &W.est);
+  double err = sym_eval_plane(B, W, &W.est);   // value of the last computeError call
+  double err_est = err;                        // error of the plane currently held in W.est
   if (lane == 0) { W.res.init_err = err; W.lambda = -1; W.ni = 2; W.nBad = 0; W.x[0] = W.x[1] = W.x[2] = 0; W.ok = 1; }
   __syncwarp();
   for (int it = 0; it < iters; it++) {
     if (!W.ok) break;
-    err = sym_eval(B, W, &W.est);
+    err = err_est;                              // computeActiveErrors() at W.est
     if (lane == 0) { W.currentChi = err * (1.0 * err); W.tempChi = W.currentChi; W.iniChi = W.currentChi; }
     // linearizeOplus (numeric, delta 1e-9) + constructQuadraticForm
+    if (lane < 2 * dim) {
+      const int d = lane >> 1;
+      const double del = (lane & 1) ? -1e-9 : 1e-9;
+      double add[3];
+      add[0] = (d == 0) ? del : 0.0; add[1] = (d == 1) ? del : 0.0; add[2] = (d == 2) ? del : 0.0;
+      dplane t = W.est;
+      sym_oplus(t, add, symtype);
+      make_pair(W.fd[lane], t);
+    }
+    __syncwarp();
     for (int d = 0; d < dim; d++) {
-      if (lane == 0) { double add[3] = {0, 0, 0}; add[d] = 1e-9; W.trial = W.est; sym_oplus(W.trial, add, symtype); }
-      __syncwarp();
-      const double e1 = sym_eval(B, W, &W.trial);
-      if (lane == 0) { double add[3] = {0, 0, 0}; add[d] = -1e-9; W.trial = W.est; sym_oplus(W.trial, add, symtype); }
-      __syncwarp();
-      const double e2 = sym_eval(B, W, &W.trial);
+      const double e1 = sym_eval(B, W, W.fd[2 * d]);
+      const double e2 = sym_eval(B, W, W.fd[2 * d + 1]);
       if (lane == 0) W.J[d] = (1.0 / (2 * 1e-9)) * (e1 - e2);
     }
     if (lane == 0) {
@@ -348,7 +375,7 @@ __device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
         sym_oplus(W.est, x, symtype);
       }
       __syncwarp();
-      err = sym_eval(B, W, &W.est);
+      err = sym_eval_plane(B, W, &W.est);
       if (lane == 0) {
         const bool ok2 = W.again != 0;
         double tempChi = err * (1.0 * err);
@@ -362,9 +389,9 @@ __device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
           double alpha = 1. - pow((2 * rho - 1), 3.0);
           alpha = fmin(alpha, 2. / 3.);
           const double sf = fmax(1. / 3., alpha);
-          W.lambda *= sf; W.ni = 2; W.currentChi = tempChi;
+          W.lambda *= sf; W.ni = 2; W.currentChi = tempChi; W.accepted = 1;
         } else {
-          W.lambda *= W.ni; W.ni *= 2; W.est = W.backup;
+          W.lambda *= W.ni; W.ni *= 2; W.est = W.backup; W.accepted = 0;
         }
         W.tempChi = tempChi; W.rho = rho; W.qmax++;
         W.again = (rho < 0 && W.qmax < 10) ? 1 : 0;
@@ -377,6 +404,7 @@ __device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
         }
       }
       __syncwarp();
+      if (W.accepted) err_est = err;   // W.est now holds the evaluated trial; otherwise it was restored to the backup (err_est unchanged)
       if (!W.again) break;
     }
   }
@@ -384,6 +412,8 @@ __device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
     W.res.final_err = err;          // e->error() after optimize(): value of the LAST computeError call (possibly a rejected trial)
     W.res.prob = exp(-err);
     W.res.plane = W.est;
+    atomicAdd(&B.st->n_evals, (unsigned long long)W.n_evals); atomicAdd(&B.st->n_queries, (unsigned long long)W.n_queries);
+    atomicAdd(&B.st->n_points, (unsigned long long)W.n_points); atomicAdd(&B.st->n_hits, (unsigned long long)W.n_hits);
   }
   __syncwarp();
 }
@@ -510,10 +540,14 @@ __global__ void __launch_bounds__(32, 28) symmetry_finalize_kernel(const uint16_
   const double *objn = W.objn + 3 * (size_t)m.off;
   const float4 *objnf = W.objnf + m.off;
   float4 *cache = W.nncache + (size_t)(obj0 * 9 + blockIdx.x) * (2 * kSymQueue);
+  uint4 *pcache = W.pixcache + (size_t)(obj0 * 9 + blockIdx.x) * (2 * kSymQueue);
   {
     const bool in_smem = M <= kSymSmemPts;
     // invalidate this warp's NN cache: a NaN x never equals a float-converted finite query
-    if (M <= kSymQueue) for (int j = lane; j < 2 * M; j += 32) cache[j] = make_float4(__uint_as_float(0x7fffffffu), 0.0f, 0.0f, 0.0f);
+    if (M <= kSymQueue) for (int j = lane; j < 2 * M; j += 32) {
+      cache[j] = make_float4(__uint_as_float(0x7fffffffu), 0.0f, 0.0f, 0.0f);
+      pcache[j] = make_uint4(0xffffffffu, 0u, 0u, 0u);   // no pixel has x = y = 65535
+    }
     if (in_smem) for (int j = lane; j < (M + 1) / 2; j += 32) {
       const float4 a = objnf[2 * j];
       const float far_ = 1.0e30f;   // (q - 1e30)^2 overflows to +inf: never < FLT_MAX, so the pad can never win
@@ -522,7 +556,8 @@ __global__ void __launch_bounds__(32, 28) symmetry_finalize_kernel(const uint16_
     }
     if (lane == 0) {
       B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch; B.st = &st;
-      B.cache = cache;
+      B.cache = cache; B.pcache = pcache;
+      Wp.n_evals = Wp.n_queries = Wp.n_points = Wp.n_hits = 0; Wp.accepted = 0;
       B.objn = objn; B.nn_g = objnf; B.M = M; B.symtype = m.symtype; B.npts = (m.symtype == 2) ? 2 * M : M; B.in_smem = in_smem ? 1 : 0;
       for (int i = 0; i < 12; i++) B.P[i] = st.P[i];
       B.cam[0] = st.T_oc[0]; B.cam[1] = st.T_oc[1]; B.cam[2] = st.T_oc[2];

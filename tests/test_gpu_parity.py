@@ -150,8 +150,18 @@ def test_pixels_outside_boxes_are_never_read(handle, kind, n_frames):
     b, _, _ = handle.estimate_ellipsoids(poison_outside_boxes(depth, fo, bb), fo, bb, lb, tw)
     assert bytes(a) == bytes(b)
     assert sum(o.status == 0 for o in a) >= len(a) // 2
-    # device-resident entry with the full frames resident (chunked over streams when the batch is large) gives the same records
+    # pinned (mapped) host input takes the SM-pull upload (pull_rects_kernel) instead of DMA copies: same records, also when the
+    # objects are not ordered by frame
     import torch
+    pinned = torch.from_numpy(np.ascontiguousarray(poison_outside_boxes(depth, fo, bb, seed=11)).view(np.int16)).pin_memory().numpy().view(np.uint16)
+    l0 = handle.launches
+    p, _, _ = handle.estimate_ellipsoids(pinned, fo, bb, lb, tw)
+    assert bytes(p) == bytes(a) and handle.launches - l0 == 3        # pull + extract + symmetry
+    perm = np.random.default_rng(1).permutation(len(fo))
+    q, _, _ = handle.estimate_ellipsoids(pinned, fo[perm], bb[perm], lb[perm], tw)
+    for k, i in enumerate(perm):
+        assert bytes(q[k]) == bytes(a[int(i)])
+    # device-resident entry with the full frames resident (chunked over streams when the batch is large) gives the same records
     d = torch.from_numpy(np.ascontiguousarray(depth).view(np.int16)).cuda()
     handle.estimate_ellipsoids_dev(d.data_ptr(), depth.shape[0], depth.shape[2], fo, bb, lb, tw)
     c = handle.fetch_ellipsoids(len(fo))
