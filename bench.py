@@ -317,10 +317,17 @@ def main():
     else:
         dom, alg, t_ms = "extract_kernel", crop_bytes, k_ms[0]
     achieved = alg / (t_ms / 1e3) / 1e9
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic, traffic_src = None, None
+    try:   # DRAM bytes per object of the same kernel from the committed ncu --set full capture, scaled to this launch's objects
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        traffic = float(tj["kernels"][dom]["dram_bytes_per_object"]) * n_obj
+        traffic_src = "profiles/r01_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per object x objects per launch)"
+    except Exception:
+        pass
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "kernel_ms": {"extract_kernel": k_ms[0], "symmetry_finalize_kernel": k_ms[1]},
                 "algorithmic_bytes_per_launch": alg,
-                "note": "both kernels are latency/ALU bound at the reference's problem sizes (per-object working set << L2); see DESIGN.md"}
+                "note": "both kernels are latency / instruction-issue bound at the reference's problem sizes (per-object working set << L2); see DESIGN.md"}
     # ---- cpu baseline (1 thread, bounded sample)
     cpu_fps, cpu_dt = oracle_fps(depth, fo, bb, lb, tw, plane, min(args.cpu_sample, args.frames), 1)
     line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -128,7 +128,8 @@ __device__ __forceinline__ bool voxel_tile_centroid(const float4 *pts, const uns
   return head;
 }
 
-__global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride, const ObjMeta *__restrict__ metas,
+template <int MINB, int SMEM_PARENTS>
+__global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride, const ObjMeta *__restrict__ metas,
                                                       ObjState *__restrict__ states, ExtractParamsDev prm, ExtractPtrs W) {
   __shared__ BlockScratch S;
   __shared__ RadixScratch RS;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(kExtractThreads, 3) extract_kernel(const uint1
   __syncthreads();
   if (tid == 0) { st.n_crop = n1; st.n_voxel = n2; st.n_plane = n3; }
   if (n3 < 1) { if (tid == 0) st.status = ESLAM_OBJ_NO_POINTS_AFTER_PLANE; return; }
-  if (n3 <= kSmemParents) parent = s_parent;   // block-uniform: pointer chasing at shared-memory instead of L2 latency
+  if (n3 <= SMEM_PARENTS) parent = s_parent;   // block-uniform: pointer chasing at shared-memory instead of L2 latency
 
   // ---------------- S5: GetCenter (EllipsoidExtractor.cpp:583-643) ----------------
   if (tid == 0) {
@@ -555,13 +556,16 @@ int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, si
                    const ExtractPtrs &ptrs) {
   ExtractWorkspace &w = *h->ex;
   if (n_obj <= 0) return ESLAM_OK;
+  // Shape: 3 CTAs/SM (80 registers, 48 KB of parents).  Measured alternative: 4 CTAs/SM with a 64-register cap and 32 KB of parents is
+  // 9 % slower (profiles/r01_kernel_shape_ab.txt).
   static bool attr_set = false;
   if (!attr_set) {
-    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemParents * (int)sizeof(int)));
-    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(extract_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(extract_kernel<3, kSmemParents>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemParents * (int)sizeof(int)));
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(extract_kernel<3, kSmemParents>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  extract_kernel<<<n_obj, kExtractThreads, kSmemParents * sizeof(int), s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs);
+  extract_kernel<3, kSmemParents><<<n_obj, kExtractThreads, kSmemParents * sizeof(int), s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0,
+                                                                                              w.state.as<ObjState>() + obj0, prm, ptrs);
   ESLAM_LAUNCHED(h);
   ESLAM_CUDA_OK(h, cudaGetLastError());
   return ESLAM_OK;

@@ -35,8 +35,6 @@ struct PlanePair {   // per-evaluation constants of GetSymmetryPointOfPlane for 
 struct SymBlock {
   const uint16_t *img; size_t pitch;
   const double *objn; const float4 *nn_g;
-  float4 *cache;   // per-warp NN cache in HBM/L2: slot i = (float query x, y, z, nearest index) of mirrored point i at its last full scan
-  uint4 *pcache;   // per-warp pixel cache: slot i = (x | y << 16, ushort range value, depth = value / scale as a double) of the last pixel it read
   int M, symtype, npts, in_smem;
   int bx0, bx2, by1, by3, rows, cols;
   ObjState *st;
@@ -45,6 +43,8 @@ struct SymBlock {
 };
 struct SeedResult { double prob, init_err, final_err; dplane plane; };
 struct SymWarp {
+  float4 *cache;   // per-warp NN cache in HBM/L2: slot i = (float query x, y, z, nearest index) of mirrored point i at its last full scan
+  uint4 *pcache;   // per-warp pixel cache: slot i = (x | y << 16, ushort range value, depth = value / scale as a double) of the last pixel it read
   PlanePair pp;
   PlanePair fd[6];   // the 2*dim finite-difference planes of one linearisation, prepared by 2*dim lanes in parallel
   dplane est, backup, trial;
@@ -223,10 +223,10 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const Pla
         int cls = 0;
         double dis = 0.0;
         if (li < cntp) {
-          const float4 c = B.cache[h0 + li];   // both cache entries are requested before the fp64 classification chain
-          const uint4 pc = B.pcache[h0 + li];
+          const float4 c = W.cache[h0 + li];   // both cache entries are requested before the fp64 classification chain
+          const uint4 pc = W.pcache[h0 + li];
           const d3 pm = mirrored(B, PP, h0 + li);
-          cls = classify(B, pm, pc, B.pcache + h0 + li);
+          cls = classify(B, pm, pc, W.pcache + h0 + li);
           // NN cache: a bit-identical float query has the same exact nearest neighbour (the +-1e-9 finite-difference perturbations
           // of the plane often leave the float-rounded mirrored point unchanged), so the brute-force scan is skipped.
           if (cls == 1 && __float_as_uint(c.x) == __float_as_uint((float)pm.x) && __float_as_uint(c.y) == __float_as_uint((float)pm.y) &&
@@ -253,7 +253,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const Pla
             const d3 pm = mirrored(B, PP, h0 + li);
             const NNRes r = nn_distance(B, pm);
             W.dis[e >> 8] = r.dis;
-            B.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
+            W.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
           }
         } else {   // partial chunk: split every query's scan over several lanes
           int slots = 1;
@@ -265,7 +265,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const Pla
           const NNRes r = nn_distance_split(B, pm, slots, active);
           if (active && lane < slots) {
             W.dis[e >> 8] = r.dis;
-            B.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
+            W.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
           }
         }
       }
@@ -510,13 +510,18 @@ __device__ __noinline__ void finalize_object(const ObjMeta &m, ObjState &st, con
 // grid = 9 * n_obj one-warp CTAs: CTA b handles seed (b % 9) of object (b / 9).  Seeds are independent until the very end; the warp
 // that finishes LAST for an object (atomic counter) performs the completion/finalisation, so no warp ever waits at a barrier for a
 // slower seed and the SM keeps ~28 independent warps in flight (the kernel is latency / issue bound, not bandwidth bound).
-__global__ void __launch_bounds__(32, 28) symmetry_finalize_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride,
-                                                                   const ObjMeta *__restrict__ metas, ObjState *__restrict__ states, ExtractParamsDev prm,
-                                                                   ExtractPtrs W, EslamEllipsoidOut *__restrict__ outs, int obj0) {
+// S = seed warps per CTA (1 or 3; the warps of a CTA work on the same object and share its shared-memory cloud), MINB = CTAs per SM.
+template <int S, int MINB>
+__global__ void __launch_bounds__(32 * S, MINB) symmetry_finalize_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride,
+                                                                         const ObjMeta *__restrict__ metas, ObjState *__restrict__ states, ExtractParamsDev prm,
+                                                                         ExtractPtrs W, EslamEllipsoidOut *__restrict__ outs, int obj0) {
+  static_assert(9 % S == 0, "the seed warps of a CTA must belong to one object");
   __shared__ SymBlock B;
-  __shared__ SymWarp Wp;
-  const int lane = threadIdx.x & 31;
-  const int obj = blockIdx.x / 9, seed = blockIdx.x - obj * 9;
+  __shared__ SymWarp Wps[S];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  SymWarp &Wp = Wps[wid];
+  const int gseed = blockIdx.x * S + wid;
+  const int obj = gseed / 9, seed = gseed - obj * 9;
   const ObjMeta &m = metas[obj];
   ObjState &st = states[obj];
   EslamEllipsoidOut &out = outs[obj];
@@ -539,8 +544,8 @@ __global__ void __launch_bounds__(32, 28) symmetry_finalize_kernel(const uint16_
   const int M = st.n_sym;
   const double *objn = W.objn + 3 * (size_t)m.off;
   const float4 *objnf = W.objnf + m.off;
-  float4 *cache = W.nncache + (size_t)(obj0 * 9 + blockIdx.x) * (2 * kSymQueue);
-  uint4 *pcache = W.pixcache + (size_t)(obj0 * 9 + blockIdx.x) * (2 * kSymQueue);
+  float4 *cache = W.nncache + (size_t)(obj0 * 9 + gseed) * (2 * kSymQueue);
+  uint4 *pcache = W.pixcache + (size_t)(obj0 * 9 + gseed) * (2 * kSymQueue);
   {
     const bool in_smem = M <= kSymSmemPts;
     // invalidate this warp's NN cache: a NaN x never equals a float-converted finite query
@@ -548,22 +553,23 @@ __global__ void __launch_bounds__(32, 28) symmetry_finalize_kernel(const uint16_
       cache[j] = make_float4(__uint_as_float(0x7fffffffu), 0.0f, 0.0f, 0.0f);
       pcache[j] = make_uint4(0xffffffffu, 0u, 0u, 0u);   // no pixel has x = y = 65535
     }
-    if (in_smem) for (int j = lane; j < (M + 1) / 2; j += 32) {
+    if (in_smem) for (int j = threadIdx.x; j < (M + 1) / 2; j += 32 * S) {
       const float4 a = objnf[2 * j];
       const float far_ = 1.0e30f;   // (q - 1e30)^2 overflows to +inf: never < FLT_MAX, so the pad can never win
       const float4 b = (2 * j + 1 < M) ? objnf[2 * j + 1] : make_float4(far_, far_, far_, 0.0f);
       B.X2[j] = f2_pack(a.x, b.x); B.Y2[j] = f2_pack(a.y, b.y); B.Z2[j] = f2_pack(a.z, b.z);
     }
-    if (lane == 0) {
+    if (lane == 0) { Wp.cache = cache; Wp.pcache = pcache; Wp.n_evals = Wp.n_queries = Wp.n_points = Wp.n_hits = 0; Wp.accepted = 0; }
+    if (threadIdx.x == 0) {
       B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch; B.st = &st;
-      B.cache = cache; B.pcache = pcache;
-      Wp.n_evals = Wp.n_queries = Wp.n_points = Wp.n_hits = 0; Wp.accepted = 0;
       B.objn = objn; B.nn_g = objnf; B.M = M; B.symtype = m.symtype; B.npts = (m.symtype == 2) ? 2 * M : M; B.in_smem = in_smem ? 1 : 0;
       for (int i = 0; i < 12; i++) B.P[i] = st.P[i];
       B.cam[0] = st.T_oc[0]; B.cam[1] = st.T_oc[1]; B.cam[2] = st.T_oc[2];
       B.bx0 = st.bbox_i[0]; B.by1 = st.bbox_i[1]; B.bx2 = st.bbox_i[2]; B.by3 = st.bbox_i[3];
       B.rows = prm.rows; B.cols = prm.cols; B.fx = prm.fx; B.cx = prm.cx; B.cy = prm.cy; B.scale = prm.scale;
       B.sinv = 1.0 / prm.sigma;
+    }
+    if (lane == 0) {
       // GenerateInitPlanes (Symmetry.cpp:44-86): seed = i*3+m, dis = -0.2 + 0.2 i, angle = -5deg + 5deg m
       const double diff_dis = 0.2, diff_angle = M_PI / 180.0 * 5;
       const double start_dis = -diff_dis * 1, start_angle = -diff_angle * 1;
@@ -571,7 +577,7 @@ __global__ void __launch_bounds__(32, 28) symmetry_finalize_kernel(const uint16_
       const double dis = start_dis + diff_dis * si, angle = start_angle + diff_angle * sm;
       Wp.est.p[0] = sin(angle); Wp.est.p[1] = -cos(angle); Wp.est.p[2] = 0; Wp.est.p[3] = -dis; Wp.est.dual = 0;   // fromDisAngleTrans
     }
-    __syncwarp();
+    if (S > 1) __syncthreads(); else __syncwarp();
   }
   sym_optimize(B, Wp, prm.symmetry_iters);
   int prev = 0;
@@ -593,10 +599,12 @@ int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *dep
                              const ExtractParamsDev &prm, const ExtractPtrs &ptrs) {
   ExtractWorkspace &w = *h->ex;
   if (n_obj <= 0) return ESLAM_OK;
+  // Shape: one seed warp per CTA, 28 CTAs/SM (72 registers).  Measured alternatives (profiles/r01_kernel_shape_ab.txt): 3 seed warps per
+  // CTA sharing the cloud at 27 warps/SM (+13 % time) and at 36 warps/SM with a 56-register cap (+18 %, spills) are both slower.
   static bool attr_set = false;
-  if (!attr_set) { ESLAM_CUDA_OK(h, cudaFuncSetAttribute(symmetry_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); attr_set = true; }
-  symmetry_finalize_kernel<<<9 * n_obj, 32, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs,
-                                                    w.out.as<EslamEllipsoidOut>() + obj0, obj0);
+  if (!attr_set) { ESLAM_CUDA_OK(h, cudaFuncSetAttribute(symmetry_finalize_kernel<1, 28>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); attr_set = true; }
+  symmetry_finalize_kernel<1, 28><<<9 * n_obj, 32, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs,
+                                                           w.out.as<EslamEllipsoidOut>() + obj0, obj0);
   ESLAM_LAUNCHED(h);
   ESLAM_CUDA_OK(h, cudaGetLastError());
   return ESLAM_OK;
