@@ -23,14 +23,17 @@ __device__ __forceinline__ int lower_bound_u32(const unsigned *a, int n, unsigne
   while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
   return lo;
 }
-__device__ __forceinline__ int vload(const int *p) { return *((const volatile int *)p); }
+// relaxed CTA-scope accesses for the lock-free union-find (one CTA per object): `volatile` would compile to system-scope strong
+// loads/stores (LD.E.STRONG.SYS), which stall the dispatcher; the parents live in shared memory or in this CTA's HBM slice
+__device__ __forceinline__ int vload(const int *p) { int v; asm volatile("ld.relaxed.cta.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void vstore(int *p, int v) { asm volatile("st.relaxed.cta.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 // find with path halving: parent pointers only ever move towards the root (a smaller index), so the racy
 // parent[i] = grandparent stores are benign (they always write an ancestor of i).
 __device__ int uf_find(int *parent, int i) {
   int p = vload(parent + i);
   while (p != i) {
     int gp = vload(parent + p);
-    if (gp != p) *((volatile int *)(parent + i)) = gp;
+    if (gp != p) vstore(parent + i, gp);
     i = p; p = gp;
   }
   return i;

@@ -13,11 +13,11 @@
 // double integral images, (b) float chamfer distances truncated with int(), (c) FLOAT accumulation of 9 moments over up to
 // ~250k pixels per region (rel. error ~1e-3 in the reference itself!) and (d) scan-order label propagation.  Each of these is
 // reproduced operation-for-operation, parallelised across frames / rows / regions instead of inside the dependent chain:
-//   (a) anti-diagonal wavefront: thread r owns image row r and runs 2 columns behind row r-1 (shared-memory ring),
+//   (a) anti-diagonal wavefront inside a warp: lane = image row of a 32-row band, 2 columns behind the lane above (shuffles),
 //   (b) row-sequential chamfer passes; the in-row recurrence is evaluated exactly with a 13-step window,
 //   (c) one warp per region walks the label image in raster order; lanes 0..8 own one float accumulator each,
 //   (d) per row: two block-wide max-scans resolve the left-to-right (right-to-left) propagation, vertical checks are parallel.
-// HBM layout per frame: pts float4[NP] (x,y,z,-), nrm float4[NP] (nx,ny,nz,plane_d), iiX/iiY double[(H+1)(W+1)3],
+// HBM layout per frame: pts float4[NP] (x,y,z,-), nrm float4[NP] (nx,ny,nz,plane_d), iiX/iiY double[3][(H+1)][pitch(W+1)] (planar),
 // dm float[NP], parent/count/maxidx int[NP].  Algorithmic bytes: 2 B/pixel of depth in, 32 B out per frame.
 #include "common.cuh"
 #include "block_prims.cuh"
@@ -78,71 +78,122 @@ __global__ void points_kernel(const uint16_t *__restrict__ depth, size_t pitch, 
 
 // ---------------------------------------------------------------------------------------------- P2: integral images (exact recurrence)
 // II(r+1,c+1) = ((II(r,c+1) + II(r+1,c)) - II(r,c)) + x(r,c)   in double, IntegralImage2D<float,3>::computeIntegralImages.
-// blockDim.x = rows rounded up to 32 (<= 1024); dynamic smem = rows * 4 * 6 doubles.
-__global__ void integral_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
-  extern __shared__ double ring[];   // [4 slots][6 channels][RH rows]: row is the fastest index -> conflict-free (thread = row)
-  const int RH = blockDim.x;
-  const int H = prm.rows, Wd = prm.cols, NP = H * Wd, IW = Wd + 1;
-  const int f = blockIdx.x;
-  const int r = threadIdx.x;
-  const float4 *pts = W.pts + (size_t)f * NP;
-  double *iiX = W.iiX + (size_t)f * (size_t)(H + 1) * IW * 3;
-  double *iiY = W.iiY + (size_t)f * (size_t)(H + 1) * IW * 3;
-  // row 0 and column 0 of the integral images are zero
-  for (int i = threadIdx.x; i < IW * 3; i += blockDim.x) { iiX[i] = 0.0; iiY[i] = 0.0; }
-  if (r < H) for (int k = 0; k < 3; k++) { iiX[((size_t)(r + 1) * IW) * 3 + k] = 0.0; iiY[((size_t)(r + 1) * IW) * 3 + k] = 0.0; }
-  double left[6] = {0, 0, 0, 0, 0, 0};
-  const bool inner_row = (r >= 1 && r <= H - 2);
-  const int steps = Wd + 2 * (H - 1);
-  // Thread r handles column c = t - 2r at step t.  The three point streams it needs (row above, row below, own row one column
-  // ahead) are prefetched FOUR steps ahead into register queues whose slot index is the position inside the 4x unrolled step loop
-  // (static indexing), so the L2/DRAM latency of the strided reads is off the 1 598-step critical path.
-  float4 Uq[4], Dq[4], Rq[4];
-  float4 pl = make_float4(0, 0, 0, 0), pc = make_float4(0, 0, 0, 0);
-  const float4 zero4 = make_float4(0, 0, 0, 0);
-  auto prefetch = [&](int c, float4 &u, float4 &d, float4 &rw) {
-    u = zero4; d = zero4; rw = zero4;
-    if (r < H && c >= 0 && c < Wd) {
-      if (inner_row) { u = pts[(size_t)(r - 1) * Wd + c]; d = pts[(size_t)(r + 1) * Wd + c]; }
-      if (c + 1 < Wd) rw = pts[(size_t)r * Wd + c + 1];
+// The rounding of every entry depends on the recurrence order, so the dependent chain is kept and parallelism comes from elsewhere:
+//   * the 6 channels (d/dx and d/dy of x, y, z) are independent: one warp per (frame, channel), 6 warps per CTA share the frame in L1;
+//   * inside a warp lane l owns image row r0 + l of a 32-row band and runs TWO columns behind lane l-1, so the value it needs from the
+//     row above is exactly lane l-1's previous result: one shuffle, issued a step ahead (off the 3-DADD critical path), no shared memory,
+//     no barrier; bands are processed top to bottom, lane 0 takes the last row of the band above from the image just written
+//     (coalesced 32-column chunks fetched one block ahead);
+//   * the channel's point-difference input is prefetched 16 steps ahead into registers.
+// Layout: planar, row pitch padded to 4 doubles: channel k of frame f at ii + ((f*3 + k) * (H+1)) * IWp; results leave as 16-byte pairs.
+__device__ __host__ __forceinline__ int ii_pitch(int Wd) { return (Wd + 1 + 3) & ~3; }
+__device__ __forceinline__ void st_global_256(double *p, double a, double b, double c, double d) {   // one full 32-byte sector (STG.256)
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+constexpr int kIntRing = 128;            // columns of the per-warp input ring (4 blocks of 32: lanes span 62 columns + the block in flight)
+constexpr int kIntRingPitch = kIntRing + 1;   // odd pitch: lane l reads column (t - 2l) of row l -> bank (t - l) mod 32, conflict free
+constexpr int kIntWarps = 6;
+__global__ void __launch_bounds__(32 * kIntWarps) integral_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  extern __shared__ float s_ring[];      // [kIntWarps][32 rows][kIntRingPitch]: this channel's point differences x(r, c), staged coalesced
+  const int H = prm.rows, Wd = prm.cols, NP = H * Wd, IWp = ii_pitch(Wd);
+  const int f = blockIdx.x, ch = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = ch % 3;
+  const bool isX = ch < 3;
+  const float *ptsf = reinterpret_cast<const float *>(W.pts + (size_t)f * NP) + k;   // component k of pixel i at ptsf[4 * i]
+  double *ii = (isX ? W.iiX : W.iiY) + ((size_t)f * 3 + k) * (size_t)(H + 1) * IWp;
+  float *ring = s_ring + (size_t)ch * 32 * kIntRingPitch;
+  for (int j = lane; j < IWp; j += 32) ii[j] = 0.0;   // row 0 of the integral image
+  const int steps = Wd + 62;                          // lane 31 starts 62 steps after lane 0
+  const int offA = isX ? 1 : 0, offB = isX ? -1 : 0, rA = isX ? 0 : 1, rB = isX ? 0 : -1;
+  // x(row, c) of this channel for 8 rows of the band at column c = cb + lane (lane = column: 512-byte spans, 16 sectors per load)
+  auto load_rows8 = [&](int row0, int cb, float (&vt)[8]) {
+    const int c = cb + lane;
+    const bool colok = c >= 1 && c <= Wd - 2;
+    const int cc = min(max(c, 1), Wd - 2);            // clamped coordinates: all 16 loads are unconditional and issue back to back
+    float a[8], b[8];
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) {
+      const int rowc = min(max(row0 + rr, 1), H - 2);
+      a[rr] = ptsf[4 * ((size_t)(rowc + rA) * Wd + cc + offA)];
+      b[rr] = ptsf[4 * ((size_t)(rowc + rB) * Wd + cc + offB)];
+    }
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) {
+      const int row = row0 + rr;
+      const float d = __fsub_rn(a[rr], b[rr]);
+      vt[rr] = (colok && row >= 1 && row <= H - 2) ? d : 0.0f;
     }
   };
-  if (r < H) pc = pts[(size_t)r * Wd];
+  // L2 prefetch of the same 16 sectors-per-row two column blocks ahead (a full 32-step period before load_rows8 asks for them): the
+  // point image was just streamed out by points_kernel and is far larger than L2, so without it every 8-step piece waits on DRAM
+  auto prefetch_rows8 = [&](int row0, int cb) {
+    const int cc = min(max(cb + lane, 1), Wd - 2);
 #pragma unroll
-  for (int u = 0; u < 4; u++) prefetch(u - 2 * r, Uq[u], Dq[u], Rq[u]);
-  for (int t0 = 0; t0 < steps; t0 += 4) {
+    for (int rr = 0; rr < 8; rr++) {
+      const int rowc = min(max(row0 + rr, 1), H - 2);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptsf + 4 * ((size_t)(rowc + rA) * Wd + cc + offA)));
+      if (!isX) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptsf + 4 * ((size_t)(rowc + rB) * Wd + cc + offB)));
+    }
+  };
+  auto store_rows8 = [&](int rr0, int cb, const float (&vt)[8]) {
+    const int col = (cb + lane) & (kIntRing - 1);
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int t = t0 + u;
-      const int c = t - 2 * r;
-      const float4 up = Uq[u], dn = Dq[u], pr = Rq[u];
-      prefetch(c + 4, Uq[u], Dq[u], Rq[u]);
-      if (t < steps && r < H && c >= 0 && c < Wd) {
-        float v[6] = {0, 0, 0, 0, 0, 0};
-        if (inner_row && c >= 1 && c <= Wd - 2) {
-          v[0] = __fsub_rn(pr.x, pl.x); v[1] = __fsub_rn(pr.y, pl.y); v[2] = __fsub_rn(pr.z, pl.z);
-          v[3] = __fsub_rn(dn.x, up.x); v[4] = __fsub_rn(dn.y, up.y); v[5] = __fsub_rn(dn.z, up.z);
-        }
-        double up1[6], ul[6];
-        if (r == 0) { for (int k = 0; k < 6; k++) { up1[k] = 0.0; ul[k] = 0.0; } }
-        else {
-          const double *a = &ring[(size_t)((c & 3) * 6) * RH + (r - 1)];
-          for (int k = 0; k < 6; k++) up1[k] = a[(size_t)k * RH];
-          if (c == 0) { for (int k = 0; k < 6; k++) ul[k] = 0.0; }
-          else { const double *b = &ring[(size_t)(((c - 1) & 3) * 6) * RH + (r - 1)]; for (int k = 0; k < 6; k++) ul[k] = b[(size_t)k * RH]; }
-        }
-        double *mine = &ring[(size_t)((c & 3) * 6) * RH + r];
-        size_t o = ((size_t)(r + 1) * IW + (c + 1)) * 3;
+    for (int rr = 0; rr < 8; rr++) ring[(rr0 + rr) * kIntRingPitch + col] = vt[rr];
+  };
+  for (int r0 = 0; r0 < H; r0 += 32) {
+    __syncwarp();                                     // the band above is complete and visible (same warp wrote it)
+    const int r = r0 + lane;
+    const bool rowok = r < H;
+    const double *uprev = ii + (size_t)r0 * IWp;      // II row r0 = sums down to pixel row r0 - 1 (zeros for the first band)
+    double *orow = ii + (size_t)(r + 1) * IWp;
+    const float *myrow = ring + lane * kIntRingPitch;
+    double last = 0.0, upleft = 0.0, h0 = 0.0, h1 = 0.0, h2 = 0.0;
+    double up = (lane == 0 && r0 > 0) ? __ldcg(uprev + 1) : 0.0;
+    double chunk_cur = 0.0, chunk_next = (r0 > 0 && 2 + lane <= Wd) ? __ldcg(uprev + 2 + lane) : 0.0;
+#pragma unroll 1
+    for (int seg = 0; seg < 4; seg++) { prefetch_rows8(r0 + 8 * seg, 32); float vt[8]; load_rows8(r0 + 8 * seg, 0, vt); store_rows8(8 * seg, 0, vt); }   // column block 0
+    __syncwarp();
+#pragma unroll 1
+    for (int t0 = 0; t0 < steps; t0 += 32) {
+      chunk_cur = chunk_next;                         // chunk_cur[i] = II(r0, t0 + 2 + i)
+      { const int j = t0 + 32 + 2 + lane; chunk_next = (r0 > 0 && j <= Wd) ? __ldcg(uprev + j) : 0.0; }
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-          double val = __dadd_rn(__dsub_rn(__dadd_rn(up1[k], left[k]), ul[k]), (double)v[k]);
-          left[k] = val; mine[(size_t)k * RH] = val;
+      for (int seg = 0; seg < 4; seg++) {
+        // the next column block arrives in four 8-row pieces: loads in flight during 8 steps, then into the ring slot nobody reads now
+        float vt[8];
+        load_rows8(r0 + 8 * seg, t0 + 32, vt);
+        if (t0 + 64 < Wd) prefetch_rows8(r0 + 8 * seg, t0 + 64);
+#pragma unroll
+        for (int i8 = 0; i8 < 8; i8++) {
+          const int i = seg * 8 + i8;
+          const int t = t0 + i;
+          const int c = t - 2 * lane;
+          // value of the row above for the NEXT step: lane l-1's latest result (column c+1 of its row), or the chunk for lane 0
+          double upn = __shfl_up_sync(0xffffffffu, last, 1);
+          const double cv = __shfl_sync(0xffffffffu, chunk_cur, i);
+          if (lane == 0) upn = cv;
+          const float v = myrow[c & (kIntRing - 1)];
+          if (rowok && c >= 0 && c < Wd) {
+            const double val = __dadd_rn(__dsub_rn(__dadd_rn(up, last), upleft), (double)v);
+            last = val;
+            if ((c & 3) == 2) st_global_256(orow + (c - 2), h0, h1, h2, val);   // integral-image columns c-2 .. c+1 (h0 = column 0 = zero at c = 2)
+            h0 = h1; h1 = h2; h2 = val;
+          }
+          upleft = up; up = upn;
         }
-        iiX[o] = left[0]; iiX[o + 1] = left[1]; iiX[o + 2] = left[2];
-        iiY[o] = left[3]; iiY[o + 1] = left[4]; iiY[o + 2] = left[5];
-        pl = pc; pc = pr;   // slide the row window
+        store_rows8(8 * seg, t0 + 32, vt);
       }
-      __syncthreads();
+      __syncwarp();                                   // the new block is visible before the next 32 steps read it
+    }
+    // columns after the last complete group of four: Wd & ~3 .. Wd (+ padding)
+    if (rowok) {
+      const int rem = Wd & 3;                         // number of results not yet stored: (Wd + 1) % 4 entries remain, the first may be pending in h*
+      const int jb = (Wd + 1) & ~3;                   // first column of the incomplete group
+      const int pend = Wd + 1 - jb;                   // 0..3 pending columns: values for columns jb .. Wd
+      if (pend == 1) st_global_256(orow + jb, h2, 0.0, 0.0, 0.0);
+      else if (pend == 2) st_global_256(orow + jb, h1, h2, 0.0, 0.0);
+      else if (pend == 3) st_global_256(orow + jb, h0, h1, h2, 0.0);
+      (void)rem;
     }
   }
 }
@@ -176,10 +227,13 @@ __global__ void distmap_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   float cur = 0.0f;
   if (ci < Wd) { cur = init_val(0, ci); dm[ci] = cur; s_prev[ci] = cur; }
   __syncthreads();
+  // the per-row recurrences are short; what would dominate a row step is the latency of the point loads behind init_val, which only
+  // depends on static data: the value of the next row is requested a full row step ahead
+  float center_next = (ci < Wd && H > 1) ? init_val(1, ci) : 0.0f;
   for (int ri = 1; ri < H; ri++) {
-    float center = 0.0f, a = 0.0f;
+    float center = center_next, a = 0.0f;
+    if (ci < Wd && ri + 1 < H) center_next = init_val(ri + 1, ci);
     if (ci < Wd) {
-      center = init_val(ri, ci);
       a = center;
       if (ci >= 1) {
         float upLeft = __fadd_rn(s_prev[ci - 1], 1.4f), up = __fadd_rn(s_prev[ci], 1.0f);
@@ -213,10 +267,11 @@ __global__ void distmap_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
     __syncthreads();
   }
   // ---- second pass (bottom-right to top-left); s_prev holds the final row H-1
+  float fwd_next = (ci < Wd && H > 1) ? dm[(size_t)(H - 2) * Wd + ci] : 0.0f;   // own column only: written by this thread in pass 1
   for (int ri = H - 2; ri >= 0; ri--) {
-    float fwd = 0.0f, a = 0.0f;
+    float fwd = fwd_next, a = 0.0f;
+    if (ci < Wd && ri >= 1) fwd_next = dm[(size_t)(ri - 1) * Wd + ci];
     if (ci < Wd) {
-      fwd = dm[(size_t)ri * Wd + ci];
       s_a[ci] = fwd;     // temporarily: forward values of this row (needed for the ci == 0 wrap: next_row[-1] == current_row[W-1])
     }
     __syncthreads();
@@ -249,7 +304,7 @@ __global__ void distmap_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
 
 // ---------------------------------------------------------------------------------------------- P4: normals + plane_d
 __global__ void normals_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
-  const int H = prm.rows, Wd = prm.cols, NP = H * Wd, IW = Wd + 1;
+  const int H = prm.rows, Wd = prm.cols, NP = H * Wd, IW = ii_pitch(Wd);
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int f = blockIdx.y;
   if (idx >= NP) return;
@@ -262,15 +317,17 @@ __global__ void normals_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
     float smoothing = fminf(W.dm[(size_t)f * NP + idx], 10.0f);
     if (smoothing > 2.0f) {
       int rw = (int)smoothing, rw2 = rw / 2;
-      const double *iiX = W.iiX + (size_t)f * (size_t)(H + 1) * IW * 3;
-      const double *iiY = W.iiY + (size_t)f * (size_t)(H + 1) * IW * 3;
+      const size_t plane = (size_t)(H + 1) * IW;   // planar integral images, padded pitch (integral_kernel)
+      const double *iiX = W.iiX + (size_t)f * 3 * plane;
+      const double *iiY = W.iiY + (size_t)f * 3 * plane;
       int sx = ci - rw2, sy = ri - rw2;
       size_t ul = (size_t)sy * IW + sx, ur = ul + rw, ll = (size_t)(sy + rw) * IW + sx, lr = ll + rw;
       double gx[3], gy[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        gx[k] = __dsub_rn(__dsub_rn(__dadd_rn(iiX[lr * 3 + k], iiX[ul * 3 + k]), iiX[ur * 3 + k]), iiX[ll * 3 + k]);
-        gy[k] = __dsub_rn(__dsub_rn(__dadd_rn(iiY[lr * 3 + k], iiY[ul * 3 + k]), iiY[ur * 3 + k]), iiY[ll * 3 + k]);
+        const double *px = iiX + k * plane, *py = iiY + k * plane;
+        gx[k] = __dsub_rn(__dsub_rn(__dadd_rn(px[lr], px[ul]), px[ur]), px[ll]);
+        gy[k] = __dsub_rn(__dsub_rn(__dadd_rn(py[lr], py[ul]), py[ur]), py[ll]);
       }
       double n0 = __dsub_rn(__dmul_rn(gy[1], gx[2]), __dmul_rn(gy[2], gx[1]));   // gradient_y.cross(gradient_x)
       double n1 = __dsub_rn(__dmul_rn(gy[2], gx[0]), __dmul_rn(gy[0], gx[2]));
@@ -290,12 +347,15 @@ __global__ void normals_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
 }
 
 // ---------------------------------------------------------------------------------------------- P5: connected components
-__device__ __forceinline__ int pvload(const int *p) { return *((const volatile int *)p); }
+// relaxed GPU-scope accesses (the CTAs of a frame share its parent array through L2); `volatile` would compile to system-scope strong
+// accesses (LDG.E.STRONG.SYS) that stall the dispatcher -- 80-95 % of the stall samples of the two union-find kernels
+__device__ __forceinline__ int pvload(const int *p) { int v; asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void pvstore(int *p, int v) { asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ int p_find(int *parent, int i) {   // path halving (benign races: only ancestors are ever written)
   int p = pvload(parent + i);
   while (p != i) {
     int gp = pvload(parent + p);
-    if (gp != p) *((volatile int *)(parent + i)) = gp;
+    if (gp != p) pvstore(parent + i, gp);
     i = p; p = gp;
   }
   return i;
@@ -443,74 +503,103 @@ __device__ void roots3f(const float *m /*3x3*/, float *roots) {   // pcl::comput
     if (roots[0] <= 0) roots2f(c2, c1, roots);
   }
 }
-// One 128-thread CTA per (frame, candidate) at a time (CTAs of a frame stride over its candidates).  The float moment sums must be
-// formed in raster order (bit parity with pcl::computeMeanAndCovarianceMatrix<float>), so the dependent FADD chain is the critical
-// path; everything else is taken off it with a producer/consumer split:
-//   warps 1..3 (producers) walk the region's bounding box in raster order, test membership with coalesced loads + ballots and
-//                          write the member points, order preserved, into one half of a double-buffered shared-memory tile;
-//   warp 0 (consumer)      lanes 0..8 own one accumulator each (xx xy xz yy yz zz x y z): per point one broadcast LDS.128, two
-//                          selects, one FMUL (x*1.0f is exact for lanes 6..8) and the FADD.
-constexpr int kFitThreads = 128;
-constexpr int kFitGroupsPerWarp = 5;                                   // 32-pixel groups per producer warp per tile
-constexpr int kFitTilePts = 3 * kFitGroupsPerWarp * 32;                // 480 points per tile
+// The float moment sums must be formed in raster order (bit parity with pcl::computeMeanAndCovarianceMatrix<float>), so one dependent
+// FADD chain per region (~4 cycles per member point) is the floor; everything else is taken off it with a producer/consumer split
+// inside a 256-thread CTA that works through the frame's candidate regions largest first (CTA b takes size ranks b, b+8, ...):
+//   warps 1..7 (producers) each own one shared-memory tile slot: producer p takes tiles p-1, p-1+7, ... of the region's bounding box
+//                          (8 groups of 32 pixels in raster order), keeps 16 coalesced loads in flight, ranks the members with ballots
+//                          and writes their 9 addends, order preserved, into its slot -- seven tiles in flight cover the DRAM latency;
+//   warp 0 (consumer)      walks the tiles in order; lanes 0..8 own one accumulator each (xx xy xz yy yz zz x y z): per point one LDS
+//                          and the FADD.
+// Slots are handed over with sequence counters in shared memory (produced / consumed per slot, cumulative over regions).
+constexpr int kFitWarps = 8;
+constexpr int kFitProducers = kFitWarps - 1;
+constexpr int kFitThreads = 32 * kFitWarps;
+constexpr int kFitGroups = 8;                                   // 32-pixel groups per tile
+constexpr int kFitTilePts = kFitGroups * 32;                    // 256 points per tile
+constexpr int kFitRankMax = 256;
+constexpr int kFitSmemBytes = kFitProducers * kFitTilePts * 9 * (int)sizeof(float);
+__device__ __forceinline__ void fit_wait_eq(volatile int *flag, int want) {   // warp-collective: lane 0 polls, the warp follows
+  if ((threadIdx.x & 31) == 0) while (*flag != want) __nanosleep(20);
+  __syncwarp();
+  __threadfence_block();
+}
 __global__ void __launch_bounds__(kFitThreads) fit_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
-  __shared__ float s_v[2][kFitTilePts * 9];    // the 9 addends of every member point (products formed by the producers)
-  __shared__ int s_cnt[2][4];
+  extern __shared__ float s_v[];               // [kFitProducers][kFitTilePts * 9]: the 9 addends of every member point of a tile
+  __shared__ volatile int s_full[kFitProducers], s_done[kFitProducers];
+  __shared__ int s_cnt[kFitProducers];
+  __shared__ int s_size[kFitRankMax], s_order[kFitRankMax];
   const int NP = prm.rows * prm.cols, Wd = prm.cols;
   const int f = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int *parent = W.parent + (size_t)f * NP;
   const float4 *pts = W.pts + (size_t)f * NP;
   const int ncand = W.cand_n[f];
-  for (int k = blockIdx.x; k < ncand; k += gridDim.x) {
+  const bool ranked = ncand <= kFitRankMax;
+  if (threadIdx.x < kFitProducers) { s_full[threadIdx.x] = 0; s_done[threadIdx.x] = 0; }
+  if (ranked) {   // size rank (descending, ties by index): the big regions start first, on different CTAs
+    for (int k = threadIdx.x; k < ncand; k += kFitThreads) s_size[k] = W.cand_size[f * kMaxRegions + k];
+    __syncthreads();
+    for (int k = threadIdx.x; k < ncand; k += kFitThreads) {
+      const int sk = s_size[k];
+      int rank = 0;
+      for (int j = 0; j < ncand; j++) { const int sj = s_size[j]; rank += (sj > sk || (sj == sk && j < k)) ? 1 : 0; }
+      s_order[rank] = k;
+    }
+  }
+  __syncthreads();
+  int prev = 0;                                // producer: code of the tile this warp's slot carried last
+  int it = 0;                                  // region counter: slot hand-over codes are (it << 20) | (tile + 1), unique per CTA
+  for (int rk = blockIdx.x; rk < ncand; rk += gridDim.x) {
+  ++it;
+  const int k = ranked ? s_order[rk] : rk;
   const int root = W.cand_root[f * kMaxRegions + k];
   const int last = W.maxidx[(size_t)f * NP + root];
   const int r0 = root / Wd, r1 = last / Wd;                       // bounding box rows / columns (32-aligned)
   const int c0 = W.cmin[(size_t)f * NP + root] & ~31, c1 = W.cmax[(size_t)f * NP + root];
   const int gpr = (c1 - c0) / 32 + 1;                             // groups per row
   const int ngroups = (r1 - r0 + 1) * gpr;
-  const int gpt = 3 * kFitGroupsPerWarp;                          // groups per tile
-  const int ntiles = (ngroups + gpt - 1) / gpt;
+  const int ntiles = (ngroups + kFitGroups - 1) / kFitGroups;
   float acc = 0.0f;
-  __syncthreads();
-  // tile t is produced during iteration t (into buffer t&1) and consumed during iteration t+1
-  for (int t = 0; t <= ntiles; t++) {
-    if (warp >= 1 && t < ntiles) {
-      const int pw = warp - 1;
-      float4 mine[kFitGroupsPerWarp]; unsigned masks[kFitGroupsPerWarp];
-      int total = 0;
+  if (warp >= 1) {
+    const int p = warp - 1;
+    float *slot = s_v + (size_t)p * kFitTilePts * 9;
+    for (int t = p; t < ntiles; t += kFitProducers) {
+      float4 mine[kFitGroups]; int labs[kFitGroups];
+      int gr = (t * kFitGroups) / gpr, gc = (t * kFitGroups) - gr * gpr;   // row / group-in-row of the tile's first group
 #pragma unroll
-      for (int q = 0; q < kFitGroupsPerWarp; q++) {
-        const int g = t * gpt + pw * kFitGroupsPerWarp + q;
-        bool in = false; mine[q] = make_float4(0, 0, 0, 0);
-        if (g < ngroups) {
-          const int rr = r0 + g / gpr, cc = c0 + (g % gpr) * 32 + lane;
-          if (cc < Wd) { const int i = rr * Wd + cc; const int lab = parent[i]; mine[q] = pts[i]; in = lab == root; }
-        }
-        masks[q] = __ballot_sync(0xffffffffu, in);
-        total += __popc(masks[q]);
+      for (int q = 0; q < kFitGroups; q++) {        // 16 independent coalesced loads
+        const int g = t * kFitGroups + q;
+        const int cc = c0 + gc * 32 + lane;
+        labs[q] = -1; mine[q] = make_float4(0, 0, 0, 0);
+        if (g < ngroups && cc < Wd) { const int i = (r0 + gr) * Wd + cc; labs[q] = parent[i]; mine[q] = pts[i]; }
+        if (++gc == gpr) { gc = 0; gr++; }
       }
-      if (lane == 0) s_cnt[t & 1][warp] = total;
-      // producers only: named barrier 1 (96 threads) orders the per-warp totals before the offsets are formed
-      asm volatile("bar.sync 1, 96;");
+      fit_wait_eq(&s_done[p], prev);                // the consumer is done with the tile this slot carried before
       int off = 0;
-      for (int w2 = 1; w2 < warp; w2++) off += s_cnt[t & 1][w2];
 #pragma unroll
-      for (int q = 0; q < kFitGroupsPerWarp; q++) {
-        if ((masks[q] >> lane) & 1u) {
-          float *o = &s_v[t & 1][(off + __popc(masks[q] & ((1u << lane) - 1u))) * 9];
-          const float4 p = mine[q];
-          o[0] = __fmul_rn(p.x, p.x); o[1] = __fmul_rn(p.x, p.y); o[2] = __fmul_rn(p.x, p.z);
-          o[3] = __fmul_rn(p.y, p.y); o[4] = __fmul_rn(p.y, p.z); o[5] = __fmul_rn(p.z, p.z);
-          o[6] = p.x; o[7] = p.y; o[8] = p.z;
+      for (int q = 0; q < kFitGroups; q++) {
+        const unsigned mask = __ballot_sync(0xffffffffu, labs[q] == root);
+        if ((mask >> lane) & 1u) {
+          float *o = slot + (off + __popc(mask & ((1u << lane) - 1u))) * 9;
+          const float4 pt = mine[q];
+          o[0] = __fmul_rn(pt.x, pt.x); o[1] = __fmul_rn(pt.x, pt.y); o[2] = __fmul_rn(pt.x, pt.z);
+          o[3] = __fmul_rn(pt.y, pt.y); o[4] = __fmul_rn(pt.y, pt.z); o[5] = __fmul_rn(pt.z, pt.z);
+          o[6] = pt.x; o[7] = pt.y; o[8] = pt.z;
         }
-        off += __popc(masks[q]);
+        off += __popc(mask);
       }
+      __syncwarp();
+      prev = (it << 20) | (t + 1);
+      if (lane == 0) { s_cnt[p] = off; __threadfence_block(); s_full[p] = prev; }
     }
-    if (warp == 0 && t >= 1) {
-      const int b = (t - 1) & 1;
-      const int n = s_cnt[b][1] + s_cnt[b][2] + s_cnt[b][3];
-      const float *buf = s_v[b] + (lane < 9 ? lane : 0);
+  } else {
+    for (int t = 0; t < ntiles; t++) {
+      const int p = t % kFitProducers;
+      const int want = (it << 20) | (t + 1);
+      fit_wait_eq(&s_full[p], want);
+      const int n = s_cnt[p];
+      const float *buf = s_v + (size_t)p * kFitTilePts * 9 + (lane < 9 ? lane : 0);
       int j = 0;
       for (; j + 8 <= n; j += 8) {   // 8 independent LDS, then the 8-long dependent FADD chain
         float v[8];
@@ -520,8 +609,9 @@ __global__ void __launch_bounds__(kFitThreads) fit_kernel(PlaneParamsDev prm, Pl
         for (int u = 0; u < 8; u++) acc = __fadd_rn(acc, v[u]);
       }
       for (; j < n; j++) acc = __fadd_rn(acc, buf[j * 9]);
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); s_done[p] = want; }
     }
-    __syncthreads();
   }
   if (warp == 0) {
   float accu[9];
@@ -567,95 +657,148 @@ __global__ void __launch_bounds__(kFitThreads) fit_kernel(PlaneParamsDev prm, Pl
 }
 
 // ---------------------------------------------------------------------------------------------- P8: refinement
-__device__ __forceinline__ int block_incl_max_scan(int v, BlockScratch &S, bool reverse) {
-  // inclusive max scan in thread order (or reverse thread order)
-  int lane = lane_id(), w = warp_id(), nw = n_warps();
+struct MaxScanScratch { int tot[2][32]; };
+// inclusive max scan in thread order (or reverse thread order): warp scan by shuffles, the warp totals cross through a double-buffered
+// shared table (one barrier per call; `phase` flips in every thread), each warp folds the totals of the warps before (after) it with
+// one load per lane and a shuffle reduction
+__device__ __forceinline__ int block_incl_max_scan(int v, MaxScanScratch &S, int &phase, bool reverse) {
+  const int lane = lane_id(), w = warp_id(), nw = n_warps();
+  const int ninf = -0x7fffffff;
   int x = v;
   if (!reverse) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x = max(x, t); }
-    if (lane == 31) S.warp_i[w] = x;
-    __syncthreads();
-    int pre = -0x7fffffff;
-    for (int i = 0; i < w; i++) pre = max(pre, S.warp_i[i]);
-    __syncthreads();
-    return max(x, pre);
+    if (lane == 31) S.tot[phase][w] = x;
   } else {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_down_sync(0xffffffffu, x, o); if (lane + o < 32) x = max(x, t); }
-    if (lane == 0) S.warp_i[w] = x;
-    __syncthreads();
-    int pre = -0x7fffffff;
-    for (int i = w + 1; i < nw; i++) pre = max(pre, S.warp_i[i]);
-    __syncthreads();
-    return max(x, pre);
+    if (lane == 0) S.tot[phase][w] = x;
   }
+  __syncthreads();
+  int y = ninf;
+  if (lane < nw && (reverse ? (lane > w) : (lane < w))) y = S.tot[phase][lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) y = max(y, __shfl_xor_sync(0xffffffffu, y, o));
+  phase ^= 1;
+  return max(x, y);
 }
 __device__ __forceinline__ bool refine_ok(const float4 c, const float4 p) {   // PlaneRefinementComparator: |a x + b y + c z + d| < 0.02
   float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c.x, p.x), __fmul_rn(c.y, p.y)), __fmul_rn(c.z, p.z)), c.w);
   return fabsf(d) < 0.02f;
 }
-// blockDim.x = cols rounded up to 32 (<= 1024); thread = column
+// Per-pixel model image for the refinement: index of the valid plane model the pixel's region carries, or -1 (what the chained lookup
+// parent -> count gave before).  Stored in the distance-map buffer, which is free after the connected components.
+__global__ void model_image_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  const int NP = prm.rows * prm.cols;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = blockIdx.y;
+  if (idx >= NP) return;
+  const int r = W.parent[(size_t)f * NP + idx];
+  const int cn = W.count[(size_t)f * NP + r];
+  reinterpret_cast<int *>(W.dm)[(size_t)f * NP + idx] = cn < 0 ? (-cn - 1) : -1;
+}
+// blockDim.x = cols rounded up to 32 (<= 1024); thread = column.  The scan-order label propagation of
+// OrganizedMultiPlaneSegmentation::refine is row-sequential (958 dependent row steps per frame), so nothing global may sit on the
+// per-step critical path: every thread carries its column's model label of the current and the next row in registers (the vertical
+// check only ever relabels the thread's own column), the labels and points of the row after are prefetched one step ahead, and the
+// plane coefficients of the first 64 models sit in shared memory.
+constexpr int kRefineCoefSmem = 64;
 __global__ void refine_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
-  __shared__ BlockScratch S;
+  __shared__ MaxScanScratch S;
+  int phase = 0;
   __shared__ int s_m[1024];
+  __shared__ float4 s_coef[kRefineCoefSmem];
+  __shared__ int s_wrap_m;
+  __shared__ float4 s_wrap_p;
+  __shared__ int s_add[kRefineCoefSmem];   // inliers gained by the first 64 models (flushed once): a row joining one plane would otherwise
+                                           // serialise hundreds of global atomics on a single counter per row step
   const int H = prm.rows, Wd = prm.cols, NP = H * Wd;
   const int f = blockIdx.x, c = threadIdx.x;
+  const bool colok = c < Wd;
   int *parent = W.parent + (size_t)f * NP;
-  const int *count = W.count + (size_t)f * NP;
+  int *mimg = reinterpret_cast<int *>(W.dm) + (size_t)f * NP;
   const float4 *pts = W.pts + (size_t)f * NP;
-  const float4 *coef = W.cand_coef + f * kMaxRegions;
+  const float4 *coef_g = W.cand_coef + f * kMaxRegions;
   const int *croot = W.cand_root + f * kMaxRegions;
   int *csize = W.cand_size + f * kMaxRegions;
-  auto model_of = [&](int pix) -> int { int r = parent[pix]; int cn = count[r]; return cn < 0 ? (-cn - 1) : -1; };
+  const int ncand = W.cand_n[f];
+  for (int i = threadIdx.x; i < kRefineCoefSmem; i += blockDim.x) { s_add[i] = 0; if (i < ncand) s_coef[i] = coef_g[i]; }
+  __syncthreads();
+  auto coef = [&](int L) -> float4 { return L < kRefineCoefSmem ? s_coef[L] : coef_g[L]; };
+  // one (shared-memory) atomic per warp and model; called by every thread of the warp
+  auto add_inlier = [&](bool pred, int L) {
+    const unsigned act = __ballot_sync(0xffffffffu, pred);
+    if (pred) {
+      const unsigned peers = __match_any_sync(act, L);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        if (L < kRefineCoefSmem) atomicAdd(&s_add[L], __popc(peers)); else atomicAdd(&csize[L], __popc(peers));
+      }
+    }
+  };
+  const float4 zero4 = make_float4(0, 0, 0, 0);
   for (int pass = 0; pass < 2; pass++) {
     const bool fwd = pass == 0;
+    const int dr = fwd ? 1 : -1;
+    const int rfirst = fwd ? 0 : H - 1;
+    __syncthreads();   // the first pass's relabelling is visible to the whole CTA
+    int m_cur = colok ? mimg[rfirst * Wd + c] : -1;
+    float4 p_cur = colok ? pts[rfirst * Wd + c] : zero4;
+    int m_nxt = colok ? mimg[(rfirst + dr) * Wd + c] : -1;
+    float4 p_nxt = colok ? pts[(rfirst + dr) * Wd + c] : zero4;
     for (int step = 0; step < H - 1; step++) {
-      const int r = fwd ? step : (H - 1 - step);          // current row
-      const int rn = fwd ? r + 1 : r - 1;                 // row hit by the vertical check
-      int m = -1;
-      if (c < Wd) m = model_of(r * Wd + c);
+      const int r = rfirst + dr * step;                   // current row
+      const int rn = r + dr;                              // row hit by the vertical check
+      int m_n2 = -1; float4 p_n2 = zero4;                 // labels / points of the row after rn: prefetched, nobody writes them this step
+      if (colok && step + 1 < H - 1) { m_n2 = mimg[(rn + dr) * Wd + c]; p_n2 = pts[(rn + dr) * Wd + c]; }
+      int m = m_cur;
       // a row without any model pixel can neither propagate sideways nor vertically: one barrier instead of eight
-      if (!__syncthreads_or((c < Wd && m >= 0) ? 1 : 0)) continue;
-      if (c < Wd) s_m[c] = m;
-      __syncthreads();
-      // ---- horizontal propagation along the row (scan direction = traversal direction); skipped when no non-model pixel has a
-      //      model pixel as its upstream neighbour (then nothing can be relabelled in this row)
-      bool cand = false;
-      if (c < Wd && m < 0) cand = fwd ? (c >= 1 && s_m[c - 1] >= 0) : (c + 1 < Wd && s_m[c + 1] >= 0);
-      int L = -1;
-      if (__syncthreads_or(cand ? 1 : 0)) {
-        int s;
-        if (fwd) s = block_incl_max_scan((c < Wd && m >= 0) ? c : -1, S, false);                 // nearest source at or left of c
-        else s = -block_incl_max_scan((c < Wd && m >= 0) ? -c : -(1 << 30), S, true);            // nearest source at or right of c
-        const bool has_src = fwd ? (s >= 0) : (s < (1 << 29));
-        bool blocked = false;
-        if (c < Wd && m < 0) {
-          if (has_src) { L = s_m[s]; blocked = !refine_ok(coef[L], pts[r * Wd + c]); }
-          else blocked = true;
+      if (__syncthreads_or((colok && m >= 0) ? 1 : 0)) {
+        if (colok) s_m[c] = m;
+        __syncthreads();
+        // ---- horizontal propagation along the row (scan direction = traversal direction); skipped when no non-model pixel has a
+        //      model pixel as its upstream neighbour (then nothing can be relabelled in this row)
+        bool cand = false;
+        if (colok && m < 0) cand = fwd ? (c >= 1 && s_m[c - 1] >= 0) : (c + 1 < Wd && s_m[c + 1] >= 0);
+        int L = -1;
+        if (__syncthreads_or(cand ? 1 : 0)) {
+          int s;
+          if (fwd) s = block_incl_max_scan((colok && m >= 0) ? c : -1, S, phase, false);                 // nearest source at or left of c
+          else s = -block_incl_max_scan((colok && m >= 0) ? -c : -(1 << 30), S, phase, true);            // nearest source at or right of c
+          const bool has_src = fwd ? (s >= 0) : (s < (1 << 29));
+          bool blocked = false;
+          if (colok && m < 0) {
+            if (has_src) { L = s_m[s]; blocked = !refine_ok(coef(L), p_cur); }
+            else blocked = true;
+          }
+          int b;
+          if (fwd) b = block_incl_max_scan((colok && m < 0 && blocked) ? c : -1, S, phase, false);       // last blocked index <= c
+          else b = -block_incl_max_scan((colok && m < 0 && blocked) ? -c : -(1 << 30), S, phase, true);  // first blocked index >= c
+          bool recv = false;
+          if (colok && m < 0 && has_src) recv = fwd ? (b < s) : (b > s);
+          // the forward pass never uses column W-1 as "current"; every receiver's chain starts at a source that IS a valid current
+          if (recv) { m = L; parent[r * Wd + c] = croot[L]; mimg[r * Wd + c] = L; }
+          add_inlier(recv, L);
         }
-        int b;
-        if (fwd) b = block_incl_max_scan((c < Wd && m < 0 && blocked) ? c : -1, S, false);       // last blocked index <= c
-        else b = -block_incl_max_scan((c < Wd && m < 0 && blocked) ? -c : -(1 << 30), S, true);  // first blocked index >= c
-        bool recv = false;
-        if (c < Wd && m < 0 && has_src) recv = fwd ? (b < s) : (b > s);
-        // the forward pass never uses column W-1 as "current"; every receiver's chain starts at a source that IS a valid current
-        if (recv) { m = L; parent[r * Wd + c] = croot[L]; atomicAdd(&csize[L], 1); }
+        // ---- vertical check from the (updated) current row: only this thread ever relabels pixel (rn, c)
+        const bool cur_ok = colok && m >= 0 && (fwd ? (c <= Wd - 2) : true);
+        const bool vhit = cur_ok && m_nxt < 0 && refine_ok(coef(m), p_nxt);
+        if (vhit) { m_nxt = m; parent[rn * Wd + c] = croot[m]; mimg[rn * Wd + c] = m; }
+        add_inlier(vhit, m);
+        if (!fwd) {   // colIdx == 0: the "left" neighbour is the last pixel of the previous row (pointer arithmetic in PCL) = (rn, W-1)
+          if (c == Wd - 1) { s_wrap_m = m_nxt; s_wrap_p = p_nxt; }
+          __syncthreads();
+          if (c == 0 && m >= 0 && s_wrap_m < 0 && refine_ok(coef(m), s_wrap_p)) {
+            s_wrap_m = m; parent[r * Wd - 1] = croot[m]; mimg[r * Wd - 1] = m; atomicAdd(&csize[m], 1);
+          }
+          __syncthreads();
+          if (c == Wd - 1) m_nxt = s_wrap_m;
+        }
       }
-      // ---- vertical check from the (updated) current row
-      bool cur_ok = (c < Wd) && m >= 0 && (fwd ? (c <= Wd - 2) : true);
-      if (cur_ok) {
-        int tp = rn * Wd + c;
-        if (model_of(tp) < 0 && refine_ok(coef[m], pts[tp])) { parent[tp] = croot[m]; atomicAdd(&csize[m], 1); }
-      }
-      __syncthreads();
-      if (!fwd && c == 0 && m >= 0) {   // colIdx == 0: "left" neighbour is the last pixel of the previous row (pointer arithmetic in PCL)
-        int tp = r * Wd - 1;
-        if (model_of(tp) < 0 && refine_ok(coef[m], pts[tp])) { parent[tp] = croot[m]; atomicAdd(&csize[m], 1); }
-      }
-      __syncthreads();
+      m_cur = m_nxt; p_cur = p_nxt; m_nxt = m_n2; p_nxt = p_n2;
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kRefineCoefSmem && i < ncand; i += blockDim.x) if (s_add[i]) atomicAdd(&csize[i], s_add[i]);
 }
 
 // ---------------------------------------------------------------------------------------------- P9: selection (PlaneExtractor.cpp:89-106,126-183)
@@ -693,7 +836,7 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   if (H > 1024 || Wd > 1024 || H < 24 || Wd < 24 || pitch < (size_t)Wd) { h->err = "plane_extract: image must be between 24 and 1024 pixels per side"; return ESLAM_ERR_BAD_ARG; }
   if (!h->pl) h->pl = new PlaneWorkspace();
   PlaneWorkspace &w = *h->pl;
-  const size_t NP = (size_t)H * Wd, NI = (size_t)(H + 1) * (Wd + 1) * 3;
+  const size_t NP = (size_t)H * Wd, NI = (size_t)(H + 1) * ii_pitch(Wd) * 3;
   const int chunk = n_frames < 256 ? n_frames : 256;   // per-frame CTAs (integral / distmap / refine) need >= 148 frames in flight
   ESLAM_CUDA_OK(h, w.pts.reserve(chunk * NP * 16)); ESLAM_CUDA_OK(h, w.nrm.reserve(chunk * NP * 16));
   ESLAM_CUDA_OK(h, w.iiX.reserve(chunk * NI * 8)); ESLAM_CUDA_OK(h, w.iiY.reserve(chunk * NI * 8));
@@ -715,17 +858,18 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   prm.dis_th = (float)h->prm.plane_dist;
   prm.ang_cos = cosf((float)(0.017453 * AngTh));   // mps.setAngularThreshold(0.017453 * AngTh) -> PlaneCoefficientComparator: cosf
   prm.min_size = h->prm.plane_min_size;
-  const size_t ring_bytes = (size_t)(((H + 31) / 32) * 32) * 4 * 6 * sizeof(double);
-  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // 2 CTAs (2 x 92 KB) per SM
-  const int tpr = ((H + 31) / 32) * 32, tpc = ((Wd + 31) / 32) * 32;
+  const int kIntSmemBytes = kIntWarps * 32 * kIntRingPitch * (int)sizeof(float);
+  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIntSmemBytes));
+  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // 2 CTAs (2 x 97 KB) per SM
+  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFitSmemBytes));
+  const int tpc = ((Wd + 31) / 32) * 32;
   const size_t frame_stride = (size_t)H * pitch;
   for (int f0 = 0; f0 < n_frames; f0 += chunk) {
     const int F = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;
     const uint16_t *d0 = depth_dev + (size_t)f0 * frame_stride;
     dim3 gpix((unsigned)((NP + 255) / 256), (unsigned)F);
     points_kernel<<<gpix, 256, 0, s>>>(d0, pitch, frame_stride, prm, P); ESLAM_LAUNCHED(h);
-    integral_kernel<<<F, tpr, ring_bytes, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    integral_kernel<<<F, 32 * kIntWarps, kIntSmemBytes, s>>>(prm, P); ESLAM_LAUNCHED(h);
     distmap_kernel<<<F, tpc, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     if (debug_stage == 1) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.dm, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
     normals_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
@@ -737,7 +881,8 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
     if (debug_stage == 3) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.parent, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
     candidates_kernel<<<F, 1024, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     dim3 gfit(8, (unsigned)F);    // 8 CTAs per frame stride over that frame's candidate regions
-    fit_kernel<<<gfit, kFitThreads, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    fit_kernel<<<gfit, kFitThreads, kFitSmemBytes, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    model_image_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     refine_kernel<<<F, tpc, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     if (debug_stage == 4) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.parent, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
     select_kernel<<<(F + 63) / 64, 64, 0, s>>>(prm, P, F); ESLAM_LAUNCHED(h);
