@@ -4,7 +4,8 @@
 // PCL algorithms behind them (PCL is an external, unpinned dependency of the reference -- see oracle/orc_plane.h for the
 // restated upstream algorithms):
 //   pcl::IntegralImageNormalEstimation (AVERAGE_3D_GRADIENT)      -> points_kernel, integral_kernel, distmap_kernel, normals_kernel
-//   pcl::OrganizedConnectedComponentSegmentation + PlaneCoefficientComparator -> ccl_union_kernel / ccl_flatten_kernel (lock-free union-find)
+//   pcl::OrganizedConnectedComponentSegmentation + PlaneCoefficientComparator -> ccl_strip_kernel (shared-memory union-find per 16-row strip),
+//                                                                    ccl_seam_kernel (strip boundaries, lock-free global union-find), ccl_flatten_kernel
 //   computeMeanAndCovarianceMatrix<float> + pcl::eigen33          -> fit_kernel (one warp per region, sequential float sums in raster order)
 //   OrganizedMultiPlaneSegmentation::refine (PlaneRefinementComparator) -> refine_kernel (row-sequential, scan-parallel inside a row)
 //   selection rules of extractGroundPlane                         -> select_kernel
@@ -40,7 +41,8 @@ struct PlaneFramePtrs {
   float4 *pts, *nrm;
   double *iiX, *iiY;
   float *dm;
-  int *parent, *count, *maxidx, *cmin, *cmax;   // per-root size, last pixel, column range (bounding box of the region)
+  int *parent, *count, *maxidx, *cmin, *cmax;   // union-find parents; per-root size, last pixel, column range (bounding box of the region)
+  int *label;          // flattened region label of every pixel (= smallest pixel index of the region), relabelled by the refinement
   int *cand_root;      // [F * kMaxRegions]
   int *cand_n;         // [F]
   float4 *cand_coef;   // [F * kMaxRegions]
@@ -51,7 +53,7 @@ struct PlaneFramePtrs {
 };
 
 struct PlaneWorkspace {
-  DevBuf pts, nrm, iiX, iiY, dm, parent, count, maxidx, cmin, cmax, cand_root, cand_n, cand_coef, cand_valid, cand_size, out_plane, out_found, out_inl;
+  DevBuf pts, nrm, iiX, iiY, dm, parent, label, count, maxidx, cmin, cmax, cand_root, cand_n, cand_coef, cand_valid, cand_size, out_plane, out_found, out_inl;
   PinBuf pin;
   int chunk = 0;
 };
@@ -69,7 +71,6 @@ __global__ void points_kernel(const uint16_t *__restrict__ depth, size_t pitch, 
   float x = (float)((n - prm.cx) * (double)z / prm.fx);
   float y = (float)((m - prm.cy) * (double)z / prm.fy);
   W.pts[(size_t)f * NP + idx] = make_float4(x, y, z, 0.0f);
-  W.parent[(size_t)f * NP + idx] = idx;
   W.count[(size_t)f * NP + idx] = 0;
   W.maxidx[(size_t)f * NP + idx] = 0;
   W.cmin[(size_t)f * NP + idx] = 0x7fffffff;
@@ -375,79 +376,131 @@ __device__ __forceinline__ bool plane_compare(const float4 *pts, const float4 *n
   float dotn = __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
   return (fabsf(__fsub_rn(a.w, b.w)) < threshold) && (dotn > ang_cos);
 }
-// Pass 1: horizontal runs inside each warp's 32 consecutive pixels get their first pixel as parent (plain stores, no atomics).
-__global__ void ccl_runs_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
-  const int Wd = prm.cols, NP = prm.rows * prm.cols;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int f = blockIdx.y, lane = threadIdx.x & 31;
-  const bool act = idx < NP;
-  const float4 *pts = W.pts + (size_t)f * NP, *nrm = W.nrm + (size_t)f * NP;
-  const int ci = act ? idx % Wd : 0;
-  const bool h = act && ci >= 1 && plane_compare(pts, nrm, idx, idx - 1, prm.dis_th, prm.ang_cos);
-  const unsigned starts = __ballot_sync(0xffffffffu, !h || lane == 0);
-  if (act) {
-    const int head_lane = 31 - __clz(starts & (0xffffffffu >> (31 - lane)));
-    W.parent[(size_t)f * NP + idx] = idx - (lane - head_lane);
+__device__ __forceinline__ bool plane_compare_vals(float z, float4 a, float4 b, float dis_th, float ang_cos) {   // plane_compare on loaded values
+  const float threshold = __fmul_rn(dis_th, __fmul_rn(z, z));
+  const float dotn = __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+  return (fabsf(__fsub_rn(a.w, b.w)) < threshold) && (dotn > ang_cos);
+}
+// shared-memory union-find of a strip (volatile on shared memory is a plain LDS/STS)
+__device__ __forceinline__ int s_find(int *par, int i) {
+  int p = *((volatile int *)(par + i));
+  while (p != i) {
+    const int gp = *((volatile int *)(par + p));
+    if (gp != p) *((volatile int *)(par + i)) = gp;
+    i = p; p = gp;
+  }
+  return i;
+}
+__device__ __forceinline__ void s_union(int *par, int a, int b) {
+  while (true) {
+    a = s_find(par, a); b = s_find(par, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }
+    if (atomicCAS(par + a, a, b) == a) return;
   }
 }
-// Pass 2: the remaining links.  A vertical link is redundant when the pixel and its left neighbour are in the same run, both link
-// upwards and the two upper pixels are linked to each other; only the non-redundant ones (run heads, seams) touch the union-find.
-__global__ void ccl_union_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+// Phase 1: one CTA labels a strip of kStripRows full image rows entirely in shared memory.  Thread = column; per row the horizontal
+// runs inside a warp get their first pixel as parent (plain stores), the links that are left -- runs continuing across a warp seam and
+// the non-redundant vertical links (a vertical link is redundant when the pixel and its left neighbour are in the same run, both link
+// upwards and the two upper pixels are linked to each other) -- go through the shared-memory union-find.  Every pixel then gets the
+// global index of its strip-local root (the smallest index of its component inside the strip) as parent.
+constexpr int kStripRows = 16;
+__global__ void ccl_strip_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  extern __shared__ int s_par[];   // [kStripRows * cols]
+  const int H = prm.rows, Wd = prm.cols, NP = H * Wd;
+  const int f = blockIdx.y, row0 = blockIdx.x * kStripRows;
+  const int nrows = min(kStripRows, H - row0);
+  const int c = threadIdx.x, lane = c & 31;
+  const bool colok = c < Wd;
+  const float4 *pts = W.pts + (size_t)f * NP + (size_t)row0 * Wd, *nrm = W.nrm + (size_t)f * NP + (size_t)row0 * Wd;
+  unsigned hbits = 0, vbits = 0;   // bit r: run continues across the warp seam / non-redundant vertical link of local row r
+  float4 n_up = make_float4(0, 0, 0, 0);
+  bool h_up = false;
+  for (int r = 0; r < nrows; r++) {
+    const int li = r * Wd + c;
+    float z = 0.0f; float4 n = make_float4(0, 0, 0, 0);
+    if (colok) { z = pts[li].z; n = nrm[li]; }
+    float4 nl;
+    nl.x = __shfl_up_sync(0xffffffffu, n.x, 1); nl.y = __shfl_up_sync(0xffffffffu, n.y, 1);
+    nl.z = __shfl_up_sync(0xffffffffu, n.z, 1); nl.w = __shfl_up_sync(0xffffffffu, n.w, 1);
+    if (lane == 0 && colok && c >= 1) nl = nrm[li - 1];
+    const bool h = colok && c >= 1 && plane_compare_vals(z, n, nl, prm.dis_th, prm.ang_cos);
+    const bool v = colok && r >= 1 && plane_compare_vals(z, n, n_up, prm.dis_th, prm.ang_cos);
+    const unsigned starts = __ballot_sync(0xffffffffu, !h || lane == 0);
+    if (colok) {
+      const int head_lane = 31 - __clz(starts & (0xffffffffu >> (31 - lane)));
+      s_par[li] = li - (lane - head_lane);
+    }
+    const bool v_left = __shfl_up_sync(0xffffffffu, v ? 1 : 0, 1) != 0;
+    const bool need_v = v && !(h && lane >= 1 && v_left && h_up);
+    if (h && lane == 0) hbits |= 1u << r;
+    if (need_v) vbits |= 1u << r;
+    n_up = n; h_up = h;
+  }
+  __syncthreads();
+  for (int r = 0; r < nrows; r++) {
+    if ((hbits >> r) & 1u) s_union(s_par, r * Wd + c, r * Wd + c - 1);
+    if ((vbits >> r) & 1u) s_union(s_par, r * Wd + c, (r - 1) * Wd + c);
+  }
+  __syncthreads();
+  // Parents out; region statistics (size, last pixel, column range) go to the strip-local root's slots: each thread walks its column
+  // and issues one set of reductions per vertical run, so the counters of a big region see a few hundred updates per strip instead
+  // of one per warp of the whole frame on four global addresses; ccl_flatten_kernel folds the local roots into the global ones.
+  if (colok) {
+    const size_t gbase = (size_t)f * NP + (size_t)row0 * Wd;
+    int cur = -1, cnt = 0, lastidx = 0;
+    for (int r = 0; r <= nrows; r++) {
+      const int root = r < nrows ? s_find(s_par, r * Wd + c) : -2;
+      if (root != cur) {
+        if (cnt > 0) {
+          atomicAdd(W.count + gbase + cur, cnt); atomicMax(W.maxidx + gbase + cur, lastidx);
+          atomicMin(W.cmin + gbase + cur, c); atomicMax(W.cmax + gbase + cur, c);
+        }
+        cur = root; cnt = 0;
+      }
+      if (r < nrows) { W.parent[gbase + r * Wd + c] = row0 * Wd + root; cnt++; lastidx = (row0 + r) * Wd + c; }
+    }
+  }
+}
+// Phase 2: the vertical links across strip boundaries (first row of every strip but the first) on the global parents.
+__global__ void ccl_seam_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   const int Wd = prm.cols, NP = prm.rows * prm.cols;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int f = blockIdx.y, lane = threadIdx.x & 31;
-  const bool act = idx < NP;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  const int f = blockIdx.z, row = (blockIdx.y + 1) * kStripRows;
+  const bool act = c < Wd && row < prm.rows;
   const float4 *pts = W.pts + (size_t)f * NP, *nrm = W.nrm + (size_t)f * NP;
-  int *parent = W.parent + (size_t)f * NP;
-  const int ri = act ? idx / Wd : 0, ci = act ? idx - ri * Wd : 0;
-  const bool h = act && ci >= 1 && plane_compare(pts, nrm, idx, idx - 1, prm.dis_th, prm.ang_cos);
-  const bool v = act && ri >= 1 && plane_compare(pts, nrm, idx, idx - Wd, prm.dis_th, prm.ang_cos);
+  const int idx = row * Wd + c;
+  const bool v = act && plane_compare(pts, nrm, idx, idx - Wd, prm.dis_th, prm.ang_cos);
+  const bool h = act && c >= 1 && plane_compare(pts, nrm, idx, idx - 1, prm.dis_th, prm.ang_cos);
   const bool v_left = __shfl_up_sync(0xffffffffu, v ? 1 : 0, 1) != 0;
   bool need_v = v;
-  if (v && h && lane >= 1 && v_left && ci >= 1) {
-    const bool h_up = plane_compare(pts, nrm, idx - Wd, idx - Wd - 1, prm.dis_th, prm.ang_cos);   // the upper pixels' own horizontal link
-    if (h_up) need_v = false;
-  }
-  if (h && lane == 0) p_union(parent, idx, idx - 1);   // run continues across the warp seam
-  if (need_v) p_union(parent, idx, idx - Wd);
+  if (v && h && lane >= 1 && v_left && plane_compare(pts, nrm, idx - Wd, idx - Wd - 1, prm.dis_th, prm.ang_cos)) need_v = false;
+  if (need_v) p_union(W.parent + (size_t)f * NP, idx, idx - Wd);
+}
+// root of pixel i once all unions are done (the parents are static now): weak L2 loads, no path compression -- the chains are a strip
+// root plus a few seam hops, and strong (ld.relaxed.gpu) loads stall the dispatcher (80 % of this kernel's stall samples before)
+__device__ __forceinline__ int p_find_static(const int *parent, int i) {
+  int p = __ldcg(parent + i);
+  while (p != i) { i = p; p = __ldcg(parent + i); }
+  return i;
 }
 __global__ void ccl_flatten_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   const int NP = prm.rows * prm.cols;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int f = blockIdx.y;
   const bool act = idx < NP;
-  int *parent = W.parent + (size_t)f * NP;
-  int r = act ? p_find(parent, idx) : -1 - (int)(threadIdx.x & 31);
-  // warp-aggregated statistics: consecutive pixels mostly share a root, so one lane per distinct root issues the atomics
-  const unsigned peers = __match_any_sync(0xffffffffu, r);
-  if (act) {
-    const int lane = threadIdx.x & 31;
-    const int lo = __ffs(peers) - 1, hi = 31 - __clz(peers);
-    const int col = idx % prm.cols;
-    const int col_lo = __shfl_sync(peers, col, lo), col_hi = __shfl_sync(peers, col, hi);
-    const int row_lo = __shfl_sync(peers, idx / prm.cols, lo), row_hi = __shfl_sync(peers, idx / prm.cols, hi);
-    if (row_lo == row_hi) {
-      if (lane == lo) {
-        atomicAdd(W.count + (size_t)f * NP + r, __popc(peers));
-        atomicMax(W.maxidx + (size_t)f * NP + r, idx + (hi - lo));
-        atomicMin(W.cmin + (size_t)f * NP + r, col_lo);
-        atomicMax(W.cmax + (size_t)f * NP + r, col_hi);
-      }
-    } else {   // the warp straddles an image row (cols not a multiple of 32): per-lane atomics
-      atomicAdd(W.count + (size_t)f * NP + r, 1);
-      atomicMax(W.maxidx + (size_t)f * NP + r, idx);
-      atomicMin(W.cmin + (size_t)f * NP + r, col);
-      atomicMax(W.cmax + (size_t)f * NP + r, col);
-    }
-    W.dm[(size_t)f * NP + idx] = __int_as_float(r);   // dm is free now: stash the flattened label (written back below)
+  const int *parent = W.parent + (size_t)f * NP;
+  if (!act) return;
+  const int r = p_find_static(parent, idx);
+  W.label[(size_t)f * NP + idx] = r;
+  // strip-local roots (the only pixels with a non-zero size) that were merged into another root hand their statistics on
+  const int cn = W.count[(size_t)f * NP + idx];
+  if (cn > 0 && r != idx) {
+    atomicAdd(W.count + (size_t)f * NP + r, cn);
+    atomicMax(W.maxidx + (size_t)f * NP + r, W.maxidx[(size_t)f * NP + idx]);
+    atomicMin(W.cmin + (size_t)f * NP + r, W.cmin[(size_t)f * NP + idx]);
+    atomicMax(W.cmax + (size_t)f * NP + r, W.cmax[(size_t)f * NP + idx]);
   }
-}
-__global__ void ccl_commit_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
-  const int NP = prm.rows * prm.cols;
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  int f = blockIdx.y;
-  if (idx >= NP) return;
-  W.parent[(size_t)f * NP + idx] = __float_as_int(W.dm[(size_t)f * NP + idx]);
 }
 
 // ---------------------------------------------------------------------------------------------- P6: candidate regions (> 100 px), label order
@@ -455,7 +508,7 @@ __global__ void candidates_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   __shared__ BlockScratch S;
   const int NP = prm.rows * prm.cols;
   const int f = blockIdx.x, tid = threadIdx.x;
-  const int *parent = W.parent + (size_t)f * NP, *count = W.count + (size_t)f * NP;
+  const int *parent = W.label + (size_t)f * NP, *count = W.count + (size_t)f * NP;
   int K = 0;
   for (int tile = 0; tile < NP; tile += blockDim.x) {
     int i = tile + tid;
@@ -532,7 +585,7 @@ __global__ void __launch_bounds__(kFitThreads) fit_kernel(PlaneParamsDev prm, Pl
   const int NP = prm.rows * prm.cols, Wd = prm.cols;
   const int f = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int *parent = W.parent + (size_t)f * NP;
+  const int *parent = W.label + (size_t)f * NP;
   const float4 *pts = W.pts + (size_t)f * NP;
   const int ncand = W.cand_n[f];
   const bool ranked = ncand <= kFitRankMax;
@@ -693,7 +746,7 @@ __global__ void model_image_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int f = blockIdx.y;
   if (idx >= NP) return;
-  const int r = W.parent[(size_t)f * NP + idx];
+  const int r = W.label[(size_t)f * NP + idx];
   const int cn = W.count[(size_t)f * NP + r];
   reinterpret_cast<int *>(W.dm)[(size_t)f * NP + idx] = cn < 0 ? (-cn - 1) : -1;
 }
@@ -715,7 +768,7 @@ __global__ void refine_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   const int H = prm.rows, Wd = prm.cols, NP = H * Wd;
   const int f = blockIdx.x, c = threadIdx.x;
   const bool colok = c < Wd;
-  int *parent = W.parent + (size_t)f * NP;
+  int *parent = W.label + (size_t)f * NP;
   int *mimg = reinterpret_cast<int *>(W.dm) + (size_t)f * NP;
   const float4 *pts = W.pts + (size_t)f * NP;
   const float4 *coef_g = W.cand_coef + f * kMaxRegions;
@@ -840,7 +893,7 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   const int chunk = n_frames < 256 ? n_frames : 256;   // per-frame CTAs (integral / distmap / refine) need >= 148 frames in flight
   ESLAM_CUDA_OK(h, w.pts.reserve(chunk * NP * 16)); ESLAM_CUDA_OK(h, w.nrm.reserve(chunk * NP * 16));
   ESLAM_CUDA_OK(h, w.iiX.reserve(chunk * NI * 8)); ESLAM_CUDA_OK(h, w.iiY.reserve(chunk * NI * 8));
-  ESLAM_CUDA_OK(h, w.dm.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.parent.reserve(chunk * NP * 4));
+  ESLAM_CUDA_OK(h, w.dm.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.parent.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.label.reserve(chunk * NP * 4));
   ESLAM_CUDA_OK(h, w.count.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.maxidx.reserve(chunk * NP * 4));
   ESLAM_CUDA_OK(h, w.cmin.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.cmax.reserve(chunk * NP * 4));
   ESLAM_CUDA_OK(h, w.cand_root.reserve((size_t)chunk * kMaxRegions * 4)); ESLAM_CUDA_OK(h, w.cand_n.reserve((size_t)chunk * 4));
@@ -849,7 +902,7 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   ESLAM_CUDA_OK(h, w.out_plane.reserve((size_t)chunk * 32)); ESLAM_CUDA_OK(h, w.out_found.reserve((size_t)chunk * 4)); ESLAM_CUDA_OK(h, w.out_inl.reserve((size_t)chunk * 4));
   PlaneFramePtrs P;
   P.pts = w.pts.as<float4>(); P.nrm = w.nrm.as<float4>(); P.iiX = w.iiX.as<double>(); P.iiY = w.iiY.as<double>(); P.dm = w.dm.as<float>();
-  P.parent = w.parent.as<int>(); P.count = w.count.as<int>(); P.maxidx = w.maxidx.as<int>(); P.cmin = w.cmin.as<int>(); P.cmax = w.cmax.as<int>();
+  P.parent = w.parent.as<int>(); P.label = w.label.as<int>(); P.count = w.count.as<int>(); P.maxidx = w.maxidx.as<int>(); P.cmin = w.cmin.as<int>(); P.cmax = w.cmax.as<int>();
   P.cand_root = w.cand_root.as<int>(); P.cand_n = w.cand_n.as<int>(); P.cand_coef = w.cand_coef.as<float4>(); P.cand_valid = w.cand_valid.as<int>();
   P.cand_size = w.cand_size.as<int>(); P.out_plane = w.out_plane.as<double>(); P.out_found = w.out_found.as<int>(); P.out_inl = w.out_inl.as<int>();
   PlaneParamsDev prm;
@@ -863,6 +916,8 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // 2 CTAs (2 x 97 KB) per SM
   ESLAM_CUDA_OK(h, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFitSmemBytes));
   const int tpc = ((Wd + 31) / 32) * 32;
+  const int strip_bytes = kStripRows * Wd * (int)sizeof(int);
+  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(ccl_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, strip_bytes));
   const size_t frame_stride = (size_t)H * pitch;
   for (int f0 = 0; f0 < n_frames; f0 += chunk) {
     const int F = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;
@@ -874,17 +929,17 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
     if (debug_stage == 1) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.dm, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
     normals_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     if (debug_stage == 2) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.nrm, NP * 16, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
-    ccl_runs_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
-    ccl_union_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    const int nstrips = (H + kStripRows - 1) / kStripRows;
+    ccl_strip_kernel<<<dim3((unsigned)nstrips, (unsigned)F), tpc, strip_bytes, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    if (nstrips > 1) { ccl_seam_kernel<<<dim3((unsigned)((Wd + 255) / 256), (unsigned)(nstrips - 1), (unsigned)F), 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h); }
     ccl_flatten_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
-    ccl_commit_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
-    if (debug_stage == 3) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.parent, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
+    if (debug_stage == 3) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.label, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
     candidates_kernel<<<F, 1024, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     dim3 gfit(8, (unsigned)F);    // 8 CTAs per frame stride over that frame's candidate regions
     fit_kernel<<<gfit, kFitThreads, kFitSmemBytes, s>>>(prm, P); ESLAM_LAUNCHED(h);
     model_image_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     refine_kernel<<<F, tpc, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
-    if (debug_stage == 4) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.parent, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
+    if (debug_stage == 4) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.label, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
     select_kernel<<<(F + 63) / 64, 64, 0, s>>>(prm, P, F); ESLAM_LAUNCHED(h);
     ESLAM_CUDA_OK(h, cudaGetLastError());
     ESLAM_CUDA_OK(h, cudaMemcpyAsync(plane_cam_host + 4 * (size_t)f0, P.out_plane, sizeof(double) * 4 * F, cudaMemcpyDeviceToHost, s));
@@ -903,7 +958,7 @@ int plane_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *
 void plane_free(EslamHandle *h) {
   if (!h->pl) return;
   PlaneWorkspace &w = *h->pl;
-  DevBuf *bufs[] = {&w.pts, &w.nrm, &w.iiX, &w.iiY, &w.dm, &w.parent, &w.count, &w.maxidx, &w.cmin, &w.cmax, &w.cand_root, &w.cand_n, &w.cand_coef, &w.cand_valid, &w.cand_size,
+  DevBuf *bufs[] = {&w.pts, &w.nrm, &w.iiX, &w.iiY, &w.dm, &w.parent, &w.label, &w.count, &w.maxidx, &w.cmin, &w.cmax, &w.cand_root, &w.cand_n, &w.cand_coef, &w.cand_valid, &w.cand_size,
                     &w.out_plane, &w.out_found, &w.out_inl};
   for (DevBuf *b : bufs) b->release();
   w.pin.release();

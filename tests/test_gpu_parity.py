@@ -168,6 +168,24 @@ def test_pixels_outside_boxes_are_never_read(handle, kind, n_frames):
     assert bytes(c) == bytes(a)
 
 
+@pytest.mark.parametrize("label", [28, 41])
+def test_large_box_takes_the_hbm_union_find_and_uncached_symmetry_paths(handle, label):
+    """A box covering the whole frame with the supporting plane moved 5 m down: 19 k points reach the clustering (> 12 288, so the
+    union-find parents live in the HBM slice, not in shared memory) and the symmetry cloud has 447 points (> 256: brute-force NN
+    from global memory, no NN / pixel cache).  Same integer counts and ellipsoid as the oracle."""
+    depth, fo, bb, lb, tw = synth.make_batch(1, "one_box")
+    big = np.array([[12.0, 12.0, 628.0, 468.0]])
+    plane = np.array(synth.GROUND_PLANE_WORLD, dtype=float).copy(); plane[3] += 5.0
+    handle.set_supporting_plane(plane)
+    g, _, _ = handle.estimate_ellipsoids(depth, [0], big, [label], tw)
+    o, _, _, _ = orc.estimate_ellipsoids(depth, [0], big, [label], tw, plane)
+    handle.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+    g, o = g[0], o[0]
+    assert o.status == 0 and o.n_plane > 12288 and o.n_sym > 256
+    assert (g.status, g.n_crop, g.n_voxel, g.n_plane, g.n_clusters, g.n_cluster, g.n_sym, g.n_final) == (o.status, o.n_crop, o.n_voxel, o.n_plane, o.n_clusters, o.n_cluster, o.n_sym, o.n_final)
+    assert ellipsoid_close(g.ellipsoid, o.ellipsoid, 1e-4) and abs(g.prob - o.prob) < 1e-5
+
+
 def test_missing_plane_is_an_error():
     h = E.Handle()
     depth, fo, bb, lb, tw = synth.make_batch(1)
