@@ -510,13 +510,25 @@ __global__ void candidates_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   const int f = blockIdx.x, tid = threadIdx.x;
   const int *parent = W.label + (size_t)f * NP, *count = W.count + (size_t)f * NP;
   int K = 0;
-  for (int tile = 0; tile < NP; tile += blockDim.x) {
-    int i = tile + tid;
-    bool acc = (i < NP) && parent[i] == i && (unsigned)count[i] > 100u;   // min_inliers_ = 100, strict
-    int tot;
-    int ex = block_excl_scan(acc ? 1 : 0, S, tot);
-    if (acc && K + ex < kMaxRegions) { W.cand_root[f * kMaxRegions + K + ex] = i; W.cand_size[f * kMaxRegions + K + ex] = count[i]; }
-    K += tot;
+  for (int tile = 0; tile < NP; tile += 4 * blockDim.x) {
+    bool acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {   // four independent label loads in flight
+      const int i = tile + u * blockDim.x + tid;
+      acc[u] = (i < NP) && parent[i] == i;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = tile + u * blockDim.x + tid; acc[u] = acc[u] && (unsigned)count[i] > 100u; }   // min_inliers_ = 100, strict
+    // almost every tile holds no region root: one barrier per four tiles instead of a scan per tile
+    if (!__syncthreads_or((acc[0] || acc[1] || acc[2] || acc[3]) ? 1 : 0)) continue;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = tile + u * blockDim.x + tid;
+      int tot;
+      int ex = block_excl_scan(acc[u] ? 1 : 0, S, tot);
+      if (acc[u] && K + ex < kMaxRegions) { W.cand_root[f * kMaxRegions + K + ex] = i; W.cand_size[f * kMaxRegions + K + ex] = count[i]; }
+      K += tot;
+    }
   }
   if (tid == 0) W.cand_n[f] = min(K, kMaxRegions);
 }
@@ -759,7 +771,7 @@ constexpr int kRefineCoefSmem = 64;
 __global__ void refine_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   __shared__ MaxScanScratch S;
   int phase = 0;
-  __shared__ int s_m[1024];
+  __shared__ int s_m[2 * 1024];
   __shared__ float4 s_coef[kRefineCoefSmem];
   __shared__ int s_wrap_m;
   __shared__ float4 s_wrap_p;
@@ -804,14 +816,15 @@ __global__ void refine_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
       int m_n2 = -1; float4 p_n2 = zero4;                 // labels / points of the row after rn: prefetched, nobody writes them this step
       if (colok && step + 1 < H - 1) { m_n2 = mimg[(rn + dr) * Wd + c]; p_n2 = pts[(rn + dr) * Wd + c]; }
       int m = m_cur;
-      // a row without any model pixel can neither propagate sideways nor vertically: one barrier instead of eight
+      // one barrier publishes the row's labels and tells whether the row holds a model pixel at all (a row without one can neither
+      // propagate sideways nor vertically); s_m alternates between two rows so the next step's stores cannot overtake this step's reads
+      int *s_mr = s_m + (step & 1) * 1024;
+      if (colok) s_mr[c] = m;
       if (__syncthreads_or((colok && m >= 0) ? 1 : 0)) {
-        if (colok) s_m[c] = m;
-        __syncthreads();
         // ---- horizontal propagation along the row (scan direction = traversal direction); skipped when no non-model pixel has a
         //      model pixel as its upstream neighbour (then nothing can be relabelled in this row)
         bool cand = false;
-        if (colok && m < 0) cand = fwd ? (c >= 1 && s_m[c - 1] >= 0) : (c + 1 < Wd && s_m[c + 1] >= 0);
+        if (colok && m < 0) cand = fwd ? (c >= 1 && s_mr[c - 1] >= 0) : (c + 1 < Wd && s_mr[c + 1] >= 0);
         int L = -1;
         if (__syncthreads_or(cand ? 1 : 0)) {
           int s;
@@ -820,7 +833,7 @@ __global__ void refine_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
           const bool has_src = fwd ? (s >= 0) : (s < (1 << 29));
           bool blocked = false;
           if (colok && m < 0) {
-            if (has_src) { L = s_m[s]; blocked = !refine_ok(coef(L), p_cur); }
+            if (has_src) { L = s_mr[s]; blocked = !refine_ok(coef(L), p_cur); }
             else blocked = true;
           }
           int b;
