@@ -249,6 +249,17 @@ def main():
     def step_e2e():
         return h.estimate_ellipsoids(host_np, fo, bb, lb, tw)[0]
 
+    def run_e2e_pipelined(steps):
+        # the streaming form of the same call: batch k+1 is submitted before the records of batch k are collected (two in flight);
+        # every step still uploads its own input from pinned host memory and reads its own records back
+        pending = h.submit_ellipsoids(host_np, fo, bb, lb, tw)
+        res = None
+        for _ in range(steps - 1):
+            nxt = h.submit_ellipsoids(host_np, fo, bb, lb, tw)
+            res = h.wait_ellipsoids(pending)
+            pending = nxt
+        return h.wait_ellipsoids(pending)
+
     # ---- resident (value)
     for _ in range(args.warmup):
         step_resident()
@@ -282,7 +293,14 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d_per_step = (h.h2d_bytes - h2d0) // args.steps    # counted by the library from the copies it issued
-    t = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    run_e2e_pipelined(2)
+    barrier()
+    t0 = time.perf_counter()
+    pip = run_e2e_pipelined(args.steps)
+    torch.cuda.synchronize()
+    e2e_pip_s = time.perf_counter() - t0
+    assert bytes(pip) == bytes(step_e2e())                # the pipelined path returns the same records
+    t = torch.tensor([ms, e2e_s * 1e3, e2e_pip_s * 1e3], device="cuda", dtype=torch.float64)
     gather_ms = None
     if world > 1:
         from eslam_b200 import shard
@@ -292,14 +310,15 @@ def main():
         allrec = shard.gather_records(out, np.arange(n_obj) + rank * n_obj, n_obj * world, device="cuda")
         torch.cuda.synchronize(); gather_ms = (time.perf_counter() - g0) * 1e3
         assert sum(1 for o in allrec if o.n_crop > 0) >= n_obj
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms, e2e_pip_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     frames_total = args.frames * world * args.steps
     value = frames_total / (ms / 1e3)
-    e2e = frames_total / (e2e_ms / 1e3)
+    e2e_sync = frames_total / (e2e_ms / 1e3)
+    e2e = frames_total / (e2e_pip_ms / 1e3)
     # ---- roofline of the dominant kernel (algorithmic bytes per SURVEY.md 8(d))
     peaks = {}
     try:
@@ -333,7 +352,9 @@ def main():
     line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config, objects_per_step_per_gpu=n_obj, ok_fraction=ok_frac, gather_ms=gather_ms),
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_per_step) * world, "d2h_bytes_per_step": int(C.sizeof(EslamEllipsoidOut) * n_obj) * world},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_per_step) * world, "d2h_bytes_per_step": int(C.sizeof(EslamEllipsoidOut) * n_obj) * world,
+                    "api": "eslam_estimate_ellipsoids_submit / _wait, two batches in flight (host pinned buffers in, records out, every step)",
+                    "single_blocking_call_value": e2e_sync},
             "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
                              "sample": f"{min(args.cpu_sample, args.frames)} frames of the same batch, {cpu_dt:.1f} s, oracle/liboracle.so single thread"}}

@@ -207,6 +207,14 @@ int eslam_estimate_ellipsoids_dev(EslamHandle *h, void *stream, int n_frames, co
                                   size_t pitch, int n_obj, const int *frame_of_obj, const double *bbox4,
                                   const int *label, const double *Twc7);
 int eslam_fetch_ellipsoids(EslamHandle *h, void *stream, int n_obj, EslamEllipsoidOut *out);
+/* pipelined form of eslam_estimate_ellipsoids_host for frame streams (the reference calls EstimateLocalEllipsoid once per box and
+ * blocks, Tracking.cpp:329; a batched caller keeps the device busy by submitting batch k+1 before collecting batch k).  At most two
+ * tickets may be outstanding; `depth` and the metadata arrays of a submitted batch must stay valid until its wait returns; the
+ * synchronous entry points refuse to run while a ticket is outstanding. */
+int eslam_estimate_ellipsoids_submit(EslamHandle *h, int n_frames, const uint16_t *depth, size_t pitch,
+                                     int n_obj, const int *frame_of_obj, const double *bbox4, const int *label,
+                                     const double *Twc7, int *ticket);
+int eslam_estimate_ellipsoids_wait(EslamHandle *h, int ticket, int n_obj, EslamEllipsoidOut *out);
 
 /* ------------------------------------------------------------------ quadric initialisation */
 /* replaces Initializer::initializeQuadric (Initializer.cpp:24-56): n_obs rows of Twc7 / det5 (x1 y1 x2 y2 rate)

@@ -31,6 +31,12 @@ void h_rot(const HQ &q, const double v[3], double o[3]) {
   for (int i = 0; i < 3; i++) o[i] = v[i] + q.w * uv[i] + c[i];
 }
 
+// selects (and lazily creates) the extraction workspace the next batch uses
+void use_slot(EslamHandle *h, int slot) {
+  if (!h->ex_slot[slot]) h->ex_slot[slot] = new ExtractWorkspace();
+  h->ex = h->ex_slot[slot];
+}
+
 ExtractParamsDev make_dev_params(const EslamHandle *h) {
   ExtractParamsDev d;
   const EslamParams &p = h->prm; const EslamCamera &c = h->cam;
@@ -53,7 +59,7 @@ ExtractParamsDev make_dev_params(const EslamHandle *h) {
 // builds ObjMeta for a batch, (re)allocates the workspace, uploads the metadata
 int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const int *frame_of_obj, const double *bbox4, const int *label, const double *Twc7,
                   bool want_dump, ExtractPtrs &P) {
-  if (!h->ex) h->ex = new ExtractWorkspace();
+  if (!h->ex) use_slot(h, 0);
   ExtractWorkspace &w = *h->ex;
   w.meta_host.resize(n_obj);
   long long off = 0;
@@ -324,13 +330,16 @@ int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHa
 void eslam_destroy(EslamHandle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (h->ex) {
-    ExtractWorkspace &w = *h->ex;
+  for (int sl = 0; sl < 2; sl++) {
+    if (!h->ex_slot[sl]) continue;
+    ExtractWorkspace &w = *h->ex_slot[sl];
     DevBuf *bufs[] = {&w.meta, &w.state, &w.out, &w.ptsA, &w.ptsB, &w.ptsC, &w.k0, &w.k1, &w.v0, &w.v1, &w.parent, &w.count, &w.objn, &w.objnf, &w.symscratch, &w.symscratch2,
                       &w.d_crop, &w.d_voxel, &w.d_world, &w.d_sym, &w.d_final, &w.d_label, &w.depth};
     for (DevBuf *b : bufs) b->release();
     w.pin_meta.release(); w.pin_out.release(); w.pin_depth.release();
-    delete h->ex;
+    delete h->ex_slot[sl];
+    if (h->slot_stream[sl]) cudaStreamDestroy(h->slot_stream[sl]);
+    if (h->slot_done[sl]) cudaEventDestroy(h->slot_done[sl]);
   }
   slam_free(h);
   graph_free(h);
@@ -383,7 +392,7 @@ int eslam_extract_ground_plane_dev(EslamHandle *h, void *stream, int n_frames, c
 int eslam_extract_ground_plane_host(EslamHandle *h, int n_frames, const uint16_t *depth, size_t pitch, double *plane_cam, int *found, int *n_inliers) {
   if (!h || n_frames <= 0 || !depth || !plane_cam || !found) return ESLAM_ERR_BAD_ARG;
   cudaSetDevice(h->device);
-  if (!h->ex) h->ex = new ExtractWorkspace();
+  use_slot(h, 0);
   size_t bytes = (size_t)n_frames * h->cam.rows * pitch * sizeof(uint16_t);
   ESLAM_CUDA_OK(h, h->ex->depth.reserve(bytes));
   ESLAM_CUDA_OK(h, cudaMemcpyAsync(h->ex->depth.p, depth, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -404,7 +413,7 @@ int eslam_debug_counters(EslamHandle *h, int obj, unsigned long long out[5]) {
 int eslam_debug_plane_stage(EslamHandle *h, const uint16_t *depth, size_t pitch, int stage, void *out) {
   if (!h || !depth || !out || stage < 1 || stage > 4) return ESLAM_ERR_BAD_ARG;
   cudaSetDevice(h->device);
-  if (!h->ex) h->ex = new ExtractWorkspace();
+  use_slot(h, 0);
   size_t bytes = (size_t)h->cam.rows * pitch * sizeof(uint16_t);
   ESLAM_CUDA_OK(h, h->ex->depth.reserve(bytes));
   ESLAM_CUDA_OK(h, cudaMemcpyAsync(h->ex->depth.p, depth, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -457,8 +466,10 @@ int eslam_calibrate_measurement(const EslamParams *p, const EslamCamera *c, cons
 int eslam_estimate_ellipsoids_dev(EslamHandle *h, void *stream, int n_frames, const uint16_t *depth_dev, size_t pitch, int n_obj, const int *frame_of_obj,
                                   const double *bbox4, const int *label, const double *Twc7) {
   if (!h) return ESLAM_ERR_BAD_ARG;
+  if (h->slot_objs[0] || h->slot_objs[1]) { h->err = "a submitted batch is still in flight (eslam_estimate_ellipsoids_wait)"; return ESLAM_ERR_BAD_ARG; }
   cudaSetDevice(h->device);
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  use_slot(h, 0);
   ExtractPtrs P;
   return run_extract(h, s, n_frames, depth_dev, pitch, n_obj, frame_of_obj, bbox4, label, Twc7, false, P);
 }
@@ -473,9 +484,10 @@ int eslam_fetch_ellipsoids(EslamHandle *h, void *stream, int n_obj, EslamEllipso
 int eslam_estimate_ellipsoids_host(EslamHandle *h, int n_frames, const uint16_t *depth, size_t pitch, int n_obj, const int *frame_of_obj, const double *bbox4,
                                    const int *label, const double *Twc7, EslamEllipsoidOut *out, EslamStageDump *dump) {
   if (!h || !depth || !out || n_frames <= 0) return ESLAM_ERR_BAD_ARG;
+  if (h->slot_objs[0] || h->slot_objs[1]) { h->err = "a submitted batch is still in flight (eslam_estimate_ellipsoids_wait)"; return ESLAM_ERR_BAD_ARG; }
   cudaSetDevice(h->device);
   cudaStream_t s = h->stream;
-  if (!h->ex) h->ex = new ExtractWorkspace();
+  use_slot(h, 0);
   size_t bytes = (size_t)n_frames * h->cam.rows * pitch * sizeof(uint16_t);
   ESLAM_CUDA_OK(h, h->ex->depth.reserve(bytes));
   ExtractPtrs P;
@@ -484,6 +496,40 @@ int eslam_estimate_ellipsoids_host(EslamHandle *h, int n_frames, const uint16_t 
   ESLAM_CUDA_OK(h, cudaMemcpyAsync(out, h->ex->out.p, sizeof(EslamEllipsoidOut) * (size_t)n_obj, cudaMemcpyDeviceToHost, s));
   ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
   if (dump) return fetch_dump(h, s, n_obj, P, out, dump);
+  return ESLAM_OK;
+}
+
+// Pipelined form of eslam_estimate_ellipsoids_host for frame streams: up to two batches in flight, each on its own workspace, so the
+// upload and the ramp-up of batch k+1 run under the kernels of batch k.  `depth` must stay valid until the matching wait.
+int eslam_estimate_ellipsoids_submit(EslamHandle *h, int n_frames, const uint16_t *depth, size_t pitch, int n_obj, const int *frame_of_obj, const double *bbox4,
+                                     const int *label, const double *Twc7, int *ticket) {
+  if (!h || !depth || !ticket || n_frames <= 0 || n_obj <= 0) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const int sl = h->next_slot;
+  if (h->slot_objs[sl]) { h->err = "both pipeline slots are busy: wait for the oldest ticket first"; return ESLAM_ERR_BAD_ARG; }
+  if (!h->slot_stream[sl]) ESLAM_CUDA_OK(h, cudaStreamCreateWithFlags(&h->slot_stream[sl], cudaStreamNonBlocking));
+  if (!h->slot_done[sl]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->slot_done[sl], cudaEventDisableTiming));
+  use_slot(h, sl);
+  cudaStream_t s = h->slot_stream[sl];
+  size_t bytes = (size_t)n_frames * h->cam.rows * pitch * sizeof(uint16_t);
+  ESLAM_CUDA_OK(h, h->ex->depth.reserve(bytes));
+  ExtractPtrs P;
+  int rc = run_extract(h, s, n_frames, h->ex->depth.as<uint16_t>(), pitch, n_obj, frame_of_obj, bbox4, label, Twc7, false, P, depth);
+  if (rc) return rc;
+  ESLAM_CUDA_OK(h, h->ex->pin_out.reserve(sizeof(EslamEllipsoidOut) * (size_t)n_obj));
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(h->ex->pin_out.p, h->ex->out.p, sizeof(EslamEllipsoidOut) * (size_t)n_obj, cudaMemcpyDeviceToHost, s));
+  ESLAM_CUDA_OK(h, cudaEventRecord(h->slot_done[sl], s));
+  h->slot_objs[sl] = n_obj;
+  h->next_slot = sl ^ 1;
+  *ticket = sl;
+  return ESLAM_OK;
+}
+int eslam_estimate_ellipsoids_wait(EslamHandle *h, int ticket, int n_obj, EslamEllipsoidOut *out) {
+  if (!h || !out || ticket < 0 || ticket > 1 || !h->slot_objs[ticket] || n_obj != h->slot_objs[ticket]) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  ESLAM_CUDA_OK(h, cudaEventSynchronize(h->slot_done[ticket]));
+  memcpy(out, h->ex_slot[ticket]->pin_out.p, sizeof(EslamEllipsoidOut) * (size_t)n_obj);
+  h->slot_objs[ticket] = 0;
   return ESLAM_OK;
 }
 

@@ -72,7 +72,12 @@ struct EslamHandle {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float stage_ms[3] = {0, 0, 0};   // extract kernel, symmetry+finalize kernel, total of the last profiled batch
   std::string err;
-  eslam::ExtractWorkspace *ex = nullptr;
+  eslam::ExtractWorkspace *ex = nullptr;             // workspace of the batch being issued / last issued (one of ex_slot[])
+  eslam::ExtractWorkspace *ex_slot[2] = {nullptr, nullptr};   // slot 0: synchronous entry points; both: pipelined submit / wait
+  cudaStream_t slot_stream[2] = {nullptr, nullptr};
+  cudaEvent_t slot_done[2] = {nullptr, nullptr};
+  int slot_objs[2] = {0, 0};                          // objects of the batch in flight on the slot (0 = free)
+  int next_slot = 0;
   eslam::GraphWorkspace *gr = nullptr;
   eslam::SlamWorkspace *sl = nullptr;
   eslam::PlaneWorkspace *pl = nullptr;

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "eslam_abi_version", "eslam_default_params", "eslam_default_camera", "eslam_create", "eslam_destroy", "eslam_last_error",
     "eslam_launch_count", "eslam_h2d_bytes", "eslam_extract_ground_plane_host", "eslam_extract_ground_plane_dev", "eslam_plane_to_world",
     "eslam_set_supporting_plane", "eslam_calibrate_measurement", "eslam_estimate_ellipsoids_host", "eslam_estimate_ellipsoids_dev",
-    "eslam_fetch_ellipsoids", "eslam_init_quadric", "eslam_edges_eval_host", "eslam_edges_upload", "eslam_edges_eval_dev",
+    "eslam_fetch_ellipsoids", "eslam_estimate_ellipsoids_submit", "eslam_estimate_ellipsoids_wait", "eslam_init_quadric", "eslam_edges_eval_host", "eslam_edges_upload", "eslam_edges_eval_dev",
     "eslam_edges_download", "eslam_optimize_objects_host", "eslam_optimize_slam_host", "eslam_pose_inverse", "eslam_pose_mul", "eslam_set_profiling", "eslam_get_stage_ms",
 ]
 
@@ -180,6 +180,25 @@ class Handle:
         self.check(self.lib.eslam_estimate_ellipsoids_host(self._h, C.c_int(depth.shape[0]), _u16p(depth), C.c_size_t(depth.shape[2]), C.c_int(n), _ip(fo), _dp(bb),
                                                            _ip(lb), _dp(tw), out, dumps), "eslam_estimate_ellipsoids_host")
         return out, dumps, keep
+
+    def submit_ellipsoids(self, depth, frame_of_obj, bbox, label, Twc):
+        """Pipelined form of estimate_ellipsoids (at most two batches in flight): returns a ticket for wait_ellipsoids.  The arrays
+        are kept alive inside the ticket until the wait."""
+        depth = np.ascontiguousarray(depth, dtype=np.uint16)
+        if depth.ndim == 2:
+            depth = depth[None]
+        fo = np.ascontiguousarray(frame_of_obj, dtype=np.int32); bb = _d(bbox).reshape(-1, 4)
+        lb = np.ascontiguousarray(label, dtype=np.int32); tw = _d(Twc).reshape(-1, 7)
+        t = C.c_int(-1)
+        self.check(self.lib.eslam_estimate_ellipsoids_submit(self._h, C.c_int(depth.shape[0]), _u16p(depth), C.c_size_t(depth.shape[2]), C.c_int(len(fo)), _ip(fo), _dp(bb),
+                                                             _ip(lb), _dp(tw), C.byref(t)), "eslam_estimate_ellipsoids_submit")
+        return (t.value, len(fo), (depth, fo, bb, lb, tw))
+
+    def wait_ellipsoids(self, ticket):
+        slot, n, _keep = ticket
+        out = (EslamEllipsoidOut * n)()
+        self.check(self.lib.eslam_estimate_ellipsoids_wait(self._h, C.c_int(slot), C.c_int(n), out), "eslam_estimate_ellipsoids_wait")
+        return out
 
     def estimate_ellipsoids_dev(self, depth_ptr, n_frames, pitch, frame_of_obj, bbox, label, Twc, stream=0):
         fo = np.ascontiguousarray(frame_of_obj, dtype=np.int32); bb = _d(bbox).reshape(-1, 4)

@@ -186,6 +186,31 @@ def test_large_box_takes_the_hbm_union_find_and_uncached_symmetry_paths(handle, 
     assert ellipsoid_close(g.ellipsoid, o.ellipsoid, 1e-4) and abs(g.prob - o.prob) < 1e-5
 
 
+def test_pipelined_submit_wait_equals_synchronous_calls(handle):
+    """eslam_estimate_ellipsoids_submit / _wait (two batches in flight on two workspaces) return the records of the synchronous call,
+    in ticket order, for pinned and pageable input; a third submit and a synchronous call are refused while tickets are outstanding."""
+    import torch
+    handle.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+    batches = [synth.make_batch(3, "one_box"), synth.make_batch(2, "multi_box"), synth.make_batch(4, "one_box")]
+    want = [bytes(handle.estimate_ellipsoids(*b)[0]) for b in batches]
+    for pin in (False, True):
+        inputs = []
+        for depth, fo, bb, lb, tw in batches:
+            d = torch.from_numpy(np.ascontiguousarray(depth).view(np.int16)).pin_memory().numpy().view(np.uint16) if pin else depth
+            inputs.append((d, fo, bb, lb, tw))
+        t0 = handle.submit_ellipsoids(*inputs[0])
+        t1 = handle.submit_ellipsoids(*inputs[1])
+        with pytest.raises(E.EslamError):
+            handle.submit_ellipsoids(*inputs[2])
+        with pytest.raises(E.EslamError):
+            handle.estimate_ellipsoids(*inputs[2])
+        assert bytes(handle.wait_ellipsoids(t0)) == want[0]
+        t2 = handle.submit_ellipsoids(*inputs[2])
+        assert bytes(handle.wait_ellipsoids(t1)) == want[1]
+        assert bytes(handle.wait_ellipsoids(t2)) == want[2]
+    assert bytes(handle.estimate_ellipsoids(*batches[0])[0]) == want[0]      # synchronous entry works again
+
+
 def test_missing_plane_is_an_error():
     h = E.Handle()
     depth, fo, bb, lb, tw = synth.make_batch(1)

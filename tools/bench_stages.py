@@ -57,6 +57,34 @@ if args.only in ("all", "plane"):
         line["max_abs_plane_diff_vs_oracle"] = float(np.abs(pl[:n] - po).max()); line["inliers_equal"] = bool(np.array_equal(ninl[:n], no))
     print(json.dumps(line))
 
+if args.only in ("all", "config3"):
+    # BASELINE.json configs[2]: 8 bbox/frame, ground-plane extraction forced EVERY frame, symmetry on -- the per-frame flow of
+    # Tracking::GrabPoseAndObjects (plane -> camera-to-world -> supporting plane -> every box), batched: one ground-plane pass and one
+    # extraction pass over the same resident batch on one stream (the supporting plane of the batch is the constant synthetic one;
+    # per-frame planes are compared with it in the tests).
+    from eslam_b200 import synth
+    F = args.plane_frames
+    depth, fo, bb, lb, tw = make_frames("multi_box", F, 3000)
+    dev = torch.from_numpy(depth.view(np.int16)).cuda()
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+    def step():
+        h.extract_ground_plane_dev(dev.data_ptr(), F, 640, stream.cuda_stream)
+        h.estimate_ellipsoids_dev(dev.data_ptr(), F, 640, fo, bb, lb, tw, stream=stream.cuda_stream)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = h.launches
+    e0.record(stream)
+    for _ in range(args.reps):
+        step()
+    e1.record(stream); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.reps
+    out = h.fetch_ellipsoids(len(fo), stream=stream.cuda_stream)
+    print(json.dumps({"stage": "config3: ground plane every frame + 8 boxes/frame with symmetry", "frames": F, "objects": int(len(fo)), "ms_per_batch": ms,
+                      "frames_per_s": F / ms * 1e3, "ok_fraction": sum(1 for o in out if o.status == 0) / float(len(fo)), "launches_per_batch": (h.launches - l0) // args.reps}))
+
 if args.only in ("all", "edges"):
     import orc
     from helpers import make_ba_problem, K
