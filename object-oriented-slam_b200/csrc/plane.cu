@@ -228,30 +228,44 @@ __global__ void distmap_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   float cur = 0.0f;
   if (ci < Wd) { cur = init_val(0, ci); dm[ci] = cur; s_prev[ci] = cur; }
   __syncthreads();
-  // the per-row recurrences are short; what would dominate a row step is the latency of the point loads behind init_val, which only
-  // depends on static data: the value of the next row is requested a full row step ahead
-  float center_next = (ci < Wd && H > 1) ? init_val(1, ci) : 0.0f;
+  // The per-row recurrences are short; what would dominate a row step is the latency of the point loads behind init_val.  They only
+  // depend on static data, so the RAW depths a row needs (left / right neighbour, the pixel two rows down) are requested one row step
+  // before they are used and the column's own depths stream through registers (up <- centre <- down).
+  const int cl = max(ci - 1, 0), cr = min(ci + 1, Wd - 1), cc = min(ci, Wd - 1);
+  auto zat = [&](int r_, int c_) -> float { return pts[(size_t)min(r_, H - 1) * Wd + c_].z; };
+  float zu = 0.0f, zc = zat(0, cc), zd = zat(1, cc);                     // column stream, positioned on row 0
+  float zl_n = zat(1, cl), zr_n = zat(1, cr), zd_n = zat(2, cc);          // row 1's neighbours and the pixel below it
+  // column 0 of the same row, followed by every thread (same addresses: one broadcast transaction per warp): the last column's
+  // "upper right" neighbour is current_row[0], whose value in this pass is just its initial one -- no exchange between threads needed
+  float yu = 0.0f, yc = zat(0, 0), yd = zat(1, 0), yr_n = zat(1, min(1, Wd - 1)), yd_n = zat(2, 0);
+  auto init_regs = [&](int ri, int c_, float u, float cz, float d, float l, float r) -> float {   // init_val(ri, c_) from registers
+    bool zero = false;
+    if (ri <= H - 2) {
+      if (c_ <= Wd - 2) { if (dc_viol(cz, r)) zero = true; if (dc_viol(cz, d)) zero = true; }
+      if (c_ >= 1) { if (dc_viol(l, cz)) zero = true; }
+    }
+    if (ri >= 1 && c_ <= Wd - 2) { if (dc_viol(u, cz)) zero = true; }
+    return zero ? 0.0f : big;
+  };
+  // two barriers per row: (1) the row's pre-scan values are complete, (2) the row's final values are complete
   for (int ri = 1; ri < H; ri++) {
-    float center = center_next, a = 0.0f;
-    if (ci < Wd && ri + 1 < H) center_next = init_val(ri + 1, ci);
+    zu = zc; zc = zd; zd = zd_n; yu = yc; yc = yd; yd = yd_n;
+    const float zl = zl_n, zr = zr_n, yr = yr_n;
+    zl_n = zat(ri + 1, cl); zr_n = zat(ri + 1, cr); zd_n = zat(ri + 2, cc);   // for the next row step
+    yr_n = zat(ri + 1, min(1, Wd - 1)); yd_n = zat(ri + 2, 0);
+    const float center = init_regs(ri, ci, zu, zc, zd, zl, zr);
+    float a = center;
     if (ci < Wd) {
-      a = center;
       if (ci >= 1) {
         float upLeft = __fadd_rn(s_prev[ci - 1], 1.4f), up = __fadd_rn(s_prev[ci], 1.0f);
         float upRight = (ci + 1 < Wd) ? __fadd_rn(s_prev[ci + 1], 1.4f) : 0.0f;
         a = fminf(a, fminf(upLeft, up));
         if (ci + 1 < Wd) a = fminf(a, upRight);
+        // previous_row[ci+1] runs into current_row[0] (never updated in this pass: its initial value)
+        if (ci == Wd - 1) a = fminf(a, __fadd_rn(init_regs(ri, 0, yu, yc, yd, 0.0f, yr), 1.4f));
       }
       s_a[ci] = a;
     }
-    __syncthreads();
-    if (ci < Wd) {
-      if (ci == Wd - 1 && ci >= 1) {   // previous_row[ci+1] runs into current_row[0] (never updated in this pass)
-        a = fminf(a, __fadd_rn(s_a[0], 1.4f));
-      }
-    }
-    __syncthreads();
-    if (ci == Wd - 1 && ci >= 1) s_a[ci] = a;
     __syncthreads();
     if (ci < Wd) {
       float v;
@@ -262,30 +276,26 @@ __global__ void distmap_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
         for (int k = k0 + 1; k <= ci; k++) v = fminf(s_a[k], __fadd_rn(v, 1.0f));
       }
       cur = v;
+      s_prev[ci] = cur; dm[(size_t)ri * Wd + ci] = cur;
     }
-    __syncthreads();
-    if (ci < Wd) { s_prev[ci] = cur; dm[(size_t)ri * Wd + ci] = cur; }
     __syncthreads();
   }
-  // ---- second pass (bottom-right to top-left); s_prev holds the final row H-1
-  float fwd_next = (ci < Wd && H > 1) ? dm[(size_t)(H - 2) * Wd + ci] : 0.0f;   // own column only: written by this thread in pass 1
+  // ---- second pass (bottom-right to top-left); s_prev holds the final row H-1.  The forward values this pass reads (own column, and
+  // the row's last column for the ci == 0 wrap: next_row[-1] == current_row[W-1]) are requested one row step ahead; the thread of the
+  // last column overwrites its value only after the barrier that follows their use.
+  float fwd_next = (H > 1) ? dm[(size_t)(H - 2) * Wd + cc] : 0.0f, wrap_next = (H > 1) ? dm[(size_t)(H - 2) * Wd + Wd - 1] : 0.0f;
   for (int ri = H - 2; ri >= 0; ri--) {
-    float fwd = fwd_next, a = 0.0f;
-    if (ci < Wd && ri >= 1) fwd_next = dm[(size_t)(ri - 1) * Wd + ci];
+    const float fwd = fwd_next, wrapf = wrap_next;
+    if (ri >= 1) { fwd_next = dm[(size_t)(ri - 1) * Wd + cc]; wrap_next = dm[(size_t)(ri - 1) * Wd + Wd - 1]; }
+    float a = fwd;
     if (ci < Wd) {
-      s_a[ci] = fwd;     // temporarily: forward values of this row (needed for the ci == 0 wrap: next_row[-1] == current_row[W-1])
-    }
-    __syncthreads();
-    if (ci < Wd) {
-      a = fwd;
       if (ci <= Wd - 2) {
-        float lowerLeft = (ci >= 1) ? __fadd_rn(s_prev[ci - 1], 1.4f) : __fadd_rn(s_a[Wd - 1], 1.4f);
+        float lowerLeft = (ci >= 1) ? __fadd_rn(s_prev[ci - 1], 1.4f) : __fadd_rn(wrapf, 1.4f);
         float lower = __fadd_rn(s_prev[ci], 1.0f), lowerRight = __fadd_rn(s_prev[ci + 1], 1.4f);
         a = fminf(a, fminf(lowerLeft, fminf(lower, lowerRight)));
       }
+      s_a[ci] = a;
     }
-    __syncthreads();
-    if (ci < Wd) s_a[ci] = a;
     __syncthreads();
     if (ci < Wd) {
       float v;
@@ -296,9 +306,8 @@ __global__ void distmap_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
         for (int k = k0 - 1; k >= ci; k--) v = fminf(s_a[k], __fadd_rn(v, 1.0f));
       }
       cur = v;
+      s_prev[ci] = cur; dm[(size_t)ri * Wd + ci] = cur;
     }
-    __syncthreads();
-    if (ci < Wd) { s_prev[ci] = cur; dm[(size_t)ri * Wd + ci] = cur; }
     __syncthreads();
   }
 }
@@ -773,12 +782,10 @@ __global__ void refine_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   int phase = 0;
   __shared__ int s_m[2 * 1024];
   __shared__ float4 s_coef[kRefineCoefSmem];
-  __shared__ int s_wrap_m;
-  __shared__ float4 s_wrap_p;
-  __shared__ int s_add[kRefineCoefSmem];   // inliers gained by the first 64 models (flushed once): a row joining one plane would otherwise
-                                           // serialise hundreds of global atomics on a single counter per row step
+  __shared__ volatile int s_post_m, s_post_seq;   // label of column 0 after its row step, handed to the thread of column W-1 (backward pass)
+  __shared__ int s_add[kRefineCoefSmem];   // inliers gained by the first 64 models (flushed once)
   const int H = prm.rows, Wd = prm.cols, NP = H * Wd;
-  const int f = blockIdx.x, c = threadIdx.x;
+  const int f = blockIdx.x, c = threadIdx.x, lane = c & 31, w = c >> 5, nw = (blockDim.x + 31) >> 5;
   const bool colok = c < Wd;
   int *parent = W.label + (size_t)f * NP;
   int *mimg = reinterpret_cast<int *>(W.dm) + (size_t)f * NP;
@@ -788,17 +795,44 @@ __global__ void refine_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   int *csize = W.cand_size + f * kMaxRegions;
   const int ncand = W.cand_n[f];
   for (int i = threadIdx.x; i < kRefineCoefSmem; i += blockDim.x) { s_add[i] = 0; if (i < ncand) s_coef[i] = coef_g[i]; }
+  if (threadIdx.x == 0) { s_post_m = -1; s_post_seq = 0; }
   __syncthreads();
   auto coef = [&](int L) -> float4 { return L < kRefineCoefSmem ? s_coef[L] : coef_g[L]; };
-  // one (shared-memory) atomic per warp and model; called by every thread of the warp
-  auto add_inlier = [&](bool pred, int L) {
-    const unsigned act = __ballot_sync(0xffffffffu, pred);
-    if (pred) {
-      const unsigned peers = __match_any_sync(act, L);
-      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
-        if (L < kRefineCoefSmem) atomicAdd(&s_add[L], __popc(peers)); else atomicAdd(&csize[L], __popc(peers));
-      }
+  // inlier counters: every thread keeps (model, count) of its current streak in registers and flushes on a change of model
+  int acc_m = -1, acc_n = 0;
+  auto flush_inliers = [&]() {
+    if (acc_n > 0) { if (acc_m < kRefineCoefSmem) atomicAdd(&s_add[acc_m], acc_n); else atomicAdd(&csize[acc_m], acc_n); }
+    acc_n = 0;
+  };
+  auto add_inlier = [&](int L) { if (L != acc_m) { flush_inliers(); acc_m = L; } acc_n++; };
+  // nearest flagged column at or before c in scan direction (-1: none).  The flags of a warp are one ballot, the nearest flagged lane
+  // a count-leading-zeros; the warps' own nearest flags cross through shared memory (one barrier, double-buffered) and are folded
+  // with one redux instruction.  Replaces two 10-step shuffle scans per call.
+  auto nearest_flag = [&](bool flag, bool fwd) -> int {
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int wbase = c - lane;
+    int x, tot;
+    if (fwd) {
+      const unsigned lo = bal & (0xffffffffu >> (31 - lane));
+      x = lo ? wbase + 31 - __clz(lo) : -1; tot = bal ? wbase + 31 - __clz(bal) : -1;
+    } else {
+      const unsigned hi = bal & (0xffffffffu << lane);
+      x = hi ? wbase + __ffs(hi) - 1 : -1; tot = bal ? wbase + __ffs(bal) - 1 : -1;
     }
+    if (lane == 0) S.tot[phase][w] = tot;
+    __syncthreads();
+    int r;
+    if (fwd) {
+      const int y = __reduce_max_sync(0xffffffffu, (lane < w) ? S.tot[phase][lane] : -1);
+      r = max(x, y);
+    } else {
+      int t = 0x7fffffff;
+      if (lane > w && lane < nw) { const int v = S.tot[phase][lane]; if (v >= 0) t = v; }
+      const int y = __reduce_min_sync(0xffffffffu, t);
+      r = x >= 0 ? x : (y == 0x7fffffff ? -1 : y);
+    }
+    phase ^= 1;
+    return r;
   };
   const float4 zero4 = make_float4(0, 0, 0, 0);
   for (int pass = 0; pass < 2; pass++) {
@@ -810,11 +844,14 @@ __global__ void refine_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
     float4 p_cur = colok ? pts[rfirst * Wd + c] : zero4;
     int m_nxt = colok ? mimg[(rfirst + dr) * Wd + c] : -1;
     float4 p_nxt = colok ? pts[(rfirst + dr) * Wd + c] : zero4;
+    ptrdiff_t off2 = (ptrdiff_t)(rfirst + 2 * dr) * Wd + c;      // pixel two rows ahead in this column
+    const ptrdiff_t doff = (ptrdiff_t)dr * Wd;
     for (int step = 0; step < H - 1; step++) {
       const int r = rfirst + dr * step;                   // current row
       const int rn = r + dr;                              // row hit by the vertical check
       int m_n2 = -1; float4 p_n2 = zero4;                 // labels / points of the row after rn: prefetched, nobody writes them this step
-      if (colok && step + 1 < H - 1) { m_n2 = mimg[(rn + dr) * Wd + c]; p_n2 = pts[(rn + dr) * Wd + c]; }
+      if (colok && step + 1 < H - 1) { m_n2 = mimg[off2]; p_n2 = pts[off2]; }
+      off2 += doff;
       int m = m_cur;
       // one barrier publishes the row's labels and tells whether the row holds a model pixel at all (a row without one can neither
       // propagate sideways nor vertically); s_m alternates between two rows so the next step's stores cannot overtake this step's reads
@@ -825,44 +862,40 @@ __global__ void refine_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
         //      model pixel as its upstream neighbour (then nothing can be relabelled in this row)
         bool cand = false;
         if (colok && m < 0) cand = fwd ? (c >= 1 && s_mr[c - 1] >= 0) : (c + 1 < Wd && s_mr[c + 1] >= 0);
-        int L = -1;
         if (__syncthreads_or(cand ? 1 : 0)) {
-          int s;
-          if (fwd) s = block_incl_max_scan((colok && m >= 0) ? c : -1, S, phase, false);                 // nearest source at or left of c
-          else s = -block_incl_max_scan((colok && m >= 0) ? -c : -(1 << 30), S, phase, true);            // nearest source at or right of c
-          const bool has_src = fwd ? (s >= 0) : (s < (1 << 29));
+          const int s = nearest_flag(colok && m >= 0, fwd);                       // nearest source at or before c
+          int L = -1;
           bool blocked = false;
           if (colok && m < 0) {
-            if (has_src) { L = s_mr[s]; blocked = !refine_ok(coef(L), p_cur); }
+            if (s >= 0) { L = s_mr[s]; blocked = !refine_ok(coef(L), p_cur); }
             else blocked = true;
           }
-          int b;
-          if (fwd) b = block_incl_max_scan((colok && m < 0 && blocked) ? c : -1, S, phase, false);       // last blocked index <= c
-          else b = -block_incl_max_scan((colok && m < 0 && blocked) ? -c : -(1 << 30), S, phase, true);  // first blocked index >= c
-          bool recv = false;
-          if (colok && m < 0 && has_src) recv = fwd ? (b < s) : (b > s);
-          // the forward pass never uses column W-1 as "current"; every receiver's chain starts at a source that IS a valid current
-          if (recv) { m = L; parent[r * Wd + c] = croot[L]; mimg[r * Wd + c] = L; }
-          add_inlier(recv, L);
+          const int b = nearest_flag(colok && m < 0 && blocked, fwd);             // nearest blocked pixel at or before c
+          // a pixel receives its source's label when no blocked pixel lies between the source and itself (the forward pass never
+          // uses column W-1 as "current"; every receiver's chain starts at a source that IS a valid current)
+          const bool recv = colok && m < 0 && s >= 0 && (b < 0 || (fwd ? (b < s) : (b > s)));
+          if (recv) { m = L; parent[r * Wd + c] = croot[L]; mimg[r * Wd + c] = L; add_inlier(L); }
         }
         // ---- vertical check from the (updated) current row: only this thread ever relabels pixel (rn, c)
         const bool cur_ok = colok && m >= 0 && (fwd ? (c <= Wd - 2) : true);
-        const bool vhit = cur_ok && m_nxt < 0 && refine_ok(coef(m), p_nxt);
-        if (vhit) { m_nxt = m; parent[rn * Wd + c] = croot[m]; mimg[rn * Wd + c] = m; }
-        add_inlier(vhit, m);
-        if (!fwd) {   // colIdx == 0: the "left" neighbour is the last pixel of the previous row (pointer arithmetic in PCL) = (rn, W-1)
-          if (c == Wd - 1) { s_wrap_m = m_nxt; s_wrap_p = p_nxt; }
-          __syncthreads();
-          if (c == 0 && m >= 0 && s_wrap_m < 0 && refine_ok(coef(m), s_wrap_p)) {
-            s_wrap_m = m; parent[r * Wd - 1] = croot[m]; mimg[r * Wd - 1] = m; atomicAdd(&csize[m], 1);
+        if (cur_ok && m_nxt < 0 && refine_ok(coef(m), p_nxt)) { m_nxt = m; parent[rn * Wd + c] = croot[m]; mimg[rn * Wd + c] = m; add_inlier(m); }
+        if (!fwd) {
+          // colIdx == 0: the "left" neighbour is the last pixel of the previous row (pointer arithmetic in PCL) = (rn, W-1), the pixel
+          // the thread of column W-1 carries as its next label: column 0 posts its label, column W-1 applies the check itself
+          const int seq = step + 1;
+          if (c == 0) { s_post_m = m; __threadfence_block(); s_post_seq = seq; }
+          if (c == Wd - 1) {
+            while (s_post_seq != seq) { }
+            __threadfence_block();
+            const int m0 = s_post_m;
+            if (m0 >= 0 && m_nxt < 0 && refine_ok(coef(m0), p_nxt)) { m_nxt = m0; parent[rn * Wd + c] = croot[m0]; mimg[rn * Wd + c] = m0; add_inlier(m0); }
           }
-          __syncthreads();
-          if (c == Wd - 1) m_nxt = s_wrap_m;
         }
       }
       m_cur = m_nxt; p_cur = p_nxt; m_nxt = m_n2; p_nxt = p_n2;
     }
   }
+  flush_inliers();
   __syncthreads();
   for (int i = threadIdx.x; i < kRefineCoefSmem && i < ncand; i += blockDim.x) if (s_add[i]) atomicAdd(&csize[i], s_add[i]);
 }
@@ -903,7 +936,10 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   if (!h->pl) h->pl = new PlaneWorkspace();
   PlaneWorkspace &w = *h->pl;
   const size_t NP = (size_t)H * Wd, NI = (size_t)(H + 1) * ii_pitch(Wd) * 3;
-  const int chunk = n_frames < 256 ? n_frames : 256;   // per-frame CTAs (integral / distmap / refine) need >= 148 frames in flight
+  // the per-frame kernels (integral / distmap / refine: one CTA per frame, two resident per SM) are bound by their sequential row
+  // chains, so a chunk is exactly two frames per SM: 296 on a B200
+  const int chunk_max = 2 * (h->sm_count > 0 ? h->sm_count : 148);
+  const int chunk = n_frames < chunk_max ? n_frames : chunk_max;
   ESLAM_CUDA_OK(h, w.pts.reserve(chunk * NP * 16)); ESLAM_CUDA_OK(h, w.nrm.reserve(chunk * NP * 16));
   ESLAM_CUDA_OK(h, w.iiX.reserve(chunk * NI * 8)); ESLAM_CUDA_OK(h, w.iiY.reserve(chunk * NI * 8));
   ESLAM_CUDA_OK(h, w.dm.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.parent.reserve(chunk * NP * 4)); ESLAM_CUDA_OK(h, w.label.reserve(chunk * NP * 4));

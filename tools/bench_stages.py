@@ -17,7 +17,7 @@ from eslam_b200.api import EdgeGraph  # noqa: E402
 from bench import make_frames  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--plane-frames", type=int, default=256)
+ap.add_argument("--plane-frames", type=int, default=592, help="two chunks of 2 x 148 frames")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--skip-cpu", action="store_true")
 ap.add_argument("--only", default="all")
