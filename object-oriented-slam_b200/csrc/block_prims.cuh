@@ -181,13 +181,23 @@ static __device__ void block_radix_sort(unsigned *k0, unsigned *v0, unsigned *k1
     for (int i = threadIdx.x; i < nw * 256; i += blockDim.x) S.radix[i] = 0;
     __syncthreads();
     unsigned *cnt = &S.radix[w * 256];
-    for (int i = beg; i < end; i += 32) {
-      int j = i + lane;
-      bool valid = j < end;
-      unsigned d = valid ? ((ki[j] >> shift) & 255u) : (256u + lane);
-      unsigned peers = __match_any_sync(0xffffffffu, d);
-      if (valid && (__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
-      __syncwarp();
+    // both loops run four 32-key groups per trip: the four (independent) global loads are issued first, so a warp pays one memory
+    // latency per 128 keys instead of one per 32 (the loops were latency bound: 15 % of the extraction kernel)
+    for (int i0 = beg; i0 < end; i0 += 128) {
+      unsigned kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int j = i0 + u * 32 + lane; kk[u] = (j < end) ? ki[j] : 0u; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = i0 + u * 32 + lane;
+        if (i0 + u * 32 < end) {   // warp-uniform
+          const bool valid = j < end;
+          const unsigned d = valid ? ((kk[u] >> shift) & 255u) : (256u + lane);
+          const unsigned peers = __match_any_sync(0xffffffffu, d);
+          if (valid && (__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
+          __syncwarp();
+        }
+      }
     }
     __syncthreads();
     // exclusive scan over (digit major, warp minor)
@@ -209,18 +219,26 @@ static __device__ void block_radix_sort(unsigned *k0, unsigned *v0, unsigned *k1
       }
     }
     __syncthreads();
-    for (int i = beg; i < end; i += 32) {
-      int j = i + lane;
-      bool valid = j < end;
-      unsigned key = valid ? ki[j] : 0u, val = valid ? vi[j] : 0u;
-      unsigned d = valid ? ((key >> shift) & 255u) : (256u + lane);
-      unsigned peers = __match_any_sync(0xffffffffu, d);
-      unsigned base = valid ? (cnt[d] + S.digit_base[d]) : 0u;
-      unsigned rank = __popc(peers & ((1u << lane) - 1u));
-      __syncwarp();
-      if (valid && (__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
-      __syncwarp();
-      if (valid) { ko[base + rank] = key; vo[base + rank] = val; }
+    for (int i0 = beg; i0 < end; i0 += 128) {
+      unsigned kk[4], vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int j = i0 + u * 32 + lane; const bool valid = j < end; kk[u] = valid ? ki[j] : 0u; vv[u] = valid ? vi[j] : 0u; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = i0 + u * 32 + lane;
+        if (i0 + u * 32 < end) {   // warp-uniform
+          const bool valid = j < end;
+          const unsigned key = kk[u], val = vv[u];
+          const unsigned d = valid ? ((key >> shift) & 255u) : (256u + lane);
+          const unsigned peers = __match_any_sync(0xffffffffu, d);
+          const unsigned base = valid ? (cnt[d] + S.digit_base[d]) : 0u;
+          const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+          __syncwarp();
+          if (valid && (__ffs(peers) - 1) == lane) cnt[d] += __popc(peers);
+          __syncwarp();
+          if (valid) { ko[base + rank] = key; vo[base + rank] = val; }
+        }
+      }
     }
     __syncthreads();
     unsigned *t;

@@ -409,6 +409,16 @@ int eslam_debug_counters(EslamHandle *h, int obj, unsigned long long out[5]) {
   return ESLAM_OK;
 }
 
+// test/bench hook: clock64() stamps of the extraction phases of object `obj` of the last batch
+int eslam_debug_phase_clocks(EslamHandle *h, int obj, long long out[9]) {
+  if (!h || !h->ex || obj < 0 || obj >= h->ex->n_obj) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  ObjState st;
+  ESLAM_CUDA_OK(h, cudaMemcpy(&st, h->ex->state.as<ObjState>() + obj, sizeof(ObjState), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 9; i++) out[i] = st.phase_clk[i];
+  return ESLAM_OK;
+}
+
 // test-only hook (not in include/eslam.h): intermediate buffers of the plane pipeline for stage-isolated parity tests
 int eslam_debug_plane_stage(EslamHandle *h, const uint16_t *depth, size_t pitch, int stage, void *out) {
   if (!h || !depth || !out || stage < 1 || stage > 4) return ESLAM_ERR_BAD_ARG;

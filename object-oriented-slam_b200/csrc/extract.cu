@@ -47,6 +47,24 @@ __device__ void uf_union(int *parent, int a, int b) {
     if (old == a) return;
   }
 }
+// lower bound of `key` in the sorted keys k0[0..n): first through the shared-memory table of every 16th key, then four steps inside
+// one 64-byte block of global memory (plain binary search when the table does not fit); uniform trip counts
+__device__ __forceinline__ int lower_bound_2l(const unsigned *k0, const unsigned *coarse, int n, int ncoarse, int pow2, int pow2c, bool use_coarse, unsigned key) {
+  int q = 0;
+  if (use_coarse) {
+    int cb = 0;   // number of 16-key blocks whose first key is < key
+    for (int st = pow2c; st > 0; st >>= 1) { int t = cb + st; if (t <= ncoarse && coarse[t - 1] < key) cb = t; }
+    if (cb > 0) {
+      q = ((cb - 1) << 4) + 1;                     // k0[(cb-1)*16] < key; the bound lies in ((cb-1)*16, cb*16]
+      const int hi = min(n, cb << 4);
+#pragma unroll
+      for (int st = 8; st > 0; st >>= 1) { int t = q + st; if (t <= hi && k0[t - 1] < key) q = t; }
+    }
+  } else {
+    for (int st = pow2; st > 0; st >>= 1) { int t = q + st; if (t <= n && k0[t - 1] < key) q = t; }
+  }
+  return q;
+}
 __device__ __forceinline__ float l2_simple(float4 a, float4 b) {  // flann::L2_Simple<float>, no contraction
   float r = 0.0f, d;
   d = __fsub_rn(a.x, b.x); r = __fadd_rn(r, __fmul_rn(d, d));
@@ -152,6 +170,7 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
     for (int s = 0; s < 9; s++) { st.seed_prob[s] = st.seed_init[s] = st.seed_final[s] = st.seed_dual[s] = 0; for (int k = 0; k < 4; k++) st.seed_plane[s][k] = 0; }
   }
   if (m.pre_status != 0) return;
+  if (tid == 0) st.phase_clk[0] = clock64();
   float4 *A = W.ptsA + m.off, *B = W.ptsB + m.off, *Cc = W.ptsC + m.off;
   unsigned *k0 = W.k0 + m.off, *k1 = W.k1 + m.off, *v0 = W.v0 + m.off, *v1 = W.v1 + m.off;
   int *parent = W.parent + m.off, *count = W.count + m.off;   // parent is re-pointed to shared memory once n3 is known
@@ -194,10 +213,12 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
     }
   }
   __syncthreads();
+  if (tid == 0) st.phase_clk[1] = clock64();
   // ---------------- S2 + S3 + S4: 1 cm voxel grid -> world -> supporting-plane filter ----------------
   int n2 = 0, n3 = 0;
   if (n1 > 0) {
     voxel_sort(A, n1, prm.voxel_leaf, k0, v0, k1, v1, S, RS);
+    if (tid == 0) st.phase_clk[2] = clock64();
     for (int tile = 0; tile < n1; tile += blockDim.x) {
       int j = tile + tid;
       bool head = false, keep = false;
@@ -220,7 +241,7 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
     }
   }
   __syncthreads();
-  if (tid == 0) { st.n_crop = n1; st.n_voxel = n2; st.n_plane = n3; }
+  if (tid == 0) { st.n_crop = n1; st.n_voxel = n2; st.n_plane = n3; st.phase_clk[3] = clock64(); }
   if (n3 < 1) { if (tid == 0) st.status = ESLAM_OBJ_NO_POINTS_AFTER_PLANE; return; }
   if (n3 <= SMEM_PARENTS) parent = s_parent;   // block-uniform: pointer chasing at shared-memory instead of L2 latency
 
@@ -283,6 +304,7 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
     }
     __syncthreads();
     block_radix_sort(k0, v0, k1, v1, n3, bits_for((unsigned)(gx * gy * gz)), RS);
+    if (tid == 0) st.phase_clk[4] = clock64();
     const float r2 = prm.cluster_r2;
     int pow2 = 1;
     while (pow2 < n3) pow2 <<= 1;
@@ -294,6 +316,10 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
     int pow2c = 1;
     while (pow2c < ncoarse) pow2c <<= 1;
     if (use_coarse) for (int b = tid; b < ncoarse; b += blockDim.x) coarse[b] = k0[b << 4];
+    // points in cell-sorted order with their original index in .w (the crop buffer A is free now): a neighbour candidate is one
+    // sequential 16-byte load instead of the dependent pair v0[q] -> B[j]
+    float4 *Bs = A;
+    for (int pos = tid; pos < n3; pos += blockDim.x) { const int j = (int)v0[pos]; float4 pj = B[j]; pj.w = __int_as_float(j); Bs[pos] = pj; }
     __syncthreads();
     // Warp-converged neighbour search over the FORWARD half of the 27-cell neighbourhood (each unordered pair is tested exactly once,
     // from the point that comes first in (z, y, x) cell order; l2_simple is symmetric to the last bit): the rest of the own cell and
@@ -306,7 +332,7 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
       int i = 0, cx = 0, cy = 0, cz = 0;
       float4 p = make_float4(0, 0, 0, 0);
       if (act) {
-        i = (int)v0[pos]; p = B[i];
+        p = Bs[pos]; i = __float_as_int(p.w);
         cx = (int)((p.x - mn[0]) / cs); cy = (int)((p.y - mn[1]) / cs); cz = (int)((p.z - mn[2]) / cs);
       }
       const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
@@ -315,37 +341,31 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
         const int zz = cz + (row >= 2 ? 1 : 0), yy = cy + (row == 0 ? 0 : (row == 1 ? 1 : row - 3));
         const bool valid = act && zz < nz && yy >= 0 && yy < ny;
         unsigned khi = 0; int q = n3;
-        if (row == 0) {
-          if (valid) { khi = (unsigned)((zz * ny + yy) * nx + xhi); q = pos + 1; }
-        } else if (valid) {
-          unsigned klo = (unsigned)((zz * ny + yy) * nx + xlo);
+        if (valid) {
           khi = (unsigned)((zz * ny + yy) * nx + xhi);
-          q = 0;
-          if (use_coarse) {
-            int cb = 0;   // number of 16-key blocks whose first key is < klo
-            for (int st = pow2c; st > 0; st >>= 1) { int t = cb + st; if (t <= ncoarse && coarse[t - 1] < klo) cb = t; }
-            if (cb > 0) {
-              q = ((cb - 1) << 4) + 1;                     // k0[(cb-1)*16] < klo; the bound lies in ((cb-1)*16, cb*16]
-              const int hi = min(n3, cb << 4);
-#pragma unroll
-              for (int st = 8; st > 0; st >>= 1) { int t = q + st; if (t <= hi && k0[t - 1] < klo) q = t; }
-            }
-          } else {
-            for (int st = pow2; st > 0; st >>= 1) { int t = q + st; if (t <= n3 && k0[t - 1] < klo) q = t; }   // lower_bound, uniform trip count
-          }
+          q = (row == 0) ? pos + 1 : lower_bound_2l(k0, coarse, n3, ncoarse, pow2, pow2c, use_coarse, (unsigned)((zz * ny + yy) * nx + xlo));
         }
+        // software pipelined walk: key and point of candidate q+1 are requested before candidate q is tested (a second lower bound for
+        // the end of the row instead of the key loads was measured slower: 65 instructions per search against ~3 per candidate)
+        unsigned kq = 0xffffffffu; float4 pq = make_float4(0, 0, 0, 0);
+        if (valid && q < n3) { kq = k0[q]; pq = Bs[q]; }
         while (true) {
-          const bool more = valid && q < n3 && k0[q] <= khi;
+          const bool more = valid && q < n3 && kq <= khi;
           if (!__any_sync(0xffffffffu, more)) break;
+          unsigned kn = 0xffffffffu; float4 pn = make_float4(0, 0, 0, 0);
+          if (more && q + 1 < n3) { kn = k0[q + 1]; pn = Bs[q + 1]; }
           if (more) {
-            int j = (int)v0[q];
-            if (l2_simple(p, B[j]) < r2) uf_union(parent, i, j);   // RadiusResultSet::addPoint: dist < radius^2
-            q++;
+            if (l2_simple(p, pq) < r2) {   // RadiusResultSet::addPoint: dist < radius^2
+              const int j = __float_as_int(pq.w);
+              if (vload(parent + i) != vload(parent + j)) uf_union(parent, i, j);   // same parent => same set already: skip the finds
+            }
+            q++; kq = kn; pq = pn;
           }
         }
       }
     }
     __syncthreads();
+    if (tid == 0) st.phase_clk[5] = clock64();
     // flatten; cluster sizes with one atomic per (warp, root)
     for (int base = 0; base < n3; base += blockDim.x) {
       const int i = base + tid;
@@ -423,6 +443,7 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
   __syncthreads();
 
   // ---------------- S7 + S8: PCA, chirality, gravity alignment, object frame ----------------
+  if (tid == 0) st.phase_clk[6] = clock64();
   {
     double s3[3] = {0, 0, 0};
     for (int i = tid; i < nc; i += blockDim.x) { float4 p = Cc[i]; s3[0] += (double)p.x; s3[1] += (double)p.y; s3[2] += (double)p.z; }
@@ -491,27 +512,42 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
   __syncthreads();
 
   // ---------------- symmetry grid (0.1 m) + transform to the object-normalised frame :322-347 ----------------
+  if (tid == 0) st.phase_clk[7] = clock64();
   int M = 0;
   voxel_sort(Cc, nc, prm.sym_leaf, k0, v0, k1, v1, S, RS);
   double *objn = W.objn + 3 * (size_t)m.off;
   float4 *objnf = W.objnf + m.off;
+  // The 0.1 m voxels hold ~50 points each, and the centroid is a sequential float sum in ascending point order: (1) the first sorted
+  // position of every voxel is compacted into v1, (2) one thread per voxel walks its members with eight independent gathers in
+  // flight per trip (a head thread chasing v0[j] -> Cc[..] one member at a time across tile boundaries was 19 % of this kernel).
   for (int tile = 0; tile < nc; tile += blockDim.x) {
-    int j = tile + tid;
-    d3 po = mk3(0, 0, 0);
-    float4 c;
-    const bool head = voxel_tile_centroid(Cc, k0, v0, tile, nc, VT, c);
-    if (head) po = hom_apply(Tow_h, mk3((double)c.x, (double)c.y, (double)c.z));
-    const bool hd[1] = {head};
+    const int j = tile + tid;
+    const bool hd[1] = {j < nc && (j == 0 || k0[j - 1] != k0[j])};
     int tot, ex[1];
     block_flag_scan<1>(hd, ex, tot, SS, phase);
-    if (head) {
-      double *q = objn + 3 * (size_t)(M + ex[0]); q[0] = po.x; q[1] = po.y; q[2] = po.z;
-      objnf[M + ex[0]] = make_float4((float)po.x, (float)po.y, (float)po.z, 0.0f);   // initializeKDTree: double -> float
-      if (W.d_sym) { double *qq = W.d_sym + 3 * (size_t)(m.off + M + ex[0]); qq[0] = po.x; qq[1] = po.y; qq[2] = po.z; }
-    }
+    if (hd[0]) v1[M + ex[0]] = (unsigned)j;
     M += tot;
   }
+  __syncthreads();
+  for (int vid = tid; vid < M; vid += blockDim.x) {
+    const int j0 = (int)v1[vid], j1 = (vid + 1 < M) ? (int)v1[vid + 1] : nc;
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    for (int jj = j0; jj < j1; jj += 8) {
+      float4 q8[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) q8[u] = Cc[v0[min(jj + u, j1 - 1)]];
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (jj + u < j1) { sx = __fadd_rn(sx, q8[u].x); sy = __fadd_rn(sy, q8[u].y); sz = __fadd_rn(sz, q8[u].z); }
+    }
+    const float cnt = (float)(j1 - j0);
+    const float4 c = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 0.0f);
+    const d3 po = hom_apply(Tow_h, mk3((double)c.x, (double)c.y, (double)c.z));
+    double *q = objn + 3 * (size_t)vid; q[0] = po.x; q[1] = po.y; q[2] = po.z;
+    objnf[vid] = make_float4((float)po.x, (float)po.y, (float)po.z, 0.0f);   // initializeKDTree: double -> float
+    if (W.d_sym) { double *qq = W.d_sym + 3 * (size_t)(m.off + vid); qq[0] = po.x; qq[1] = po.y; qq[2] = po.z; }
+  }
   if (tid == 0) {
+    st.phase_clk[8] = clock64();
     st.n_sym = M;
     st.run_sym = (prm.symmetry_open && m.symtype > 0 && M >= 1) ? 1 : 0;
   }

@@ -24,6 +24,8 @@ struct ObjState {  // device resident, one per object
   double T_oc[7];           // camera pose in the object-normalised frame
   double P[12];             // K[I|0] hom(T_oc^-1)
   double seed_prob[9], seed_init[9], seed_final[9], seed_plane[9][4], seed_dual[9];
+  long long phase_clk[9];   // clock64() stamps of the extraction phases (thread 0): start, crop, voxel sort, voxel+plane filter, cluster sort,
+                            // neighbour search, flatten+select+gather, PCA, symmetry grid (tools/extract_phases.py)
   unsigned long long n_evals, n_queries, n_points, n_hits;   // symmetry work counters (cost evaluations, NN scans, mirrored points, NN cache hits)
 };
 

@@ -1,0 +1,27 @@
+"""Per-phase cycle counts of extract_kernel (clock64 stamps of thread 0, averaged over the objects of one resident batch)."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "object-oriented-slam_b200")]
+import numpy as np
+import torch
+import eslam_b200 as E
+from eslam_b200 import synth
+import bench
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 444
+depth, fo, bb, lb, tw = bench.make_frames("one_box", n, 1000)
+h = E.Handle(); h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+d = torch.from_numpy(depth.view(np.int16)).cuda()
+h.set_profiling(True)
+for _ in range(3):
+    h.estimate_ellipsoids_dev(d.data_ptr(), n, depth.shape[2], fo, bb, lb, tw); torch.cuda.synchronize()
+clk = np.zeros((n, 9), np.int64)
+for i in range(n):
+    out = (C.c_longlong * 9)()
+    assert h.lib.eslam_debug_phase_clocks(h._h, C.c_int(i), out) == 0
+    clk[i] = list(out)
+dt = np.diff(clk, axis=1).astype(float)
+names = ["crop", "voxel sort", "voxel centroid + plane filter", "centre + cluster keys + sort", "neighbour search", "flatten + select + gather", "PCA + frame", "symmetry grid"]
+tot = dt.sum(axis=1).mean()
+print("stage ms", h.stage_ms(), " mean cycles per CTA %.0f (%.3f ms at 1.965 GHz)" % (tot, tot / 1.965e6))
+for k, nm in enumerate(names):
+    print("  %-32s %9.0f cycles  %5.1f %%" % (nm, dt[:, k].mean(), 100 * dt[:, k].mean() / tot))
