@@ -95,10 +95,15 @@ int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const
   P.k0 = w.k0.as<unsigned>(); P.k1 = w.k1.as<unsigned>(); P.v0 = w.v0.as<unsigned>(); P.v1 = w.v1.as<unsigned>();
   P.parent = w.parent.as<int>(); P.count = w.count.as<int>();
   P.objn = w.objn.as<double>(); P.objnf = w.objnf.as<float4>();
-  ESLAM_CUDA_OK(h, w.symscratch.reserve((size_t)n_obj * 9 * 2 * 256 * sizeof(float4)));   // 2 * kSymQueue slots per seed warp
-  P.nncache = w.symscratch.as<float4>();
-  ESLAM_CUDA_OK(h, w.symscratch2.reserve((size_t)n_obj * 9 * 2 * 256 * sizeof(uint4)));
-  P.pixcache = w.symscratch2.as<uint4>();
+  if (!h->sym_slotmask.p) {   // 2 * kSymQueue entries per slot, 32 slots (= CTA slots) per SM id
+    // %smid is not dense: a B200 exposes 148 SMs of a larger die, so ids run past sm_count; the tables cover kMaxSmId ids
+    const size_t slots = (size_t)kMaxSmId * 32;
+    ESLAM_CUDA_OK(h, h->sym_pool_nn.reserve(slots * 2 * 256 * sizeof(float4)));
+    ESLAM_CUDA_OK(h, h->sym_pool_px.reserve(slots * 2 * 256 * sizeof(uint4)));
+    ESLAM_CUDA_OK(h, h->sym_slotmask.reserve((size_t)kMaxSmId * sizeof(unsigned)));
+    ESLAM_CUDA_OK(h, cudaMemset(h->sym_slotmask.p, 0, (size_t)kMaxSmId * sizeof(unsigned)));   // once per handle, blocking
+  }
+  P.nncache = h->sym_pool_nn.as<float4>(); P.pixcache = h->sym_pool_px.as<uint4>(); P.slotmask = h->sym_slotmask.as<unsigned>();
   P.d_crop = P.d_voxel = P.d_world = P.d_sym = P.d_final = nullptr; P.d_label = nullptr;
   if (want_dump) {
     ESLAM_CUDA_OK(h, w.d_crop.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_voxel.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_world.reserve(CAP * 24));
@@ -333,7 +338,7 @@ void eslam_destroy(EslamHandle *h) {
   for (int sl = 0; sl < 2; sl++) {
     if (!h->ex_slot[sl]) continue;
     ExtractWorkspace &w = *h->ex_slot[sl];
-    DevBuf *bufs[] = {&w.meta, &w.state, &w.out, &w.ptsA, &w.ptsB, &w.ptsC, &w.k0, &w.k1, &w.v0, &w.v1, &w.parent, &w.count, &w.objn, &w.objnf, &w.symscratch, &w.symscratch2,
+    DevBuf *bufs[] = {&w.meta, &w.state, &w.out, &w.ptsA, &w.ptsB, &w.ptsC, &w.k0, &w.k1, &w.v0, &w.v1, &w.parent, &w.count, &w.objn, &w.objnf,
                       &w.d_crop, &w.d_voxel, &w.d_world, &w.d_sym, &w.d_final, &w.d_label, &w.depth};
     for (DevBuf *b : bufs) b->release();
     w.pin_meta.release(); w.pin_out.release(); w.pin_depth.release();
@@ -341,6 +346,7 @@ void eslam_destroy(EslamHandle *h) {
     if (h->slot_stream[sl]) cudaStreamDestroy(h->slot_stream[sl]);
     if (h->slot_done[sl]) cudaEventDestroy(h->slot_done[sl]);
   }
+  h->sym_pool_nn.release(); h->sym_pool_px.release(); h->sym_slotmask.release();
   slam_free(h);
   graph_free(h);
   plane_free(h);
@@ -410,12 +416,13 @@ int eslam_debug_counters(EslamHandle *h, int obj, unsigned long long out[5]) {
 }
 
 // test/bench hook: clock64() stamps of the extraction phases of object `obj` of the last batch
-int eslam_debug_phase_clocks(EslamHandle *h, int obj, long long out[9]) {
+int eslam_debug_phase_clocks(EslamHandle *h, int obj, long long out[13]) {
   if (!h || !h->ex || obj < 0 || obj >= h->ex->n_obj) return ESLAM_ERR_BAD_ARG;
   cudaSetDevice(h->device);
   ObjState st;
   ESLAM_CUDA_OK(h, cudaMemcpy(&st, h->ex->state.as<ObjState>() + obj, sizeof(ObjState), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 9; i++) out[i] = st.phase_clk[i];
+  for (int i = 0; i < 4; i++) out[9 + i] = st.sym_clk[i];
   return ESLAM_OK;
 }
 

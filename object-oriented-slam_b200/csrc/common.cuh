@@ -43,6 +43,7 @@ struct PinBuf {
 };
 
 constexpr int kMaxChunks = 8;
+constexpr int kMaxSmId = 256;   // upper bound of %smid + 1 the symmetry cache tables are sized for
 struct ExtractWorkspace;  // extract.cu
 struct GraphWorkspace;    // edges.cu
 struct SlamWorkspace;     // slam.cu
@@ -64,6 +65,9 @@ struct EslamHandle {
                          // 3 = union rectangle of each frame's boxes, one batched DMA call per chunk; 2 = same, one call per frame;
                          // 1 = the boxes' rows (contiguous), 0 = whole frames (env ESLAM_H2D_MODE)
   int host_chunks = 8;   // pipeline depth of the host entry (env ESLAM_HOST_CHUNKS, 1..8)
+  // symmetry kernel caches: one slot per RESIDENT seed warp (sm_count x 32 CTA slots), handed out through a per-SM bitmask, so the
+  // same ~40 MB are reused by every batch and stay L2 resident
+  eslam::DevBuf sym_pool_nn, sym_pool_px, sym_slotmask;
   unsigned long long h2d_bytes = 0;    // depth bytes uploaded by the *_host extraction entry (running total)
   bool plane_set = false;
   double plane_world[4] = {0, 0, 1, 0};

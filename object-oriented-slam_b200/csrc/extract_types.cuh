@@ -26,6 +26,7 @@ struct ObjState {  // device resident, one per object
   double seed_prob[9], seed_init[9], seed_final[9], seed_plane[9][4], seed_dual[9];
   long long phase_clk[9];   // clock64() stamps of the extraction phases (thread 0): start, crop, voxel sort, voxel+plane filter, cluster sort,
                             // neighbour search, flatten+select+gather, PCA, symmetry grid (tools/extract_phases.py)
+  long long sym_clk[4];     // symmetry kernel, summed over the 9 seed warps: classification, NN scans, ordered sums, rest
   unsigned long long n_evals, n_queries, n_points, n_hits;   // symmetry work counters (cost evaluations, NN scans, mirrored points, NN cache hits)
 };
 
@@ -52,15 +53,16 @@ struct ExtractPtrs {  // device pointers of the per-point workspace (total capac
   int *parent, *count;
   double *objn;     // [cap*3] object-normalised cloud (double)
   float4 *objnf;    // float copy for the NN search
-  float4 *nncache;  // [n_obj*9][2*kSymQueue] per-seed NN cache of the symmetry kernel (query float3 + neighbour index)
+  float4 *nncache;  // [sm_count*32][2*kSymQueue] NN cache slot of a resident seed warp of the symmetry kernel (query float3 + neighbour index)
   uint4 *pixcache;  // same shape: per-point pixel cache (pixel key, range value, depth)
+  unsigned *slotmask;  // [sm_count] bit b set = cache slot sm*32+b in use
   // optional stage dump (device mirrors, NULL when no dump requested)
   double *d_crop, *d_voxel, *d_world, *d_sym, *d_final;  // d_final has 4x capacity
   int *d_label;
 };
 
 struct ExtractWorkspace {
-  DevBuf meta, state, out, ptsA, ptsB, ptsC, k0, k1, v0, v1, parent, count, objn, objnf, symscratch, symscratch2;   // symscratch = NN cache, symscratch2 = pixel cache
+  DevBuf meta, state, out, ptsA, ptsB, ptsC, k0, k1, v0, v1, parent, count, objn, objnf;
   DevBuf d_crop, d_voxel, d_world, d_sym, d_final, d_label;
   DevBuf depth;   // staging for the *_host entry point
   PinBuf pin_meta, pin_out, pin_depth;

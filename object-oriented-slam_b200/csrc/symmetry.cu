@@ -52,6 +52,7 @@ struct SymWarp {
   double lambda, ni, currentChi, tempChi, iniChi, rho, e1;
   int nBad, ok, qmax, again, accepted;
   unsigned n_evals, n_queries, n_points, n_hits;   // work counters, flushed once per seed
+  long long clk[4];   // cycles in: classification passes, NN scans, ordered sums, everything else of the seed (clock64, lane 0)
   SeedResult res;
   unsigned short queue[kSymQueue];
   double dis[kSymQueue];
@@ -218,6 +219,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const Pla
     for (int h0 = 0; h0 < npts; h0 += B.M) {
       const int cntp = min(B.M, npts - h0);
       int qn = 0, nzn = 0, hits = 0;
+      const long long t_a = clock64();
       for (int base = 0; base < cntp; base += 32) {
         const int li = base + lane;
         int cls = 0;
@@ -244,6 +246,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const Pla
         invalid += __popc(__ballot_sync(0xffffffffu, cls == 2));
       }
       __syncwarp();
+      const long long t_b = clock64();
       if (lane == 0) { W.n_evals++; W.n_queries += qn; W.n_points += cntp; W.n_hits += hits; }
       for (int qb = 0; qb < qn; qb += 32) {
         const int cq = min(32, qn - qb);
@@ -270,6 +273,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const Pla
         }
       }
       __syncwarp();
+      const long long t_c = clock64();
       for (int base = 0; base < nzn; base += 32) {
         const double dis = (base + lane < nzn) ? W.dis[base + lane] : 0.0;
         const double lnP = -0.5 * sinv * sinv * dis * dis;
@@ -277,6 +281,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const Pla
         for (int k = 0; k < cnt; k++) ln_total += __shfl_sync(0xffffffffu, lnP, k);
       }
       __syncwarp();
+      if (lane == 0) { const long long t_d = clock64(); W.clk[0] += t_b - t_a; W.clk[1] += t_c - t_b; W.clk[2] += t_d - t_c; }
     }
   } else {
     const double sinv = B.sinv;
@@ -544,8 +549,27 @@ __global__ void __launch_bounds__(32 * S, MINB) symmetry_finalize_kernel(const u
   const int M = st.n_sym;
   const double *objn = W.objn + 3 * (size_t)m.off;
   const float4 *objnf = W.objnf + m.off;
-  float4 *cache = W.nncache + (size_t)(obj0 * 9 + gseed) * (2 * kSymQueue);
-  uint4 *pcache = W.pixcache + (size_t)(obj0 * 9 + gseed) * (2 * kSymQueue);
+  // cache slot of this resident warp: a free bit of this SM's mask (at most 32 CTAs are resident per SM)
+  unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (smid >= (unsigned)kMaxSmId) __trap();
+  unsigned *slotword = W.slotmask + smid;
+  int slotbit = -1;
+  while (slotbit < 0) {   // warp-uniform control flow: lane 0 reads and claims, every lane follows the broadcast outcome
+    unsigned cur = 0;
+    if (lane == 0) cur = *((volatile unsigned *)slotword);
+    cur = __shfl_sync(0xffffffffu, cur, 0);
+    const unsigned freeb = ~cur;
+    if (freeb) {
+      const int b = __ffs(freeb) - 1;
+      unsigned old = 0;
+      if (lane == 0) old = atomicOr(slotword, 1u << b);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (!(old & (1u << b))) slotbit = b;
+    }
+  }
+  const size_t slot = (size_t)smid * 32 + slotbit;
+  float4 *cache = W.nncache + slot * (2 * kSymQueue);
+  uint4 *pcache = W.pixcache + slot * (2 * kSymQueue);
   {
     const bool in_smem = M <= kSymSmemPts;
     // invalidate this warp's NN cache: a NaN x never equals a float-converted finite query
@@ -559,7 +583,7 @@ __global__ void __launch_bounds__(32 * S, MINB) symmetry_finalize_kernel(const u
       const float4 b = (2 * j + 1 < M) ? objnf[2 * j + 1] : make_float4(far_, far_, far_, 0.0f);
       B.X2[j] = f2_pack(a.x, b.x); B.Y2[j] = f2_pack(a.y, b.y); B.Z2[j] = f2_pack(a.z, b.z);
     }
-    if (lane == 0) { Wp.cache = cache; Wp.pcache = pcache; Wp.n_evals = Wp.n_queries = Wp.n_points = Wp.n_hits = 0; Wp.accepted = 0; }
+    if (lane == 0) { Wp.cache = cache; Wp.pcache = pcache; Wp.n_evals = Wp.n_queries = Wp.n_points = Wp.n_hits = 0; Wp.accepted = 0; Wp.clk[0] = Wp.clk[1] = Wp.clk[2] = Wp.clk[3] = 0; }
     if (threadIdx.x == 0) {
       B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch; B.st = &st;
       B.objn = objn; B.nn_g = objnf; B.M = M; B.symtype = m.symtype; B.npts = (m.symtype == 2) ? 2 * M : M; B.in_smem = in_smem ? 1 : 0;
@@ -579,9 +603,14 @@ __global__ void __launch_bounds__(32 * S, MINB) symmetry_finalize_kernel(const u
     }
     if (S > 1) __syncthreads(); else __syncwarp();
   }
+  const long long t_seed0 = clock64();
   sym_optimize(B, Wp, prm.symmetry_iters);
   int prev = 0;
   if (lane == 0) {
+    __threadfence();                          // this warp's cache stores are ordered before the next owner's
+    atomicAnd(slotword, ~(1u << slotbit));    // hand the cache slot back
+    Wp.clk[3] = clock64() - t_seed0 - Wp.clk[0] - Wp.clk[1] - Wp.clk[2];
+    for (int k = 0; k < 4; k++) atomicAdd((unsigned long long *)&st.sym_clk[k], (unsigned long long)Wp.clk[k]);
     const SeedResult &r = Wp.res;
     st.seed_prob[seed] = r.prob; st.seed_init[seed] = r.init_err; st.seed_final[seed] = r.final_err; st.seed_dual[seed] = r.plane.dual;
     for (int k = 0; k < 4; k++) st.seed_plane[seed][k] = r.plane.p[k];

@@ -14,14 +14,18 @@ d = torch.from_numpy(depth.view(np.int16)).cuda()
 h.set_profiling(True)
 for _ in range(3):
     h.estimate_ellipsoids_dev(d.data_ptr(), n, depth.shape[2], fo, bb, lb, tw); torch.cuda.synchronize()
-clk = np.zeros((n, 9), np.int64)
+clk = np.zeros((n, 9), np.int64); sclk = np.zeros((n, 4), np.int64)
 for i in range(n):
-    out = (C.c_longlong * 9)()
+    out = (C.c_longlong * 13)()
     assert h.lib.eslam_debug_phase_clocks(h._h, C.c_int(i), out) == 0
-    clk[i] = list(out)
+    clk[i] = list(out)[:9]; sclk[i] = list(out)[9:]
 dt = np.diff(clk, axis=1).astype(float)
 names = ["crop", "voxel sort", "voxel centroid + plane filter", "centre + cluster keys + sort", "neighbour search", "flatten + select + gather", "PCA + frame", "symmetry grid"]
 tot = dt.sum(axis=1).mean()
 print("stage ms", h.stage_ms(), " mean cycles per CTA %.0f (%.3f ms at 1.965 GHz)" % (tot, tot / 1.965e6))
 for k, nm in enumerate(names):
     print("  %-32s %9.0f cycles  %5.1f %%" % (nm, dt[:, k].mean(), 100 * dt[:, k].mean() / tot))
+st = sclk.sum(axis=1).mean()
+print("symmetry kernel: mean cycles per seed warp %.0f (%.3f ms)" % (st / 9, st / 9 / 1.965e6))
+for k, nm in enumerate(["classification passes (mirror + project + caches)", "nearest-neighbour scans", "ordered ln P sums", "rest (LM scalar code, oplus, plane pairs, set-up)"]):
+    print("  %-52s %9.0f cycles  %5.1f %%" % (nm, sclk[:, k].mean() / 9, 100 * sclk[:, k].mean() / st))
