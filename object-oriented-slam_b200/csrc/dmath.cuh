@@ -135,8 +135,10 @@ DEV quat q_from_R(const mat3 &m) {
 }
 DEV quat q_axis_angle(double angle, d3 axis) {
   double ha = 0.5 * angle;
-  double s = sin(ha);
-  quat q; q.x = s * axis.x; q.y = s * axis.y; q.z = s * axis.z; q.w = cos(ha);
+  // sin(+-0) = +-0 and cos(+-0) = 1 exactly: the symmetry planes are vertical, so half of these calls see a zero elevation
+  const bool zero = (ha == 0.0);
+  double s = zero ? ha : sin(ha);
+  quat q; q.x = s * axis.x; q.y = s * axis.y; q.z = s * axis.z; q.w = zero ? 1.0 : cos(ha);
   return q;
 }
 DEV mat3 R_axis_angle(double angle, d3 axis) {  // Eigen::AngleAxis::toRotationMatrix
@@ -355,12 +357,14 @@ DEV double plane_signed_dist(const double *p, d3 pt) {  // Plane.cpp:108-115 (ke
 }
 DEV mat3 plane_rotation(d3 v) {  // Plane.h:88-92
   double az = atan2(v.y, v.x);
-  double el = atan2(v.z, sqrt(v.x * v.x + v.y * v.y));
+  const double rxy = sqrt(v.x * v.x + v.y * v.y);
+  double el = (v.z == 0.0 && rxy > 0.0) ? v.z : atan2(v.z, rxy);   // atan2(+-0, r > 0) = +-0 exactly
   quat q = q_mul(q_axis_angle(az, mk3(0, 0, 1)), q_axis_angle(-el, mk3(0, 1, 0)));
   return q_to_R(q);
 }
 DEV void plane_oplus_common(dplane &pl, double az, double el, double dd) {
-  double s = sin(el), c = cos(el);
+  const bool el0 = (el == 0.0);
+  double s = el0 ? el : sin(el), c = el0 ? 1.0 : cos(el);   // exact for +-0 (VertexPlane / VertexDualPlane always pass el = 0)
   d3 n = mk3(c * cos(az), c * sin(az), s);
   mat3 R = plane_rotation(mk3(pl.p[0], pl.p[1], pl.p[2]));
   double d = -pl.p[3] + dd;
