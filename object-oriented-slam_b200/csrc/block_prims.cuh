@@ -19,8 +19,8 @@ struct BlockScratch {            // shared-memory scratch, one per CTA
 
 constexpr int kRadixWarps = 16;   // block_radix_sort supports CTAs of up to 512 threads
 struct RadixScratch {
-  unsigned int radix[kRadixWarps * 256];   // per-warp digit counters
-  unsigned int digit_base[256];
+  unsigned int radix[kRadixWarps * 256];   // per-warp digit counters (8-bit digits), or 8 warps x 1024 16-bit counters (wide digits)
+  unsigned int digit_base[1024];
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -163,6 +163,85 @@ __device__ __forceinline__ unsigned block_max_u32(unsigned v, BlockScratch &S) {
   for (int i = 1; i < nw; i++) r = max(r, (unsigned)S.warp_i[i]);
   __syncthreads();
   return r;
+}
+
+// Two-pass variant for 256-thread CTAs: keys of up to 20 bits are sorted with two digits of ceil(bits/2) <= 10 bits instead of three
+// 8-bit passes.  The per-warp counters are 16 bit (8 warps x 1024 digits in the same 16 KB), which bounds n at 65 535.  Same stable
+// ranking as the 8-bit version (match_any inside a 32-key group, warp-major offsets across the CTA).
+static __device__ void block_radix_sort_wide(unsigned *k0, unsigned *v0, unsigned *k1, unsigned *v1, int n, int bits, RadixScratch &S, BlockScratch &BS) {
+  const int lane = lane_id(), w = warp_id();
+  constexpr int NW = 8;
+  const int dbits = (bits + 1) >> 1;           // <= 10
+  const int D = 1 << dbits;
+  const unsigned dmask = (unsigned)D - 1u;
+  unsigned short *cnt16 = reinterpret_cast<unsigned short *>(S.radix);   // [NW][1024]
+  int chunk = (n + NW - 1) / NW;
+  chunk = (chunk + 31) & ~31;
+  const int beg = min(n, w * chunk), end = min(n, beg + chunk);
+  unsigned *ki = k0, *vi = v0, *ko = k1, *vo = v1;
+  for (int p = 0; p < 2; p++) {
+    const int shift = p * dbits;
+    for (int i = threadIdx.x; i < NW * 1024 / 2; i += blockDim.x) S.radix[i] = 0;
+    __syncthreads();
+    unsigned short *cnt = cnt16 + w * 1024;
+    for (int i0 = beg; i0 < end; i0 += 128) {
+      unsigned kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int j = i0 + u * 32 + lane; kk[u] = (j < end) ? ki[j] : 0u; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = i0 + u * 32 + lane;
+        if (i0 + u * 32 < end) {   // warp-uniform
+          const bool valid = j < end;
+          const unsigned d = valid ? ((kk[u] >> shift) & dmask) : (0x10000u + lane);
+          const unsigned peers = __match_any_sync(0xffffffffu, d);
+          if (valid && (__ffs(peers) - 1) == lane) cnt[d] = (unsigned short)(cnt[d] + __popc(peers));
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+    // (digit major, warp minor) exclusive offsets: thread t owns digits 4t .. 4t+3
+    unsigned tot4[4]; unsigned mine = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int d = threadIdx.x * 4 + q;
+      unsigned run = 0;
+      if (d < D) for (int ww = 0; ww < NW; ww++) { const unsigned c = cnt16[ww * 1024 + d]; cnt16[ww * 1024 + d] = (unsigned short)run; run += c; }
+      tot4[q] = run; mine += run;
+    }
+    int total;
+    unsigned ex = (unsigned)block_excl_scan((int)mine, BS, total);
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const int d = threadIdx.x * 4 + q; if (d < D) S.digit_base[d] = ex; ex += tot4[q]; }
+    __syncthreads();
+    for (int i0 = beg; i0 < end; i0 += 128) {
+      unsigned kk[4], vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int j = i0 + u * 32 + lane; const bool valid = j < end; kk[u] = valid ? ki[j] : 0u; vv[u] = valid ? vi[j] : 0u; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int j = i0 + u * 32 + lane;
+        if (i0 + u * 32 < end) {   // warp-uniform
+          const bool valid = j < end;
+          const unsigned key = kk[u], val = vv[u];
+          const unsigned d = valid ? ((key >> shift) & dmask) : (0x10000u + lane);
+          const unsigned peers = __match_any_sync(0xffffffffu, d);
+          const unsigned base = valid ? ((unsigned)cnt[d] + S.digit_base[d]) : 0u;
+          const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+          __syncwarp();
+          if (valid && (__ffs(peers) - 1) == lane) cnt[d] = (unsigned short)(cnt[d] + __popc(peers));
+          __syncwarp();
+          if (valid) { ko[base + rank] = key; vo[base + rank] = val; }
+        }
+      }
+    }
+    __syncthreads();
+    unsigned *t;
+    t = ki; ki = ko; ko = t;
+    t = vi; vi = vo; vo = t;
+  }
+  // two passes: the result is back in (k0, v0)
 }
 
 // Stable LSD radix sort of n (key,val) pairs, 8-bit digits, keys < 2^bits.  Warp w owns the contiguous chunk

@@ -111,7 +111,8 @@ __device__ void voxel_sort(const float4 *pts, int n, float leaf, unsigned *k0, u
   __syncthreads();
   unsigned long long maxkey = (unsigned long long)divb[0] * (unsigned long long)divb[1] * (unsigned long long)divb[2];
   int bits = (maxkey >= 0xffffffffULL) ? 32 : bits_for((unsigned)maxkey);
-  block_radix_sort(k0, v0, k1, v1, n, bits, RS);
+  if (bits > 8 && bits <= 20 && n <= 65535 && blockDim.x == 256) block_radix_sort_wide(k0, v0, k1, v1, n, bits, RS, S);
+  else block_radix_sort(k0, v0, k1, v1, n, bits, RS);
 }
 
 constexpr int kExtractThreads = 256;   // 3 CTAs/SM: different objects sit in different phases, hiding the many block barriers
@@ -303,7 +304,11 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
       parent[i] = i; count[i] = 0;
     }
     __syncthreads();
-    block_radix_sort(k0, v0, k1, v1, n3, bits_for((unsigned)(gx * gy * gz)), RS);
+    {
+      const int cbits = bits_for((unsigned)(gx * gy * gz));
+      if (cbits > 8 && cbits <= 20 && n3 <= 65535) block_radix_sort_wide(k0, v0, k1, v1, n3, cbits, RS, S);
+      else block_radix_sort(k0, v0, k1, v1, n3, cbits, RS);
+    }
     if (tid == 0) st.phase_clk[4] = clock64();
     const float r2 = prm.cluster_r2;
     int pow2 = 1;
