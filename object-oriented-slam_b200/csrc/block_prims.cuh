@@ -168,22 +168,27 @@ __device__ __forceinline__ unsigned block_max_u32(unsigned v, BlockScratch &S) {
 // Two-pass variant for 256-thread CTAs: keys of up to 20 bits are sorted with two digits of ceil(bits/2) <= 10 bits instead of three
 // 8-bit passes.  The per-warp counters are 16 bit (8 warps x 1024 digits in the same 16 KB), which bounds n at 65 535.  Same stable
 // ranking as the 8-bit version (match_any inside a 32-key group, warp-major offsets across the CTA).
-static __device__ void block_radix_sort_wide(unsigned *k0, unsigned *v0, unsigned *k1, unsigned *v1, int n, int bits, RadixScratch &S, BlockScratch &BS) {
+// cnt16: NW x dstride 16-bit counters, dbase: 2^ceil(bits/2) words -- both in shared memory (RadixScratch for <= 10-bit digits, the idle
+// 48 KB union-find region for 11-bit digits).
+static __device__ void block_radix_sort_wide(unsigned *k0, unsigned *v0, unsigned *k1, unsigned *v1, int n, int bits, unsigned short *cnt16, unsigned *dbase, int dstride,
+                                             BlockScratch &BS) {
   const int lane = lane_id(), w = warp_id();
   constexpr int NW = 8;
-  const int dbits = (bits + 1) >> 1;           // <= 10
+  const int passes = (bits + 10) / 11 < 2 ? 2 : (bits + 10) / 11;   // two passes up to 22 bits, three up to 33
+  const int dbits = (bits + passes - 1) / passes;
   const int D = 1 << dbits;
   const unsigned dmask = (unsigned)D - 1u;
-  unsigned short *cnt16 = reinterpret_cast<unsigned short *>(S.radix);   // [NW][1024]
+  unsigned *cntw = reinterpret_cast<unsigned *>(cnt16);
+  const int per = (D + 255) >> 8;              // digits per thread in the offset scan (<= 8)
   int chunk = (n + NW - 1) / NW;
   chunk = (chunk + 31) & ~31;
   const int beg = min(n, w * chunk), end = min(n, beg + chunk);
   unsigned *ki = k0, *vi = v0, *ko = k1, *vo = v1;
-  for (int p = 0; p < 2; p++) {
+  for (int p = 0; p < passes; p++) {
     const int shift = p * dbits;
-    for (int i = threadIdx.x; i < NW * 1024 / 2; i += blockDim.x) S.radix[i] = 0;
+    for (int i = threadIdx.x; i < NW * dstride / 2; i += blockDim.x) cntw[i] = 0;
     __syncthreads();
-    unsigned short *cnt = cnt16 + w * 1024;
+    unsigned short *cnt = cnt16 + w * dstride;
     for (int i0 = beg; i0 < end; i0 += 128) {
       unsigned kk[4];
 #pragma unroll
@@ -201,19 +206,19 @@ static __device__ void block_radix_sort_wide(unsigned *k0, unsigned *v0, unsigne
       }
     }
     __syncthreads();
-    // (digit major, warp minor) exclusive offsets: thread t owns digits 4t .. 4t+3
-    unsigned tot4[4]; unsigned mine = 0;
+    // (digit major, warp minor) exclusive offsets: thread t owns digits t*per .. t*per+per-1
+    unsigned tot8[8]; unsigned mine = 0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int d = threadIdx.x * 4 + q;
+    for (int q = 0; q < 8; q++) {
+      const int d = threadIdx.x * per + q;
       unsigned run = 0;
-      if (d < D) for (int ww = 0; ww < NW; ww++) { const unsigned c = cnt16[ww * 1024 + d]; cnt16[ww * 1024 + d] = (unsigned short)run; run += c; }
-      tot4[q] = run; mine += run;
+      if (q < per && d < D) for (int ww = 0; ww < NW; ww++) { const unsigned c = cnt16[ww * dstride + d]; cnt16[ww * dstride + d] = (unsigned short)run; run += c; }
+      tot8[q] = run; mine += run;
     }
     int total;
     unsigned ex = (unsigned)block_excl_scan((int)mine, BS, total);
 #pragma unroll
-    for (int q = 0; q < 4; q++) { const int d = threadIdx.x * 4 + q; if (d < D) S.digit_base[d] = ex; ex += tot4[q]; }
+    for (int q = 0; q < 8; q++) { const int d = threadIdx.x * per + q; if (q < per && d < D) dbase[d] = ex; ex += tot8[q]; }
     __syncthreads();
     for (int i0 = beg; i0 < end; i0 += 128) {
       unsigned kk[4], vv[4];
@@ -227,7 +232,7 @@ static __device__ void block_radix_sort_wide(unsigned *k0, unsigned *v0, unsigne
           const unsigned key = kk[u], val = vv[u];
           const unsigned d = valid ? ((key >> shift) & dmask) : (0x10000u + lane);
           const unsigned peers = __match_any_sync(0xffffffffu, d);
-          const unsigned base = valid ? ((unsigned)cnt[d] + S.digit_base[d]) : 0u;
+          const unsigned base = valid ? ((unsigned)cnt[d] + dbase[d]) : 0u;
           const unsigned rank = __popc(peers & ((1u << lane) - 1u));
           __syncwarp();
           if (valid && (__ffs(peers) - 1) == lane) cnt[d] = (unsigned short)(cnt[d] + __popc(peers));
@@ -241,7 +246,10 @@ static __device__ void block_radix_sort_wide(unsigned *k0, unsigned *v0, unsigne
     t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;
   }
-  // two passes: the result is back in (k0, v0)
+  if (ki != k0) {  // odd number of passes: copy back
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { k0[i] = ki[i]; v0[i] = vi[i]; }
+    __syncthreads();
+  }
 }
 
 // Stable LSD radix sort of n (key,val) pairs, 8-bit digits, keys < 2^bits.  Warp w owns the contiguous chunk

@@ -74,7 +74,9 @@ __device__ __forceinline__ float l2_simple(float4 a, float4 b) {  // flann::L2_S
 }
 
 // PCL VoxelGrid indexing + stable sort.  On return k0[j]/v0[j] hold sorted voxel keys / original indices.
-__device__ void voxel_sort(const float4 *pts, int n, float leaf, unsigned *k0, unsigned *v0, unsigned *k1, unsigned *v1, BlockScratch &S, RadixScratch &RS) {
+// `wide`: >= 40 KB of shared memory that is idle during the sort (8 x 2048 16-bit counters + 2048 digit offsets)
+__device__ void voxel_sort(const float4 *pts, int n, float leaf, unsigned *k0, unsigned *v0, unsigned *k1, unsigned *v1, BlockScratch &S, RadixScratch &RS, int *wide, long long *dbg = nullptr) {
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float4 p = pts[i];
@@ -82,6 +84,7 @@ __device__ void voxel_sort(const float4 *pts, int n, float leaf, unsigned *k0, u
     mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
   }
   block_minmax3(mn, mx, S);
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
   const float inv = __fdiv_rn(1.0f, leaf);
   long long dx = (long long)__fmul_rn(__fsub_rn(mx[0], mn[0]), inv) + 1;
   long long dy = (long long)__fmul_rn(__fsub_rn(mx[1], mn[1]), inv) + 1;
@@ -109,9 +112,13 @@ __device__ void voxel_sort(const float4 *pts, int n, float leaf, unsigned *k0, u
     v0[i] = (unsigned)i;
   }
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[2] = clock64();
   unsigned long long maxkey = (unsigned long long)divb[0] * (unsigned long long)divb[1] * (unsigned long long)divb[2];
   int bits = (maxkey >= 0xffffffffULL) ? 32 : bits_for((unsigned)maxkey);
-  if (bits > 8 && bits <= 20 && n <= 65535 && blockDim.x == 256) block_radix_sort_wide(k0, v0, k1, v1, n, bits, RS, S);
+  // wide passes (digits of up to 11 bits: two passes up to 22 key bits, three up to 32) instead of 8-bit ones; the counters live in the
+  // idle union-find region.  The 1 cm grid over a crop that reaches the 6 m range limit has 27-bit keys: 3 passes instead of 4.
+  if (bits > 8 && n <= 65535 && blockDim.x == 256)
+    block_radix_sort_wide(k0, v0, k1, v1, n, bits, reinterpret_cast<unsigned short *>(wide), reinterpret_cast<unsigned *>(wide) + 8 * 2048 / 2, 2048, S);
   else block_radix_sort(k0, v0, k1, v1, n, bits, RS);
 }
 
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
   // ---------------- S2 + S3 + S4: 1 cm voxel grid -> world -> supporting-plane filter ----------------
   int n2 = 0, n3 = 0;
   if (n1 > 0) {
-    voxel_sort(A, n1, prm.voxel_leaf, k0, v0, k1, v1, S, RS);
+    voxel_sort(A, n1, prm.voxel_leaf, k0, v0, k1, v1, S, RS, s_parent);
     if (tid == 0) st.phase_clk[2] = clock64();
     for (int tile = 0; tile < n1; tile += blockDim.x) {
       int j = tile + tid;
@@ -306,7 +313,8 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
     __syncthreads();
     {
       const int cbits = bits_for((unsigned)(gx * gy * gz));
-      if (cbits > 8 && cbits <= 20 && n3 <= 65535) block_radix_sort_wide(k0, v0, k1, v1, n3, cbits, RS, S);
+      if (cbits > 8 && cbits <= 20 && n3 <= 65535)
+        block_radix_sort_wide(k0, v0, k1, v1, n3, cbits, reinterpret_cast<unsigned short *>(RS.radix), RS.digit_base, 1024, S);
       else block_radix_sort(k0, v0, k1, v1, n3, cbits, RS);
     }
     if (tid == 0) st.phase_clk[4] = clock64();
@@ -519,7 +527,7 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
   // ---------------- symmetry grid (0.1 m) + transform to the object-normalised frame :322-347 ----------------
   if (tid == 0) st.phase_clk[7] = clock64();
   int M = 0;
-  voxel_sort(Cc, nc, prm.sym_leaf, k0, v0, k1, v1, S, RS);
+  voxel_sort(Cc, nc, prm.sym_leaf, k0, v0, k1, v1, S, RS, s_parent);
   double *objn = W.objn + 3 * (size_t)m.off;
   float4 *objnf = W.objnf + m.off;
   // The 0.1 m voxels hold ~50 points each, and the centroid is a sequential float sum in ascending point order: (1) the first sorted
