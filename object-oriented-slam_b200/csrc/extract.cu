@@ -570,8 +570,11 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
 // loads, 4 in flight per thread) into the device-side frame buffer the extraction kernels read.  One launch per chunk replaces one
 // DMA submission per frame (each costs ~5 us on the copy engine, more than moving a 200 KB rectangle), and only the pixels the path
 // can read cross the bus.  Runs on the high-priority copy stream next to the compute kernels of the previous chunks.
-__global__ void __launch_bounds__(256) pull_rects_kernel(const uint16_t *__restrict__ host_src, uint16_t *__restrict__ dst, size_t pitch, size_t frame_stride,
-                                                         const ObjMeta *__restrict__ metas, int n_obj, int rows, int cols) {
+// CTA shape: 128 threads x <= 32 registers = 4096 registers, exactly what three resident extract_kernel CTAs (3 x 20 480) leave free on an
+// SM -- a 256-thread, 62-register version displaced one extraction CTA on every SM it ran on while the uploads were in flight.
+constexpr int kPullThreads = 128;
+__global__ void __launch_bounds__(kPullThreads, 16) pull_rects_kernel(const uint16_t *__restrict__ host_src, uint16_t *__restrict__ dst, size_t pitch, size_t frame_stride,
+                                                                      const ObjMeta *__restrict__ metas, int n_obj, int rows, int cols) {
   for (int k = blockIdx.x; k < n_obj; k += gridDim.x) {
     const ObjMeta &m = metas[k];
     if (m.pre_status != 0) continue;
@@ -580,25 +583,30 @@ __global__ void __launch_bounds__(256) pull_rects_kernel(const uint16_t *__restr
     const int upr = (x1 - x0) >> 3;               // 16-byte units per row
     const int total = upr * (y1 - y0);
     const size_t base = (size_t)m.frame * frame_stride + (size_t)y0 * pitch + x0;
-    for (int u0 = threadIdx.x; u0 < total; u0 += 4 * 256) {
-      uint4 v[4]; size_t off[4];
+    const uint16_t *src = host_src + base;
+    uint16_t *out = dst + base;
+    const unsigned p32 = (unsigned)pitch;
+    for (int u0 = threadIdx.x; u0 < total; u0 += 4 * kPullThreads) {
+      uint4 v[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const int u = u0 + j * 256;
+        const int u = min(u0 + j * kPullThreads, total - 1);
         const int r = u / upr, c = u - r * upr;
-        off[j] = base + (size_t)r * pitch + (size_t)c * 8;
-        if (u < total) v[j] = __ldcs(reinterpret_cast<const uint4 *>(host_src + off[j]));
+        v[j] = __ldcs(reinterpret_cast<const uint4 *>(src + (r * p32 + c * 8u)));
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) if (u0 + j * 256 < total) *reinterpret_cast<uint4 *>(dst + off[j]) = v[j];
+      for (int j = 0; j < 4; j++) {
+        const int u = u0 + j * kPullThreads;
+        if (u < total) { const int r = u / upr, c = u - r * upr; *reinterpret_cast<uint4 *>(out + (r * p32 + c * 8u)) = v[j]; }
+      }
     }
   }
 }
 int pull_rects_launch(EslamHandle *h, cudaStream_t s, const uint16_t *host_mapped, uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj) {
   ExtractWorkspace &w = *h->ex;
   if (n_obj <= 0) return ESLAM_OK;
-  const int grid = n_obj < 96 ? n_obj : 96;
-  pull_rects_kernel<<<grid, 256, 0, s>>>(host_mapped, depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, n_obj, h->cam.rows, h->cam.cols);
+  const int grid = n_obj < h->sm_count ? n_obj : h->sm_count;
+  pull_rects_kernel<<<grid, kPullThreads, 0, s>>>(host_mapped, depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, n_obj, h->cam.rows, h->cam.cols);
   ESLAM_LAUNCHED(h);
   ESLAM_CUDA_OK(h, cudaGetLastError());
   return ESLAM_OK;
