@@ -206,7 +206,7 @@ __device__ __noinline__ NNRes nn_distance_split(const SymBlock &B, d3 pm, int sl
 // NN cache or are compacted into a per-warp queue so that (2) the brute-force searches run with full lanes; (3) ln P accumulated in
 // the reference's point order -- over the points with a distance only: every other point contributes -0.0, which never changes the sum.
 // (__noinline__: the kernel is instruction-fetch bound when the ~1k-instruction evaluation body is replicated at its call sites)
-__device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const PlanePair &PP) {
+__device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const PlanePair &PP, bool update_cache = true) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const int npts = B.npts;
@@ -256,7 +256,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const Pla
             const d3 pm = mirrored(B, PP, h0 + li);
             const NNRes r = nn_distance(B, pm);
             W.dis[e >> 8] = r.dis;
-            W.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
+            if (update_cache) W.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
           }
         } else {   // partial chunk: split every query's scan over several lanes
           int slots = 1;
@@ -268,7 +268,7 @@ __device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const Pla
           const NNRes r = nn_distance_split(B, pm, slots, active);
           if (active && lane < slots) {
             W.dis[e >> 8] = r.dis;
-            W.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
+            if (update_cache) W.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
           }
         }
       }
@@ -353,8 +353,10 @@ __device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
     }
     __syncwarp();
     for (int d = 0; d < dim; d++) {
-      const double e1 = sym_eval(B, W, W.fd[2 * d]);
-      const double e2 = sym_eval(B, W, W.fd[2 * d + 1]);
+      // the finite-difference evaluations leave the NN cache on the queries of the base plane: their own queries are the base query or
+      // one float ulp beside it, so comparing against the base hits more often than comparing against the previous perturbation
+      const double e1 = sym_eval(B, W, W.fd[2 * d], false);
+      const double e2 = sym_eval(B, W, W.fd[2 * d + 1], false);
       if (lane == 0) W.J[d] = (1.0 / (2 * 1e-9)) * (e1 - e2);
     }
     if (lane == 0) {
