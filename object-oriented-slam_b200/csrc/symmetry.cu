@@ -82,7 +82,7 @@ __device__ __forceinline__ d3 mirrored(const SymBlock &B, const PlanePair &P, in
 // `pc` is the point's pixel-cache entry: when the mirrored point projects to the same pixel as last time (always, for the 1e-9
 // finite-difference perturbations) the range value of that pixel -- a function of the pixel alone -- is reused instead of being
 // reloaded and recomputed (1 gather, 1 sqrt, 2 divisions).
-__device__ __noinline__ int classify(const SymBlock &B, d3 pm, uint4 pc, uint4 *slot) {
+__device__ __forceinline__ int classify(const SymBlock &B, d3 pm, uint4 pc, uint4 *slot) {
   double uvh[3];
 #pragma unroll
   for (int r = 0; r < 3; r++) { double s = B.P[r * 4] * pm.x; s += B.P[r * 4 + 1] * pm.y; s += B.P[r * 4 + 2] * pm.z; s += B.P[r * 4 + 3] * 1.0; uvh[r] = s; }
