@@ -89,7 +89,8 @@ void orc_plane_to_world(const double plane_cam[4], const double Twc7[7], double 
 void orc_plane_oplus(double p4[4], double *dual_dis, const double v3[3], int dual) {
   Plane pl; for (int i = 0; i < 4; i++) pl.p[i] = p4[i]; pl.dual_dis = *dual_dis;
   if (dual) plane_oplus_dual(pl, v3); else plane_oplus(pl, v3);
-  for (int i = 0; i < 4; i++) p4[i] = pl.p[i]; *dual_dis = pl.dual_dis;
+  for (int i = 0; i < 4; i++) p4[i] = pl.p[i];
+  *dual_dis = pl.dual_dis;
 }
 void orc_pose_inverse(const double T7[7], double out7[7]) { se3_to_vector(se3_inverse(se3_from_vector(T7)), out7); }
 
