@@ -220,6 +220,8 @@ def main():
     from eslam_b200._structs import EslamEllipsoidOut
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line (rank 0): NCCL's version banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     depth, fo, bb, lb, tw = make_frames(args.workload, args.frames, 1000 + 100000 * rank)
     n_obj = len(fo)
