@@ -220,9 +220,21 @@ def main():
     from eslam_b200._structs import EslamEllipsoidOut
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries exactly one JSON line (rank 0): NCCL's version banner / debug output goes to stderr
+        # stdout carries exactly one JSON line (rank 0).  NCCL prints its version banner (NCCL_DEBUG=VERSION is set on the GPU boxes) with
+        # a plain write to fd 1 when the communicator is created, whatever NCCL_DEBUG_FILE says (measured), so fd 1 points at stderr
+        # while the process group and its first collective are set up.
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     depth, fo, bb, lb, tw = make_frames(args.workload, args.frames, 1000 + 100000 * rank)
     n_obj = len(fo)
     h = E.Handle(device=local)
