@@ -618,11 +618,10 @@ int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, si
   if (n_obj <= 0) return ESLAM_OK;
   // Shape: 3 CTAs/SM (80 registers, 48 KB of parents).  Measured alternative: 4 CTAs/SM with a 64-register cap and 32 KB of parents is
   // 9 % slower (profiles/r01_kernel_shape_ab.txt).
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->attr_extract) {
     ESLAM_CUDA_OK(h, cudaFuncSetAttribute(extract_kernel<3, kSmemParents>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemParents * (int)sizeof(int)));
     ESLAM_CUDA_OK(h, cudaFuncSetAttribute(extract_kernel<3, kSmemParents>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
+    h->attr_extract = true;
   }
   extract_kernel<3, kSmemParents><<<n_obj, kExtractThreads, kSmemParents * sizeof(int), s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0,
                                                                                               w.state.as<ObjState>() + obj0, prm, ptrs);

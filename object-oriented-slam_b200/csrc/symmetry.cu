@@ -632,8 +632,7 @@ int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *dep
   if (n_obj <= 0) return ESLAM_OK;
   // Shape: one seed warp per CTA, 28 CTAs/SM (72 registers).  Measured alternatives (profiles/r01_kernel_shape_ab.txt): 3 seed warps per
   // CTA sharing the cloud at 27 warps/SM (+13 % time) and at 36 warps/SM with a 56-register cap (+18 %, spills) are both slower.
-  static bool attr_set = false;
-  if (!attr_set) { ESLAM_CUDA_OK(h, cudaFuncSetAttribute(symmetry_finalize_kernel<1, 28>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); attr_set = true; }
+  if (!h->attr_symmetry) { ESLAM_CUDA_OK(h, cudaFuncSetAttribute(symmetry_finalize_kernel<1, 28>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); h->attr_symmetry = true; }
   symmetry_finalize_kernel<1, 28><<<9 * n_obj, 32, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs,
                                                            w.out.as<EslamEllipsoidOut>() + obj0, obj0);
   ESLAM_LAUNCHED(h);
