@@ -143,7 +143,7 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
   // caller's stream joins them at the end.  Device-resident input: chunks of objects.  Host input: chunks of frames (objects must be
   // ordered by frame, which is how a frame stream arrives; otherwise one chunk).
   int n_chunks = 1;
-  if (!host_depth) n_chunks = n_obj >= 512 ? kMaxChunks : (n_obj >= 256 ? 4 : 2);
+  if (!host_depth) n_chunks = n_obj >= 512 ? h->dev_chunks : (n_obj >= 256 ? 4 : 2);
   else if (sorted && n_frames >= 64) n_chunks = h->host_chunks;
   if (host_depth && !h->copy_stream) {
     int lo = 0, hi = 0;
@@ -164,8 +164,8 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
     if (!h->chunk_done[c]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
     if (!h->chunk_stream[c]) ESLAM_CUDA_OK(h, cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
   }
-  if (!h->chunk_ev[15]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->chunk_ev[15], cudaEventDisableTiming));
-  ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_ev[15], s));   // metadata upload (prepare_batch) happened on s; earlier work on s is ordered too
+  if (!h->chunk_ev[16]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->chunk_ev[16], cudaEventDisableTiming));
+  ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_ev[16], s));   // metadata upload (prepare_batch) happened on s; earlier work on s is ordered too
   const ExtractWorkspace &w = *h->ex;
   const int rows = h->cam.rows, cols = h->cam.cols;
   const bool trace = getenv("ESLAM_TRACE") != nullptr;
@@ -180,7 +180,7 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
       if (sorted) { while (o1 < n_obj && frame_of_obj[o1] < f1) o1++; } else o1 = n_obj;
       if (c == n_chunks - 1) o1 = n_obj;
       if (host_mapped) {
-        ESLAM_CUDA_OK(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[15], 0));   // needs the ObjMeta table
+        ESLAM_CUDA_OK(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[16], 0));   // needs the ObjMeta table
         if ((rc = pull_rects_launch(h, h->copy_stream, host_mapped, const_cast<uint16_t *>(depth_dev), pitch, frame_stride, o, o1 - o))) return rc;
         for (int k = o; k < o1; k++) {
           const ObjMeta &m = w.meta_host[k];
@@ -249,7 +249,7 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
     } else {
       o1 = (int)((long long)n_obj * (c + 1) / n_chunks);
     }
-    if (cs != s) ESLAM_CUDA_OK(h, cudaStreamWaitEvent(cs, h->chunk_ev[15], 0));
+    if (cs != s) ESLAM_CUDA_OK(h, cudaStreamWaitEvent(cs, h->chunk_ev[16], 0));
     if ((rc = extract_launch(h, cs, depth_dev, pitch, frame_stride, o, o1 - o, prm, P))) return rc;
     if ((rc = symmetry_finalize_launch(h, cs, depth_dev, pitch, frame_stride, o, o1 - o, prm, P))) return rc;
     if (cs != s) { ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_done[c], cs)); ESLAM_CUDA_OK(h, cudaStreamWaitEvent(s, h->chunk_done[c], 0)); }
@@ -326,6 +326,7 @@ int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHa
   if (!h) return ESLAM_ERR_CUDA;
   h->prm = *p; h->cam = *c; h->device = device; h->sm_count = prop.multiProcessorCount;
   if (const char *e = getenv("ESLAM_H2D_MODE")) { int v = atoi(e); if (v >= 0 && v <= 4) h->h2d_mode = v; }
+  if (const char *e = getenv("ESLAM_DEV_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= kMaxChunks) h->dev_chunks = v; }
   if (const char *e = getenv("ESLAM_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= kMaxChunks) h->host_chunks = v; }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return ESLAM_ERR_CUDA; }
   *out = h;
@@ -351,7 +352,7 @@ void eslam_destroy(EslamHandle *h) {
   graph_free(h);
   plane_free(h);
   for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-  for (int i = 0; i < 16; i++) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
+  for (int i = 0; i < 17; i++) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int i = 0; i < kMaxChunks; i++) { if (h->chunk_stream[i]) cudaStreamDestroy(h->chunk_stream[i]); if (h->chunk_done[i]) cudaEventDestroy(h->chunk_done[i]); }
   if (h->stream) cudaStreamDestroy(h->stream);

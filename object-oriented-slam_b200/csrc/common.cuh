@@ -42,7 +42,7 @@ struct PinBuf {
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-constexpr int kMaxChunks = 8;
+constexpr int kMaxChunks = 16;
 constexpr int kMaxSmId = 256;   // upper bound of %smid + 1 the symmetry cache tables are sized for
 struct ExtractWorkspace;  // extract.cu
 struct GraphWorkspace;    // edges.cu
@@ -58,13 +58,14 @@ struct EslamHandle {
   int sm_count = 148;
   cudaStream_t stream = nullptr;  // owned stream used by the *_host entry points
   cudaStream_t copy_stream = nullptr;  // H2D stream of the pipelined *_host extraction
-  cudaEvent_t chunk_ev[16] = {};
-  cudaStream_t chunk_stream[8] = {};   // per-chunk compute streams: chunks overlap each other and the remaining uploads
-  cudaEvent_t chunk_done[8] = {};
+  cudaEvent_t chunk_ev[17] = {};       // [16]: metadata upload of the batch
+  cudaStream_t chunk_stream[16] = {};   // per-chunk compute streams: chunks overlap each other and the remaining uploads
+  cudaEvent_t chunk_done[16] = {};
   int h2d_mode = 4;      // upload: 4 = SMs pull each box rectangle from pinned host memory (falls back to 3 for pageable input);
                          // 3 = union rectangle of each frame's boxes, one batched DMA call per chunk; 2 = same, one call per frame;
                          // 1 = the boxes' rows (contiguous), 0 = whole frames (env ESLAM_H2D_MODE)
-  int host_chunks = 8;   // pipeline depth of the host entry (env ESLAM_HOST_CHUNKS, 1..8)
+  int host_chunks = 8;   // pipeline depth of the host entry (env ESLAM_HOST_CHUNKS, 1..16)
+  int dev_chunks = 8;    // object chunks / streams of the device-resident entry for batches of >= 512 objects (env ESLAM_DEV_CHUNKS)
   // symmetry kernel caches: one slot per RESIDENT seed warp (sm_count x 32 CTA slots), handed out through a per-SM bitmask, so the
   // same ~40 MB are reused by every batch and stay L2 resident
   eslam::DevBuf sym_pool_nn, sym_pool_px, sym_slotmask;
