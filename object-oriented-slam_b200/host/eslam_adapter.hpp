@@ -126,6 +126,20 @@ class EllipsoidExtractor {
                                               out.data(), nullptr), "EstimateLocalEllipsoids");
     return out;
   }
+  // frame streams: submit batch k+1 before collecting batch k (at most two tickets outstanding; the input arrays of a submitted
+  // batch must stay valid until its Collect returns) -- eslam_estimate_ellipsoids_submit / _wait
+  int SubmitLocalEllipsoids(int n_frames, const uint16_t *depth, size_t pitch, const std::vector<int> &frame_of_obj, const std::vector<double> &bbox4,
+                            const std::vector<int> &label, const std::vector<double> &Twc7) {
+    int ticket = -1;
+    ctx_.check(eslam_estimate_ellipsoids_submit(ctx_.get(), n_frames, depth, pitch, (int)frame_of_obj.size(), frame_of_obj.data(), bbox4.data(), label.data(), Twc7.data(),
+                                                &ticket), "SubmitLocalEllipsoids");
+    return ticket;
+  }
+  std::vector<EslamEllipsoidOut> CollectLocalEllipsoids(int ticket, size_t n_obj) {
+    std::vector<EslamEllipsoidOut> out(n_obj);
+    ctx_.check(eslam_estimate_ellipsoids_wait(ctx_.get(), ticket, (int)n_obj, out.data()), "CollectLocalEllipsoids");
+    return out;
+  }
   bool GetResult() const { return mResult; }
   SymmetryOutputData GetSymmetryOutputData() const { return mSym; }
   int miSystemState = 0;
