@@ -195,6 +195,17 @@ def main():
         if rank != 0:
             return
         threads = os.cpu_count() or 1
+        try:
+            threads = min(threads, len(os.sched_getaffinity(0)))      # CPUs this process may actually run on
+        except Exception:
+            pass
+        quota = "none"
+        try:   # a cgroup CPU quota caps the useful parallelism below the thread count (reported, not enforced)
+            mx, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+            if mx != "max":
+                quota = "%.1f CPUs" % (float(mx) / float(per))
+        except Exception:
+            pass
         sample = min(args.frames, 16 * threads, 2048)
         depth, fo, bb, lb, tw = make_frames(args.workload, sample, 1000)
         for _ in range(args.warmup):
@@ -208,7 +219,7 @@ def main():
                 "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": dict(config, frames_per_step_per_gpu=sample),
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                                 "sample": f"{sample} frames per step, {threads} host threads, oracle/liboracle.so (the reference itself cannot be built here: needs Eigen/PCL/OpenCV)"},
+                                 "sample": f"{sample} frames per step, {threads} host threads (cgroup cpu quota: {quota}), oracle/liboracle.so (the reference itself cannot be built here: needs Eigen/PCL/OpenCV)"},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
