@@ -373,6 +373,7 @@ __device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
     }
     __syncwarp();
     while (true) {
+      __syncwarp();   // every lane has read W.again / W.accepted of the previous trial before lane 0 overwrites them (racecheck: WAR)
       if (lane == 0) {
         W.backup = W.est;
         double x[3] = {W.x[0], W.x[1], W.x[2]};
