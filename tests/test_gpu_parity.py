@@ -211,6 +211,35 @@ def test_pipelined_submit_wait_equals_synchronous_calls(handle):
     assert bytes(handle.estimate_ellipsoids(*batches[0])[0]) == want[0]      # synchronous entry works again
 
 
+def test_odd_image_size_matches_oracle():
+    """275 x 402 sub-images (no multiple of 32 / 16 / 8 / 4 in either direction) with the principal point moved accordingly: the
+    plane kernels (32-row bands, 16-row strips, 4-column store groups, one thread per column) and the extraction path must not
+    depend on the 640 x 480 shape.  Plane parameters / inlier counts and the ellipsoids are compared with the oracle."""
+    depth, fo, bb, lb, tw = synth.make_batch(2, "one_box")
+    r0, c0, H, W = 130, 150, 275, 402
+    sub = np.ascontiguousarray(depth[:, r0:r0 + H, c0:c0 + W])
+    cam_g = E.default_camera(); cam_o = orc.default_camera()
+    for cam in (cam_g, cam_o):
+        cam.cx -= c0; cam.cy -= r0; cam.rows = H; cam.cols = W
+    bb2 = bb.copy(); bb2[:, [0, 2]] -= c0; bb2[:, [1, 3]] -= r0
+    bb2[:, 0] = np.maximum(bb2[:, 0], 11); bb2[:, 1] = np.maximum(bb2[:, 1], 11)
+    bb2[:, 2] = np.minimum(bb2[:, 2], W - 12); bb2[:, 3] = np.minimum(bb2[:, 3], H - 12)
+    h = E.Handle(camera=cam_g)
+    try:
+        pg, fg, ng = h.extract_ground_plane(sub)
+        po, fo_, no = orc.extract_ground_plane(sub, cam=cam_o)
+        assert list(fg) == list(fo_) == [1, 1] and list(ng) == list(no)
+        assert np.abs(pg - po).max() <= 1e-6
+        h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+        g, _, _ = h.estimate_ellipsoids(sub, fo, bb2, lb, tw)
+        o, _, _, _ = orc.estimate_ellipsoids(sub, fo, bb2, lb, tw, synth.GROUND_PLANE_WORLD, cam=cam_o)
+        for a, b in zip(g, o):
+            assert (a.status, a.n_crop, a.n_voxel, a.n_plane, a.n_cluster, a.n_sym, a.n_final) == (b.status, b.n_crop, b.n_voxel, b.n_plane, b.n_cluster, b.n_sym, b.n_final)
+            assert b.status == 0 and ellipsoid_close(a.ellipsoid, b.ellipsoid, 1e-4)
+    finally:
+        h.close()
+
+
 def test_missing_plane_is_an_error():
     h = E.Handle()
     depth, fo, bb, lb, tw = synth.make_batch(1)
