@@ -113,3 +113,49 @@ def test_symmetry_cloud_nearest_neighbours_match_kdtree(dumps):
         r = ((diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]).astype(np.float32) + diff[..., 2] * diff[..., 2]).astype(np.float32)
         ib = r.argmin(axis=1)                             # L2_Simple order, first minimum
         assert np.allclose(np.sqrt(r[np.arange(200), ib].astype(np.float64)), dk, rtol=1e-5)
+
+
+@pytest.mark.parametrize("source", ["synthetic", "fr3_cabinet"])
+def test_plane_regions_match_scipy_components_of_the_comparator_graph(source):
+    """OrganizedConnectedComponentSegmentation + PlaneCoefficientComparator: the oracle labels with PCL's two-pass scan and label
+    equivalences; here the same 4-neighbour comparator links (float arithmetic, same operation order, the oracle's own normals) go
+    through scipy's connected components.  Every plane region the oracle reports must start at the first pixel of one of scipy's
+    components of more than 100 pixels, contain that whole component after refinement, and be no smaller than it."""
+    import os
+    if source == "synthetic":
+        depth = synth.make_batch(1, "one_box")[0][0]
+    else:
+        depth = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cabinet_golden.npz"))["depth"][0]
+    cam, prm = orc.default_camera(), orc.default_params()
+    normals, dm, labels, coef, size, first = orc.extract_planes_debug(depth, cap=256)
+    H, W = depth.shape
+    f32 = np.float32
+    z = (depth.astype(np.float64) / cam.scale).astype(f32)                                   # PlaneExtractor.cpp:36-47
+    n_idx, m_idx = np.meshgrid(np.arange(W), np.arange(H))
+    x = ((n_idx - cam.cx) * z.astype(np.float64) / cam.fx).astype(f32)
+    y = ((m_idx - cam.cy) * z.astype(np.float64) / cam.fy).astype(f32)
+    nx, ny, nz = normals[..., 0], normals[..., 1], normals[..., 2]
+    with np.errstate(invalid="ignore"):
+        pd = ((x * nx).astype(f32) + (y * ny).astype(f32)).astype(f32) + (z * nz).astype(f32)
+        thr = (f32(prm.plane_dist) * (z * z).astype(f32)).astype(f32)                        # depth dependent threshold, z of the CURRENT pixel
+        ang = np.cos(f32(0.017453 * f32(prm.plane_angle_deg)), dtype=f32)
+
+        def link(cur, nb):                                                                   # compare(cur, neighbour) on array slices
+            dot = ((nx[cur] * nx[nb]).astype(f32) + (ny[cur] * ny[nb]).astype(f32)).astype(f32) + (nz[cur] * nz[nb]).astype(f32)
+            return (np.abs(pd[cur] - pd[nb]) < thr[cur]) & (dot > ang)
+        hl = link((slice(None), slice(1, None)), (slice(None), slice(0, -1)))                # pixel vs its left neighbour
+        vl = link((slice(1, None), slice(None)), (slice(0, -1), slice(None)))                # pixel vs its upper neighbour
+    idx = np.arange(H * W).reshape(H, W)
+    a = np.concatenate([idx[:, 1:][hl], idx[1:, :][vl]]); b = np.concatenate([idx[:, :-1][hl], idx[:-1, :][vl]])
+    ncomp, comp = connected_components(coo_matrix((np.ones(len(a)), (a, b)), shape=(H * W, H * W)), directed=False)
+    sizes = np.bincount(comp)
+    first_of = np.full(ncomp, H * W, dtype=np.int64)
+    np.minimum.at(first_of, comp, np.arange(H * W))
+    big_first = {int(first_of[c]): c for c in np.flatnonzero(sizes > 100)}
+    assert len(first) >= 1
+    flat = labels.reshape(-1)
+    for fp, sz in zip(first, size):
+        assert int(fp) in big_first, (fp, sorted(big_first)[:10])
+        c = big_first[int(fp)]
+        assert sz >= sizes[c]
+        assert len(np.unique(flat[comp == c])) == 1                                          # the component stayed one region
