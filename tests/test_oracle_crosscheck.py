@@ -159,3 +159,39 @@ def test_plane_regions_match_scipy_components_of_the_comparator_graph(source):
         c = big_first[int(fp)]
         assert sz >= sizes[c]
         assert len(np.unique(flat[comp == c])) == 1                                          # the component stayed one region
+
+
+def test_integral_image_normals_match_direct_box_sums():
+    """IntegralImageNormalEstimation (AVERAGE_3D_GRADIENT): the oracle evaluates the gradient box sums through PCL's double integral
+    images; here they are direct sums over the same rectangles (no integral image at all).  Same NaN pattern, normals to 1e-5."""
+    depth = synth.make_batch(1, "one_box")[0][0]
+    cam = orc.default_camera()
+    normals, dm, labels, coef, size, first = orc.extract_planes_debug(depth, cap=8)
+    H, W = depth.shape
+    f32 = np.float32
+    z = (depth.astype(np.float64) / cam.scale).astype(f32)
+    n_idx, m_idx = np.meshgrid(np.arange(W), np.arange(H))
+    P = np.stack([((n_idx - cam.cx) * z.astype(np.float64) / cam.fx).astype(f32), ((m_idx - cam.cy) * z.astype(np.float64) / cam.fy).astype(f32), z], axis=-1)
+    GX = np.zeros((H, W, 3), np.float64); GY = np.zeros((H, W, 3), np.float64)       # horizontal / vertical central differences (float), 0 on the border
+    GX[1:-1, 1:-1] = (P[1:-1, 2:] - P[1:-1, :-2]).astype(f32)
+    GY[1:-1, 1:-1] = (P[2:, 1:-1] - P[:-2, 1:-1]).astype(f32)
+    rng = np.random.default_rng(5)
+    rows = rng.integers(10, H - 10, 400); cols = rng.integers(10, W - 10, 400)
+    checked = 0
+    for ri, ci in zip(rows, cols):
+        smoothing = min(float(dm[ri, ci]), 10.0)
+        got = normals[ri, ci]
+        if not smoothing > 2.0:
+            assert np.isnan(got).all()
+            continue
+        rw = int(smoothing); r2 = rw // 2
+        gx = GX[ri - r2:ri - r2 + rw, ci - r2:ci - r2 + rw].sum(axis=(0, 1)); gy = GY[ri - r2:ri - r2 + rw, ci - r2:ci - r2 + rw].sum(axis=(0, 1))
+        nv = np.cross(gy, gx)
+        if not np.dot(nv, nv) > 0:
+            continue
+        nv = nv / np.linalg.norm(nv)
+        if np.dot(-P[ri, ci].astype(np.float64), nv) < 0:
+            nv = -nv
+        assert np.allclose(got, nv, atol=1e-5), (ri, ci, got, nv)
+        checked += 1
+    assert checked > 200
