@@ -228,7 +228,6 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
     voxel_sort(A, n1, prm.voxel_leaf, k0, v0, k1, v1, S, RS, s_parent);
     if (tid == 0) st.phase_clk[2] = clock64();
     for (int tile = 0; tile < n1; tile += blockDim.x) {
-      int j = tile + tid;
       bool head = false, keep = false;
       d3 pc = mk3(0, 0, 0), pw = mk3(0, 0, 0);
       float4 c;
