@@ -372,8 +372,12 @@ def main():
                 "peak_source": peak_src, "kernel_ms": {"extract_kernel": k_ms[0], "symmetry_finalize_kernel": k_ms[1]},
                 "algorithmic_bytes_per_launch": alg,
                 "note": "both kernels are latency / instruction-issue bound at the reference's problem sizes (per-object working set << L2); see DESIGN.md"}
-    # ---- cpu baseline (1 thread, bounded sample)
-    cpu_fps, cpu_dt = oracle_fps(depth, fo, bb, lb, tw, plane, min(args.cpu_sample, args.frames), 1)
+    # ---- cpu baseline (1 thread, bounded sample): rank 0 at N = 1 only
+    cpu_baseline = None
+    if world == 1:
+        cpu_fps, cpu_dt = oracle_fps(depth, fo, bb, lb, tw, plane, min(args.cpu_sample, args.frames), 1)
+        cpu_baseline = {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                        "sample": f"{min(args.cpu_sample, args.frames)} frames of the same batch, {cpu_dt:.1f} s, oracle/liboracle.so single thread"}
     line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(config, objects_per_step_per_gpu=n_obj, ok_fraction=ok_frac, gather_ms=gather_ms, pipelined_records_equal_blocking=pip_same),
@@ -381,8 +385,7 @@ def main():
                     "api": "eslam_estimate_ellipsoids_submit / _wait, two batches in flight (host pinned buffers in, records out, every step)",
                     "single_blocking_call_value": e2e_sync},
             "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
-                             "sample": f"{min(args.cpu_sample, args.frames)} frames of the same batch, {cpu_dt:.1f} s, oracle/liboracle.so single thread"}}
+            "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
