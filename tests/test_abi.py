@@ -68,3 +68,28 @@ def test_host_helpers_match_oracle():
     assert np.allclose(E.plane_to_world(pl, Tn), orc.plane_to_world(pl, Tn), atol=1e-13)
     for bb in ([50, 50, 300, 300], [5, 50, 300, 300], [50, 50, 630, 300], [50, 50, 300, 470]):
         assert E.calibrate_measurement(bb) == bool(orc.calibrate_measurement(bb))
+
+
+def test_entry_points_reject_a_null_handle_without_crashing():
+    """every handle-taking entry point returns ESLAM_ERR_BAD_ARG (no dereference) for a NULL handle -- checked without a GPU."""
+    lib = E.load_library()
+    null = C.c_void_p(None)
+    z = C.c_int(0)
+    buf = (C.c_double * 16)()
+    calls = [
+        lambda: lib.eslam_set_supporting_plane(null, buf),
+        lambda: lib.eslam_extract_ground_plane_host(null, 1, None, C.c_size_t(640), buf, C.byref(z), C.byref(z)),
+        lambda: lib.eslam_estimate_ellipsoids_host(null, 1, None, C.c_size_t(640), 1, C.byref(z), buf, C.byref(z), buf, None, None),
+        lambda: lib.eslam_estimate_ellipsoids_dev(null, None, 1, None, C.c_size_t(640), 1, C.byref(z), buf, C.byref(z), buf),
+        lambda: lib.eslam_estimate_ellipsoids_submit(null, 1, None, C.c_size_t(640), 1, C.byref(z), buf, C.byref(z), buf, C.byref(z)),
+        lambda: lib.eslam_estimate_ellipsoids_wait(null, 0, 1, None),
+        lambda: lib.eslam_fetch_ellipsoids(null, None, 1, None),
+        lambda: lib.eslam_init_quadric(null, 1, buf, buf, buf, 480, 640, buf, C.byref(z)),
+        lambda: lib.eslam_edges_eval_dev(null, None),
+        lambda: lib.eslam_set_profiling(null, 1),
+    ]
+    for f in calls:
+        assert f() != 0
+    lib.eslam_launch_count.restype = C.c_longlong
+    assert lib.eslam_launch_count(null) == 0 and lib.eslam_h2d_bytes(null) == 0
+    lib.eslam_destroy(null)       # no-op
