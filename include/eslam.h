@@ -207,6 +207,15 @@ int eslam_estimate_ellipsoids_dev(EslamHandle *h, void *stream, int n_frames, co
                                   size_t pitch, int n_obj, const int *frame_of_obj, const double *bbox4,
                                   const int *label, const double *Twc7);
 int eslam_fetch_ellipsoids(EslamHandle *h, void *stream, int n_obj, EslamEllipsoidOut *out);
+/* device-to-device form of the fetch (multi-GPU "gather of map"): copies the n_obj records of the last
+ * eslam_estimate_ellipsoids_dev batch into caller-owned DEVICE memory on `stream` (no synchronisation, no host round trip), so a
+ * collective (ncclAllGather) can be enqueued on the same stream right behind it. */
+int eslam_copy_ellipsoids_dev(EslamHandle *h, void *stream, int n_obj, void *records_dev);
+/* work statistics of the last extraction batch, summed over its objects (bench.py roofline: the algorithmic bytes of the symmetry
+ * kernel are counted, not assumed).  out[0] cost evaluations the reference performs (GetPointCloudProb calls, SymmetrySolver.cpp:49),
+ * out[1] mirrored points those evaluations visit, out[2] evaluations this library actually ran, out[3] points it visited,
+ * out[4] nearest-neighbour scans, out[5] NN cache hits, out[6] largest n_sym of the batch, out[7] objects with symmetry. */
+int eslam_batch_counters(EslamHandle *h, unsigned long long out[8]);
 /* pipelined form of eslam_estimate_ellipsoids_host for frame streams (the reference calls EstimateLocalEllipsoid once per box and
  * blocks, Tracking.cpp:329; a batched caller keeps the device busy by submitting batch k+1 before collecting batch k).  At most two
  * tickets may be outstanding; `depth` and the metadata arrays of a submitted batch must stay valid until its wait returns; the

@@ -69,11 +69,17 @@ int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const
     m.frame = frame_of_obj[i]; m.label = label[i];
     m.symtype = h->prm.symmetry_open ? symmetry_type_of_label(label[i]) : -1;
     for (int k = 0; k < 4; k++) m.bbox[k] = bbox4[4 * i + k];
-    m.x1 = (int)m.bbox[0]; m.y1 = (int)m.bbox[1]; m.x2 = (int)m.bbox[2]; m.y2 = (int)m.bbox[3];
-    bool inside = m.frame >= 0 && m.frame < n_frames && m.x1 >= 0 && m.y1 >= 0 && m.x2 <= h->cam.cols && m.y2 <= h->cam.rows;
+    // non-finite coordinates never reach the int casts (UB); an inverted box (x2 < x1 or y2 < y1) is an empty crop like in the
+    // reference (status NO_POINTS_AFTER_PLANE through nx = ny = 0) and is skipped by every upload path
+    const bool finite = isfinite(m.bbox[0]) && isfinite(m.bbox[1]) && isfinite(m.bbox[2]) && isfinite(m.bbox[3]) && fabs(m.bbox[0]) < 1e9 && fabs(m.bbox[1]) < 1e9 &&
+                        fabs(m.bbox[2]) < 1e9 && fabs(m.bbox[3]) < 1e9;
+    if (!finite) { m.x1 = m.y1 = m.x2 = m.y2 = -1; }
+    else { m.x1 = (int)m.bbox[0]; m.y1 = (int)m.bbox[1]; m.x2 = (int)m.bbox[2]; m.y2 = (int)m.bbox[3]; }
+    bool inside = finite && m.frame >= 0 && m.frame < n_frames && m.x1 >= 0 && m.y1 >= 0 && m.x2 <= h->cam.cols && m.y2 <= h->cam.rows;
     m.pre_status = inside ? 0 : ESLAM_OBJ_BBOX_OUTSIDE;
     m.nx = (inside && m.x2 > m.x1) ? (m.x2 - m.x1 + 2) / 3 : 0;
     m.ny = (inside && m.y2 > m.y1) ? (m.y2 - m.y1 + 2) / 3 : 0;
+    if (m.nx == 0 || m.ny == 0) m.nx = m.ny = 0;   // empty crop: nothing of this box is ever read
     long long cap = (long long)m.nx * m.ny;
     cap = (cap + 31) & ~31LL;
     if (cap < 32) cap = 32;
@@ -184,7 +190,7 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
         if ((rc = pull_rects_launch(h, h->copy_stream, host_mapped, const_cast<uint16_t *>(depth_dev), pitch, frame_stride, o, o1 - o))) return rc;
         for (int k = o; k < o1; k++) {
           const ObjMeta &m = w.meta_host[k];
-          if (m.pre_status != 0) continue;
+          if (m.pre_status != 0 || m.nx == 0) continue;
           const int x0 = m.x1 & ~7, x1 = (m.x2 + 8) & ~7, y1 = m.y2 + 1;
           h->h2d_bytes += (size_t)((x1 < cols ? x1 : cols) - x0) * (size_t)((y1 < rows ? y1 : rows) - m.y1) * sizeof(uint16_t);
         }
@@ -200,7 +206,7 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
           int x0 = cols, y0 = rows, x1 = -1, y1 = -1;
           for (; k < o1 && frame_of_obj[k] == f; k++) {
             const ObjMeta &m = w.meta_host[k];
-            if (m.pre_status != 0) continue;
+            if (m.pre_status != 0 || m.nx == 0) continue;
             x0 = m.x1 < x0 ? m.x1 : x0; y0 = m.y1 < y0 ? m.y1 : y0; x1 = m.x2 > x1 ? m.x2 : x1; y1 = m.y2 > y1 ? m.y2 : y1;
           }
           if (x1 < 0) continue;
@@ -347,7 +353,7 @@ void eslam_destroy(EslamHandle *h) {
     if (h->slot_stream[sl]) cudaStreamDestroy(h->slot_stream[sl]);
     if (h->slot_done[sl]) cudaEventDestroy(h->slot_done[sl]);
   }
-  h->sym_pool_nn.release(); h->sym_pool_px.release(); h->sym_slotmask.release();
+  h->sym_pool_nn.release(); h->sym_pool_px.release(); h->sym_slotmask.release(); h->plane_depth.release();
   slam_free(h);
   graph_free(h);
   plane_free(h);
@@ -397,13 +403,13 @@ int eslam_extract_ground_plane_dev(EslamHandle *h, void *stream, int n_frames, c
   return plane_extract(h, s, n_frames, depth_dev, pitch, plane_cam_host, found_host, n_inliers_host);
 }
 int eslam_extract_ground_plane_host(EslamHandle *h, int n_frames, const uint16_t *depth, size_t pitch, double *plane_cam, int *found, int *n_inliers) {
-  if (!h || n_frames <= 0 || !depth || !plane_cam || !found) return ESLAM_ERR_BAD_ARG;
+  if (!h || n_frames <= 0 || !depth || !plane_cam || !found || pitch < (size_t)h->cam.cols) return ESLAM_ERR_BAD_ARG;
   cudaSetDevice(h->device);
-  use_slot(h, 0);
+  // own staging buffer: never aliases the extraction slots, so a batch submitted through _submit may still be in flight
   size_t bytes = (size_t)n_frames * h->cam.rows * pitch * sizeof(uint16_t);
-  ESLAM_CUDA_OK(h, h->ex->depth.reserve(bytes));
-  ESLAM_CUDA_OK(h, cudaMemcpyAsync(h->ex->depth.p, depth, bytes, cudaMemcpyHostToDevice, h->stream));
-  return plane_extract(h, h->stream, n_frames, h->ex->depth.as<uint16_t>(), pitch, plane_cam, found, n_inliers);
+  ESLAM_CUDA_OK(h, h->plane_depth.reserve(bytes));
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(h->plane_depth.p, depth, bytes, cudaMemcpyHostToDevice, h->stream));
+  return plane_extract(h, h->stream, n_frames, h->plane_depth.as<uint16_t>(), pitch, plane_cam, found, n_inliers);
 }
 
 // test/bench hook: symmetry work counters of object `obj` of the last batch: out = {cost evaluations (per half), NN scans, mirrored points, n_sym, NN cache hits}
@@ -429,14 +435,13 @@ int eslam_debug_phase_clocks(EslamHandle *h, int obj, long long out[13]) {
 
 // test-only hook (not in include/eslam.h): intermediate buffers of the plane pipeline for stage-isolated parity tests
 int eslam_debug_plane_stage(EslamHandle *h, const uint16_t *depth, size_t pitch, int stage, void *out) {
-  if (!h || !depth || !out || stage < 1 || stage > 4) return ESLAM_ERR_BAD_ARG;
+  if (!h || !depth || !out || stage < 1 || stage > 4 || pitch < (size_t)h->cam.cols) return ESLAM_ERR_BAD_ARG;
   cudaSetDevice(h->device);
-  use_slot(h, 0);
   size_t bytes = (size_t)h->cam.rows * pitch * sizeof(uint16_t);
-  ESLAM_CUDA_OK(h, h->ex->depth.reserve(bytes));
-  ESLAM_CUDA_OK(h, cudaMemcpyAsync(h->ex->depth.p, depth, bytes, cudaMemcpyHostToDevice, h->stream));
+  ESLAM_CUDA_OK(h, h->plane_depth.reserve(bytes));
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(h->plane_depth.p, depth, bytes, cudaMemcpyHostToDevice, h->stream));
   double pl[4]; int found = 0, inl = 0;
-  return plane_extract_dbg(h, h->stream, 1, h->ex->depth.as<uint16_t>(), pitch, pl, &found, &inl, stage, out);
+  return plane_extract_dbg(h, h->stream, 1, h->plane_depth.as<uint16_t>(), pitch, pl, &found, &inl, stage, out);
 }
 
 void eslam_plane_to_world(const double pc[4], const double Twc[7], double pw[4]) {
@@ -497,6 +502,26 @@ int eslam_fetch_ellipsoids(EslamHandle *h, void *stream, int n_obj, EslamEllipso
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
   ESLAM_CUDA_OK(h, cudaMemcpyAsync(out, h->ex->out.p, sizeof(EslamEllipsoidOut) * (size_t)n_obj, cudaMemcpyDeviceToHost, s));
   ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
+  return ESLAM_OK;
+}
+int eslam_copy_ellipsoids_dev(EslamHandle *h, void *stream, int n_obj, void *records_dev) {
+  if (!h || !h->ex || !records_dev || n_obj <= 0 || n_obj > h->ex->n_obj) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(records_dev, h->ex->out.p, sizeof(EslamEllipsoidOut) * (size_t)n_obj, cudaMemcpyDeviceToDevice, s));
+  return ESLAM_OK;
+}
+int eslam_batch_counters(EslamHandle *h, unsigned long long out[8]) {
+  if (!h || !h->ex || !out || h->ex->n_obj <= 0) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  std::vector<ObjState> st((size_t)h->ex->n_obj);
+  ESLAM_CUDA_OK(h, cudaMemcpy(st.data(), h->ex->state.p, sizeof(ObjState) * st.size(), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 8; k++) out[k] = 0;
+  for (const ObjState &o : st) {
+    out[0] += o.n_ref_evals; out[1] += o.n_ref_points; out[2] += o.n_evals; out[3] += o.n_points; out[4] += o.n_queries; out[5] += o.n_hits;
+    if ((unsigned long long)o.n_sym > out[6]) out[6] = (unsigned long long)o.n_sym;
+    if (o.run_sym) out[7]++;
+  }
   return ESLAM_OK;
 }
 int eslam_estimate_ellipsoids_host(EslamHandle *h, int n_frames, const uint16_t *depth, size_t pitch, int n_obj, const int *frame_of_obj, const double *bbox4,
@@ -608,6 +633,7 @@ void eslam_pose_mul(const double A[7], const double B[7], double out[7]) {  // S
 int eslam_optimize_slam_host(EslamHandle *h, const EslamEdgeBatch *g, const double *odom_meas7, double odom_info, int iters, double *ell, double *Tcw_out7,
                              EslamLmStats *stats) {
   if (!h || !g || !ell) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
   return slam_optimize(h, g, odom_meas7, odom_info, iters, ell, Tcw_out7, stats, h->stream);
 }
 

@@ -69,7 +69,8 @@ struct EslamHandle {
   // symmetry kernel caches: one slot per RESIDENT seed warp (sm_count x 32 CTA slots), handed out through a per-SM bitmask, so the
   // same ~40 MB are reused by every batch and stay L2 resident
   eslam::DevBuf sym_pool_nn, sym_pool_px, sym_slotmask;
-  bool attr_extract = false, attr_symmetry = false;   // kernel attributes are per device: set once per handle, not once per process
+  eslam::DevBuf plane_depth;           // staging of eslam_extract_ground_plane_host (separate from the extraction slots)
+  bool attr_extract = false, attr_symmetry = false, attr_plane = false;   // kernel attributes are per device: set once per handle, not once per process
   unsigned long long h2d_bytes = 0;    // depth bytes uploaded by the *_host extraction entry (running total)
   bool plane_set = false;
   double plane_world[4] = {0, 0, 1, 0};

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
   if (tid == 0) {
     st.status = m.pre_status;
     st.n_crop = st.n_voxel = st.n_plane = st.n_clusters = st.n_cluster = st.n_sym = st.n_final = 0;
-    st.run_sym = 0; st.symtype = m.symtype; st.best_seed = -1; st.done = 0; st.n_evals = 0; st.n_queries = 0; st.n_points = 0; st.n_hits = 0; for (int k = 0; k < 4; k++) st.sym_clk[k] = 0;
+    st.run_sym = 0; st.symtype = m.symtype; st.best_seed = -1; st.done = 0; st.n_evals = 0; st.n_queries = 0; st.n_points = 0; st.n_hits = 0; st.n_ref_evals = 0; st.n_ref_points = 0; for (int k = 0; k < 4; k++) st.sym_clk[k] = 0;
     for (int k = 0; k < 4; k++) st.bbox_i[k] = (int)m.bbox[k];
     for (int s = 0; s < 9; s++) { st.seed_prob[s] = st.seed_init[s] = st.seed_final[s] = st.seed_dual[s] = 0; for (int k = 0; k < 4; k++) st.seed_plane[s][k] = 0; }
   }
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(kPullThreads, 16) pull_rects_kernel(const uint
                                                                       const ObjMeta *__restrict__ metas, int n_obj, int rows, int cols) {
   for (int k = blockIdx.x; k < n_obj; k += gridDim.x) {
     const ObjMeta &m = metas[k];
-    if (m.pre_status != 0) continue;
+    if (m.pre_status != 0 || m.nx == 0) continue;   // outside the image / empty (or inverted) box: no pixel of it is ever read
     const int x0 = m.x1 & ~7, x1 = min(cols, (m.x2 + 8) & ~7);
     const int y0 = m.y1, y1 = min(rows, m.y2 + 1);
     const int upr = (x1 - x0) >> 3;               // 16-byte units per row

@@ -28,6 +28,7 @@ struct ObjState {  // device resident, one per object
                             // neighbour search, flatten+select+gather, PCA, symmetry grid (tools/extract_phases.py)
   long long sym_clk[4];     // symmetry kernel, summed over the 9 seed warps: classification, NN scans, ordered sums, rest
   unsigned long long n_evals, n_queries, n_points, n_hits;   // symmetry work counters (cost evaluations, NN scans, mirrored points, NN cache hits)
+  unsigned long long n_ref_evals, n_ref_points;              // what the reference's call sequence performs (incl. the evaluations memoised here)
 };
 
 struct ExtractParamsDev {

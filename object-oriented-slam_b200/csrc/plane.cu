@@ -961,12 +961,15 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   prm.ang_cos = cosf((float)(0.017453 * AngTh));   // mps.setAngularThreshold(0.017453 * AngTh) -> PlaneCoefficientComparator: cosf
   prm.min_size = h->prm.plane_min_size;
   const int kIntSmemBytes = kIntWarps * 32 * kIntRingPitch * (int)sizeof(float);
-  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIntSmemBytes));
-  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // 2 CTAs (2 x 97 KB) per SM
-  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFitSmemBytes));
   const int tpc = ((Wd + 31) / 32) * 32;
   const int strip_bytes = kStripRows * Wd * (int)sizeof(int);
-  ESLAM_CUDA_OK(h, cudaFuncSetAttribute(ccl_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, strip_bytes));
+  if (!h->attr_plane) {   // kernel attributes are per device: once per handle (the image size is fixed per handle)
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIntSmemBytes));
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // 2 CTAs (2 x 97 KB) per SM
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFitSmemBytes));
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(ccl_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, strip_bytes));
+    h->attr_plane = true;
+  }
   const size_t frame_stride = (size_t)H * pitch;
   for (int f0 = 0; f0 < n_frames; f0 += chunk) {
     const int F = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;

@@ -51,7 +51,7 @@ struct SymWarp {
   double H[9], b[3], x[3], J[3];
   double lambda, ni, currentChi, tempChi, iniChi, rho, e1;
   int nBad, ok, qmax, again, accepted;
-  unsigned n_evals, n_queries, n_points, n_hits;   // work counters, flushed once per seed
+  unsigned n_evals, n_queries, n_points, n_hits, n_ref;   // work counters, flushed once per seed (n_ref: cost evaluations of the reference's call sequence)
   long long clk[4];   // cycles in: classification passes, NN scans, ordered sums, everything else of the seed (clock64, lane 0)
   SeedResult res;
   unsigned short queue[kSymQueue];
@@ -335,12 +335,12 @@ __device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
   const int dim = (symtype == 1) ? 2 : 3;
   double err = sym_eval_plane(B, W, &W.est);   // value of the last computeError call
   double err_est = err;                        // error of the plane currently held in W.est
-  if (lane == 0) { W.res.init_err = err; W.lambda = -1; W.ni = 2; W.nBad = 0; W.x[0] = W.x[1] = W.x[2] = 0; W.ok = 1; }
+  if (lane == 0) { W.n_ref = 1; W.res.init_err = err; W.lambda = -1; W.ni = 2; W.nBad = 0; W.x[0] = W.x[1] = W.x[2] = 0; W.ok = 1; }
   __syncwarp();
   for (int it = 0; it < iters; it++) {
     if (!W.ok) break;
     err = err_est;                              // computeActiveErrors() at W.est
-    if (lane == 0) { W.currentChi = err * (1.0 * err); W.tempChi = W.currentChi; W.iniChi = W.currentChi; }
+    if (lane == 0) { W.n_ref += 1 + 2 * dim; W.currentChi = err * (1.0 * err); W.tempChi = W.currentChi; W.iniChi = W.currentChi; }
     // linearizeOplus (numeric, delta 1e-9) + constructQuadraticForm
     if (lane < 2 * dim) {
       const int d = lane >> 1;
@@ -386,6 +386,7 @@ __device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
       err = sym_eval_plane(B, W, &W.est);
       if (lane == 0) {
         const bool ok2 = W.again != 0;
+        W.n_ref++;
         double tempChi = err * (1.0 * err);
         if (!ok2) tempChi = DBL_MAX;
         double rho = (W.currentChi - tempChi);
@@ -422,6 +423,7 @@ __device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
     W.res.plane = W.est;
     atomicAdd(&B.st->n_evals, (unsigned long long)W.n_evals); atomicAdd(&B.st->n_queries, (unsigned long long)W.n_queries);
     atomicAdd(&B.st->n_points, (unsigned long long)W.n_points); atomicAdd(&B.st->n_hits, (unsigned long long)W.n_hits);
+    atomicAdd(&B.st->n_ref_evals, (unsigned long long)W.n_ref); atomicAdd(&B.st->n_ref_points, (unsigned long long)W.n_ref * (unsigned long long)B.npts);
   }
   __syncwarp();
 }

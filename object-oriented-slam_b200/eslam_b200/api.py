@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "eslam_abi_version", "eslam_default_params", "eslam_default_camera", "eslam_create", "eslam_destroy", "eslam_last_error",
     "eslam_launch_count", "eslam_h2d_bytes", "eslam_extract_ground_plane_host", "eslam_extract_ground_plane_dev", "eslam_plane_to_world",
     "eslam_set_supporting_plane", "eslam_calibrate_measurement", "eslam_estimate_ellipsoids_host", "eslam_estimate_ellipsoids_dev",
-    "eslam_fetch_ellipsoids", "eslam_estimate_ellipsoids_submit", "eslam_estimate_ellipsoids_wait", "eslam_init_quadric", "eslam_edges_eval_host", "eslam_edges_upload", "eslam_edges_eval_dev",
+    "eslam_fetch_ellipsoids", "eslam_copy_ellipsoids_dev", "eslam_batch_counters", "eslam_estimate_ellipsoids_submit", "eslam_estimate_ellipsoids_wait", "eslam_init_quadric", "eslam_edges_eval_host", "eslam_edges_upload", "eslam_edges_eval_dev",
     "eslam_edges_download", "eslam_optimize_objects_host", "eslam_optimize_slam_host", "eslam_pose_inverse", "eslam_pose_mul", "eslam_set_profiling", "eslam_get_stage_ms",
 ]
 
@@ -211,6 +211,16 @@ class Handle:
         out = (EslamEllipsoidOut * n_obj)()
         self.check(self.lib.eslam_fetch_ellipsoids(self._h, C.c_void_p(stream), C.c_int(n_obj), out), "eslam_fetch_ellipsoids")
         return out
+
+    def copy_ellipsoids_dev(self, n_obj, dst_ptr, stream=0):
+        """records of the last *_dev batch -> caller-owned device memory (D2D on `stream`, asynchronous)."""
+        self.check(self.lib.eslam_copy_ellipsoids_dev(self._h, C.c_void_p(stream), C.c_int(n_obj), C.c_void_p(dst_ptr)), "eslam_copy_ellipsoids_dev")
+
+    def batch_counters(self):
+        out = (C.c_ulonglong * 8)()
+        self.check(self.lib.eslam_batch_counters(self._h, out), "eslam_batch_counters")
+        keys = ("ref_evals", "ref_points", "evals", "points", "nn_scans", "nn_hits", "max_n_sym", "objects_with_symmetry")
+        return {k: int(v) for k, v in zip(keys, out)}
 
     def init_quadric(self, Twc, det5, K, rows=None, cols=None):
         tw, d, k = _d(Twc).reshape(-1, 7), _d(det5).reshape(-1, 5), _d(K).reshape(-1)

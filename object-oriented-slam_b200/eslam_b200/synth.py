@@ -192,3 +192,100 @@ def ba_graph(n_frames=500, n_objects=50, edges_per_frame=50, seed=4242):
     noise3d = rng.normal(0, 0.02, size=(n_frames, edges_per_frame - half, 9))
     init_noise = rng.normal(0, 0.03, size=(n_objects, 9))
     return dict(objs=objs, Twc=Twc, pick2d=pick2d, pick3d=pick3d, noise2d=noise2d, noise3d=noise3d, init_noise=init_noise)
+
+
+# ---- oracle-free measurement generation for the BA graph (numpy only: bench.py's product arm must not touch oracle/) ----
+def quat_mul(a, b):
+    """Hamilton product of x y z w quaternions."""
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw,
+                     aw * bw - ax * bx - ay * by - az * bz])
+
+
+def quat_to_rot(q):
+    x, y, z, w = q / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def pose_inv(T7):
+    R = quat_to_rot(T7[3:7])
+    q = np.array([-T7[3], -T7[4], -T7[5], T7[6]])
+    return np.concatenate([-R.T @ T7[:3], q])
+
+
+def pose_compose(A7, B7):
+    q = quat_mul(A7[3:7], B7[3:7])
+    if q[3] < 0:
+        q = -q
+    return np.concatenate([A7[:3] + quat_to_rot(A7[3:7]) @ B7[:3], q / np.linalg.norm(q)])
+
+
+def ellipsoid_bbox_numpy(e10, Tcw7, K):
+    """Tangent-line bounding box of the projected ellipsoid (dual quadric Q* = T diag(a^2,b^2,c^2,-1) T^T, dual conic C* = P Q* P^T;
+    the lines x = u tangent to the conic satisfy l^T C* l = 0 with l = (1, 0, -u)).  Returns x1 y1 x2 y2."""
+    T = np.eye(4)
+    T[:3, :3] = quat_to_rot(e10[3:7])
+    T[:3, 3] = e10[:3]
+    Q = T @ np.diag([e10[7] ** 2, e10[8] ** 2, e10[9] ** 2, -1.0]) @ T.T
+    Tc = np.eye(4)
+    Tc[:3, :3] = quat_to_rot(Tcw7[3:7])
+    Tc[:3, 3] = Tcw7[:3]
+    P = np.asarray(K, dtype=np.float64).reshape(3, 3) @ Tc[:3, :]
+    Cs = P @ Q @ P.T
+    du = np.sqrt(Cs[0, 2] ** 2 - Cs[0, 0] * Cs[2, 2])
+    dv = np.sqrt(Cs[1, 2] ** 2 - Cs[1, 1] * Cs[2, 2])
+    xs = sorted([(Cs[0, 2] - du) / Cs[2, 2], (Cs[0, 2] + du) / Cs[2, 2]])
+    ys = sorted([(Cs[1, 2] - dv) / Cs[2, 2], (Cs[1, 2] + dv) / Cs[2, 2]])
+    return np.array([xs[0], ys[0], xs[1], ys[1]])
+
+
+def _perturb_ellipsoid(e10, n9):
+    """Small perturbation of an ellipsoid: translation, rotation vector (left-multiplied), half-axes."""
+    out = np.array(e10, dtype=np.float64)
+    out[:3] += n9[:3]
+    w = n9[3:6]
+    ang = np.linalg.norm(w)
+    dq = np.array([0, 0, 0, 1.0]) if ang < 1e-12 else np.concatenate([np.sin(ang / 2) * w / ang, [np.cos(ang / 2)]])
+    q = quat_mul(dq, out[3:7])
+    out[3:7] = q / np.linalg.norm(q) * (1.0 if q[3] >= 0 else -1.0)
+    out[7:10] = np.abs(out[7:10] + n9[6:9])
+    return out
+
+
+def ba_problem(n_frames=500, n_objects=50, edges_per_frame=50, seed=4242, with_gravity=True, pose_noise=0.0):
+    """BASELINE.json configs[3] as plain arrays (type/frame/object/meas/info/Tcw/init), measurements generated with numpy only.
+    pose_noise > 0 also returns SLAM-mode inputs (odometry from the true poses, perturbed initial poses)."""
+    Kmat = np.array([[FX, 0, CX], [0, FY, CY], [0, 0, 1.0]])
+    g = ba_graph(n_frames, n_objects, edges_per_frame, seed)
+    objs, Twc = g["objs"], g["Twc"]
+    Tcw = np.array([pose_inv(T) for T in Twc])
+    et, fr, ob, meas, info = [], [], [], [], []
+    if with_gravity:
+        for o in range(n_objects):
+            et.append(2); fr.append(0); ob.append(o); meas.append(np.r_[0, 0, 1, 0, np.zeros(6)]); info.append(100.0 ** 2)
+    for f in range(n_frames):
+        for k, o in enumerate(g["pick2d"][f]):
+            bb = ellipsoid_bbox_numpy(objs[o], Tcw[f], Kmat) + g["noise2d"][f, k]
+            et.append(0); fr.append(f); ob.append(int(o)); meas.append(np.r_[bb, np.zeros(6)]); info.append(1.0)
+    for f in range(n_frames):
+        for k, o in enumerate(g["pick3d"][f]):
+            e = _perturb_ellipsoid(objs[o], g["noise3d"][f, k])
+            local = np.concatenate([pose_compose(Tcw[f], e[:7]), e[7:10]])
+            et.append(1); fr.append(f); ob.append(int(o)); meas.append(local); info.append(10000.0 * 0.9)
+    init = np.array([_perturb_ellipsoid(objs[o], g["init_noise"][o]) for o in range(n_objects)])
+    p = dict(type=np.asarray(et, np.int32), frame=np.asarray(fr, np.int32), object=np.asarray(ob, np.int32), meas=np.array(meas), info=np.asarray(info, np.float64),
+             Tcw=Tcw, n_objects=n_objects, K=Kmat, init=init, truth=objs)
+    if pose_noise > 0:
+        rng = np.random.default_rng(seed + 1)
+        p["odom"] = np.array([pose_compose(Tcw[k + 1], pose_inv(Tcw[k])) for k in range(n_frames - 1)])
+        Tn = Tcw.copy()
+        for f in range(1, n_frames):
+            w = rng.normal(0, pose_noise, 6)
+            ang = np.linalg.norm(w[3:])
+            dq = np.array([0, 0, 0, 1.0]) if ang < 1e-12 else np.concatenate([np.sin(ang / 2) * w[3:] / ang, [np.cos(ang / 2)]])
+            Tn[f] = pose_compose(np.concatenate([w[:3], dq]), Tcw[f])
+        p["Tcw_true"], p["Tcw"] = Tcw, Tn
+    return p
