@@ -214,8 +214,10 @@ int eslam_copy_ellipsoids_dev(EslamHandle *h, void *stream, int n_obj, void *rec
 /* work statistics of the last extraction batch, summed over its objects (bench.py roofline: the algorithmic bytes of the symmetry
  * kernel are counted, not assumed).  out[0] cost evaluations the reference performs (GetPointCloudProb calls, SymmetrySolver.cpp:49),
  * out[1] mirrored points those evaluations visit, out[2] evaluations this library actually ran, out[3] points it visited,
- * out[4] nearest-neighbour scans, out[5] NN cache hits, out[6] largest n_sym of the batch, out[7] objects with symmetry. */
-int eslam_batch_counters(EslamHandle *h, unsigned long long out[8]);
+ * out[4] nearest-neighbour scans, out[5] NN cache hits, out[6] largest n_sym of the batch, out[7] objects with symmetry,
+ * out[8] shortcut decisions that disagreed with the full path (only counted under ESLAM_SYM_VERIFY=1; must be 0),
+ * out[9..11] clock64 cycles of the seed warps in single-plane evaluations / NN scans / scalar LM code. */
+int eslam_batch_counters(EslamHandle *h, unsigned long long out[12]);
 /* pipelined form of eslam_estimate_ellipsoids_host for frame streams (the reference calls EstimateLocalEllipsoid once per box and
  * blocks, Tracking.cpp:329; a batched caller keeps the device busy by submitting batch k+1 before collecting batch k).  At most two
  * tickets may be outstanding; `depth` and the metadata arrays of a submitted batch must stay valid until its wait returns; the

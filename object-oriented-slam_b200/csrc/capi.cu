@@ -101,15 +101,32 @@ int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const
   P.k0 = w.k0.as<unsigned>(); P.k1 = w.k1.as<unsigned>(); P.v0 = w.v0.as<unsigned>(); P.v1 = w.v1.as<unsigned>();
   P.parent = w.parent.as<int>(); P.count = w.count.as<int>();
   P.objn = w.objn.as<double>(); P.objnf = w.objnf.as<float4>();
-  if (!h->sym_slotmask.p) {   // 2 * kSymQueue entries per slot, 32 slots (= CTA slots) per SM id
-    // %smid is not dense: a B200 exposes 148 SMs of a larger die, so ids run past sm_count; the tables cover kMaxSmId ids
-    const size_t slots = (size_t)kMaxSmId * 32;
-    ESLAM_CUDA_OK(h, h->sym_pool_nn.reserve(slots * 2 * 256 * sizeof(float4)));
-    ESLAM_CUDA_OK(h, h->sym_pool_px.reserve(slots * 2 * 256 * sizeof(uint4)));
-    ESLAM_CUDA_OK(h, h->sym_slotmask.reserve((size_t)kMaxSmId * sizeof(unsigned)));
-    ESLAM_CUDA_OK(h, cudaMemset(h->sym_slotmask.p, 0, (size_t)kMaxSmId * sizeof(unsigned)));   // once per handle, blocking
+  P.nncache = nullptr; P.pixcache = nullptr; P.slotmask = nullptr;
+  if (h->sym_impl == 1) {
+    if (!h->sym_slotmask.p) {   // round-1 kernel: 2 * 256 entries per slot, 32 slots per SM id
+      const size_t slots = (size_t)kMaxSmId * 32;
+      ESLAM_CUDA_OK(h, h->sym_pool_nn.reserve(slots * 2 * 256 * sizeof(float4)));
+      ESLAM_CUDA_OK(h, h->sym_pool_px.reserve(slots * 2 * 256 * sizeof(uint4)));
+      ESLAM_CUDA_OK(h, h->sym_slotmask.reserve((size_t)kMaxSmId * sizeof(unsigned)));
+      ESLAM_CUDA_OK(h, cudaMemset(h->sym_slotmask.p, 0, (size_t)kMaxSmId * sizeof(unsigned)));
+    }
+    P.nncache = h->sym_pool_nn.as<float4>(); P.pixcache = h->sym_pool_px.as<uint4>(); P.slotmask = h->sym_slotmask.as<unsigned>();
   }
-  P.nncache = h->sym_pool_nn.as<float4>(); P.pixcache = h->sym_pool_px.as<uint4>(); P.slotmask = h->sym_slotmask.as<unsigned>();
+  if (!h->sym_slotmask2.p) {   // once per handle (blocking): pools sized by the SM count, not by the batch
+    const size_t sms = (size_t)h->sm_count;
+    ESLAM_CUDA_OK(h, h->sym_pool256.reserve(sms * kSymSlots256 * symmetry_pool_bytes(256)));   // slot = sm * kSymSlots + bit, one per resident CTA
+    ESLAM_CUDA_OK(h, h->sym_pool512.reserve(sms * kSymSlots512 * symmetry_pool_bytes(512)));
+    ESLAM_CUDA_OK(h, h->sym_slotmask2.reserve(2 * sms * sizeof(unsigned)));
+    ESLAM_CUDA_OK(h, h->sym_smid_map.reserve((kMaxSmId + 1) * sizeof(int)));
+    std::vector<unsigned> mask(2 * sms);
+    for (size_t i = 0; i < sms; i++) { mask[i] = ~0u << kSymSlots256; mask[sms + i] = ~0u << kSymSlots512; }
+    std::vector<int> map(kMaxSmId + 1, -1);
+    map[kMaxSmId] = 0;
+    ESLAM_CUDA_OK(h, cudaMemcpy(h->sym_slotmask2.p, mask.data(), mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    ESLAM_CUDA_OK(h, cudaMemcpy(h->sym_smid_map.p, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  P.sympool256 = h->sym_pool256.as<unsigned char>(); P.sympool512 = h->sym_pool512.as<unsigned char>();
+  P.slotmask2 = h->sym_slotmask2.as<unsigned>(); P.smid_map = h->sym_smid_map.as<int>(); P.sm_count = h->sm_count;
   P.d_crop = P.d_voxel = P.d_world = P.d_sym = P.d_final = nullptr; P.d_label = nullptr;
   if (want_dump) {
     ESLAM_CUDA_OK(h, w.d_crop.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_voxel.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_world.reserve(CAP * 24));
@@ -332,6 +349,9 @@ int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHa
   if (!h) return ESLAM_ERR_CUDA;
   h->prm = *p; h->cam = *c; h->device = device; h->sm_count = prop.multiProcessorCount;
   if (const char *e = getenv("ESLAM_H2D_MODE")) { int v = atoi(e); if (v >= 0 && v <= 4) h->h2d_mode = v; }
+  if (const char *e = getenv("ESLAM_SYM_IMPL")) { int v = atoi(e); if (v == 1 || v == 2) h->sym_impl = v; }
+  if (const char *e = getenv("ESLAM_SYM_OCC")) h->sym_occ = atoi(e);
+  if (const char *e = getenv("ESLAM_SYM_VERIFY")) h->sym_verify = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_DEV_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= kMaxChunks) h->dev_chunks = v; }
   if (const char *e = getenv("ESLAM_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= kMaxChunks) h->host_chunks = v; }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return ESLAM_ERR_CUDA; }
@@ -354,6 +374,7 @@ void eslam_destroy(EslamHandle *h) {
     if (h->slot_done[sl]) cudaEventDestroy(h->slot_done[sl]);
   }
   h->sym_pool_nn.release(); h->sym_pool_px.release(); h->sym_slotmask.release(); h->plane_depth.release();
+  h->sym_pool256.release(); h->sym_pool512.release(); h->sym_slotmask2.release(); h->sym_smid_map.release();
   slam_free(h);
   graph_free(h);
   plane_free(h);
@@ -511,15 +532,17 @@ int eslam_copy_ellipsoids_dev(EslamHandle *h, void *stream, int n_obj, void *rec
   ESLAM_CUDA_OK(h, cudaMemcpyAsync(records_dev, h->ex->out.p, sizeof(EslamEllipsoidOut) * (size_t)n_obj, cudaMemcpyDeviceToDevice, s));
   return ESLAM_OK;
 }
-int eslam_batch_counters(EslamHandle *h, unsigned long long out[8]) {
+int eslam_batch_counters(EslamHandle *h, unsigned long long out[12]) {
   if (!h || !h->ex || !out || h->ex->n_obj <= 0) return ESLAM_ERR_BAD_ARG;
   cudaSetDevice(h->device);
   std::vector<ObjState> st((size_t)h->ex->n_obj);
   ESLAM_CUDA_OK(h, cudaMemcpy(st.data(), h->ex->state.p, sizeof(ObjState) * st.size(), cudaMemcpyDeviceToHost));
-  for (int k = 0; k < 8; k++) out[k] = 0;
+  for (int k = 0; k < 12; k++) out[k] = 0;
   for (const ObjState &o : st) {
     out[0] += o.n_ref_evals; out[1] += o.n_ref_points; out[2] += o.n_evals; out[3] += o.n_points; out[4] += o.n_queries; out[5] += o.n_hits;
     if ((unsigned long long)o.n_sym > out[6]) out[6] = (unsigned long long)o.n_sym;
+    out[8] += o.n_verify_fail;
+    for (int k = 0; k < 3; k++) out[9 + k] += (unsigned long long)o.sym_clk[k == 2 ? 3 : k];
     if (o.run_sym) out[7]++;
   }
   return ESLAM_OK;

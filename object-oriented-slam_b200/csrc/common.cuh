@@ -44,6 +44,8 @@ struct PinBuf {
 
 constexpr int kMaxChunks = 16;
 constexpr int kMaxSmId = 256;   // upper bound of %smid + 1 the symmetry cache tables are sized for
+constexpr int kSymCtas256 = 3, kSymCtas512 = 2;    // launch bounds (resident nine-warp CTAs per SM) of the two symmetry instantiations
+constexpr int kSymSlots256 = 4, kSymSlots512 = 2;  // cache slots per SM: what shared memory admits at most (~50 KB / ~87 KB per CTA)
 struct ExtractWorkspace;  // extract.cu
 struct GraphWorkspace;    // edges.cu
 struct SlamWorkspace;     // slam.cu
@@ -68,9 +70,13 @@ struct EslamHandle {
   int dev_chunks = 8;    // object chunks / streams of the device-resident entry for batches of >= 512 objects (env ESLAM_DEV_CHUNKS)
   // symmetry kernel caches: one slot per RESIDENT seed warp (sm_count x 32 CTA slots), handed out through a per-SM bitmask, so the
   // same ~40 MB are reused by every batch and stay L2 resident
-  eslam::DevBuf sym_pool_nn, sym_pool_px, sym_slotmask;
+  eslam::DevBuf sym_pool_nn, sym_pool_px, sym_slotmask;   // round-1 kernel (ESLAM_SYM_IMPL=1) only
+  eslam::DevBuf sym_pool256, sym_pool512, sym_slotmask2, sym_smid_map;
+  int sym_occ = 0;         // env ESLAM_SYM_OCC (tuning): 2 / 4 resident CTAs per SM instead of kSymCtas256
+  int sym_impl = 2;        // env ESLAM_SYM_IMPL: 1 = round-1 kernel (A/B baseline), 2 = current
+  bool sym_verify = false; // env ESLAM_SYM_VERIFY=1: every shortcut decision of the symmetry kernel is re-derived the long way and counted when it differs
   eslam::DevBuf plane_depth;           // staging of eslam_extract_ground_plane_host (separate from the extraction slots)
-  bool attr_extract = false, attr_symmetry = false, attr_plane = false;   // kernel attributes are per device: set once per handle, not once per process
+  bool attr_extract = false, attr_symmetry = false, attr_symmetry_v1 = false, attr_plane = false;   // kernel attributes are per device: set once per handle, not once per process
   unsigned long long h2d_bytes = 0;    // depth bytes uploaded by the *_host extraction entry (running total)
   bool plane_set = false;
   double plane_world[4] = {0, 0, 1, 0};

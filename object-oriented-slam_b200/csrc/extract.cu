@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
   if (tid == 0) {
     st.status = m.pre_status;
     st.n_crop = st.n_voxel = st.n_plane = st.n_clusters = st.n_cluster = st.n_sym = st.n_final = 0;
-    st.run_sym = 0; st.symtype = m.symtype; st.best_seed = -1; st.done = 0; st.n_evals = 0; st.n_queries = 0; st.n_points = 0; st.n_hits = 0; st.n_ref_evals = 0; st.n_ref_points = 0; for (int k = 0; k < 4; k++) st.sym_clk[k] = 0;
+    st.run_sym = 0; st.symtype = m.symtype; st.best_seed = -1; st.done = 0; st.n_evals = 0; st.n_queries = 0; st.n_points = 0; st.n_hits = 0; st.n_ref_evals = 0; st.n_ref_points = 0; st.n_verify_fail = 0; for (int k = 0; k < 4; k++) st.sym_clk[k] = 0;
     for (int k = 0; k < 4; k++) st.bbox_i[k] = (int)m.bbox[k];
     for (int s = 0; s < 9; s++) { st.seed_prob[s] = st.seed_init[s] = st.seed_final[s] = st.seed_dual[s] = 0; for (int k = 0; k < 4; k++) st.seed_plane[s][k] = 0; }
   }

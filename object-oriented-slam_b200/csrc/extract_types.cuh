@@ -29,6 +29,7 @@ struct ObjState {  // device resident, one per object
   long long sym_clk[4];     // symmetry kernel, summed over the 9 seed warps: classification, NN scans, ordered sums, rest
   unsigned long long n_evals, n_queries, n_points, n_hits;   // symmetry work counters (cost evaluations, NN scans, mirrored points, NN cache hits)
   unsigned long long n_ref_evals, n_ref_points;              // what the reference's call sequence performs (incl. the evaluations memoised here)
+  unsigned long long n_verify_fail;                          // ESLAM_SYM_VERIFY=1: shortcut decisions that disagreed with the full path (must stay 0)
 };
 
 struct ExtractParamsDev {
@@ -56,7 +57,12 @@ struct ExtractPtrs {  // device pointers of the per-point workspace (total capac
   float4 *objnf;    // float copy for the NN search
   float4 *nncache;  // [sm_count*32][2*kSymQueue] NN cache slot of a resident seed warp of the symmetry kernel (query float3 + neighbour index)
   uint4 *pixcache;  // same shape: per-point pixel cache (pixel key, range value, depth)
-  unsigned *slotmask;  // [sm_count] bit b set = cache slot sm*32+b in use
+  unsigned *slotmask;  // [sm_count] bit b set = cache slot sm*32+b in use   (these three: round-1 kernel only, ESLAM_SYM_IMPL=1)
+  // symmetry kernel caches: one slot per RESIDENT seed warp, handed out per SM through a bitmask (slot = dense_sm * 32 + bit)
+  unsigned char *sympool256, *sympool512;   // slot = [2 NN banks][2*CAP] float4 + [2*CAP] uint4 pixel cache = CAP * 96 bytes
+  unsigned *slotmask2;   // [2][sm_count]: CAP = 256 words, then CAP = 512 words; bits beyond the variant's slot count are pre-set
+  int *smid_map;         // [kMaxSmId + 1]: dense SM index per %smid (first touch), last entry = next free index
+  int sm_count;
   // optional stage dump (device mirrors, NULL when no dump requested)
   double *d_crop, *d_voxel, *d_world, *d_sym, *d_final;  // d_final has 4x capacity
   int *d_label;

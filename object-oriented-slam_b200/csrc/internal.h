@@ -27,6 +27,8 @@ int pull_rects_launch(EslamHandle *h, cudaStream_t s, const uint16_t *host_mappe
 int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj,
                              const ExtractParamsDev &prm, const ExtractPtrs &ptrs);
 
+size_t symmetry_pool_bytes(int cap);   // NN + pixel cache bytes of one resident symmetry CTA
+
 // plane.cu
 int plane_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *depth_dev, size_t pitch, double *plane_cam_host, int *found_host,
                   int *n_inliers_host);

@@ -1,5 +1,5 @@
-// symmetry.cu -- symmetry-plane estimation (9 seeds x in-register Levenberg-Marquardt) + point-cloud completion +
-// final ellipsoid, one CTA per object, ONE WARP PER SEED.
+// symmetry.cu -- symmetry-plane estimation (9 seeds x Levenberg-Marquardt on the symmetry cost) + point-cloud completion +
+// final ellipsoid.  ONE CTA PER OBJECT, ONE WARP PER SEED, the nine seeds advancing in ROUNDS.
 //
 // Replaces
 //   Symmetry::estimateSymmetry / GenerateInitPlanes / getProjDepthMat     src/symmetry/Symmetry.cpp:44-161
@@ -8,14 +8,30 @@
 //   EdgeSymmetry(Dual)Plane::computeError, Vertex(Dual)Plane::oplusImpl    src/symmetry/SymmetrySolver.cpp:375-396,458-481,527-547
 //   the g2o LM loop + numeric Jacobian + dense LDLT they run on            (see edges.cu header for citations)
 //   completion, re-centring, extents, ellipsoid assembly                   src/pca/EllipsoidExtractor.cpp:399-492,495-531
-// B200 design notes
-//   * the range image of getProjDepthMat (307 200 sqrt per object in the reference) is never materialised: the
-//     ushort range value is computed lazily for the <= 2M pixels a cost evaluation actually reads;
-//   * the kd-tree is replaced by an exact brute-force float NN over the <= ~500-point cloud staged in shared memory
-//     (same argmin as FLANN's exact search; distance recomputed in fp64 from the float neighbour, SymmetrySolver.cpp:159-163);
-//   * each warp owns one seed end-to-end: the LM control flow (fp64 scalars) is warp-uniform, every cost evaluation
-//     streams the mirrored points 32 at a time and accumulates ln P in the reference's sequential order via shuffles,
-//     so no block barrier and no scratch memory is needed inside the ~45 sequential evaluations of a seed.
+//
+// The cost of a plane is  -mean_i ln P_i  over the mirrored cloud: each mirrored point is projected into the depth image, classified
+// (occluded / no depth: cost 0; otherwise its distance to the nearest cloud point) and the ln P are summed IN POINT ORDER in fp64.  The
+// numeric Jacobian (delta 1e-9, amplification 5e8) makes every rounding of that sum matter, so the arithmetic that produces a VALUE
+// (mirroring, the fp64 distance to the float neighbour, the ordered sum) is the reference's operation for operation, while every
+// DECISION (which pixel, occluded or not, which neighbour) is taken by the cheapest test that provably gives the reference's answer:
+//   * pixel:      u = uvh0 / uvh2 is only truncated to an int, so a reciprocal-multiply estimate decides it unless it lies within a
+//                 margin of an integer (then the exact division runs);
+//   * occlusion:  sqrt(s) > depth is decided on s - depth^2 unless the two are within a margin (then the exact sqrt runs);
+//   * neighbour:  every full scan of the float cloud also yields the second-best distance; the scanned query q0 is cached with the
+//                 radius rho = (d2 - d1) / 2 (rounded down): any later query within rho of q0 has the same unique nearest neighbour
+//                 (triangle inequality, slack for the float rounding of the reference's own scan), so the scan is skipped;
+//   * the 2*dim finite-difference planes of a linearisation move every mirrored point by < 4e-6 m (checked per linearisation from the
+//     plane parameters): a point whose decisions at the base plane hold with that margin ("robust") needs no projection at all for
+//     the finite-difference planes -- only the mirrored point and its distance to the known neighbour, for all 2*dim planes in ONE
+//     pass over the points (one point load, 2*dim independent fp64 chains per lane); the few non-robust points take the full path.
+//   The range image of getProjDepthMat is never materialised (lazy per pixel, cached per point); the kd-tree is an exact brute-force
+//   float scan over the <= 512-point cloud in shared memory (same argmin as FLANN's exact search, first index on ties).
+// The ordered sums of the 2*dim planes run on 2*dim lanes side by side (values staged through shared memory).
+// Structure: the kernel is bound by instruction issue / fetch, not by memory, so what matters is how many instructions run and how
+// well they stay in the instruction caches.  The nine seeds of an object are the nine warps of one CTA and advance in rounds: in a
+// round every live seed runs its next cost evaluation (a finite-difference pass or a trial plane), then -- one barrier later -- warp 0
+// runs the scalar Levenberg-Marquardt step of all nine seeds in nine LANES (solve, oplus, plane constants: ~2 k scalar fp64
+// instructions per step, sin / cos / atan2 shared as non-inlined routines), instead of nine warps each running it in one lane.
 #include "common.cuh"
 #include "dmath.cuh"
 #include "block_prims.cuh"
@@ -23,409 +39,686 @@
 #include "internal.h"
 
 namespace eslam {
+namespace {
 
-constexpr int kSymSmemPts = 256;   // cloud staged in shared memory (pair-interleaved SoA) up to this many points
-constexpr int kSymQueue = 256;     // per-warp query queue / distance slots / NN cache (fast path when #mirrored points <= 256)
+constexpr double kFdDelta = 4.0e-6;        // verified bound on |pm_fd - pm_base| per coordinate for the finite-difference planes [m]
+constexpr double kPixMargin = 4.04e-6;     // kFdDelta * 1.01 (denominator shift), scaled per point to pixels
+constexpr double kDepthMargin = 5.0e-6;    // |s - t| >= kDepthMargin * (2 + s + t)  =>  |sqrt s - sqrt t| >= 1e-5 > sqrt(3) * kFdDelta
+constexpr float kNnSafe = 1.0e-5f;         // a cached neighbour is final for the finite-difference planes when rho - |q - q0| exceeds this
+constexpr double kQMax = 14.0;             // float rounding of a query (2^-23 |q|) stays below kNnSafe - sqrt(3) kFdDelta for |q| <= kQMax
+constexpr int kSlowMax = 16;               // non-robust points of one half handled by the finite-difference pass (more: generic evaluations)
+constexpr int kSeeds = 9;
+constexpr unsigned kIdxMask = 1023u;       // neighbour index packed into the low mantissa bits of rho^2 (rounded down: conservative)
 
 struct PlanePair {   // per-evaluation constants of GetSymmetryPointOfPlane for the plane and its dual (hoisted, same rounding)
   double p1[4], p2[4], down1, down2, n1[3], n2[3];
 };
-// Everything that is uniform across a block (object) or a warp (seed) lives in SHARED memory, not in per-lane registers:
-// the kernel is latency bound (long fp64 div/sqrt chains), so occupancy -- registers per thread -- is what buys throughput.
-struct SymBlock {
+struct SeedResult { double prob, init_err, final_err; dplane plane; };
+
+// Shared memory of a CTA: the object (constants + float cloud) and nine seeds (LM state + evaluation scratch).
+template <int CAP>
+struct SymObj {
   const uint16_t *img; size_t pitch;
-  const double *objn; const float4 *nn_g;
+  const double *objn; const float4 *nn_g; ObjState *st;
   int M, symtype, npts, in_smem;
   int bx0, bx2, by1, by3, rows, cols;
-  ObjState *st;
-  double P[12], cam[3], fx, cx, cy, scale, sinv;
-  unsigned long long X2[kSymSmemPts / 2], Y2[kSymSmemPts / 2], Z2[kSymSmemPts / 2];   // pair-interleaved SoA float cloud (odd tail padded far away)
+  double P[12], cam[3], fx, cx, cy, scale, coef, A0, A1, A2, R2;
+  int n_live, slotbit, sm, iters;
+  int n_tasks, next_task;                       // work list of the current phase (any warp takes any task)
+  unsigned short tasks[kSeeds + kSeeds * 2 * (CAP / 32)];   // kind << 12 | seed << 8 | half << 7 | chunk   (kind 0: FD pass, 1: classify chunk, 2: scan chunk)
+  // float cloud, pair-interleaved SoA (odd tail padded far away)
+  unsigned long long X2[CAP / 2], Y2[CAP / 2], Z2[CAP / 2];
 };
-struct SeedResult { double prob, init_err, final_err; dplane plane; };
-struct SymWarp {
-  float4 *cache;   // per-warp NN cache in HBM/L2: slot i = (float query x, y, z, nearest index) of mirrored point i at its last full scan
-  uint4 *pcache;   // per-warp pixel cache: slot i = (x | y << 16, ushort range value, depth = value / scale as a double) of the last pixel it read
-  PlanePair pp;
-  PlanePair fd[6];   // the 2*dim finite-difference planes of one linearisation, prepared by 2*dim lanes in parallel
-  dplane est, backup, trial;
+enum { kActDone = 0, kActInit = 1, kActFd = 2, kActTrial = 3 };
+template <int CAP>
+struct SymSeed {
+  float4 *nnc[2];          // NN cache, two banks: [bank][point] = (q0.x, q0.y, q0.z, rho^2 | neighbour index)
+  uint4 *pxc;              // pixel cache: [point] = (x | y << 16, ushort range value, depth = value / scale as a double)
+  // ---- Levenberg-Marquardt state of the one-vertex problem
+  PlanePair pp, base, fd[6];
+  dplane est, backup;
   double H[9], b[3], x[3], J[3];
-  double lambda, ni, currentChi, tempChi, iniChi, rho, e1;
-  int nBad, ok, qmax, again, accepted;
-  unsigned n_evals, n_queries, n_points, n_hits, n_ref;   // work counters, flushed once per seed (n_ref: cost evaluations of the reference's call sequence)
-  long long clk[4];   // cycles in: classification passes, NN scans, ordered sums, everything else of the seed (clock64, lane 0)
+  double lambda, ni, currentChi, iniChi, err_last, err_est;   // err_last: value of the last computeError call; err_est: error of `est`
+  int nBad, ok, qmax, ok2, it, cur, fd_ok, action;
+  int wbank, qn, invalid;  // the running single-plane evaluation: bank it writes, points queued for a scan, invalid points
+  unsigned n_evals, n_queries, n_points, n_hits, n_ref, n_verify_fail;
   SeedResult res;
-  unsigned short queue[kSymQueue];
-  double dis[kSymQueue];
+  int inv_s[6];
+  // ---- per-evaluation scratch
+  alignas(16) double lnp[2 * CAP];    // ln P of every mirrored point (-0.0 where it carries no distance), point order; FD passes stage their tiles here
+  alignas(16) unsigned short queue[2 * CAP];   // points that need a scan: li | half << 9 | robust << 15 (FD passes keep their side buffer here)
+  unsigned short list[CAP];           // FD pass: active points of the current half
+  unsigned short slow[kSlowMax];
+  unsigned mA[2][2][CAP / 32];        // [bank][half][word]: point needs work for a finite-difference plane (cost != 0, or not robust)
+  unsigned mF[2][2][CAP / 32];        //                     point is robust, carries a distance and its cached neighbour is final
+  double pad_[2];                     // sizeof % 128 == 16: the nine lanes of the scalar step hit different banks
 };
+static_assert(6 * 33 <= 256 && 6 * kSlowMax * 2 <= 256, "FD staging tiles alias lnp / queue");
 
 __device__ __forceinline__ int x86_int(double a) { return (a > -2147483649.0 && a < 2147483648.0) ? (int)a : (int)0x80000000; }
+__device__ __forceinline__ double rcp_fast(double a) {   // ~1 ulp reciprocal without the special-case path (guarded use only)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = __fma_rn(-a, r, 1.0); r = __fma_rn(r, e, r);
+  e = __fma_rn(-a, r, 1.0); r = __fma_rn(r, e, r);
+  return r;
+}
 
+// sin / cos / atan2 exist ONCE in the kernel (the scalar LM step calls them ~11 times; inlined they were 40 KB of cold code)
+__device__ __noinline__ double n_sin(double a) { return sin(a); }
+__device__ __noinline__ double n_cos(double a) { return cos(a); }
+__device__ __noinline__ double n_atan2(double y, double x) { return atan2(y, x); }
+// dmath.cuh's q_axis_angle / plane_rotation / plane_oplus_common / plane_another on the shared trig routines (same arithmetic)
+__device__ __forceinline__ quat s_axis_angle(double angle, d3 axis) {
+  const double ha = 0.5 * angle;
+  const bool zero = (ha == 0.0);   // sin(+-0) = +-0 and cos(+-0) = 1 exactly
+  const double sn = zero ? ha : n_sin(ha);
+  quat q; q.x = sn * axis.x; q.y = sn * axis.y; q.z = sn * axis.z; q.w = zero ? 1.0 : n_cos(ha);
+  return q;
+}
+__device__ __forceinline__ mat3 s_plane_rotation(d3 v) {  // Plane.h:88-92
+  const double az = n_atan2(v.y, v.x);
+  const double rxy = sqrt(v.x * v.x + v.y * v.y);
+  const double el = (v.z == 0.0 && rxy > 0.0) ? v.z : n_atan2(v.z, rxy);   // atan2(+-0, r > 0) = +-0 exactly
+  return q_to_R(q_mul(s_axis_angle(az, mk3(0, 0, 1)), s_axis_angle(-el, mk3(0, 1, 0))));
+}
+// VertexPlane (yaw, 0, dis) :527-532 / VertexDualPlane (+ dual) :544-547 on Plane.h:46-77 with elevation 0
+__device__ __noinline__ void sym_oplus(dplane &pl, const double *u, int symtype) {
+  const double az = u[0], dd = u[1];
+  const d3 n = mk3(1.0 * n_cos(az), 1.0 * n_sin(az), 0.0);   // c = cos(0) = 1, s = sin(0) = 0
+  const mat3 R = s_plane_rotation(mk3(pl.p[0], pl.p[1], pl.p[2]));
+  const double d = -pl.p[3] + dd;
+  const d3 rn = m3_vec(R, n);
+  pl.p[0] = rn.x; pl.p[1] = rn.y; pl.p[2] = rn.z; pl.p[3] = -d;
+  const double nn = sqrt(pl.p[0] * pl.p[0] + pl.p[1] * pl.p[1] + pl.p[2] * pl.p[2]);
+  const double inv = 1. / nn;
+  pl.p[0] = pl.p[0] * inv; pl.p[1] = pl.p[1] * inv; pl.p[2] = pl.p[2] * inv; pl.p[3] = pl.p[3] * inv;
+  if (symtype != 1) pl.dual += u[2];
+}
+// a / b with the zero numerators of the vertical planes (p[2] = 0, dual = 0) answered without the division's slow path: +-0 / b = +-0 for b > 0
+__device__ __forceinline__ double div_z(double a, double b) { return (a == 0.0 && b > 0.0) ? a : a / b; }
 __device__ __noinline__ void make_pair(PlanePair &P, const dplane &pl) {
   for (int k = 0; k < 4; k++) P.p1[k] = pl.p[k];
-  plane_another(pl, P.p2);
+  const double ang = n_atan2(pl.p[1], pl.p[0]);                              // plane_another: Plane.cpp:137-144 + :97-105
+  P.p2[0] = n_sin(ang); P.p2[1] = -n_cos(ang); P.p2[2] = 0; P.p2[3] = -pl.dual;
   P.down1 = sqrt(P.p1[0] * P.p1[0] + P.p1[1] * P.p1[1] + P.p1[2] * P.p1[2]);
   P.down2 = sqrt(P.p2[0] * P.p2[0] + P.p2[1] * P.p2[1] + P.p2[2] * P.p2[2]);
-  for (int k = 0; k < 3; k++) { P.n1[k] = P.p1[k] / P.down1; P.n2[k] = P.p2[k] / P.down2; }
+  for (int k = 0; k < 3; k++) { P.n1[k] = div_z(P.p1[k], P.down1); P.n2[k] = div_z(P.p2[k], P.down2); }
 }
-__device__ __forceinline__ d3 mirrored(const SymBlock &B, const PlanePair &P, int idx) {   // GetSymmetryPointOfPlane :193-214
-  const int second = idx >= B.M;
-  const int j = idx - (second ? B.M : 0);
-  const d3 pt = mk3(B.objn[3 * j], B.objn[3 * j + 1], B.objn[3 * j + 2]);
-  const double *q = second ? P.p2 : P.p1;
-  const double *n = second ? P.n2 : P.n1;
+// GetSymmetryPointOfPlane :193-214 with q = plane, n = its unit normal, down = |q.xyz|
+__device__ __forceinline__ d3 mirror_q(d3 pt, const double *q, const double *n, double down) {
   const double val = q[0] * pt.x + q[1] * pt.y + q[2] * pt.z + q[3] * 1.0;
-  const double dis_pl = fabs(val) / (second ? P.down2 : P.down1);
+  const double dis_pl = fabs(val) / down;
   const double kk = 2 * ((val > 0) ? -1.0 : 1.0) * dis_pl;
   return mk3(pt.x + kk * n[0], pt.y + kk * n[1], pt.z + kk * n[2]);
 }
-// 0 = cost 0 (occluded / no depth), 1 = needs the nearest-neighbour distance, 2 = invalid (not counted)   SymmetrySolver.cpp:62-116
-// `pc` is the point's pixel-cache entry: when the mirrored point projects to the same pixel as last time (always, for the 1e-9
-// finite-difference perturbations) the range value of that pixel -- a function of the pixel alone -- is reused instead of being
-// reloaded and recomputed (1 gather, 1 sqrt, 2 divisions).
-__device__ __forceinline__ int classify(const SymBlock &B, d3 pm, uint4 pc, uint4 *slot) {
+template <int CAP>
+__device__ __forceinline__ d3 load_pt(const SymObj<CAP> &O, int j) { return mk3(O.objn[3 * j], O.objn[3 * j + 1], O.objn[3 * j + 2]); }
+
+// Classification of a mirrored point (SymmetrySolver.cpp:62-116): 0 = cost 0 (occluded / no depth), 1 = needs the nearest-neighbour
+// distance, 2 = invalid (not counted).  `rob` = every decision holds for any point within kFdDelta (per coordinate) of pm.
+// `pc` is the point's pixel-cache entry: the range value of a pixel is a function of the pixel alone.
+template <int CAP>
+__device__ __forceinline__ int classify(const SymObj<CAP> &O, d3 pm, uint4 pc, uint4 *slot, bool &rob) {
   double uvh[3];
 #pragma unroll
-  for (int r = 0; r < 3; r++) { double s = B.P[r * 4] * pm.x; s += B.P[r * 4 + 1] * pm.y; s += B.P[r * 4 + 2] * pm.z; s += B.P[r * 4 + 3] * 1.0; uvh[r] = s; }
-  const double u = uvh[0] / uvh[2], v = uvh[1] / uvh[2];
-  const int x = x86_int(u), y = x86_int(v);
+  for (int r = 0; r < 3; r++) { double s = O.P[r * 4] * pm.x; s += O.P[r * 4 + 1] * pm.y; s += O.P[r * 4 + 2] * pm.z; s += O.P[r * 4 + 3] * 1.0; uvh[r] = s; }
+  // pixel: the reference truncates u = uvh0 / uvh2 (cvttsd2si); the estimate decides unless it is within the margin of an integer
+  const double rw = rcp_fast(uvh[2]);
+  const double ua = uvh[0] * rw, va = uvh[1] * rw;
+  const double arw = fabs(rw) * kPixMargin;
+  const double mu = (O.A0 + fabs(ua) * O.A2) * arw + 1e-6, mv = (O.A1 + fabs(va) * O.A2) * arw + 1e-6;   // 1e-6 px also covers the estimate's own error
+  const double fu = ua - floor(ua), fv = va - floor(va);
+  int x, y;
+  rob = fabs(uvh[2]) > 1e-3 && fabs(ua) < 1e5 && fabs(va) < 1e5 && fu > mu && fu < 1.0 - mu && fv > mv && fv < 1.0 - mv;
+  if (rob) { x = (int)ua; y = (int)va; }
+  else { const double u = uvh[0] / uvh[2], v = uvh[1] / uvh[2]; x = x86_int(u); y = x86_int(v); }
   const bool valid = isfinite(pm.x) && isfinite(pm.y) && isfinite(pm.z);
-  bool inrange = (B.bx0 < x && x < B.bx2) && (B.by1 < y && y < B.by3);
-  if (inrange && (x < 0 || y < 0 || x >= B.cols || y >= B.rows)) inrange = false;
+  rob = rob && valid;
+  bool inrange = (O.bx0 < x && x < O.bx2) && (O.by1 < y && y < O.by3);
+  if (inrange && (x < 0 || y < 0 || x >= O.cols || y >= O.rows)) inrange = false;
   if (inrange) {
     const unsigned key = (unsigned)x | ((unsigned)y << 16);
     unsigned d; double depth;
     if (pc.x == key) {
       d = pc.y; depth = __hiloint2double((int)pc.w, (int)pc.z);
     } else {
-      const unsigned short d0 = B.img[(size_t)y * B.pitch + x];
-      const double xi = (x - B.cx), yi = (y - B.cy), f = B.fx;
+      const unsigned short d0 = O.img[(size_t)y * O.pitch + x];
+      const double xi = (x - O.cx), yi = (y - O.cy), f = O.fx;
       const double realz = (double)d0 * sqrt(xi * xi + f * f + yi * yi) / f;   // calculateProjZ, Symmetry.cpp:137-139 (lazy range image)
       d = (unsigned short)(int)realz;                                            // ushort(realz)
-      depth = d / B.scale;
+      depth = d / O.scale;
       *slot = make_uint4(key, d, (unsigned)__double2loint(depth), (unsigned)__double2hiint(depth));
     }
     if (d == 0) return 0;
-    const double ax = B.cam[0] - pm.x, ay = B.cam[1] - pm.y, az = B.cam[2] - pm.z;
-    const double dis_cam = sqrt(ax * ax + ay * ay + az * az);
-    if (dis_cam > depth) return 0;
+    const double ax = O.cam[0] - pm.x, ay = O.cam[1] - pm.y, az = O.cam[2] - pm.z;
+    const double s = ax * ax + ay * ay + az * az, t = depth * depth;
+    bool occluded;
+    if (fabs(s - t) >= kDepthMargin * (2.0 + s + t)) occluded = s > t;   // sqrt(s) > depth with >= 1e-5 to spare
+    else { occluded = sqrt(s) > depth; rob = false; }
+    if (occluded) return 0;
   }
   return valid ? 1 : 2;
 }
+
 // packed fp32x2 arithmetic (Blackwell FADD2/FMUL2): two cloud points per instruction, each half rounded (rn) exactly like the scalar op
 __device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) { return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32); }
 
-struct NNRes { double dis; int best; };
 // fp64 distance from the query to the FLOAT neighbour `best` of the shared-memory cloud (findMinimalDistanceWithKdTree :159-163)
-__device__ __forceinline__ double dist_to_neighbour(const SymBlock &B, d3 pm, int best) {
-  const unsigned long long X = B.X2[best >> 1], Y = B.Y2[best >> 1], Z = B.Z2[best >> 1];
+template <int CAP>
+__device__ __forceinline__ double dist_to_neighbour(const SymObj<CAP> &O, d3 pm, int best) {
+  const unsigned long long X = O.X2[best >> 1], Y = O.Y2[best >> 1], Z = O.Z2[best >> 1];
   const int sh = (best & 1) * 32;
   const double bx = (double)__uint_as_float((unsigned)(X >> sh)), by = (double)__uint_as_float((unsigned)(Y >> sh)), bz = (double)__uint_as_float((unsigned)(Z >> sh));
   const double dx = pm.x - bx, dy = pm.y - by, dz = pm.z - bz;
   return sqrt(dx * dx + dy * dy + dz * dz);
 }
-// Exact float NN (flann::L2_Simple operation order; minimum r = ((dx^2 + dy^2) + dz^2), first index on ties -- the oracle's linear
-// scan) + fp64 distance to the float neighbour (findMinimalDistanceWithKdTree :140-166).  All lanes scan the same pair of cloud
-// points at the same time (broadcast LDS.64 of the pair-interleaved SoA copy); the loop body is branch free.
-__device__ __noinline__ NNRes nn_distance(const SymBlock &B, d3 pm) {
-  const float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
-  float bd = FLT_MAX; int best = 0;
-  const int M = B.M;
-  float bx, by, bz;
-  if (B.in_smem) {
-    const unsigned long long qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
-    const int pairs = (M + 1) >> 1;
-#pragma unroll 2
-    for (int j = 0; j < pairs; j++) {
-      unsigned long long dx = f2_sub(qx2, B.X2[j]), dy = f2_sub(qy2, B.Y2[j]), dz = f2_sub(qz2, B.Z2[j]);
-      // products packed (FMUL2), sums scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false,
-      // which would change the rounding; scalar add.rn.f32 is never contracted.
-      const unsigned long long sx = f2_mul(dx, dx), sy = f2_mul(dy, dy), sz = f2_mul(dz, dz);
-      const float r0 = __fadd_rn(__fadd_rn(__uint_as_float((unsigned)sx), __uint_as_float((unsigned)sy)), __uint_as_float((unsigned)sz));
-      const float r1 = __fadd_rn(__fadd_rn(__uint_as_float((unsigned)(sx >> 32)), __uint_as_float((unsigned)(sy >> 32))), __uint_as_float((unsigned)(sz >> 32)));
-      if (r0 < bd) { bd = r0; best = 2 * j; }
-      if (r1 < bd) { bd = r1; best = 2 * j + 1; }
-    }
-    const unsigned long long X = B.X2[best >> 1], Y = B.Y2[best >> 1], Z = B.Z2[best >> 1];
-    const int sh = (best & 1) * 32;
-    bx = __uint_as_float((unsigned)(X >> sh)); by = __uint_as_float((unsigned)(Y >> sh)); bz = __uint_as_float((unsigned)(Z >> sh));
-  } else {
-    for (int k = 0; k < M; k++) {
-      const float4 q = B.nn_g[k];
-      float dd = __fsub_rn(qx, q.x);
-      float r = __fmul_rn(dd, dd);
-      dd = __fsub_rn(qy, q.y); r = __fadd_rn(r, __fmul_rn(dd, dd));
-      dd = __fsub_rn(qz, q.z); r = __fadd_rn(r, __fmul_rn(dd, dd));
-      if (r < bd) { bd = r; best = k; }
-    }
-    const float4 q = B.nn_g[best];
-    bx = q.x; by = q.y; bz = q.z;
-  }
-  const double dx = pm.x - (double)bx, dy = pm.y - (double)by, dz = pm.z - (double)bz;
-  NNRes r; r.dis = sqrt(dx * dx + dy * dy + dz * dz); r.best = best;
-  return r;
-}
 
-// Warp-cooperative variant for a PARTIAL chunk of cq <= 16 queries (shared-memory cloud): the 32 lanes are split into
-// L = 32 / pow2ceil(cq) parts, part p scans the p-th slice of the cloud for query (lane % slots); the parts are merged with an
-// (r, index) lexicographic butterfly -- slices are index-ordered, so "smallest r, then smallest index" is exactly the linear scan's
-// first-minimum rule.  Returns the distance for lanes with part == 0 && q < cq (other lanes: 0).
-__device__ __noinline__ NNRes nn_distance_split(const SymBlock &B, d3 pm, int slots, bool active) {
-  const int lane = threadIdx.x & 31;
-  const int L = 32 / slots;
-  const int part = lane / slots;
-  const float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
+struct NN2 { float r1, r2; int best; };   // smallest and second smallest float distance (flann::L2_Simple order), first index of the smallest
+// Exact float NN over pairs [j0, j1) of the shared-memory cloud: minimum of r = ((dx^2 + dy^2) + dz^2), first index on ties -- the
+// reference's linear scan -- plus the runner-up distance (equal to r1 on a tie).  Branch free; all lanes scan the same pair at the
+// same time (broadcast LDS.64).  Products packed (FMUL2), sums scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
+// under -fmad=false, which would change the rounding; scalar add.rn.f32 is never contracted.
+template <int CAP>
+__device__ __forceinline__ NN2 nn_scan_range(const SymObj<CAP> &O, float qx, float qy, float qz, int j0, int j1) {
   const unsigned long long qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
-  const int pairs = (B.M + 1) >> 1;
-  const int pp = (pairs + L - 1) / L;
-  const int j0 = part * pp, j1 = min(pairs, j0 + pp);
-  float bd = FLT_MAX; int best = 0x7fffffff;
+  float bd = FLT_MAX, sd = FLT_MAX; int best = 0x7fffffff;
+#pragma unroll 2
   for (int j = j0; j < j1; j++) {
-    unsigned long long dx = f2_sub(qx2, B.X2[j]), dy = f2_sub(qy2, B.Y2[j]), dz = f2_sub(qz2, B.Z2[j]);
+    const unsigned long long dx = f2_sub(qx2, O.X2[j]), dy = f2_sub(qy2, O.Y2[j]), dz = f2_sub(qz2, O.Z2[j]);
     const unsigned long long sx = f2_mul(dx, dx), sy = f2_mul(dy, dy), sz = f2_mul(dz, dz);
     const float r0 = __fadd_rn(__fadd_rn(__uint_as_float((unsigned)sx), __uint_as_float((unsigned)sy)), __uint_as_float((unsigned)sz));
     const float r1 = __fadd_rn(__fadd_rn(__uint_as_float((unsigned)(sx >> 32)), __uint_as_float((unsigned)(sy >> 32))), __uint_as_float((unsigned)(sz >> 32)));
+    sd = fminf(sd, fmaxf(r0, bd));
     if (r0 < bd) { bd = r0; best = 2 * j; }
+    sd = fminf(sd, fmaxf(r1, bd));
     if (r1 < bd) { bd = r1; best = 2 * j + 1; }
   }
-  for (int o = slots; o < 32; o <<= 1) {   // merge the parts of the same query (lanes q, q+slots, q+2*slots, ...)
-    const float obd = __shfl_xor_sync(0xffffffffu, bd, o);
-    const int obest = __shfl_xor_sync(0xffffffffu, best, o);
-    if (obd < bd || (obd == bd && obest < best)) { bd = obd; best = obest; }
-  }
-  NNRes r; r.dis = 0.0; r.best = -1;
-  if (!active || part != 0 || best == 0x7fffffff) return r;
-  r.dis = dist_to_neighbour(B, pm, best); r.best = best;
+  NN2 r; r.r1 = bd; r.r2 = sd; r.best = best;
   return r;
 }
+template <int CAP>
+__device__ __noinline__ NN2 nn_scan(const SymObj<CAP> &O, float qx, float qy, float qz) {
+  NN2 r = nn_scan_range(O, qx, qy, qz, 0, (O.M + 1) >> 1);
+  if (r.best == 0x7fffffff) r.best = 0;   // every distance is +inf / NaN: the linear scan keeps index 0
+  return r;
+}
+// Warp-cooperative variant for a PARTIAL chunk of cq <= 16 queries: the 32 lanes are split into L = 32 / slots parts, part p scans the
+// p-th slice of the cloud for query (lane % slots); the parts are merged with an (r, index) lexicographic butterfly -- slices are
+// index-ordered, so "smallest r, then smallest index" is the linear scan's first-minimum rule.
+template <int CAP>
+__device__ __noinline__ NN2 nn_scan_split(const SymObj<CAP> &O, float qx, float qy, float qz, int slots) {
+  const int lane = threadIdx.x & 31;
+  const int L = 32 / slots, part = lane / slots;
+  const int pairs = (O.M + 1) >> 1, pp = (pairs + L - 1) / L;
+  const int j0 = part * pp, j1 = min(pairs, j0 + pp);
+  NN2 r = nn_scan_range(O, qx, qy, qz, j0, j1);
+  for (int o = slots; o < 32; o <<= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, r.r1, o), os = __shfl_xor_sync(0xffffffffu, r.r2, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, r.best, o);
+    r.r2 = fminf(fminf(r.r2, os), fmaxf(r.r1, ob));
+    if (ob < r.r1 || (ob == r.r1 && oi < r.best)) { r.r1 = ob; r.best = oi; }
+  }
+  if (r.best == 0x7fffffff) r.best = 0;
+  return r;
+}
+// cache word of a scanned query: rho^2 (rounded down, low mantissa bits cleared) | neighbour index.  rho = (d2 - d1) / 2 with both
+// distances moved 8e-6 relative against us (float rounding of the reference's r, of this scan and of the later |q - q0|^2).
+__device__ __forceinline__ float nn_pack(const NN2 &r) {
+  const float a = sqrtf(r.r1), b = sqrtf(r.r2);
+  const float gap = b * (1.0f - 8e-6f) - a * (1.0f + 8e-6f);
+  float rho2 = 0.0f;
+  if (gap > 0.0f) { const float hh = 0.5f * gap; rho2 = fminf(hh * hh * (1.0f - 1e-4f), 1e30f); }
+  return __uint_as_float((__float_as_uint(rho2) & ~kIdxMask) | (unsigned)r.best);
+}
+// does the cached entry c decide the neighbour of float query (qx, qy, qz)?  `safe`: also for any query within kNnSafe of it
+__device__ __forceinline__ bool nn_cached(float4 c, float qx, float qy, float qz, bool &safe) {
+  const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+  const float s2 = dx * dx + dy * dy + dz * dz;
+  const float rho2 = __uint_as_float(__float_as_uint(c.w) & ~kIdxMask);
+  const bool same = __float_as_uint(qx) == __float_as_uint(c.x) && __float_as_uint(qy) == __float_as_uint(c.y) && __float_as_uint(qz) == __float_as_uint(c.z);
+  const bool hit = (s2 < rho2) || same;
+  // safe <=> sqrt(s2) (1 + 1e-6) + kNnSafe < sqrt(rho2) (1 - 1e-6), decided on squares: (a + k)^2 <= 2 a^2 + 2 k^2
+  safe = hit && (2.0f * s2 * (1.0f + 4e-6f) + 2.0f * kNnSafe * kNnSafe < rho2 * (1.0f - 4e-6f));
+  return hit;
+}
 
-// edge error (= -mean ln P) for the prepared plane pair PP (shared memory); warp-collective, every lane returns the same value.
-// Fast path (#points <= kSymQueue): (1) classify all mirrored points; points that need a nearest-neighbour distance either hit the
-// NN cache or are compacted into a per-warp queue so that (2) the brute-force searches run with full lanes; (3) ln P accumulated in
-// the reference's point order -- over the points with a distance only: every other point contributes -0.0, which never changes the sum.
-// (__noinline__: the kernel is instruction-fetch bound when the ~1k-instruction evaluation body is replicated at its call sites)
-__device__ __noinline__ double sym_eval(const SymBlock &B, SymWarp &W, const PlanePair &PP, bool update_cache = true) {
+// ---------------------------------------------------------------------------------------------------------------- generic path
+// M > CAP (never seen at the reference's 0.1 m grid; kept for completeness): global-memory cloud, no caches, point by point.
+template <int CAP>
+__device__ __noinline__ double eval_generic(const SymObj<CAP> &O, SymSeed<CAP> &S, const PlanePair &PP) {
+  const int lane = threadIdx.x & 31;
+  const int npts = O.npts, M = O.M;
+  double ln_total = 0.0; int invalid = 0;
+  for (int base = 0; base < npts; base += 32) {
+    const int idx = base + lane;
+    double lnP = 0.0; int cls = 0;
+    if (idx < npts) {
+      const bool second = idx >= M;
+      const d3 pm = mirror_q(load_pt(O, idx - (second ? M : 0)), second ? PP.p2 : PP.p1, second ? PP.n2 : PP.n1, second ? PP.down2 : PP.down1);
+      uint4 scratch; bool rob;
+      cls = classify(O, pm, make_uint4(0xffffffffu, 0u, 0u, 0u), &scratch, rob);
+      double dis = 0.0;
+      if (cls == 1) {
+        const float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
+        float bd = FLT_MAX; int best = 0;
+        for (int k = 0; k < M; k++) {
+          const float4 q = O.nn_g[k];
+          float dd = __fsub_rn(qx, q.x);
+          float r = __fmul_rn(dd, dd);
+          dd = __fsub_rn(qy, q.y); r = __fadd_rn(r, __fmul_rn(dd, dd));
+          dd = __fsub_rn(qz, q.z); r = __fadd_rn(r, __fmul_rn(dd, dd));
+          if (r < bd) { bd = r; best = k; }
+        }
+        const float4 q = O.nn_g[best];
+        const double dx = pm.x - (double)q.x, dy = pm.y - (double)q.y, dz = pm.z - (double)q.z;
+        dis = sqrt(dx * dx + dy * dy + dz * dz);
+      }
+      lnP = O.coef * dis * dis;
+    }
+    const int cnt = min(32, npts - base);
+    for (int k = 0; k < cnt; k++) ln_total += __shfl_sync(0xffffffffu, lnP, k);
+    invalid += __popc(__ballot_sync(0xffffffffu, cls == 2));
+  }
+  if (lane == 0) { S.n_evals++; S.n_points += npts; }
+  const int num_valid = npts - invalid;
+  const double aver = (num_valid > 0) ? (ln_total / (double)num_valid) : -INFINITY;
+  return -aver;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- one plane, one warp
+// (fallback of the finite-difference pass; the trial planes go through classify_chunk / scan_chunk below)
+// Edge error (= -mean ln P) of the prepared plane pair PP; warp-collective, every lane returns the same value.
+// wbank >= 0: the evaluation becomes the state of bank `wbank` (NN cache entries + robust masks), read from bank S.cur;
+// wbank < 0:  read-only (finite-difference fallback).
+// (1) classify all mirrored points of a half; a point that needs a distance either hits the NN cache or is queued, (2) the queued
+// points are scanned with full lanes, (3) ln P accumulated in point order over the points that carry a distance (every other point
+// contributes -0.0, which never changes the sum).
+template <int CAP, bool VERIFY>
+__device__ __noinline__ double eval_single(const SymObj<CAP> &O, SymSeed<CAP> &S, const PlanePair &PP, int wbank) {
+  if (CAP > 256 && !O.in_smem) return eval_generic(O, S, PP);
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const int npts = B.npts;
+  const int npts = O.npts, M = O.M;
+  const double coef = O.coef;
+  const float4 *rc = S.nnc[S.cur];
+  unsigned *queue = reinterpret_cast<unsigned *>(S.lnp + CAP);   // warp-local evaluation: compact ln P list in the first half, queue in the second
+  float4 *wc = wbank >= 0 ? S.nnc[wbank] : nullptr;
   double ln_total = 0.0;
   int invalid = 0;
-  if (B.M <= kSymQueue) {
-    // the mirrored cloud is processed in halves of M points (plane 1, then the dual plane), so the per-warp queue / distance slots
-    // only need M entries; ln P keeps accumulating in the reference's point order across the halves
-    const double sinv = B.sinv;
-    for (int h0 = 0; h0 < npts; h0 += B.M) {
-      const int cntp = min(B.M, npts - h0);
-      int qn = 0, nzn = 0, hits = 0;
-      const long long t_a = clock64();
-      for (int base = 0; base < cntp; base += 32) {
-        const int li = base + lane;
-        int cls = 0;
-        double dis = 0.0;
-        if (li < cntp) {
-          const float4 c = W.cache[h0 + li];   // both cache entries are requested before the fp64 classification chain
-          const uint4 pc = W.pcache[h0 + li];
-          const d3 pm = mirrored(B, PP, h0 + li);
-          cls = classify(B, pm, pc, W.pcache + h0 + li);
-          // NN cache: a bit-identical float query has the same exact nearest neighbour (the +-1e-9 finite-difference perturbations
-          // of the plane often leave the float-rounded mirrored point unchanged), so the brute-force scan is skipped.
-          if (cls == 1 && __float_as_uint(c.x) == __float_as_uint((float)pm.x) && __float_as_uint(c.y) == __float_as_uint((float)pm.y) &&
-              __float_as_uint(c.z) == __float_as_uint((float)pm.z)) {
-            dis = dist_to_neighbour(B, pm, __float_as_int(c.w));
-            cls = 3;
+  for (int half = 0; half * M < npts; half++) {
+    const int h0 = half * M;
+    const double *q = half ? PP.p2 : PP.p1, *n = half ? PP.n2 : PP.n1;
+    const double down = half ? PP.down2 : PP.down1;
+    int qn = 0, nzn = 0, hits = 0;
+    for (int base = 0; base < M; base += 32) {
+      const int li = base + lane;
+      int cls = 0; bool rob = true, safe = false, hit = false;
+      double dis = 0.0;
+      if (li < M) {
+        const float4 c = rc[h0 + li];   // both cache entries are requested before the fp64 classification chain
+        const uint4 pc = S.pxc[h0 + li];
+        const d3 pm = mirror_q(load_pt(O, li), q, n, down);
+        cls = classify(O, pm, pc, S.pxc + h0 + li, rob);
+        if (cls == 1) {
+          hit = nn_cached(c, (float)pm.x, (float)pm.y, (float)pm.z, safe);
+          if (hit) {
+            const int best = (int)(__float_as_uint(c.w) & kIdxMask);
+            dis = dist_to_neighbour(O, pm, best);
+            if (VERIFY) { const NN2 r = nn_scan(O, (float)pm.x, (float)pm.y, (float)pm.z); if (r.best != best) atomicAdd(&S.n_verify_fail, 1u); }
           }
         }
-        const unsigned need = __ballot_sync(0xffffffffu, cls == 1);
-        const unsigned hit = __ballot_sync(0xffffffffu, cls == 3);
-        const int pos = nzn + __popc((need | hit) & lt);    // slot in the ordered list of points that carry a distance
-        if (cls == 3) W.dis[pos] = dis;
-        if (cls == 1) W.queue[qn + __popc(need & lt)] = (unsigned short)(li | (pos << 8));   // li, pos < 256
-        qn += __popc(need); nzn += __popc(need | hit); hits += __popc(hit);
-        invalid += __popc(__ballot_sync(0xffffffffu, cls == 2));
+        if (wc && !(cls == 1 && !hit)) wc[h0 + li] = c;   // carried forward (the scanned points write their new entry below)
       }
-      __syncwarp();
-      const long long t_b = clock64();
-      if (lane == 0) { W.n_evals++; W.n_queries += qn; W.n_points += cntp; W.n_hits += hits; }
-      for (int qb = 0; qb < qn; qb += 32) {
-        const int cq = min(32, qn - qb);
-        if (cq > 16) {
-          if (lane < cq) {
-            const int e = W.queue[qb + lane], li = e & 255;
-            const d3 pm = mirrored(B, PP, h0 + li);
-            const NNRes r = nn_distance(B, pm);
-            W.dis[e >> 8] = r.dis;
-            if (update_cache) W.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
-          }
-        } else {   // partial chunk: split every query's scan over several lanes
-          int slots = 1;
-          while (slots < cq) slots <<= 1;
-          const int q = lane % slots;
-          const bool active = q < cq;
-          const int e = W.queue[qb + (active ? q : 0)], li = e & 255;
-          const d3 pm = mirrored(B, PP, h0 + li);
-          const NNRes r = nn_distance_split(B, pm, slots, active);
-          if (active && lane < slots) {
-            W.dis[e >> 8] = r.dis;
-            if (update_cache) W.cache[h0 + li] = make_float4((float)pm.x, (float)pm.y, (float)pm.z, __int_as_float(r.best));
-          }
-        }
-      }
-      __syncwarp();
-      const long long t_c = clock64();
-      for (int base = 0; base < nzn; base += 32) {
-        const double dis = (base + lane < nzn) ? W.dis[base + lane] : 0.0;
-        const double lnP = -0.5 * sinv * sinv * dis * dis;
-        const int cnt = min(32, nzn - base);
-        for (int k = 0; k < cnt; k++) ln_total += __shfl_sync(0xffffffffu, lnP, k);
-      }
-      __syncwarp();
-      if (lane == 0) { const long long t_d = clock64(); W.clk[0] += t_b - t_a; W.clk[1] += t_c - t_b; W.clk[2] += t_d - t_c; }
-    }
-  } else {
-    const double sinv = B.sinv;
-    for (int base = 0; base < npts; base += 32) {
-      const int idx = base + lane;
-      double lnP = 0.0; int cls = 0;
-      if (idx < npts) {
-        const d3 pm = mirrored(B, PP, idx);
-        uint4 scratch;
-        cls = classify(B, pm, make_uint4(0xffffffffu, 0u, 0u, 0u), &scratch);
-        const double dis = (cls == 1) ? nn_distance(B, pm).dis : 0.0;
-        lnP = -0.5 * sinv * sinv * dis * dis;
-      }
-      const int cnt = min(32, npts - base);
-      for (int k = 0; k < cnt; k++) ln_total += __shfl_sync(0xffffffffu, lnP, k);
+      const unsigned need = __ballot_sync(0xffffffffu, cls == 1 && !hit);
+      const unsigned hitm = __ballot_sync(0xffffffffu, hit);
+      const int pos = nzn + __popc((need | hitm) & lt);    // slot in the ordered list of points that carry a distance
+      if (hit) S.lnp[pos] = coef * dis * dis;
+      if (cls == 1 && !hit) queue[qn + __popc(need & lt)] = (unsigned)li | ((unsigned)pos << 9) | (rob ? 0x80000000u : 0u);
+      qn += __popc(need); nzn += __popc(need | hitm); hits += __popc(hitm);
       invalid += __popc(__ballot_sync(0xffffffffu, cls == 2));
+      if (wbank >= 0) {
+        const unsigned a = __ballot_sync(0xffffffffu, cls == 1 || !rob), f = __ballot_sync(0xffffffffu, cls == 1 && rob && safe);
+        if (lane == 0) { S.mA[wbank][half][base >> 5] = a; S.mF[wbank][half][base >> 5] = f; }
+      }
     }
+    __syncwarp();
+    if (lane == 0) { S.n_evals++; S.n_queries += qn; S.n_points += M; S.n_hits += hits; }
+    for (int qb = 0; qb < qn; qb += 32) {
+      const int cq = min(32, qn - qb);
+      int slots = 32;
+      if (cq <= 16) { slots = 1; while (slots < cq) slots <<= 1; }
+      const int ql = lane % slots;
+      const bool active = ql < cq;
+      const unsigned e = queue[qb + (active ? ql : 0)];
+      const int li = (int)(e & 511u), pos = (int)((e >> 9) & 511u);
+      const d3 pm = mirror_q(load_pt(O, li), q, n, down);
+      const float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
+      NN2 r;
+      if (slots == 32) { if (active) r = nn_scan(O, qx, qy, qz); }
+      else r = nn_scan_split(O, qx, qy, qz, slots);
+      if (active && lane < slots) {
+        const double dis = dist_to_neighbour(O, pm, r.best);
+        S.lnp[pos] = coef * dis * dis;
+        if (wbank >= 0) {
+          const float w = nn_pack(r);
+          wc[h0 + li] = make_float4(qx, qy, qz, w);
+          const float rho2 = __uint_as_float(__float_as_uint(w) & ~kIdxMask);
+          if ((e & 0x80000000u) && rho2 * (1.0f - 4e-6f) > kNnSafe * kNnSafe) atomicOr(&S.mF[wbank][half][li >> 5], 1u << (li & 31));
+        }
+      }
+    }
+    __syncwarp();
+    {   // ordered sum: every lane runs the same chain on broadcast loads
+      int k = 0;
+      for (; k + 4 <= nzn; k += 4) {
+        const double2 a = *reinterpret_cast<const double2 *>(&S.lnp[k]), b = *reinterpret_cast<const double2 *>(&S.lnp[k + 2]);
+        ln_total += a.x; ln_total += a.y; ln_total += b.x; ln_total += b.y;
+      }
+      for (; k < nzn; k++) ln_total += S.lnp[k];
+    }
+    __syncwarp();
   }
   const int num_valid = npts - invalid;
   const double aver = (num_valid > 0) ? (ln_total / (double)num_valid) : -INFINITY;
   return -aver;
 }
-// evaluation of a single plane: lane 0 prepares the pair
-__device__ __forceinline__ double sym_eval_plane(const SymBlock &B, SymWarp &W, const dplane *pl) {
-  if ((threadIdx.x & 31) == 0) make_pair(W.pp, *pl);
-  __syncwarp();
-  return sym_eval(B, W, W.pp);
+
+// ---------------------------------------------------------------------------------------------------------------- one plane, any warps
+// The evaluation of a trial plane (S.pp, result = state of bank S.wbank) cut into independent tasks: classify_chunk takes 32 points of
+// one half (ln P of the cache hits and -0.0 of the cost-free points into S.lnp[point], scan candidates into S.queue), scan_chunk
+// takes 32 queued points; the ordered sum over S.lnp runs in the scalar phase.
+template <int CAP, bool VERIFY>
+__device__ __noinline__ void classify_chunk(const SymObj<CAP> &O, SymSeed<CAP> &S, int half, int chunk) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int M = O.M, h0 = half * M, wbank = S.wbank;
+  const PlanePair &PP = S.pp;
+  const double *q = half ? PP.p2 : PP.p1, *n = half ? PP.n2 : PP.n1;
+  const double down = half ? PP.down2 : PP.down1;
+  const int li = chunk * 32 + lane;
+  int cls = 0; bool rob = true, safe = false, hit = false;
+  if (li < M) {
+    const float4 c = S.nnc[S.cur][h0 + li];   // both cache entries are requested before the fp64 classification chain
+    const uint4 pc = S.pxc[h0 + li];
+    const d3 pm = mirror_q(load_pt(O, li), q, n, down);
+    cls = classify(O, pm, pc, S.pxc + h0 + li, rob);
+    double lnp = -0.0;
+    if (cls == 1) {
+      hit = nn_cached(c, (float)pm.x, (float)pm.y, (float)pm.z, safe);
+      if (hit) {
+        const int best = (int)(__float_as_uint(c.w) & kIdxMask);
+        const double dis = dist_to_neighbour(O, pm, best);
+        lnp = O.coef * dis * dis;
+        if (VERIFY) { const NN2 r = nn_scan(O, (float)pm.x, (float)pm.y, (float)pm.z); if (r.best != best) atomicAdd(&S.n_verify_fail, 1u); }
+      }
+    }
+    S.lnp[h0 + li] = lnp;
+    if (!(cls == 1 && !hit)) S.nnc[wbank][h0 + li] = c;   // carried forward (the scanned points write their new entry later)
+  }
+  const unsigned need = __ballot_sync(0xffffffffu, cls == 1 && !hit);
+  const unsigned a = __ballot_sync(0xffffffffu, cls == 1 || !rob), f = __ballot_sync(0xffffffffu, cls == 1 && rob && safe);
+  const int ninv = __popc(__ballot_sync(0xffffffffu, cls == 2));
+  const int nhit = __popc(__ballot_sync(0xffffffffu, hit));
+  int qbase = 0;
+  if (lane == 0) {
+    S.mA[wbank][half][chunk] = a; S.mF[wbank][half][chunk] = f;
+    if (need) qbase = atomicAdd(&S.qn, __popc(need));
+    if (ninv) atomicAdd(&S.invalid, ninv);
+    if (nhit) atomicAdd(&S.n_hits, (unsigned)nhit);
+  }
+  qbase = __shfl_sync(0xffffffffu, qbase, 0);
+  if (cls == 1 && !hit) S.queue[qbase + __popc(need & lt)] = (unsigned short)(li | (half << 9) | (rob ? 0x8000 : 0));
+}
+template <int CAP, bool VERIFY>
+__device__ __noinline__ void scan_chunk(const SymObj<CAP> &O, SymSeed<CAP> &S, int qb) {
+  const int lane = threadIdx.x & 31;
+  const int M = O.M, wbank = S.wbank;
+  const PlanePair &PP = S.pp;
+  const int cq = min(32, S.qn - qb);
+  int slots = 32;
+  if (cq <= 16) { slots = 1; while (slots < cq) slots <<= 1; }
+  const int ql = lane % slots;
+  const bool active = ql < cq;
+  const unsigned e = S.queue[qb + (active ? ql : 0)];
+  const int li = (int)(e & 511u), half = (int)((e >> 9) & 1u), h0 = half * M;
+  const d3 pm = mirror_q(load_pt(O, li), half ? PP.p2 : PP.p1, half ? PP.n2 : PP.n1, half ? PP.down2 : PP.down1);
+  const float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
+  NN2 r;
+  if (slots == 32) { if (active) r = nn_scan(O, qx, qy, qz); }
+  else r = nn_scan_split(O, qx, qy, qz, slots);
+  if (active && lane < slots) {
+    const double dis = dist_to_neighbour(O, pm, r.best);
+    S.lnp[h0 + li] = O.coef * dis * dis;
+    const float w = nn_pack(r);
+    S.nnc[wbank][h0 + li] = make_float4(qx, qy, qz, w);
+    const float rho2 = __uint_as_float(__float_as_uint(w) & ~kIdxMask);
+    if ((e & 0x8000u) && rho2 * (1.0f - 4e-6f) > kNnSafe * kNnSafe) atomicOr(&S.mF[wbank][half][li >> 5], 1u << (li & 31));
+  }
 }
 
-__device__ __noinline__ void sym_oplus(dplane &p, const double *u, int symtype) {
-  if (symtype == 1) plane_oplus_common(p, u[0], 0.0, u[1]);           // VertexPlane: (yaw, 0, dis)   :527-532, Plane.h:46-59
-  else { plane_oplus_common(p, u[0], 0.0, u[1]); p.dual += u[2]; }    // VertexDualPlane             :544-547, Plane.h:62-77
+// ---------------------------------------------------------------------------------------------------------------- 2*dim planes
+// All finite-difference planes of one linearisation in ONE pass over the points of bank S.cur (the evaluation of S.est).  Writes
+// S.J[0..DIM).  Returns false (nothing written) when a half has more than kSlowMax non-robust points: the caller falls back to
+// read-only single-plane evaluations.
+template <int CAP, int DIM, bool VERIFY>
+__device__ __noinline__ bool eval_fd(const SymObj<CAP> &O, SymSeed<CAP> &S) {
+  constexpr int NFD = 2 * DIM;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int npts = O.npts, M = O.M, cur = S.cur;
+  const double coef = O.coef;
+  const float4 *rc = S.nnc[cur];
+  double (*stage)[33] = reinterpret_cast<double (*)[33]>(S.lnp);
+  double (*side)[kSlowMax] = reinterpret_cast<double (*)[kSlowMax]>(S.queue);
+  double ln_tot = 0.0;   // lanes < NFD: ordered sum of plane `lane`
+  if (lane < 6) S.inv_s[lane] = 0;
+  unsigned visited = 0;
+  for (int half = 0; half * M < npts; half++) {
+    const int h0 = half * M;
+    // compact lists of the active and of the slow (active, not fast) points, in point order
+    int n_act = 0, n_slow = 0;
+    for (int w = 0; w * 32 < M; w++) {
+      const unsigned A = S.mA[cur][half][w], F = S.mF[cur][half][w], Sl = A & ~F;
+      if (A >> lane & 1u) S.list[n_act + __popc(A & lt)] = (unsigned short)(w * 32 + lane);
+      if (Sl >> lane & 1u) { const int k = n_slow + __popc(Sl & lt); if (k < kSlowMax) S.slow[k] = (unsigned short)(w * 32 + lane); }
+      n_act += __popc(A); n_slow += __popc(Sl);
+    }
+    if (n_slow > kSlowMax) return false;   // warp uniform
+    __syncwarp();
+    visited += (unsigned)n_act;
+    // slow points: one lane per (point, plane), full classification, cached or scanned neighbour
+    for (int it = lane; it < n_slow * NFD; it += 32) {
+      const int s = it / NFD, k = it - s * NFD;
+      const int li = S.slow[s];
+      const PlanePair &Q = S.fd[k];
+      const d3 pm = mirror_q(load_pt(O, li), half ? Q.p2 : Q.p1, half ? Q.n2 : Q.n1, half ? Q.down2 : Q.down1);
+      bool rob, safe;
+      uint4 scratch;   // several lanes may hold the same point: the pixel cache is read, not written
+      const int cls = classify(O, pm, S.pxc[h0 + li], &scratch, rob);
+      double val = -0.0;
+      if (cls == 1) {
+        const float qx = (float)pm.x, qy = (float)pm.y, qz = (float)pm.z;
+        const float4 c = rc[h0 + li];
+        int best;
+        if (nn_cached(c, qx, qy, qz, safe)) best = (int)(__float_as_uint(c.w) & kIdxMask);
+        else best = nn_scan(O, qx, qy, qz).best;
+        const double dis = dist_to_neighbour(O, pm, best);
+        val = coef * dis * dis;
+      }
+      if (cls == 2) atomicAdd(&S.inv_s[k], 1);
+      side[k][s] = val;
+    }
+    __syncwarp();
+    const double *objn = O.objn;
+    for (int base = 0; base < n_act; base += 32) {
+      const bool e = base + lane < n_act;
+      const int li = e ? (int)S.list[base + lane] : 0;
+      const bool fast = e && ((S.mF[cur][half][li >> 5] >> (li & 31)) & 1u);
+      d3 pt = mk3(0, 0, 0);
+      double bx = 0, by = 0, bz = 0;
+      int best = 0, sslot = 0;
+      if (fast) {
+        best = (int)(__float_as_uint(rc[h0 + li].w) & kIdxMask);
+        pt = mk3(objn[3 * li], objn[3 * li + 1], objn[3 * li + 2]);
+        const unsigned long long X = O.X2[best >> 1], Y = O.Y2[best >> 1], Z = O.Z2[best >> 1];
+        const int sh = (best & 1) * 32;
+        bx = (double)__uint_as_float((unsigned)(X >> sh)); by = (double)__uint_as_float((unsigned)(Y >> sh)); bz = (double)__uint_as_float((unsigned)(Z >> sh));
+      } else if (e) {
+        for (int s = 0; s < n_slow; s++) if ((int)S.slow[s] == li) sslot = s;
+      }
+#pragma unroll 2
+      for (int k = 0; k < NFD; k++) {
+        double val = -0.0;
+        if (fast) {
+          const PlanePair &Q = S.fd[k];
+          const d3 pm = mirror_q(pt, half ? Q.p2 : Q.p1, half ? Q.n2 : Q.n1, half ? Q.down2 : Q.down1);
+          const double dx = pm.x - bx, dy = pm.y - by, dz = pm.z - bz;
+          const double dis = sqrt(dx * dx + dy * dy + dz * dz);
+          val = coef * dis * dis;
+          if (VERIFY) {   // the full path must agree: same class, same neighbour
+            bool rob2; uint4 scratch;
+            const int cls = classify(O, pm, make_uint4(0xffffffffu, 0u, 0u, 0u), &scratch, rob2);
+            const NN2 r = nn_scan(O, (float)pm.x, (float)pm.y, (float)pm.z);
+            if (cls != 1 || r.best != best) atomicAdd(&S.n_verify_fail, 1u);
+          }
+        } else if (e) {
+          val = side[k][sslot];
+        }
+        stage[k][lane] = val;
+      }
+      __syncwarp();
+      if (lane < NFD) {
+        const int cnt = min(32, n_act - base);
+        const double *row = stage[lane];
+#pragma unroll 4
+        for (int i = 0; i < cnt; i++) ln_tot += row[i];
+      }
+      __syncwarp();
+    }
+  }
+  double err = 0.0;
+  if (lane < NFD) {
+    const int num_valid = npts - S.inv_s[lane];
+    const double aver = (num_valid > 0) ? (ln_tot / (double)num_valid) : -INFINITY;
+    err = -aver;
+  }
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    const double e1 = __shfl_sync(0xffffffffu, err, 2 * d), e2 = __shfl_sync(0xffffffffu, err, 2 * d + 1);
+    if (lane == 0) S.J[d] = (1.0 / (2 * 1e-9)) * (e1 - e2);
+  }
+  if (lane == 0) { S.n_evals += NFD; S.n_points += visited * NFD; }
+  __syncwarp();
+  return true;
 }
 
 template <int DIM>
 __device__ __noinline__ bool lm_solve_dim(const double *H, const double *b, double lambda, double *x) {
-  double M[DIM * DIM];
-  for (int i = 0; i < DIM * DIM; i++) M[i] = H[i];
-  for (int i = 0; i < DIM; i++) M[i * DIM + i] += lambda;
-  return ldlt_solve_small<DIM>(M, b, x);
+  double Mx[DIM * DIM];
+  for (int i = 0; i < DIM * DIM; i++) Mx[i] = H[i];
+  for (int i = 0; i < DIM; i++) Mx[i * DIM + i] += lambda;
+  return ldlt_solve_small<DIM>(Mx, b, x);
+}
+// Upper bound of the per-coordinate displacement of any mirrored point between plane pairs A (base) and B:
+// pm = pt - 2 (n.pt + c) n with c = p3 / |p|;  |d pm| <= 2 [ (|dn| R + |dc|) |n'| + (R + |c|) |dn| ].
+__device__ __forceinline__ bool fd_pair_ok(const PlanePair &A, const PlanePair &B, double R) {
+  bool ok = true;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const double *na = h ? A.n2 : A.n1, *nb = h ? B.n2 : B.n1;
+    const double ca = div_z(h ? A.p2[3] : A.p1[3], h ? A.down2 : A.down1), cb = div_z(h ? B.p2[3] : B.p1[3], h ? B.down2 : B.down1);
+    const double dn = 1.7320508075688774 * fmax(fmax(fabs(nb[0] - na[0]), fabs(nb[1] - na[1])), fabs(nb[2] - na[2]));
+    const double dc = fabs(cb - ca), cabs = fabs(ca);
+    const double dpm = 2.0 * ((dn * R + dc) * 1.001 + (R + cabs) * dn) + 1e-12;
+    ok = ok && (dpm <= kFdDelta) && (3.0 * R + 2.0 * cabs + 1e-3 <= kQMax);   // NaN anywhere -> false
+  }
+  return ok;
 }
 
-// OptimizeSymmetryPlane / OptimizeSymmetryDualPlane: one vertex, one unary edge (information 1), optimize(iters).
-// Warp-collective: lane 0 runs the scalar Levenberg-Marquardt bookkeeping on the shared-memory state, all lanes evaluate costs.
-// Two exact economies over the literal g2o call sequence: (1) computeActiveErrors() at the top of an iteration re-evaluates the plane
-// whose error is already known (the accepted trial, or the restored backup) -- the cost is a pure function, so the value is reused;
-// (2) the 2*dim finite-difference planes of a linearisation are prepared (oplus + mirror constants) by 2*dim lanes at once.
-__device__ void sym_optimize(const SymBlock &B, SymWarp &W, int iters) {
-  const int lane = threadIdx.x & 31;
-  const int symtype = B.symtype;
+// One scalar Levenberg-Marquardt step of a seed (OptimizeSymmetryPlane / OptimizeSymmetryDualPlane: one vertex, one unary edge with
+// information 1, optimize(iters); g2o optimization_algorithm_levenberg.cpp:61-164), run between two evaluation rounds by ONE LANE.
+// It consumes the result of the seed's last action (S.err_last / S.J) and prepares the next one.  Exact economy over the literal call
+// sequence: computeActiveErrors() at the top of an iteration re-evaluates the plane whose error is already known (the accepted trial,
+// or the restored backup) -- the cost is a pure function, so the value is reused.
+template <int CAP>
+__device__ __noinline__ void lm_step(const SymObj<CAP> &O, SymSeed<CAP> &S) {
+  const int symtype = O.symtype;
   const int dim = (symtype == 1) ? 2 : 3;
-  double err = sym_eval_plane(B, W, &W.est);   // value of the last computeError call
-  double err_est = err;                        // error of the plane currently held in W.est
-  if (lane == 0) { W.n_ref = 1; W.res.init_err = err; W.lambda = -1; W.ni = 2; W.nBad = 0; W.x[0] = W.x[1] = W.x[2] = 0; W.ok = 1; }
-  __syncwarp();
-  for (int it = 0; it < iters; it++) {
-    if (!W.ok) break;
-    err = err_est;                              // computeActiveErrors() at W.est
-    if (lane == 0) { W.n_ref += 1 + 2 * dim; W.currentChi = err * (1.0 * err); W.tempChi = W.currentChi; W.iniChi = W.currentChi; }
-    // linearizeOplus (numeric, delta 1e-9) + constructQuadraticForm
-    if (lane < 2 * dim) {
-      const int d = lane >> 1;
-      const double del = (lane & 1) ? -1e-9 : 1e-9;
-      double add[3];
-      add[0] = (d == 0) ? del : 0.0; add[1] = (d == 1) ? del : 0.0; add[2] = (d == 2) ? del : 0.0;
-      dplane t = W.est;
-      sym_oplus(t, add, symtype);
-      make_pair(W.fd[lane], t);
+  bool start_trial = false, begin_iter = false;
+  if (S.action == kActInit) {
+    S.n_ref = 1; S.res.init_err = S.err_last; S.err_est = S.err_last;
+    S.lambda = -1; S.ni = 2; S.nBad = 0; S.x[0] = S.x[1] = S.x[2] = 0; S.ok = 1; S.it = 0;
+    begin_iter = true;
+  } else if (S.action == kActFd) {
+    const double err = S.err_est;   // constructQuadraticForm with the error of `est`
+    for (int i = 0; i < dim; i++) {
+      S.b[i] = 0.0 - (S.J[i] * 1.0) * err;
+      for (int j = 0; j < dim; j++) S.H[i * dim + j] = 0.0 + (S.J[i] * 1.0) * S.J[j];
     }
-    __syncwarp();
-    for (int d = 0; d < dim; d++) {
-      // the finite-difference evaluations leave the NN cache on the queries of the base plane: their own queries are the base query or
-      // one float ulp beside it, so comparing against the base hits more often than comparing against the previous perturbation
-      const double e1 = sym_eval(B, W, W.fd[2 * d], false);
-      const double e2 = sym_eval(B, W, W.fd[2 * d + 1], false);
-      if (lane == 0) W.J[d] = (1.0 / (2 * 1e-9)) * (e1 - e2);
+    if (S.it == 0) {
+      double mx = 0;
+      for (int j = 0; j < dim; j++) mx = fmax(fabs(S.H[j * dim + j]), mx);
+      S.lambda = 1e-5 * mx; S.ni = 2; S.nBad = 0;
     }
-    if (lane == 0) {
-      for (int i = 0; i < dim; i++) {
-        W.b[i] = 0.0 - (W.J[i] * 1.0) * err;
-        for (int j = 0; j < dim; j++) W.H[i * dim + j] = 0.0 + (W.J[i] * 1.0) * W.J[j];
-      }
-      if (it == 0) {
-        double mx = 0;
-        for (int j = 0; j < dim; j++) mx = fmax(fabs(W.H[j * dim + j]), mx);
-        W.lambda = 1e-5 * mx; W.ni = 2; W.nBad = 0;
-      }
-      W.rho = 0; W.qmax = 0;
+    S.qmax = 0;
+    start_trial = true;
+  } else if (S.action == kActTrial) {
+    const double err = S.err_last;
+    S.n_ref++;
+    double tempChi = err * (1.0 * err);
+    if (!S.ok2) tempChi = DBL_MAX;
+    double rho = (S.currentChi - tempChi);
+    double scale = 0;
+    for (int j = 0; j < dim; j++) scale += S.x[j] * (S.lambda * S.x[j] + S.b[j]);
+    scale += 1e-3;
+    rho /= scale;
+    if (rho > 0 && isfinite(tempChi)) {
+      double alpha = 1. - pow((2 * rho - 1), 3.0);
+      alpha = fmin(alpha, 2. / 3.);
+      const double sf = fmax(1. / 3., alpha);
+      S.lambda *= sf; S.ni = 2; S.currentChi = tempChi;
+      S.err_est = err; S.cur ^= 1;   // the trial's evaluation is the state of `est` from now on
+    } else {
+      S.lambda *= S.ni; S.ni *= 2; S.est = S.backup;
     }
-    __syncwarp();
-    while (true) {
-      __syncwarp();   // every lane has read W.again / W.accepted of the previous trial before lane 0 overwrites them (racecheck: WAR)
-      if (lane == 0) {
-        W.backup = W.est;
-        double x[3] = {W.x[0], W.x[1], W.x[2]};
-        bool ok2 = (dim == 2) ? lm_solve_dim<2>(W.H, W.b, W.lambda, x) : lm_solve_dim<3>(W.H, W.b, W.lambda, x);
-        W.x[0] = x[0]; W.x[1] = x[1]; W.x[2] = x[2];
-        W.again = ok2 ? 1 : 0;   // reused as "ok2" until the decision below
-        sym_oplus(W.est, x, symtype);
+    S.qmax++;
+    if (rho < 0 && S.qmax < 10) start_trial = true;
+    else {
+      if (S.qmax == 10 || rho == 0) S.ok = 0;
+      else {
+        if ((S.iniChi - S.currentChi) * 1e3 < S.iniChi) S.nBad++; else S.nBad = 0;
+        if (S.nBad >= 3) S.ok = 0;
       }
-      __syncwarp();
-      err = sym_eval_plane(B, W, &W.est);
-      if (lane == 0) {
-        const bool ok2 = W.again != 0;
-        W.n_ref++;
-        double tempChi = err * (1.0 * err);
-        if (!ok2) tempChi = DBL_MAX;
-        double rho = (W.currentChi - tempChi);
-        double scale = 0;
-        for (int j = 0; j < dim; j++) scale += W.x[j] * (W.lambda * W.x[j] + W.b[j]);
-        scale += 1e-3;
-        rho /= scale;
-        if (rho > 0 && isfinite(tempChi)) {
-          double alpha = 1. - pow((2 * rho - 1), 3.0);
-          alpha = fmin(alpha, 2. / 3.);
-          const double sf = fmax(1. / 3., alpha);
-          W.lambda *= sf; W.ni = 2; W.currentChi = tempChi; W.accepted = 1;
-        } else {
-          W.lambda *= W.ni; W.ni *= 2; W.est = W.backup; W.accepted = 0;
-        }
-        W.tempChi = tempChi; W.rho = rho; W.qmax++;
-        W.again = (rho < 0 && W.qmax < 10) ? 1 : 0;
-        if (!W.again) {
-          if (W.qmax == 10 || rho == 0) W.ok = 0;
-          else {
-            if ((W.iniChi - W.currentChi) * 1e3 < W.iniChi) W.nBad++; else W.nBad = 0;
-            if (W.nBad >= 3) W.ok = 0;
-          }
-        }
-      }
-      __syncwarp();
-      if (W.accepted) err_est = err;   // W.est now holds the evaluated trial; otherwise it was restored to the backup (err_est unchanged)
-      if (!W.again) break;
+      S.it++;
+      begin_iter = true;
     }
   }
-  if (lane == 0) {
-    W.res.final_err = err;          // e->error() after optimize(): value of the LAST computeError call (possibly a rejected trial)
-    W.res.prob = exp(-err);
-    W.res.plane = W.est;
-    atomicAdd(&B.st->n_evals, (unsigned long long)W.n_evals); atomicAdd(&B.st->n_queries, (unsigned long long)W.n_queries);
-    atomicAdd(&B.st->n_points, (unsigned long long)W.n_points); atomicAdd(&B.st->n_hits, (unsigned long long)W.n_hits);
-    atomicAdd(&B.st->n_ref_evals, (unsigned long long)W.n_ref); atomicAdd(&B.st->n_ref_points, (unsigned long long)W.n_ref * (unsigned long long)B.npts);
+  if (begin_iter) {
+    if (S.it >= O.iters || !S.ok) {
+      S.res.final_err = S.err_last;   // e->error() after optimize(): value of the LAST computeError call (possibly a rejected trial)
+      S.res.prob = exp(-S.err_last);
+      S.res.plane = S.est;
+      S.action = kActDone;
+    } else {
+      S.err_last = S.err_est;         // computeActiveErrors() at `est`
+      S.n_ref += 1 + 2 * dim;
+      S.currentChi = S.err_est * (1.0 * S.err_est); S.iniChi = S.currentChi;
+      S.action = kActFd;
+    }
   }
-  __syncwarp();
+  if (start_trial) {
+    S.backup = S.est;
+    double x[3] = {S.x[0], S.x[1], S.x[2]};
+    const bool ok2 = (dim == 2) ? lm_solve_dim<2>(S.H, S.b, S.lambda, x) : lm_solve_dim<3>(S.H, S.b, S.lambda, x);
+    S.x[0] = x[0]; S.x[1] = x[1]; S.x[2] = x[2];
+    S.ok2 = ok2 ? 1 : 0;
+    sym_oplus(S.est, x, symtype);
+    make_pair(S.pp, S.est);
+    S.action = kActTrial;
+  }
 }
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -517,27 +810,43 @@ __device__ __noinline__ void finalize_object(const ObjMeta &m, ObjState &st, con
   }
 }
 
-// grid = 9 * n_obj one-warp CTAs: CTA b handles seed (b % 9) of object (b / 9).  Seeds are independent until the very end; the warp
-// that finishes LAST for an object (atomic counter) performs the completion/finalisation, so no warp ever waits at a barrier for a
-// slower seed and the SM keeps ~28 independent warps in flight (the kernel is latency / issue bound, not bandwidth bound).
-// S = seed warps per CTA (1 or 3; the warps of a CTA work on the same object and share its shared-memory cloud), MINB = CTAs per SM.
-template <int S, int MINB>
-__global__ void __launch_bounds__(32 * S, MINB) symmetry_finalize_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride,
-                                                                         const ObjMeta *__restrict__ metas, ObjState *__restrict__ states, ExtractParamsDev prm,
-                                                                         ExtractPtrs W, EslamEllipsoidOut *__restrict__ outs, int obj0) {
-  static_assert(9 % S == 0, "the seed warps of a CTA must belong to one object");
-  __shared__ SymBlock B;
-  __shared__ SymWarp Wps[S];
+// dense index of this SM (first touch): %smid is not dense on a B200 (148 SMs of a larger die), the cache pool is sized for sm_count
+__device__ __forceinline__ int dense_sm(int *map) {
+  unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (smid >= (unsigned)kMaxSmId) __trap();
+  volatile int *slot = map + smid;
+  int idx = *slot;
+  if (idx < 0) {
+    if (atomicCAS(map + smid, -1, -2) == -1) { idx = atomicAdd(map + kMaxSmId, 1); *slot = idx; __threadfence(); }
+    else { while ((idx = *slot) < 0) {} }
+  }
+  return idx;
+}
+
+template <int CAP> constexpr size_t sym_smem_bytes() { return sizeof(SymObj<CAP>) + kSeeds * sizeof(SymSeed<CAP>); }
+
+// grid = n_obj CTAs of nine warps: warp w owns seed w of the CTA's object.  Two instantiations share the launch: CAP = 256 takes the
+// objects with n_sym <= 256, CAP = 512 the rest (n_sym <= 512 on the cached path, larger clouds on the generic path); a CTA whose
+// object belongs to the other instantiation exits at once.
+template <int CAP, int MINB, bool VERIFY>
+__global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride,
+                                                                              const ObjMeta *__restrict__ metas, ObjState *__restrict__ states, ExtractParamsDev prm,
+                                                                              ExtractPtrs W, EslamEllipsoidOut *__restrict__ outs) {
+  extern __shared__ __align__(16) unsigned char sym_smem_raw[];
+  SymObj<CAP> &O = *reinterpret_cast<SymObj<CAP> *>(sym_smem_raw);
+  SymSeed<CAP> *seeds = reinterpret_cast<SymSeed<CAP> *>(sym_smem_raw + sizeof(SymObj<CAP>));
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  SymWarp &Wp = Wps[wid];
-  const int gseed = blockIdx.x * S + wid;
-  const int obj = gseed / 9, seed = gseed - obj * 9;
+  const int obj = blockIdx.x;
   const ObjMeta &m = metas[obj];
   ObjState &st = states[obj];
   EslamEllipsoidOut &out = outs[obj];
   const int status = st.status;
   const int run_sym = st.run_sym;
-  if (seed == 0 && lane == 0) {
+  const int M = st.n_sym;
+  const bool small = (CAP == 256);
+  if (status == 0 && run_sym) { if (small != (M <= 256)) return; }   // the other instantiation's object
+  else if (!small) return;                                           // objects without symmetry are closed by the CAP = 256 launch
+  if (threadIdx.x == 0) {
     for (int i = 0; i < 10; i++) out.ellipsoid[i] = 0;
     out.prob = 0; out.status = status; out.symmetry_type = m.symtype > 0 ? m.symtype : 0; out.symmetry_result = 0; out.best_seed = -1;
     for (int i = 0; i < 4; i++) { out.sym_plane_world[i] = 0; out.sym_plane2_world[i] = 0; }
@@ -547,99 +856,257 @@ __global__ void __launch_bounds__(32 * S, MINB) symmetry_finalize_kernel(const u
     if (!prm.symmetry_open) out.symmetry_type = 0;
   }
   if (status != 0) return;
-  if (!run_sym) {   // no symmetry for this label: seed 0 finalises directly
-    if (seed == 0) { __syncwarp(); finalize_object(m, st, prm, W, out); }
+  if (!run_sym) {   // no symmetry for this label: warp 0 finalises directly
+    if (wid == 0) { __syncwarp(); finalize_object(m, st, prm, W, out); }
     return;
   }
-  const int M = st.n_sym;
   const double *objn = W.objn + 3 * (size_t)m.off;
   const float4 *objnf = W.objnf + m.off;
-  // cache slot of this resident warp: a free bit of this SM's mask (at most 32 CTAs are resident per SM)
-  unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid));
-  if (smid >= (unsigned)kMaxSmId) __trap();
-  unsigned *slotword = W.slotmask + smid;
-  int slotbit = -1;
-  while (slotbit < 0) {   // warp-uniform control flow: lane 0 reads and claims, every lane follows the broadcast outcome
-    unsigned cur = 0;
-    if (lane == 0) cur = *((volatile unsigned *)slotword);
-    cur = __shfl_sync(0xffffffffu, cur, 0);
-    const unsigned freeb = ~cur;
-    if (freeb) {
-      const int b = __ffs(freeb) - 1;
-      unsigned old = 0;
-      if (lane == 0) old = atomicOr(slotword, 1u << b);
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if (!(old & (1u << b))) slotbit = b;
+  const bool in_smem = M <= CAP;
+  const int npts = (m.symtype == 2) ? 2 * M : M;
+  // cache slot of this resident CTA: a free bit of this SM's mask
+  if (threadIdx.x == 0) {
+    const int sm = dense_sm(W.smid_map);
+    if (sm >= W.sm_count) __trap();
+    unsigned *slotword = W.slotmask2 + (small ? 0 : W.sm_count) + sm;
+    int slotbit = -1;
+    while (slotbit < 0) {
+      const unsigned freeb = ~*((volatile unsigned *)slotword);
+      if (freeb) {
+        const int b = __ffs(freeb) - 1;
+        if (!(atomicOr(slotword, 1u << b) & (1u << b))) slotbit = b;
+      }
     }
+    O.sm = sm; O.slotbit = slotbit;
+    O.img = depth + (size_t)m.frame * frame_stride; O.pitch = pitch; O.st = &st;
+    O.objn = objn; O.nn_g = objnf; O.M = M; O.symtype = m.symtype; O.npts = npts; O.in_smem = in_smem ? 1 : 0;
+    for (int i = 0; i < 12; i++) O.P[i] = st.P[i];
+    O.A0 = fabs(O.P[0]) + fabs(O.P[1]) + fabs(O.P[2]); O.A1 = fabs(O.P[4]) + fabs(O.P[5]) + fabs(O.P[6]); O.A2 = fabs(O.P[8]) + fabs(O.P[9]) + fabs(O.P[10]);
+    O.cam[0] = st.T_oc[0]; O.cam[1] = st.T_oc[1]; O.cam[2] = st.T_oc[2];
+    O.bx0 = st.bbox_i[0]; O.by1 = st.bbox_i[1]; O.bx2 = st.bbox_i[2]; O.by3 = st.bbox_i[3];
+    O.rows = prm.rows; O.cols = prm.cols; O.fx = prm.fx; O.cx = prm.cx; O.cy = prm.cy; O.scale = prm.scale;
+    const double sinv = 1.0 / prm.sigma;
+    O.coef = -0.5 * sinv * sinv;   // ln P = -0.5 * Sigma_inv * Sigma_inv * d * d, evaluated left to right (:117-118)
+    O.iters = prm.symmetry_iters; O.n_live = kSeeds; O.R2 = 0.0;
   }
-  const size_t slot = (size_t)smid * 32 + slotbit;
-  float4 *cache = W.nncache + slot * (2 * kSymQueue);
-  uint4 *pcache = W.pixcache + slot * (2 * kSymQueue);
+  __syncthreads();
+  SymSeed<CAP> &S = seeds[wid];
   {
-    const bool in_smem = M <= kSymSmemPts;
-    // invalidate this warp's NN cache: a NaN x never equals a float-converted finite query
-    if (M <= kSymQueue) for (int j = lane; j < 2 * M; j += 32) {
-      cache[j] = make_float4(__uint_as_float(0x7fffffffu), 0.0f, 0.0f, 0.0f);
-      pcache[j] = make_uint4(0xffffffffu, 0u, 0u, 0u);   // no pixel has x = y = 65535
-    }
-    if (in_smem) for (int j = threadIdx.x; j < (M + 1) / 2; j += 32 * S) {
-      const float4 a = objnf[2 * j];
-      const float far_ = 1.0e30f;   // (q - 1e30)^2 overflows to +inf: never < FLT_MAX, so the pad can never win
-      const float4 b = (2 * j + 1 < M) ? objnf[2 * j + 1] : make_float4(far_, far_, far_, 0.0f);
-      B.X2[j] = f2_pack(a.x, b.x); B.Y2[j] = f2_pack(a.y, b.y); B.Z2[j] = f2_pack(a.z, b.z);
-    }
-    if (lane == 0) { Wp.cache = cache; Wp.pcache = pcache; Wp.n_evals = Wp.n_queries = Wp.n_points = Wp.n_hits = 0; Wp.accepted = 0; Wp.clk[0] = Wp.clk[1] = Wp.clk[2] = Wp.clk[3] = 0; }
-    if (threadIdx.x == 0) {
-      B.img = depth + (size_t)m.frame * frame_stride; B.pitch = pitch; B.st = &st;
-      B.objn = objn; B.nn_g = objnf; B.M = M; B.symtype = m.symtype; B.npts = (m.symtype == 2) ? 2 * M : M; B.in_smem = in_smem ? 1 : 0;
-      for (int i = 0; i < 12; i++) B.P[i] = st.P[i];
-      B.cam[0] = st.T_oc[0]; B.cam[1] = st.T_oc[1]; B.cam[2] = st.T_oc[2];
-      B.bx0 = st.bbox_i[0]; B.by1 = st.bbox_i[1]; B.bx2 = st.bbox_i[2]; B.by3 = st.bbox_i[3];
-      B.rows = prm.rows; B.cols = prm.cols; B.fx = prm.fx; B.cx = prm.cx; B.cy = prm.cy; B.scale = prm.scale;
-      B.sinv = 1.0 / prm.sigma;
+    constexpr int kSlots = small ? kSymSlots256 : kSymSlots512;
+    const size_t slot = (size_t)O.sm * kSlots + O.slotbit;
+    unsigned char *pool = (small ? W.sympool256 : W.sympool512) + (slot * kSeeds + wid) * ((size_t)CAP * 96);
+    float4 *nn0 = reinterpret_cast<float4 *>(pool), *nn1 = nn0 + 2 * CAP;
+    uint4 *pxc = reinterpret_cast<uint4 *>(nn1 + 2 * CAP);
+    if (in_smem) {
+      // invalidate this seed's caches: a NaN x never equals / is never within rho of a float query; no pixel has x = y = 65535
+      for (int j = lane; j < npts; j += 32) {
+        nn0[j] = make_float4(__uint_as_float(0x7fffffffu), 0.0f, 0.0f, 0.0f);
+        nn1[j] = make_float4(__uint_as_float(0x7fffffffu), 0.0f, 0.0f, 0.0f);
+        pxc[j] = make_uint4(0xffffffffu, 0u, 0u, 0u);
+      }
+      for (int j = threadIdx.x; j < (M + 1) / 2; j += blockDim.x) {
+        const float4 a = objnf[2 * j];
+        const float far_ = 1.0e30f;   // (q - 1e30)^2 overflows to +inf: never < FLT_MAX, so the pad can never win
+        const float4 b = (2 * j + 1 < M) ? objnf[2 * j + 1] : make_float4(far_, far_, far_, 0.0f);
+        O.X2[j] = f2_pack(a.x, b.x); O.Y2[j] = f2_pack(a.y, b.y); O.Z2[j] = f2_pack(a.z, b.z);
+      }
+      if (wid == 0) {
+        double r2 = 0.0;
+        for (int j = lane; j < M; j += 32) { const double x = objn[3 * j], y = objn[3 * j + 1], z = objn[3 * j + 2]; r2 = fmax(r2, x * x + y * y + z * z); }
+        r2 = warp_max_d(r2);
+        if (lane == 0) O.R2 = sqrt(r2) * 1.000001 + 1e-9;
+      }
     }
     if (lane == 0) {
+      S.nnc[0] = nn0; S.nnc[1] = nn1; S.pxc = pxc;
+      S.cur = 0; S.fd_ok = 0; S.action = kActInit;
+      S.n_evals = S.n_queries = S.n_points = S.n_hits = S.n_ref = S.n_verify_fail = 0;
       // GenerateInitPlanes (Symmetry.cpp:44-86): seed = i*3+m, dis = -0.2 + 0.2 i, angle = -5deg + 5deg m
       const double diff_dis = 0.2, diff_angle = M_PI / 180.0 * 5;
       const double start_dis = -diff_dis * 1, start_angle = -diff_angle * 1;
-      const int si = seed / 3, sm = seed % 3;
-      const double dis = start_dis + diff_dis * si, angle = start_angle + diff_angle * sm;
-      Wp.est.p[0] = sin(angle); Wp.est.p[1] = -cos(angle); Wp.est.p[2] = 0; Wp.est.p[3] = -dis; Wp.est.dual = 0;   // fromDisAngleTrans
+      const int si = wid / 3, sm_ = wid % 3;
+      const double dis = start_dis + diff_dis * si, angle = start_angle + diff_angle * sm_;
+      S.est.p[0] = sin(angle); S.est.p[1] = -cos(angle); S.est.p[2] = 0; S.est.p[3] = -dis; S.est.dual = 0;   // fromDisAngleTrans
+      make_pair(S.pp, S.est);
     }
-    if (S > 1) __syncthreads(); else __syncwarp();
   }
-  const long long t_seed0 = clock64();
-  sym_optimize(B, Wp, prm.symmetry_iters);
-  int prev = 0;
+  __syncthreads();
+  // Rounds.  Scalar phase (warp 0, one lane per seed): close the seed's running single-plane evaluation (ordered sum over S.lnp) and
+  // run its LM step; then the work of all live seeds is cut into tasks that ANY warp takes: a finite-difference pass per linearising
+  // seed (the longest tasks, handed out first), a classification task per 32 points of every trial plane, and -- one barrier
+  // later -- a scan task per 32 queued points.  Round 0 is the cost of the initial plane (bank 0), entered as a trial.
+  const int dim = (O.symtype == 1) ? 2 : 3;
+  const int nchunks = (M + 31) >> 5, nhalves = (npts > M) ? 2 : 1;
+  bool first = true;
+  while (true) {
+    if (wid == 0) {
+      if (lane < kSeeds) {
+        SymSeed<CAP> &T = seeds[lane];
+        if (first) { T.wbank = 0; T.qn = 0; T.invalid = 0; }
+        else if (T.action != kActDone) {
+          if (T.action != kActFd) {   // kActInit / kActTrial: the evaluation of T.pp is complete, sum ln P in point order
+            double ln_total = 0.0;
+            if (O.in_smem) {
+              int k = 0;
+              for (; k + 4 <= npts; k += 4) {
+                const double2 u = *reinterpret_cast<const double2 *>(&T.lnp[k]), v = *reinterpret_cast<const double2 *>(&T.lnp[k + 2]);
+                ln_total += u.x; ln_total += u.y; ln_total += v.x; ln_total += v.y;
+              }
+              for (; k < npts; k++) ln_total += T.lnp[k];
+              const int num_valid = npts - T.invalid;
+              const double aver = (num_valid > 0) ? (ln_total / (double)num_valid) : -INFINITY;
+              T.err_last = -aver;
+              T.n_evals += nhalves; T.n_queries += (unsigned)T.qn; T.n_points += (unsigned)npts;
+            }
+          }
+          lm_step(O, T);
+          T.wbank = T.cur ^ 1; T.qn = 0; T.invalid = 0;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {   // task list of the round: FD passes first, then the classification chunks
+        int nt = 0, live = 0;
+        for (int sd = 0; sd < kSeeds; sd++) if (seeds[sd].action == kActFd) { O.tasks[nt++] = (unsigned short)(sd << 8); live++; }
+        for (int sd = 0; sd < kSeeds; sd++) {
+          const int act = seeds[sd].action;
+          if (act != kActInit && act != kActTrial) continue;
+          live++;
+          if (!O.in_smem) { O.tasks[nt++] = (unsigned short)(0x3000 | (sd << 8)); continue; }   // generic path: the whole evaluation is one task
+          for (int hf = 0; hf < nhalves; hf++) for (int c = 0; c < nchunks; c++) O.tasks[nt++] = (unsigned short)(0x1000 | (sd << 8) | (hf << 7) | c);
+        }
+        O.n_tasks = nt; O.next_task = 0; O.n_live = live;
+      }
+    }
+    first = false;
+    __syncthreads();
+    if (O.n_live == 0) break;
+    while (true) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(&O.next_task, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= O.n_tasks) break;
+      const unsigned task = O.tasks[t];
+      SymSeed<CAP> &T = seeds[(task >> 8) & 15u];
+      const unsigned kind = task >> 12;
+      if (kind == 1) classify_chunk<CAP, VERIFY>(O, T, (int)((task >> 7) & 1u), (int)(task & 127u));
+      else if (kind == 3) { const double err = eval_generic(O, T, T.pp); if (lane == 0) T.err_last = err; }
+      else {
+        // linearizeOplus (numeric, delta 1e-9): the 2*dim perturbed planes prepared by 2*dim lanes, the base pair by lane 6
+        if (lane == 0) T.fd_ok = 1;
+        __syncwarp();
+        if (lane < 2 * dim) {
+          const int d = lane >> 1;
+          const double del = (lane & 1) ? -1e-9 : 1e-9;
+          double add[3];
+          add[0] = (d == 0) ? del : 0.0; add[1] = (d == 1) ? del : 0.0; add[2] = (d == 2) ? del : 0.0;
+          dplane tp = T.est;
+          sym_oplus(tp, add, O.symtype);
+          make_pair(T.fd[lane], tp);
+        } else if (lane == 6) {
+          make_pair(T.base, T.est);
+        }
+        __syncwarp();
+        if (lane < 2 * dim && !fd_pair_ok(T.base, T.fd[lane], O.R2)) T.fd_ok = 0;
+        __syncwarp();
+        bool done = false;
+        if (T.fd_ok && O.in_smem) done = (dim == 2) ? eval_fd<CAP, 2, VERIFY>(O, T) : eval_fd<CAP, 3, VERIFY>(O, T);
+        if (!done) {
+          for (int d = 0; d < dim; d++) {
+            const double e1 = eval_single<CAP, VERIFY>(O, T, T.fd[2 * d], -1);
+            const double e2 = eval_single<CAP, VERIFY>(O, T, T.fd[2 * d + 1], -1);
+            if (lane == 0) T.J[d] = (1.0 / (2 * 1e-9)) * (e1 - e2);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (O.in_smem) {   // scan tasks: 32 queued points of one trial plane each
+      if (threadIdx.x == 0) {
+        int nt = 0;
+        for (int sd = 0; sd < kSeeds; sd++) {
+          const int act = seeds[sd].action;
+          if (act != kActInit && act != kActTrial) continue;
+          for (int qb = 0; qb < seeds[sd].qn; qb += 32) O.tasks[nt++] = (unsigned short)((sd << 8) | (qb >> 5));
+        }
+        O.n_tasks = nt; O.next_task = 0;
+      }
+      __syncthreads();
+      while (true) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&O.next_task, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= O.n_tasks) break;
+        const unsigned task = O.tasks[t];
+        scan_chunk<CAP, VERIFY>(O, seeds[(task >> 8) & 15u], (int)(task & 255u) << 5);
+      }
+    }
+    __syncthreads();
+  }
+  // all seeds done: results to the object state, the slot back to the SM, completion by warp 0
   if (lane == 0) {
-    __threadfence();                          // this warp's cache stores are ordered before the next owner's
-    atomicAnd(slotword, ~(1u << slotbit));    // hand the cache slot back
-    Wp.clk[3] = clock64() - t_seed0 - Wp.clk[0] - Wp.clk[1] - Wp.clk[2];
-    for (int k = 0; k < 4; k++) atomicAdd((unsigned long long *)&st.sym_clk[k], (unsigned long long)Wp.clk[k]);
-    const SeedResult &r = Wp.res;
-    st.seed_prob[seed] = r.prob; st.seed_init[seed] = r.init_err; st.seed_final[seed] = r.final_err; st.seed_dual[seed] = r.plane.dual;
-    for (int k = 0; k < 4; k++) st.seed_plane[seed][k] = r.plane.p[k];
+    const SeedResult &r = S.res;
+    st.seed_prob[wid] = r.prob; st.seed_init[wid] = r.init_err; st.seed_final[wid] = r.final_err; st.seed_dual[wid] = r.plane.dual;
+    for (int k = 0; k < 4; k++) st.seed_plane[wid][k] = r.plane.p[k];
+    atomicAdd(&st.n_evals, (unsigned long long)S.n_evals); atomicAdd(&st.n_queries, (unsigned long long)S.n_queries);
+    atomicAdd(&st.n_points, (unsigned long long)S.n_points); atomicAdd(&st.n_hits, (unsigned long long)S.n_hits);
+    atomicAdd(&st.n_ref_evals, (unsigned long long)S.n_ref); atomicAdd(&st.n_ref_points, (unsigned long long)S.n_ref * (unsigned long long)O.npts);
+    if (VERIFY) atomicAdd(&st.n_verify_fail, (unsigned long long)S.n_verify_fail);
     __threadfence();
-    prev = atomicAdd(&st.done, 1);
   }
-  prev = __shfl_sync(0xffffffffu, prev, 0);
-  if (prev == 8) {   // last seed of this object: every other seed's results are visible (fence + atomic)
-    __threadfence();
-    finalize_object(m, st, prm, W, out);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();   // the cache stores of this CTA are ordered before the next owner's
+    atomicAnd(W.slotmask2 + (small ? 0 : W.sm_count) + O.sm, ~(1u << O.slotbit));
   }
+  if (wid == 0) finalize_object(m, st, prm, W, out);
 }
+
+template <int CAP, int MINB, bool VERIFY>
+cudaError_t launch_variant(cudaStream_t s, int n_obj, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, const ObjMeta *metas, ObjState *states,
+                           const ExtractParamsDev &prm, const ExtractPtrs &ptrs, EslamEllipsoidOut *outs) {
+  static bool attr[16] = {};   // per device
+  int dev = 0; cudaGetDevice(&dev);
+  const size_t smem = sym_smem_bytes<CAP>();
+  if (dev < 16 && !attr[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(symmetry_finalize_kernel<CAP, MINB, VERIFY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(symmetry_finalize_kernel<CAP, MINB, VERIFY>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    attr[dev] = true;
+  }
+  symmetry_finalize_kernel<CAP, MINB, VERIFY><<<n_obj, 32 * kSeeds, smem, s>>>(depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int symmetry_v1_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj, const ExtractParamsDev &prm,
+                       const ExtractPtrs &ptrs);
+
+size_t symmetry_pool_bytes(int cap) { return (size_t)kSeeds * (size_t)cap * 96; }   // cache bytes of one resident CTA
 
 int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj,
                              const ExtractParamsDev &prm, const ExtractPtrs &ptrs) {
   ExtractWorkspace &w = *h->ex;
   if (n_obj <= 0) return ESLAM_OK;
-  // Shape: one seed warp per CTA, 28 CTAs/SM (72 registers).  Measured alternatives (profiles/r01_kernel_shape_ab.txt): 3 seed warps per
-  // CTA sharing the cloud at 27 warps/SM (+13 % time) and at 36 warps/SM with a 56-register cap (+18 %, spills) are both slower.
-  if (!h->attr_symmetry) { ESLAM_CUDA_OK(h, cudaFuncSetAttribute(symmetry_finalize_kernel<1, 28>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); h->attr_symmetry = true; }
-  symmetry_finalize_kernel<1, 28><<<9 * n_obj, 32, 0, s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs,
-                                                           w.out.as<EslamEllipsoidOut>() + obj0, obj0);
-  ESLAM_LAUNCHED(h);
-  ESLAM_CUDA_OK(h, cudaGetLastError());
+  if (h->sym_impl == 1) return symmetry_v1_launch(h, s, depth_dev, pitch, frame_stride, obj0, n_obj, prm, ptrs);
+  const ObjMeta *metas = w.meta.as<ObjMeta>() + obj0;
+  ObjState *states = w.state.as<ObjState>() + obj0;
+  EslamEllipsoidOut *outs = w.out.as<EslamEllipsoidOut>() + obj0;
+  cudaError_t e;
+  if (h->sym_verify) {
+    e = launch_variant<256, 1, true>(s, n_obj, depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs);
+    if (e == cudaSuccess) e = launch_variant<512, 1, true>(s, n_obj, depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs);
+  } else {
+    switch (h->sym_occ) {   // env ESLAM_SYM_OCC: resident CTAs per SM of the CAP = 256 instantiation (register budget), tuning hook
+      case 2: e = launch_variant<256, 2, false>(s, n_obj, depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs); break;
+      case 4: e = launch_variant<256, 4, false>(s, n_obj, depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs); break;
+      default: e = launch_variant<256, kSymCtas256, false>(s, n_obj, depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs); break;
+    }
+    if (e == cudaSuccess) e = launch_variant<512, kSymCtas512, false>(s, n_obj, depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs);
+  }
+  ESLAM_CUDA_OK(h, e);
+  ESLAM_LAUNCHED(h); ESLAM_LAUNCHED(h);
   return ESLAM_OK;
 }
 

@@ -217,9 +217,10 @@ class Handle:
         self.check(self.lib.eslam_copy_ellipsoids_dev(self._h, C.c_void_p(stream), C.c_int(n_obj), C.c_void_p(dst_ptr)), "eslam_copy_ellipsoids_dev")
 
     def batch_counters(self):
-        out = (C.c_ulonglong * 8)()
+        out = (C.c_ulonglong * 12)()
         self.check(self.lib.eslam_batch_counters(self._h, out), "eslam_batch_counters")
-        keys = ("ref_evals", "ref_points", "evals", "points", "nn_scans", "nn_hits", "max_n_sym", "objects_with_symmetry")
+        keys = ("ref_evals", "ref_points", "evals", "points", "nn_scans", "nn_hits", "max_n_sym", "objects_with_symmetry", "verify_failures",
+                "clk_single_eval", "clk_nn_scan", "clk_scalar")
         return {k: int(v) for k, v in zip(keys, out)}
 
     def init_quadric(self, Twc, det5, K, rows=None, cols=None):

@@ -156,7 +156,7 @@ def test_pixels_outside_boxes_are_never_read(handle, kind, n_frames):
     pinned = torch.from_numpy(np.ascontiguousarray(poison_outside_boxes(depth, fo, bb, seed=11)).view(np.int16)).pin_memory().numpy().view(np.uint16)
     l0 = handle.launches
     p, _, _ = handle.estimate_ellipsoids(pinned, fo, bb, lb, tw)
-    assert bytes(p) == bytes(a) and handle.launches - l0 == 3        # pull + extract + symmetry
+    assert bytes(p) == bytes(a) and handle.launches - l0 == 4        # pull + extract + the two symmetry instantiations
     perm = np.random.default_rng(1).permutation(len(fo))
     q, _, _ = handle.estimate_ellipsoids(pinned, fo[perm], bb[perm], lb[perm], tw)
     for k, i in enumerate(perm):
@@ -441,3 +441,75 @@ def test_slam_mode_full_size_properties(handle):
     e1, T1, s1 = handle.optimize_slam(gg, p["init"], 10, odom_meas=p["odom"])
     assert np.isfinite(e1).all() and np.isfinite(T1).all()
     assert s1.chi2_final < 0.5 * s1.chi2_initial, (s1.chi2_initial, s1.chi2_final)
+
+
+# ------------------------------------------------------------------ symmetry kernel: shortcut decisions vs the long way
+def _handle_with_env(env, **params):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        prm = None
+        if params:
+            prm = E.default_params()
+            for k, v in params.items():
+                setattr(prm, k, v)
+        return E.Handle(params=prm)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _mixed_batch():
+    d1, f1, b1, l1, t1 = synth.make_batch(6, "one_box")
+    d2, f2, b2, l2, t2 = synth.make_batch(3, "multi_box")
+    return (np.concatenate([d1, d2]), np.concatenate([f1, f2 + len(d1)]).astype(np.int32), np.concatenate([b1, b2]), np.concatenate([l1, l2]).astype(np.int32),
+            np.concatenate([t1, t2]))
+
+
+def test_symmetry_kernel_equals_the_round1_kernel_bit_for_bit():
+    """The guarded decisions (pixel by reciprocal estimate, occlusion on squares, cached neighbour inside the safety radius, robust
+    points skipping the projection for the finite-difference planes) must reproduce the point-by-point kernel of round 1 exactly:
+    identical records, byte for byte, on single- and dual-symmetry objects."""
+    batch = _mixed_batch()
+    recs = []
+    for impl in ("1", "2"):
+        h = _handle_with_env({"ESLAM_SYM_IMPL": impl})
+        h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+        recs.append(bytes(h.estimate_ellipsoids(*batch)[0]))
+        h.close()
+    assert recs[0] == recs[1]
+
+
+def test_symmetry_verify_mode_finds_no_disagreement(handle):
+    """ESLAM_SYM_VERIFY=1 re-derives every shortcut decision the long way inside the kernel (full classification + brute-force scan)
+    and counts disagreements: none, and the records equal the normal run's."""
+    batch = _mixed_batch()
+    handle.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+    want = bytes(handle.estimate_ellipsoids(*batch)[0])
+    h = _handle_with_env({"ESLAM_SYM_VERIFY": "1"})
+    h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+    got = bytes(h.estimate_ellipsoids(*batch)[0])
+    c = h.batch_counters()
+    h.close()
+    assert c["verify_failures"] == 0 and c["objects_with_symmetry"] > 0 and c["nn_hits"] > 0
+    assert got == want
+
+
+@pytest.mark.parametrize("grid,lo,hi", [(0.05, 257, 512), (0.03, 513, 100000)])
+def test_symmetry_cloud_sizes_beyond_the_small_instantiation(grid, lo, hi):
+    """n_sym in (256, 512] runs on the cached CAP = 512 instantiation, n_sym > 512 on the generic global-memory path: both match the
+    oracle run with the same Symmetry.GridSize."""
+    depth, fo, bb, lb, tw = synth.make_batch(2, "one_box")
+    h = _handle_with_env({}, symmetry_grid=grid)
+    h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+    g, dg, kg = h.estimate_ellipsoids(depth, fo, bb, lb, tw, dump_cap=40000)
+    prm = E.default_params(); prm.symmetry_grid = grid
+    o, do, ko, _ = orc.estimate_ellipsoids(depth, fo, bb, lb, tw, synth.GROUND_PLANE_WORLD, prm=prm, dump_cap=40000)
+    h.close()
+    assert all(lo <= x.n_sym <= hi for x in o), [x.n_sym for x in o]
+    msgs = _compare_objects(g, dg, kg, o, do, ko)
+    assert not msgs, "\n".join(msgs)
