@@ -64,8 +64,11 @@ struct SymObj {
   int bx0, bx2, by1, by3, rows, cols;
   double P[12], cam[3], fx, cx, cy, scale, coef, A0, A1, A2, R2;
   int n_live, slotbit, sm, iters;
-  int n_tasks, next_task;                       // work list of the current phase (any warp takes any task)
-  unsigned short tasks[kSeeds + kSeeds * 2 * (CAP / 32)];   // kind << 12 | seed << 8 | half << 7 | chunk   (kind 0: FD pass, 1: classify chunk, 2: scan chunk)
+  // work list of the current phase (any warp takes any task): task t < n_fd is the FD pass of fd_seed[t]; then every trial seed
+  // contributes nhalves * nchunks classification tasks; scan phase: seed tr_seed[k] owns tasks [scan_first[k], scan_first[k + 1])
+  int n_tasks, next_task, n_fd, n_tr;
+  unsigned char fd_seed[kSeeds + 3], tr_seed[kSeeds + 3];
+  int scan_first[kSeeds + 1];
   // float cloud, pair-interleaved SoA (odd tail padded far away)
   unsigned long long X2[CAP / 2], Y2[CAP / 2], Z2[CAP / 2];
 };
@@ -184,10 +187,13 @@ __device__ __forceinline__ int classify(const SymObj<CAP> &O, d3 pm, uint4 pc, u
       d = pc.y; depth = __hiloint2double((int)pc.w, (int)pc.z);
     } else {
       const unsigned short d0 = O.img[(size_t)y * O.pitch + x];
-      const double xi = (x - O.cx), yi = (y - O.cy), f = O.fx;
-      const double realz = (double)d0 * sqrt(xi * xi + f * f + yi * yi) / f;   // calculateProjZ, Symmetry.cpp:137-139 (lazy range image)
-      d = (unsigned short)(int)realz;                                            // ushort(realz)
-      depth = d / O.scale;
+      if (d0 == 0) { d = 0; depth = 0.0; }   // 0 * sqrt(..) / f = +0 -> ushort 0 (and 0 / x is the division's slow path)
+      else {
+        const double xi = (x - O.cx), yi = (y - O.cy), f = O.fx;
+        const double realz = (double)d0 * sqrt(xi * xi + f * f + yi * yi) / f;   // calculateProjZ, Symmetry.cpp:137-139 (lazy range image)
+        d = (unsigned short)(int)realz;                                            // ushort(realz)
+        depth = d / O.scale;
+      }
       *slot = make_uint4(key, d, (unsigned)__double2loint(depth), (unsigned)__double2hiint(depth));
     }
     if (d == 0) return 0;
@@ -964,17 +970,16 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
         }
       }
       __syncwarp();
-      if (lane == 0) {   // task list of the round: FD passes first, then the classification chunks
-        int nt = 0, live = 0;
-        for (int sd = 0; sd < kSeeds; sd++) if (seeds[sd].action == kActFd) { O.tasks[nt++] = (unsigned short)(sd << 8); live++; }
-        for (int sd = 0; sd < kSeeds; sd++) {
-          const int act = seeds[sd].action;
-          if (act != kActInit && act != kActTrial) continue;
-          live++;
-          if (!O.in_smem) { O.tasks[nt++] = (unsigned short)(0x3000 | (sd << 8)); continue; }   // generic path: the whole evaluation is one task
-          for (int hf = 0; hf < nhalves; hf++) for (int c = 0; c < nchunks; c++) O.tasks[nt++] = (unsigned short)(0x1000 | (sd << 8) | (hf << 7) | c);
+      {   // task list of the round: FD passes first (the longest tasks), then the classification chunks of the trial planes
+        const int act = lane < kSeeds ? seeds[lane].action : kActDone;
+        const unsigned mfd = __ballot_sync(0xffffffffu, act == kActFd), mtr = __ballot_sync(0xffffffffu, act == kActInit || act == kActTrial);
+        const unsigned lt = (1u << lane) - 1u;
+        if (act == kActFd) O.fd_seed[__popc(mfd & lt)] = (unsigned char)lane;
+        if (act == kActInit || act == kActTrial) O.tr_seed[__popc(mtr & lt)] = (unsigned char)lane;
+        if (lane == 0) {
+          O.n_fd = __popc(mfd); O.n_tr = __popc(mtr);
+          O.n_tasks = O.n_fd + O.n_tr * (O.in_smem ? nhalves * nchunks : 1); O.next_task = 0; O.n_live = O.n_fd + O.n_tr;
         }
-        O.n_tasks = nt; O.next_task = 0; O.n_live = live;
       }
     }
     first = false;
@@ -985,12 +990,18 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
       if (lane == 0) t = atomicAdd(&O.next_task, 1);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= O.n_tasks) break;
-      const unsigned task = O.tasks[t];
-      SymSeed<CAP> &T = seeds[(task >> 8) & 15u];
-      const unsigned kind = task >> 12;
-      if (kind == 1) classify_chunk<CAP, VERIFY>(O, T, (int)((task >> 7) & 1u), (int)(task & 127u));
-      else if (kind == 3) { const double err = eval_generic(O, T, T.pp); if (lane == 0) T.err_last = err; }
-      else {
+      if (t >= O.n_fd) {
+        const int u = t - O.n_fd;
+        if (O.in_smem) {
+          const int per = nhalves * nchunks, k = u / per, r = u - k * per, hf = r / nchunks;
+          classify_chunk<CAP, VERIFY>(O, seeds[O.tr_seed[k]], hf, r - hf * nchunks);
+        } else {   // generic path: the whole evaluation is one task
+          SymSeed<CAP> &T = seeds[O.tr_seed[u]];
+          const double err = eval_generic(O, T, T.pp);
+          if (lane == 0) T.err_last = err;
+        }
+      } else {
+        SymSeed<CAP> &T = seeds[O.fd_seed[t]];
         // linearizeOplus (numeric, delta 1e-9): the 2*dim perturbed planes prepared by 2*dim lanes, the base pair by lane 6
         if (lane == 0) T.fd_ok = 1;
         __syncwarp();
@@ -1021,14 +1032,14 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
     }
     __syncthreads();
     if (O.in_smem) {   // scan tasks: 32 queued points of one trial plane each
-      if (threadIdx.x == 0) {
-        int nt = 0;
-        for (int sd = 0; sd < kSeeds; sd++) {
-          const int act = seeds[sd].action;
-          if (act != kActInit && act != kActTrial) continue;
-          for (int qb = 0; qb < seeds[sd].qn; qb += 32) O.tasks[nt++] = (unsigned short)((sd << 8) | (qb >> 5));
-        }
-        O.n_tasks = nt; O.next_task = 0;
+      if (wid == 0) {
+        int cnt = (lane < O.n_tr) ? (seeds[O.tr_seed[lane]].qn + 31) >> 5 : 0, incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane <= kSeeds) O.scan_first[lane] = incl - cnt;   // exclusive prefix; entry n_tr (and beyond) = total
+        if (lane == 0) O.next_task = 0;
+        const int total = __shfl_sync(0xffffffffu, incl, 15);   // lanes 0..15 are covered by the 4-step scan (only 9 lanes are non-zero)
+        if (lane == 0) O.n_tasks = total;
       }
       __syncthreads();
       while (true) {
@@ -1036,8 +1047,9 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
         if (lane == 0) t = atomicAdd(&O.next_task, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= O.n_tasks) break;
-        const unsigned task = O.tasks[t];
-        scan_chunk<CAP, VERIFY>(O, seeds[(task >> 8) & 15u], (int)(task & 255u) << 5);
+        int k = 0;
+        while (k + 1 < O.n_tr && O.scan_first[k + 1] <= t) k++;
+        scan_chunk<CAP, VERIFY>(O, seeds[O.tr_seed[k]], (t - O.scan_first[k]) << 5);
       }
     }
     __syncthreads();
