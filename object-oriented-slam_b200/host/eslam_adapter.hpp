@@ -10,7 +10,9 @@
 // Eigen/OpenCV); (2) Eigen / cv::Mat overloads with the reference's exact signatures, enabled when those headers exist
 // (compile-verified elsewhere).  No compute happens here: every method forwards to libeslam_b200.so (CUDA only, no CPU fallback).
 #pragma once
+#include <algorithm>
 #include <array>
+#include <cmath>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -69,6 +71,21 @@ class Frame {   // src/core/Frame.cpp:7-27
     frame_seq_id = total_frame++;
     mvbOutlier.assign(bboxMat.size(), false);
   }
+#ifdef ESLAM_HAVE_EIGEN_OPENCV
+  // Frame(double timestamp, const Eigen::VectorXd &pose, const Eigen::MatrixXd &bboxMap, const cv::Mat &imDepth, const cv::Mat &imRGB)
+  // (include/core/Frame.h:18-20; the last 7 entries of `pose` are x y z qx qy qz qw, Frame.cpp:13; the RGB image is only drawn on)
+  Frame(double timestamp_, const Eigen::VectorXd &pose, const Eigen::MatrixXd &bboxMap, const cv::Mat &imDepth, const cv::Mat & /*imRGB*/ = cv::Mat())
+      : timestamp(timestamp_) {
+    for (int i = 0; i < 7; i++) cam_pose_Twc[i] = pose[pose.size() - 7 + i];
+    eslam_pose_inverse(cam_pose_Twc.data(), cam_pose_Tcw.data());
+    frame_seq_id = total_frame++;
+    for (int r = 0; r < bboxMap.rows(); r++) { std::array<double, 8> row{}; for (int k = 0; k < 8 && k < bboxMap.cols(); k++) row[k] = bboxMap(r, k); mmObservations.push_back(row); }
+    mvbOutlier.assign(mmObservations.size(), false);
+    frame_img.resize((size_t)imDepth.rows * imDepth.cols);
+    for (int r = 0; r < imDepth.rows; r++) std::copy(imDepth.ptr<uint16_t>(r), imDepth.ptr<uint16_t>(r) + imDepth.cols, frame_img.begin() + (size_t)r * imDepth.cols);
+  }
+  Frame(const Eigen::VectorXd &pose, const Eigen::MatrixXd &bboxMap, const cv::Mat &imDepth, const cv::Mat &imRGB = cv::Mat()) : Frame(0.0, pose, bboxMap, imDepth, imRGB) {}
+#endif
   double timestamp; int frame_seq_id;
   Pose7 cam_pose_Twc{}, cam_pose_Tcw{};
   std::vector<std::array<double, 8>> mmObservations;   // id x1 y1 x2 y2 label rate instanceID
@@ -140,6 +157,20 @@ class EllipsoidExtractor {
     ctx_.check(eslam_estimate_ellipsoids_wait(ctx_.get(), ticket, (int)n_obj, out.data()), "CollectLocalEllipsoids");
     return out;
   }
+#ifdef ESLAM_HAVE_EIGEN_OPENCV
+  // the reference's exact call (src/pca/EllipsoidExtractor.h:57): depth CV_16UC1, bbox x1 y1 x2 y2, pose with x y z qx qy qz qw in
+  // its last 7 entries; `camera` must be the intrinsics the Context was created with (checked).  to_reference<g2o::ellipsoid>() below
+  // turns the result into the reference's own type.
+  ellipsoid_pod EstimateLocalEllipsoid(cv::Mat &depth, Eigen::Vector4d &bbox, int label, Eigen::VectorXd &pose, camera_intrinsic &camera) {
+    const EslamCamera &c = ctx_.camera();
+    if (camera.fx != c.fx || camera.fy != c.fy || camera.cx != c.cx || camera.cy != c.cy || camera.scale != c.scale || depth.rows != c.rows || depth.cols != c.cols)
+      throw std::runtime_error("EstimateLocalEllipsoid: camera / image size differ from the Context's (intrinsics are creation-time parameters)");
+    Pose7 T; for (int i = 0; i < 7; i++) T[i] = pose[pose.size() - 7 + i];
+    return EstimateLocalEllipsoid(depth.ptr<uint16_t>(0), depth.step / sizeof(uint16_t), {bbox[0], bbox[1], bbox[2], bbox[3]}, label, T);
+  }
+  // void SetSupportingPlane(g2o::plane *pPlane)  (EllipsoidExtractor.h:54): any type with a 4-vector member `param`
+  template <class PlaneT> void SetSupportingPlane(PlaneT *pPlane) { SetSupportingPlane(Plane4{pPlane->param[0], pPlane->param[1], pPlane->param[2], pPlane->param[3]}); }
+#endif
   bool GetResult() const { return mResult; }
   SymmetryOutputData GetSymmetryOutputData() const { return mSym; }
   int miSystemState = 0;
@@ -163,6 +194,38 @@ class Initializer {
     if (mbResult && !obs.empty()) e.miLabel = obs[0]->label;
     return e;
   }
+#ifdef ESLAM_HAVE_EIGEN_OPENCV
+  // g2o::ellipsoid initializeQuadric(MatrixXd &pose_mat, MatrixXd &detection_mat, Matrix3d &calib)   (include/core/Initializer.h:46)
+  // pose_mat rows: x y z qx qy qz qw (last 7 columns), detection_mat rows: x1 y1 x2 y2 (rate)
+  ellipsoid_pod initializeQuadric(Eigen::MatrixXd &pose_mat, Eigen::MatrixXd &detection_mat, Eigen::Matrix3d &calib) {
+    std::vector<double> tw, det; double K[9];
+    for (int r = 0; r < pose_mat.rows(); r++) {
+      for (int k = 0; k < 7; k++) tw.push_back(pose_mat(r, pose_mat.cols() - 7 + k));
+      for (int k = 0; k < 4; k++) det.push_back(detection_mat(r, k));
+      det.push_back(detection_mat.cols() > 4 ? detection_mat(r, 4) : 1.0);
+    }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) K[3 * i + j] = calib(i, j);
+    ellipsoid_pod e; int ok = 0;
+    ctx_.check(eslam_init_quadric(ctx_.get(), (int)pose_mat.rows(), tw.data(), det.data(), K, rows_, cols_, e.vec.data(), &ok), "initializeQuadric");
+    mbResult = ok != 0;
+    return e;
+  }
+  // g2o::ellipsoid initializeQuadric(Observations &obs, Matrix3d &calib)   (include/core/Initializer.h:47) for the REFERENCE's own
+  // Observation / Frame types: obs[i]->label, ->bbox (Vector4d), ->rate, ->pFrame->cam_pose_Twc (g2o::SE3Quat, toVector())
+  template <class ObsVec> ellipsoid_pod initializeQuadric(ObsVec &obs, Eigen::Matrix3d &calib) {
+    Eigen::MatrixXd pose_mat((int)obs.size(), 7), det_mat((int)obs.size(), 5);
+    int r = 0;
+    for (auto *o : obs) {
+      const auto v = o->pFrame->cam_pose_Twc.toVector();
+      for (int k = 0; k < 7; k++) pose_mat(r, k) = v[k];
+      for (int k = 0; k < 4; k++) det_mat(r, k) = o->bbox[k];
+      det_mat(r, 4) = o->rate; r++;
+    }
+    ellipsoid_pod e = initializeQuadric(pose_mat, det_mat, calib);
+    if (mbResult && obs.size() > 0) e.miLabel = (*obs.begin())->label;
+    return e;
+  }
+#endif
   bool getInitializeResult() const { return mbResult; }
  private:
   Context &ctx_; int rows_, cols_; bool mbResult = false;
@@ -220,8 +283,59 @@ class Optimizer {
     for (size_t k = 0; k < inst.size(); k++) for (int i = 0; i < 10; i++) ellipsoids[inst[k]]->vec[i] = ell[k * 10 + i];
     return st;
   }
+#ifdef ESLAM_HAVE_EIGEN_OPENCV
+  void SetGroundPlane(Eigen::Vector4d &normal) { SetGroundPlane(Plane4{normal[0], normal[1], normal[2], normal[3]}); }   // Optimizer.h:23
+  // void GlobalObjectGraphOptimization(std::vector<Frame *> &pFrames, Map *pMap, int rows, int cols, Matrix3d &mCalib,
+  //                                    std::map<int, Observations> &objectObservations, bool save_graph, bool withAssociation, bool check_visibility)
+  // (include/core/Optimizer.h:19-21) on the REFERENCE's own Frame / Map / Observation / g2o::ellipsoid types (a template, so this header
+  // does not need them): pMap->GetAllEllipsoidsMap() -> std::map<int, g2o::ellipsoid *>, updated in place through fromVector();
+  // frames give cam_pose_Tcw.toVector(), frame_seq_id and mpLocalObjects (toVector(), prob, miInstanceID).
+  template <class FrameT, class MapT, class ObsMapT>
+  void GlobalObjectGraphOptimization(std::vector<FrameT *> &pFrames, MapT *pMap, int /*rows*/, int /*cols*/, Eigen::Matrix3d &mCalib, ObsMapT &objectObservations,
+                                     bool /*save_graph*/ = false, bool /*withAssociation*/ = false, bool /*check_visibility*/ = false) {
+    auto emap = pMap->GetAllEllipsoidsMap();
+    std::map<int, ellipsoid_pod> pods; std::map<int, ellipsoid_pod *> podp;
+    for (auto &kv : emap) { ellipsoid_pod e; const auto v = kv.second->toVector(); for (int i = 0; i < 10; i++) e.vec[i] = v[i]; e.prob = kv.second->prob; e.miInstanceID = kv.first; pods[kv.first] = e; }
+    for (auto &kv : pods) podp[kv.first] = &kv.second;
+    std::vector<Frame> frames; frames.reserve(pFrames.size());
+    std::vector<std::vector<ellipsoid_pod>> locals(pFrames.size());
+    for (size_t f = 0; f < pFrames.size(); f++) {
+      const auto tw = pFrames[f]->cam_pose_Twc.toVector();
+      frames.emplace_back(pFrames[f]->timestamp, &tw[0], std::vector<std::array<double, 8>>(), nullptr, 0, 0);
+      frames.back().frame_seq_id = pFrames[f]->frame_seq_id;
+      for (auto *o : pFrames[f]->mpLocalObjects) {
+        ellipsoid_pod e; e.miInstanceID = -1;
+        if (o) { const auto v = o->toVector(); for (int i = 0; i < 10; i++) e.vec[i] = v[i]; e.prob = o->prob; e.miInstanceID = o->miInstanceID; e.miLabel = o->miLabel; }
+        locals[f].push_back(e);
+      }
+    }
+    std::vector<Frame *> fp;
+    for (size_t f = 0; f < frames.size(); f++) { for (auto &e : locals[f]) frames[f].mpLocalObjects.push_back(e.miInstanceID >= 0 ? &e : nullptr); fp.push_back(&frames[f]); }
+    std::vector<Observation> obs_store; std::map<int, Observations> obs;
+    size_t total = 0; for (auto &kv : objectObservations) total += kv.second.size();
+    obs_store.reserve(total);
+    for (auto &kv : objectObservations) for (auto *o : kv.second) {
+      Frame *pf = nullptr;
+      for (size_t f = 0; f < pFrames.size(); f++) if (pFrames[f] == o->pFrame) pf = &frames[f];
+      obs_store.push_back(Observation{o->label, {o->bbox[0], o->bbox[1], o->bbox[2], o->bbox[3]}, o->rate, pf});
+      obs[kv.first].push_back(&obs_store.back());
+    }
+    double K[9]; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) K[3 * i + j] = mCalib(i, j);
+    GlobalObjectGraphOptimization(fp, podp, K, obs, 10);
+    for (auto &kv : emap) { Eigen::Matrix<double, 10, 1> v; for (int i = 0; i < 10; i++) v[i] = pods[kv.first].vec[i]; kv.second->fromVector(v); }
+  }
+#endif
  private:
   Context &ctx_; bool mbGroundPlaneSet = false; Plane4 mGroundPlaneNormal{};
 };
+
+#ifdef ESLAM_HAVE_EIGEN_OPENCV
+// ellipsoid_pod -> the reference's g2o::ellipsoid (or any type with fromVector(Vector10d), prob, miLabel, miInstanceID)
+template <class EllipsoidT> EllipsoidT to_reference(const ellipsoid_pod &p) {
+  EllipsoidT e; Eigen::Matrix<double, 10, 1> v; for (int i = 0; i < 10; i++) v[i] = p.vec[i];
+  e.fromVector(v); e.prob = p.prob; e.miLabel = p.miLabel; e.miInstanceID = p.miInstanceID;
+  return e;
+}
+#endif
 
 }  // namespace EllipsoidSLAM

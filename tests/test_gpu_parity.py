@@ -513,3 +513,53 @@ def test_symmetry_cloud_sizes_beyond_the_small_instantiation(grid, lo, hi):
     assert all(lo <= x.n_sym <= hi for x in o), [x.n_sym for x in o]
     msgs = _compare_objects(g, dg, kg, o, do, ko)
     assert not msgs, "\n".join(msgs)
+
+
+# ------------------------------------------------------------------ C++ host adapter on the device
+def test_cpp_adapter_end_to_end(tmp_path):
+    """host/eslam_adapter.hpp (reference-named C++ classes over the C-ABI) run end to end on the device -- ground plane, one local
+    ellipsoid per frame, quadric initialisation, object graph optimisation -- must print exactly what the ctypes path computes."""
+    import os
+    import subprocess
+    from eslam_b200 import api
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    depth, fo, bb, lb, tw = synth.make_batch(3, "one_box")
+    blob = str(tmp_path / "frames.bin")
+    with open(blob, "wb") as f:
+        f.write(np.array([3, 480, 640], dtype=np.int32).tobytes()); f.write(depth.tobytes()); f.write(bb.astype(np.float64).tobytes())
+        f.write(lb.astype(np.int32).tobytes()); f.write(tw.astype(np.float64).tobytes())
+    exe = str(tmp_path / "host_adapter_e2e")
+    libdir = os.path.join(root, "object-oriented-slam_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(root, "tests", "host_adapter_e2e.cpp"), "-L" + libdir, "-leslam_b200",
+                           "-L/usr/local/cuda/lib64", "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"])
+    run = subprocess.run([exe, blob], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    rows = {}
+    for ln in run.stdout.splitlines():
+        p = ln.split()
+        rows.setdefault(p[0], []).append([float(x) for x in p[1:]])
+    h = E.Handle()
+    pl, found, _ = h.extract_ground_plane(depth[0])
+    pw = api.plane_to_world(pl[0], tw[0])
+    assert rows["plane"][0][0] == float(found[0]) == 1.0 and np.array_equal(rows["plane"][0][1:], pw)
+    h.set_supporting_plane(pw)
+    api.Frame.total_frame = 0
+    ex, opt, ini = api.EllipsoidExtractor(h), api.Optimizer(h), api.Initializer(h, 480, 640)
+    opt.SetGroundPlane(pw)
+    frames, obs = [], []
+    for f in range(3):
+        fr = api.Frame(0.1 * f, tw[f], np.array([[0, *bb[f], lb[f], 1.0, 0]]), depth[f])
+        e = ex.EstimateLocalEllipsoid(depth[f], bb[f], int(lb[f]), tw[f])
+        e["miInstanceID"] = 0
+        want = rows["local"][f]
+        assert want[0] == f and want[1] == ex.miSystemState and np.array_equal(want[2:12], e["vec"]) and want[12] == e["prob"]
+        fr.mpLocalObjects.append(e if ex.GetResult() else None)
+        frames.append(fr); obs.append(api.Observation(int(lb[f]), bb[f], 1.0, fr))
+    e0 = ini.initializeQuadric(obs, K)
+    assert rows["init"][0][0] == float(ini.getInitializeResult()) and np.array_equal(rows["init"][0][1:], e0["vec"])
+    glob = dict(frames[0].mpLocalObjects[0]); glob["vec"] = np.r_[api.pose_mul(tw[0], glob["vec"][:7]), glob["vec"][7:]]
+    res = opt.GlobalObjectGraphOptimization(frames, {0: glob}, 480, 640, K, {0: obs}, iters=10)
+    st = opt.last_stats
+    assert rows["opt"][0][0] == st.iterations and rows["opt"][0][1] == st.trials_total
+    assert np.array_equal(rows["opt"][0][2:12], res[0]["vec"]) and rows["opt"][0][12] == st.chi2_final
+    h.close()
