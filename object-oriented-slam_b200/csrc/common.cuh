@@ -72,6 +72,7 @@ struct EslamHandle {
   // same ~40 MB are reused by every batch and stay L2 resident
   eslam::DevBuf sym_pool_nn, sym_pool_px, sym_slotmask;   // round-1 kernel (ESLAM_SYM_IMPL=1) only
   eslam::DevBuf sym_pool256, sym_pool512, sym_slotmask2, sym_smid_map;
+  bool pull_tma = true;    // SM pull of the box rectangles through cp.async.bulk (TMA); env ESLAM_PULL_TMA=0: the LDG/STG pull kernel
   int sym_occ = 0;         // env ESLAM_SYM_OCC (tuning): 2 / 4 resident CTAs per SM instead of kSymCtas256
   int sym_impl = 2;        // env ESLAM_SYM_IMPL: 1 = round-1 kernel (A/B baseline), 2 = current
   bool sym_verify = false; // env ESLAM_SYM_VERIFY=1: every shortcut decision of the symmetry kernel is re-derived the long way and counted when it differs

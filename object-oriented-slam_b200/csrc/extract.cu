@@ -601,9 +601,77 @@ __global__ void __launch_bounds__(kPullThreads, 16) pull_rects_kernel(const uint
     }
   }
 }
+// The same upload driven by the bulk-copy engine (TMA, cp.async.bulk + mbarrier; SASS: UBLKCP / SYNCS) instead of LDG/STG: one elected
+// thread per one-warp CTA keeps kTmaStages row segments of its objects in flight -- bulk load host (mapped, pinned) -> shared memory
+// with an mbarrier transaction count, bulk store shared -> device frame buffer -- so the pull costs no load/store issue slots and
+// 352 bytes of registers next to the resident extraction / symmetry CTAs.  Row segments are 16-byte aligned multiples of 16 bytes.
+constexpr int kTmaStages = 8;
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+struct PullCursor {   // (object, row) items of this CTA in a fixed order
+  const ObjMeta *metas; int n_obj, rows, cols, k, r, nr, step;
+  __device__ void settle() {   // move to the next object that has rows
+    while (k < n_obj) {
+      const ObjMeta &m = metas[k];
+      if (m.pre_status == 0 && m.nx != 0) { nr = min(rows, m.y2 + 1) - m.y1; if (nr > 0) return; }
+      k += step; r = 0;
+    }
+  }
+  __device__ bool valid() const { return k < n_obj; }
+  __device__ void next() { if (++r >= nr) { k += step; r = 0; settle(); } }
+  __device__ void item(size_t pitch, size_t frame_stride, size_t &off, unsigned &bytes) const {
+    const ObjMeta &m = metas[k];
+    const int x0 = m.x1 & ~7, x1 = min(cols, (m.x2 + 8) & ~7);
+    off = (size_t)m.frame * frame_stride + (size_t)(m.y1 + r) * pitch + x0;
+    bytes = (unsigned)(x1 - x0) * 2u;
+  }
+};
+__global__ void __launch_bounds__(32, 8) pull_rects_tma_kernel(const uint16_t *__restrict__ host_src, uint16_t *__restrict__ dst, size_t pitch, size_t frame_stride,
+                                                               const ObjMeta *__restrict__ metas, int n_obj, int rows, int cols, int stage_bytes) {
+  extern __shared__ __align__(128) unsigned char tma_buf[];   // [kTmaStages][stage_bytes]
+  __shared__ __align__(8) unsigned long long bar[kTmaStages];
+  if (threadIdx.x != 0) return;
+  for (int s = 0; s < kTmaStages; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[s])));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  PullCursor ld{metas, n_obj, rows, cols, (int)blockIdx.x, 0, 0, (int)gridDim.x}, st = ld;
+  ld.settle(); st.settle();
+  auto issue_load = [&](int stage) {
+    size_t off; unsigned bytes;
+    ld.item(pitch, frame_stride, off, bytes);
+    const unsigned b = smem_u32(&bar[stage]), d = smem_u32(tma_buf + (size_t)stage * stage_bytes);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(host_src + off), "r"(bytes), "r"(b) : "memory");
+    ld.next();
+  };
+  int issued = 0;
+  for (; issued < kTmaStages && ld.valid(); issued++) issue_load(issued);
+  for (int i = 0; st.valid(); i++) {
+    const int stage = i % kTmaStages;
+    const unsigned parity = (unsigned)(i / kTmaStages) & 1u, b = smem_u32(&bar[stage]);
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
+    size_t off; unsigned bytes;
+    st.item(pitch, frame_stride, off, bytes);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(smem_u32(tma_buf + (size_t)stage * stage_bytes)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    st.next();
+    if (ld.valid()) {   // the stage is reused once the store has read it
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      issue_load(stage);
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 int pull_rects_launch(EslamHandle *h, cudaStream_t s, const uint16_t *host_mapped, uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj) {
   ExtractWorkspace &w = *h->ex;
   if (n_obj <= 0) return ESLAM_OK;
+  if (h->pull_tma) {   // default: bulk-copy engine instead of LDG/STG (+10 % end to end, profiles/r02_pull_tma_ab.txt); ESLAM_PULL_TMA=0 disables
+    const int stage_bytes = (((h->cam.cols + 8) * 2) + 127) & ~127;
+    const int want = 2 * h->sm_count, grid = n_obj < want ? n_obj : want;
+    pull_rects_tma_kernel<<<grid, 32, (size_t)kTmaStages * stage_bytes, s>>>(host_mapped, depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, n_obj, h->cam.rows,
+                                                                              h->cam.cols, stage_bytes);
+    ESLAM_LAUNCHED(h);
+    ESLAM_CUDA_OK(h, cudaGetLastError());
+    return ESLAM_OK;
+  }
   const int grid = n_obj < h->sm_count ? n_obj : h->sm_count;
   pull_rects_kernel<<<grid, kPullThreads, 0, s>>>(host_mapped, depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, n_obj, h->cam.rows, h->cam.cols);
   ESLAM_LAUNCHED(h);
