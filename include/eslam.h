@@ -226,6 +226,14 @@ int eslam_estimate_ellipsoids_submit(EslamHandle *h, int n_frames, const uint16_
                                      int n_obj, const int *frame_of_obj, const double *bbox4, const int *label,
                                      const double *Twc7, int *ticket);
 int eslam_estimate_ellipsoids_wait(EslamHandle *h, int ticket, int n_obj, EslamEllipsoidOut *out);
+/* the same pipelining for DEVICE-resident depth and records (no host copies, no host synchronisation): submit issues the batch on an
+ * internal stream ordered after the work already enqueued on `stream` (the depth batch must stay valid until the matching collect);
+ * collect makes `stream` wait for the batch and copies its n_obj records into caller-owned device memory on `stream`.  Tickets are
+ * shared with the host form: at most two outstanding. */
+int eslam_estimate_ellipsoids_dev_submit(EslamHandle *h, void *stream, int n_frames, const uint16_t *depth_dev, size_t pitch,
+                                         int n_obj, const int *frame_of_obj, const double *bbox4, const int *label,
+                                         const double *Twc7, int *ticket);
+int eslam_estimate_ellipsoids_dev_collect(EslamHandle *h, void *stream, int ticket, int n_obj, void *records_dev);
 
 /* ------------------------------------------------------------------ quadric initialisation */
 /* replaces Initializer::initializeQuadric (Initializer.cpp:24-56): n_obs rows of Twc7 / det5 (x1 y1 x2 y2 rate)

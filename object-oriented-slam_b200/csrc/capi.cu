@@ -373,6 +373,7 @@ void eslam_destroy(EslamHandle *h) {
     delete h->ex_slot[sl];
     if (h->slot_stream[sl]) cudaStreamDestroy(h->slot_stream[sl]);
     if (h->slot_done[sl]) cudaEventDestroy(h->slot_done[sl]);
+    if (h->slot_start[sl]) cudaEventDestroy(h->slot_start[sl]);
   }
   h->sym_pool_nn.release(); h->sym_pool_px.release(); h->sym_slotmask.release(); h->plane_depth.release();
   h->sym_pool256.release(); h->sym_pool512.release(); h->sym_slotmask2.release(); h->sym_smid_map.release();
@@ -596,6 +597,41 @@ int eslam_estimate_ellipsoids_wait(EslamHandle *h, int ticket, int n_obj, EslamE
   cudaSetDevice(h->device);
   ESLAM_CUDA_OK(h, cudaEventSynchronize(h->slot_done[ticket]));
   memcpy(out, h->ex_slot[ticket]->pin_out.p, sizeof(EslamEllipsoidOut) * (size_t)n_obj);
+  h->slot_objs[ticket] = 0;
+  return ESLAM_OK;
+}
+
+int eslam_estimate_ellipsoids_dev_submit(EslamHandle *h, void *stream, int n_frames, const uint16_t *depth_dev, size_t pitch, int n_obj, const int *frame_of_obj,
+                                         const double *bbox4, const int *label, const double *Twc7, int *ticket) {
+  if (!h || !depth_dev || !ticket || n_frames <= 0 || n_obj <= 0) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const int sl = h->next_slot;
+  if (h->slot_objs[sl]) { h->err = "both pipeline slots are busy: collect the oldest ticket first"; return ESLAM_ERR_BAD_ARG; }
+  if (!h->slot_stream[sl]) ESLAM_CUDA_OK(h, cudaStreamCreateWithFlags(&h->slot_stream[sl], cudaStreamNonBlocking));
+  if (!h->slot_done[sl]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->slot_done[sl], cudaEventDisableTiming));
+  if (!h->slot_start[sl]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->slot_start[sl], cudaEventDisableTiming));
+  use_slot(h, sl);
+  cudaStream_t s = h->slot_stream[sl], user = stream ? (cudaStream_t)stream : h->stream;
+  ESLAM_CUDA_OK(h, cudaEventRecord(h->slot_start[sl], user));          // ordered after what the caller enqueued (e.g. the producer of the depth batch)
+  ESLAM_CUDA_OK(h, cudaStreamWaitEvent(s, h->slot_start[sl], 0));
+  ExtractPtrs P;
+  int rc = run_extract(h, s, n_frames, depth_dev, pitch, n_obj, frame_of_obj, bbox4, label, Twc7, false, P);
+  if (rc) return rc;
+  ESLAM_CUDA_OK(h, cudaEventRecord(h->slot_done[sl], s));
+  h->slot_objs[sl] = n_obj;
+  h->next_slot = sl ^ 1;
+  *ticket = sl;
+  return ESLAM_OK;
+}
+int eslam_estimate_ellipsoids_dev_collect(EslamHandle *h, void *stream, int ticket, int n_obj, void *records_dev) {
+  if (!h || !records_dev || ticket < 0 || ticket > 1 || !h->slot_objs[ticket] || n_obj != h->slot_objs[ticket]) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  cudaStream_t user = stream ? (cudaStream_t)stream : h->stream;
+  ESLAM_CUDA_OK(h, cudaStreamWaitEvent(user, h->slot_done[ticket], 0));
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(records_dev, h->ex_slot[ticket]->out.p, sizeof(EslamEllipsoidOut) * (size_t)n_obj, cudaMemcpyDeviceToDevice, user));
+  // the slot's workspace may be reused by the next submit: its kernels run on the slot stream, which must not start before this copy
+  ESLAM_CUDA_OK(h, cudaEventRecord(h->slot_start[ticket], user));
+  ESLAM_CUDA_OK(h, cudaStreamWaitEvent(h->slot_stream[ticket], h->slot_start[ticket], 0));
   h->slot_objs[ticket] = 0;
   return ESLAM_OK;
 }

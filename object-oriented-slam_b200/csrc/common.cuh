@@ -90,6 +90,7 @@ struct EslamHandle {
   eslam::ExtractWorkspace *ex_slot[2] = {nullptr, nullptr};   // slot 0: synchronous entry points; both: pipelined submit / wait
   cudaStream_t slot_stream[2] = {nullptr, nullptr};
   cudaEvent_t slot_done[2] = {nullptr, nullptr};
+  cudaEvent_t slot_start[2] = {nullptr, nullptr};   // device-resident pipelining: orders a slot's stream after the caller's stream
   int slot_objs[2] = {0, 0};                          // objects of the batch in flight on the slot (0 = free)
   int next_slot = 0;
   eslam::GraphWorkspace *gr = nullptr;

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "eslam_abi_version", "eslam_default_params", "eslam_default_camera", "eslam_create", "eslam_destroy", "eslam_last_error",
     "eslam_launch_count", "eslam_h2d_bytes", "eslam_extract_ground_plane_host", "eslam_extract_ground_plane_dev", "eslam_plane_to_world",
     "eslam_set_supporting_plane", "eslam_calibrate_measurement", "eslam_estimate_ellipsoids_host", "eslam_estimate_ellipsoids_dev",
-    "eslam_fetch_ellipsoids", "eslam_copy_ellipsoids_dev", "eslam_batch_counters", "eslam_estimate_ellipsoids_submit", "eslam_estimate_ellipsoids_wait", "eslam_init_quadric", "eslam_edges_eval_host", "eslam_edges_upload", "eslam_edges_eval_dev",
+    "eslam_fetch_ellipsoids", "eslam_estimate_ellipsoids_dev_submit", "eslam_estimate_ellipsoids_dev_collect", "eslam_copy_ellipsoids_dev", "eslam_batch_counters", "eslam_estimate_ellipsoids_submit", "eslam_estimate_ellipsoids_wait", "eslam_init_quadric", "eslam_edges_eval_host", "eslam_edges_upload", "eslam_edges_eval_dev",
     "eslam_edges_download", "eslam_optimize_objects_host", "eslam_optimize_slam_host", "eslam_pose_inverse", "eslam_pose_mul", "eslam_set_profiling", "eslam_get_stage_ms",
 ]
 
@@ -211,6 +211,21 @@ class Handle:
         out = (EslamEllipsoidOut * n_obj)()
         self.check(self.lib.eslam_fetch_ellipsoids(self._h, C.c_void_p(stream), C.c_int(n_obj), out), "eslam_fetch_ellipsoids")
         return out
+
+    def dev_submit(self, depth_ptr, n_frames, pitch, frame_of_obj, bbox, label, Twc, stream=0):
+        """Pipelined device-resident form (two batches in flight): returns a ticket for dev_collect."""
+        fo = np.ascontiguousarray(frame_of_obj, dtype=np.int32); bb = _d(bbox).reshape(-1, 4)
+        lb = np.ascontiguousarray(label, dtype=np.int32); tw = _d(Twc).reshape(-1, 7)
+        t = C.c_int(-1)
+        self.check(self.lib.eslam_estimate_ellipsoids_dev_submit(self._h, C.c_void_p(stream), C.c_int(n_frames), C.c_void_p(depth_ptr), C.c_size_t(pitch), C.c_int(len(fo)),
+                                                                 _ip(fo), _dp(bb), _ip(lb), _dp(tw), C.byref(t)), "eslam_estimate_ellipsoids_dev_submit")
+        return (t.value, len(fo))
+
+    def dev_collect(self, ticket, dst_ptr, stream=0):
+        """`stream` waits for the ticket's batch, then its records are copied (D2D, asynchronous) to dst_ptr."""
+        slot, n = ticket
+        self.check(self.lib.eslam_estimate_ellipsoids_dev_collect(self._h, C.c_void_p(stream), C.c_int(slot), C.c_int(n), C.c_void_p(dst_ptr)),
+                   "eslam_estimate_ellipsoids_dev_collect")
 
     def copy_ellipsoids_dev(self, n_obj, dst_ptr, stream=0):
         """records of the last *_dev batch -> caller-owned device memory (D2D on `stream`, asynchronous)."""

@@ -563,3 +563,27 @@ def test_cpp_adapter_end_to_end(tmp_path):
     assert rows["opt"][0][0] == st.iterations and rows["opt"][0][1] == st.trials_total
     assert np.array_equal(rows["opt"][0][2:12], res[0]["vec"]) and rows["opt"][0][12] == st.chi2_final
     h.close()
+
+
+def test_device_resident_submit_collect_equals_blocking_call(handle):
+    """eslam_estimate_ellipsoids_dev_submit / _collect (two resident batches in flight, records collected D2D on the caller's stream)
+    return the blocking call's records, in ticket order; a third submit is refused."""
+    import torch
+    handle.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+    batches = [synth.make_batch(3, "one_box"), synth.make_batch(2, "multi_box"), synth.make_batch(4, "one_box")]
+    want = [bytes(handle.estimate_ellipsoids(*b)[0]) for b in batches]
+    devs = [torch.from_numpy(np.ascontiguousarray(b[0]).view(np.int16)).cuda() for b in batches]
+    stream = torch.cuda.Stream()
+    bufs = [torch.zeros(len(w), dtype=torch.uint8, device="cuda") for w in want]
+    with torch.cuda.stream(stream):
+        t0 = handle.dev_submit(devs[0].data_ptr(), devs[0].shape[0], 640, *batches[0][1:], stream=stream.cuda_stream)
+        t1 = handle.dev_submit(devs[1].data_ptr(), devs[1].shape[0], 640, *batches[1][1:], stream=stream.cuda_stream)
+        with pytest.raises(E.EslamError):
+            handle.dev_submit(devs[2].data_ptr(), devs[2].shape[0], 640, *batches[2][1:], stream=stream.cuda_stream)
+        handle.dev_collect(t0, bufs[0].data_ptr(), stream=stream.cuda_stream)
+        t2 = handle.dev_submit(devs[2].data_ptr(), devs[2].shape[0], 640, *batches[2][1:], stream=stream.cuda_stream)
+        handle.dev_collect(t1, bufs[1].data_ptr(), stream=stream.cuda_stream)
+        handle.dev_collect(t2, bufs[2].data_ptr(), stream=stream.cuda_stream)
+    stream.synchronize()
+    for b, w in zip(bufs, want):
+        assert b.cpu().numpy().tobytes() == w
