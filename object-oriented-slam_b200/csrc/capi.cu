@@ -350,6 +350,8 @@ int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHa
   h->prm = *p; h->cam = *c; h->device = device; h->sm_count = prop.multiProcessorCount;
   if (const char *e = getenv("ESLAM_H2D_MODE")) { int v = atoi(e); if (v >= 0 && v <= 4) h->h2d_mode = v; }
   if (const char *e = getenv("ESLAM_SYM_IMPL")) { int v = atoi(e); if (v == 1 || v == 2) h->sym_impl = v; }
+  if (const char *e = getenv("ESLAM_PLANE_STREAMS")) h->plane_streams = atoi(e);
+  if (const char *e = getenv("ESLAM_PLANE_EXACT")) h->plane_exact = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_PULL_TMA")) h->pull_tma = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_SYM_OCC")) h->sym_occ = atoi(e);
   if (const char *e = getenv("ESLAM_SYM_VERIFY")) h->sym_verify = atoi(e) != 0;

@@ -72,6 +72,9 @@ struct EslamHandle {
   // same ~40 MB are reused by every batch and stay L2 resident
   eslam::DevBuf sym_pool_nn, sym_pool_px, sym_slotmask;   // round-1 kernel (ESLAM_SYM_IMPL=1) only
   eslam::DevBuf sym_pool256, sym_pool512, sym_slotmask2, sym_smid_map;
+  cudaStream_t plane_stream2 = nullptr; cudaEvent_t plane_ev[2] = {nullptr, nullptr};   // second half of a ground-plane chunk
+XX
+  bool plane_exact = true;  // env ESLAM_PLANE_EXACT=0: every frame takes the integral-image recurrence (A/B, fallback test)
   bool pull_tma = true;    // SM pull of the box rectangles through cp.async.bulk (TMA); env ESLAM_PULL_TMA=0: the LDG/STG pull kernel
   int sym_occ = 0;         // env ESLAM_SYM_OCC (tuning): 2 / 4 resident CTAs per SM instead of kSymCtas256
   int sym_impl = 2;        // env ESLAM_SYM_IMPL: 1 = round-1 kernel (A/B baseline), 2 = current

@@ -50,10 +50,13 @@ struct PlaneFramePtrs {
   int *cand_size;      // [F * kMaxRegions]  inlier count (grows during refinement)
   double *out_plane;   // [F*4]
   int *out_found, *out_inl;
+  unsigned *cpart;     // [F * blocks * 6]: per-block partial ranges written by points_kernel
+  unsigned *crange;    // [F * 6]: float bits of the smallest non-zero |x|, |y|, |z| and of the largest |x|, |y|, |z| of the frame's points
+  int exact_mode;      // 1: frames whose integral images are provably exact take the fused tile kernel, 0: every frame takes the recurrence
 };
 
 struct PlaneWorkspace {
-  DevBuf pts, nrm, iiX, iiY, dm, parent, label, count, maxidx, cmin, cmax, cand_root, cand_n, cand_coef, cand_valid, cand_size, out_plane, out_found, out_inl;
+  DevBuf pts, nrm, iiX, iiY, dm, parent, label, count, maxidx, cmin, cmax, cand_root, cand_n, cand_coef, cand_valid, cand_size, out_plane, out_found, out_inl, crange, cpart;
   PinBuf pin;
   int chunk = 0;
 };
@@ -63,7 +66,7 @@ __global__ void points_kernel(const uint16_t *__restrict__ depth, size_t pitch, 
   const int NP = prm.rows * prm.cols;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int f = blockIdx.y;
-  if (idx >= NP) return;
+  if (idx >= NP) idx = NP - 1;   // the tail threads redo the last pixel (same values): the warp reductions below need full warps
   int m = idx / prm.cols, n = idx - m * prm.cols;
   unsigned short dv = depth[(size_t)f * frame_stride + (size_t)m * pitch + n];
   double d = dv / prm.scale;
@@ -71,10 +74,170 @@ __global__ void points_kernel(const uint16_t *__restrict__ depth, size_t pitch, 
   float x = (float)((n - prm.cx) * (double)z / prm.fx);
   float y = (float)((m - prm.cy) * (double)z / prm.fy);
   W.pts[(size_t)f * NP + idx] = make_float4(x, y, z, 0.0f);
+  {   // per-block range of the coordinates -> W.cpart[f][block][6] (crange_kernel folds the blocks): decides frame_ii_exact()
+    __shared__ unsigned s_rng[8][6];
+    unsigned mn[3], mx[3];
+    const float c3[3] = {fabsf(x), fabsf(y), fabsf(z)};
+#pragma unroll
+    for (int k = 0; k < 3; k++) { const unsigned b = __float_as_uint(c3[k]); mx[k] = b; mn[k] = b ? b : 0xffffffffu; }   // positive floats order like their bits
+#pragma unroll
+    for (int k = 0; k < 3; k++) { mn[k] = __reduce_min_sync(0xffffffffu, mn[k]); mx[k] = __reduce_max_sync(0xffffffffu, mx[k]); }
+    const int wp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) { s_rng[wp][k] = mn[k]; s_rng[wp][3 + k] = mx[k]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      unsigned v = s_rng[0][threadIdx.x];
+      for (int q = 1; q < (int)(blockDim.x >> 5); q++) v = threadIdx.x < 3 ? min(v, s_rng[q][threadIdx.x]) : max(v, s_rng[q][threadIdx.x]);
+      W.cpart[((size_t)f * gridDim.x + blockIdx.x) * 6 + threadIdx.x] = v;
+    }
+  }
   W.count[(size_t)f * NP + idx] = 0;
   W.maxidx[(size_t)f * NP + idx] = 0;
   W.cmin[(size_t)f * NP + idx] = 0x7fffffff;
   W.cmax[(size_t)f * NP + idx] = -1;
+}
+
+// folds the per-block coordinate ranges of a frame: 6 warps, warp q owns quantity q (min |x| |y| |z|, max |x| |y| |z|)
+__global__ void crange_kernel(PlaneFramePtrs W, int nblocks) {
+  const int f = blockIdx.x, q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned v = q < 3 ? 0xffffffffu : 0u;
+  for (int b = lane; b < nblocks; b += 32) { const unsigned u = W.cpart[((size_t)f * nblocks + b) * 6 + q]; v = q < 3 ? min(v, u) : max(v, u); }
+  v = q < 3 ? __reduce_min_sync(0xffffffffu, v) : __reduce_max_sync(0xffffffffu, v);
+  if (lane == 0) W.crange[6 * f + q] = v;
+}
+
+// ---------------------------------------------------------------------------------------------- exactness of the integral images
+// Every addend of an integral image is a float difference of two coordinates of the same component, hence an integer multiple of
+// u = ulp(smallest non-zero |coordinate|) of that component; every entry and every intermediate of PCL's recurrence
+// ((II(r,c+1) + II(r+1,c)) - II(r,c)) + v is bounded by 2 B + V with B <= max(H, W) * 4 * Cmax (the row / column sums telescope up to
+// the float rounding of the differences) and V <= 2 Cmax.  When (2 B + V) / u < 2^52 for x, y and z every one of those doubles is
+// exactly representable: NO rounding happens anywhere in the recurrence, the integral images are the exact sums, and a box sum
+// ((lr + ul) - ur) - ll equals the exact sum of the addends inside the box -- whatever the summation order and whatever the origin of
+// the integral image.  Such frames (every realistic frame: depths of 8 cm and more with the TUM intrinsics) take normals_exact_kernel,
+// which builds TILE-LOCAL integral images in shared memory; the others keep the wavefront recurrence + normals_kernel.
+__device__ __forceinline__ bool frame_ii_exact(const unsigned *crange, int f, int H, int Wd) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const unsigned mnb = crange[6 * f + k], mxb = crange[6 * f + 3 + k];
+    if (mnb == 0xffffffffu) continue;                          // the component is zero everywhere
+    if ((mxb >> 23) >= 255u || (mnb >> 23) == 0u) { ok = false; continue; }   // inf / NaN / subnormal coordinates
+    const double cmax = (double)__uint_as_float(mxb);
+    const double bound = 2.0 * (double)max(H, Wd) * 4.0 * cmax * 1.01 + 2.0 * cmax;
+    const double ulp = scalbn(1.0, (int)(mnb >> 23) - 127 - 23);
+    ok = ok && (bound < ulp * 4503599627370496.0);            // 2^52
+  }
+  return ok;
+}
+// One CTA per 32 x 32 output tile: the six gradient channels of the (32 + 10)^2 pixel window as tile-local integral images in
+// shared memory (exact doubles), then pcl::IntegralImageNormalEstimation's AVERAGE_3D_GRADIENT normal per pixel -- the integral
+// images of these frames never exist in HBM.
+constexpr int kNxT = 32, kNxHalo = 5, kNxW = kNxT + 2 * kNxHalo, kNxP = kNxW + 1;   // window 42, integral image 43 x 43 (odd pitch: no bank conflicts)
+constexpr int kNxPW = kNxW + 3;                                                       // coordinate tile: window + 1 pixel around it, pitch 45 (odd)
+constexpr int kNxSmemBytes = 6 * kNxP * kNxP * (int)sizeof(double) + 3 * (kNxW + 2) * kNxPW * (int)sizeof(float);
+__global__ void __launch_bounds__(512, 2) normals_exact_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
+  extern __shared__ __align__(16) unsigned char nx_smem[];
+  double *II = reinterpret_cast<double *>(nx_smem);                                   // [6][43][43]
+  float *P = reinterpret_cast<float *>(nx_smem + 6 * kNxP * kNxP * sizeof(double));   // [3][44][45]
+  const int H = prm.rows, Wd = prm.cols, NP = H * Wd;
+  const int f = blockIdx.z;
+  if (!W.exact_mode || !frame_ii_exact(W.crange, f, H, Wd)) return;
+  const int R0 = blockIdx.y * kNxT - kNxHalo, C0 = blockIdx.x * kNxT - kNxHalo;   // first pixel of the window
+  const float4 *pts = W.pts + (size_t)f * NP;
+  constexpr int PW = kNxPW, PH = kNxW + 2, PS = PH * PW;
+  for (int i = threadIdx.x; i < PH * (kNxW + 2); i += blockDim.x) {
+    const int rr = i / (kNxW + 2), cc = i - rr * (kNxW + 2);
+    const int pr = R0 - 1 + rr, pc = C0 - 1 + cc;
+    float4 p = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (pr >= 0 && pr < H && pc >= 0 && pc < Wd) p = pts[(size_t)pr * Wd + pc];
+    const int o = rr * PW + cc;
+    P[o] = p.x; P[PS + o] = p.y; P[2 * PS + o] = p.z;
+  }
+  for (int t = threadIdx.x; t < 6 * kNxP; t += blockDim.x) II[(size_t)(t / kNxP) * kNxP * kNxP + (t % kNxP)] = 0.0;   // row 0 of every channel
+  __syncthreads();
+  // row prefix sums of the addends: thread = (channel, window row), lanes = rows; channel k < 3: d/dx of component k, else d/dy of k - 3.
+  // Addends are zero outside image rows 1 .. H-2 / columns 1 .. W-2 (IntegralImageNormalEstimation::initAverage3DGradientMethod).
+  for (int t = threadIdx.x; t < 6 * kNxW; t += blockDim.x) {
+    const int ch = t / kNxW, i = t - ch * kNxW, k = ch % 3;
+    const int r = R0 + i;
+    const float *Pk = P + k * PS + (i + 1) * PW + 1;   // Pk[j] = component k of window pixel (i, j)
+    double *row = II + ((size_t)ch * kNxP + (i + 1)) * kNxP;
+    const bool rowok = r >= 1 && r <= H - 2;
+    const int jlo = rowok ? max(0, 1 - C0) : kNxW, jhi = rowok ? min(kNxW, Wd - 1 - C0) : kNxW;   // columns with a non-zero addend: [jlo, jhi)
+    double acc = 0.0;
+    row[0] = 0.0;
+    int j = 0;
+    for (; j < jlo && j < kNxW; j++) row[j + 1] = 0.0;
+    if (ch < 3) {
+      float left = (j < kNxW) ? Pk[j - 1] : 0.0f, mid = (j < kNxW) ? Pk[j] : 0.0f;
+#pragma unroll 6
+      for (; j < jhi; j++) {
+        const float right = Pk[j + 1];
+        acc = __dadd_rn(acc, (double)__fsub_rn(right, left));
+        row[j + 1] = acc;
+        left = mid; mid = right;
+      }
+    } else {
+#pragma unroll 6
+      for (; j < jhi; j++) {
+        acc = __dadd_rn(acc, (double)__fsub_rn(Pk[j + PW], Pk[j - PW]));
+        row[j + 1] = acc;
+      }
+    }
+    for (; j < kNxW; j++) row[j + 1] = acc;
+  }
+  __syncthreads();
+  // column prefix sums: thread = (channel, column), lanes = columns
+  for (int t = threadIdx.x; t < 6 * kNxW; t += blockDim.x) {
+    const int ch = t / kNxW, j = t - ch * kNxW;
+    double *col = II + (size_t)ch * kNxP * kNxP + kNxP + (j + 1);
+    double acc = 0.0;
+#pragma unroll 6
+    for (int i = 0; i < kNxW; i++) { acc = __dadd_rn(acc, col[(size_t)i * kNxP]); col[(size_t)i * kNxP] = acc; }
+  }
+  __syncthreads();
+  const float nanf_ = __int_as_float(0x7fc00000);
+  const int border = 10;   // int(normal_smoothing_size_)
+  for (int t = threadIdx.x; t < kNxT * kNxT; t += blockDim.x) {
+    const int ti = t / kNxT, tj = t - ti * kNxT;
+    const int ri = blockIdx.y * kNxT + ti, ci = blockIdx.x * kNxT + tj;
+    if (ri >= H || ci >= Wd) continue;
+    const size_t idx = (size_t)ri * Wd + ci;
+    const int pi = (ti + kNxHalo + 1) * PW + (tj + kNxHalo + 1);
+    const float px = P[pi], py = P[PS + pi], pz = P[2 * PS + pi];
+    float nx = nanf_, ny = nanf_, nz = nanf_;
+    if (ri >= border && ri < H - border && ci >= border && ci < Wd - border && isfinite(pz)) {
+      const float smoothing = fminf(W.dm[(size_t)f * NP + idx], 10.0f);
+      if (smoothing > 2.0f) {
+        const int rw = (int)smoothing, rw2 = rw / 2;
+        const int sy = ti + kNxHalo - rw2, sx = tj + kNxHalo - rw2;   // window coordinates of the box
+        const int ul = sy * kNxP + sx, ur = ul + rw, ll = (sy + rw) * kNxP + sx, lr = ll + rw;
+        double g[6];
+#pragma unroll
+        for (int ch = 0; ch < 6; ch++) {
+          const double *q = II + (size_t)ch * kNxP * kNxP;
+          g[ch] = __dsub_rn(__dsub_rn(__dadd_rn(q[lr], q[ul]), q[ur]), q[ll]);
+        }
+        const double *gx = g, *gy = g + 3;
+        const double n0 = __dsub_rn(__dmul_rn(gy[1], gx[2]), __dmul_rn(gy[2], gx[1]));   // gradient_y.cross(gradient_x)
+        const double n1 = __dsub_rn(__dmul_rn(gy[2], gx[0]), __dmul_rn(gy[0], gx[2]));
+        const double n2 = __dsub_rn(__dmul_rn(gy[0], gx[1]), __dmul_rn(gy[1], gx[0]));
+        const double nl = __dadd_rn(__dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1)), __dmul_rn(n2, n2));
+        if (nl != 0.0) {
+          const double s = sqrt(nl);
+          nx = (float)(n0 / s); ny = (float)(n1 / s); nz = (float)(n2 / s);
+          const float vx = __fsub_rn(0.0f, px), vy = __fsub_rn(0.0f, py), vz = __fsub_rn(0.0f, pz);   // flipNormalTowardsViewpoint, vp = 0
+          const float cos_theta = __fadd_rn(__fadd_rn(__fmul_rn(vx, nx), __fmul_rn(vy, ny)), __fmul_rn(vz, nz));
+          if (cos_theta < 0) { nx *= -1; ny *= -1; nz *= -1; }
+        }
+      }
+    }
+    const float pd = __fadd_rn(__fadd_rn(__fmul_rn(px, nx), __fmul_rn(py, ny)), __fmul_rn(pz, nz));   // plane_d = p . n
+    W.nrm[(size_t)f * NP + idx] = make_float4(nx, ny, nz, pd);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- P2: integral images (exact recurrence)
@@ -98,6 +261,7 @@ __global__ void __launch_bounds__(32 * kIntWarps) integral_kernel(PlaneParamsDev
   extern __shared__ float s_ring[];      // [kIntWarps][32 rows][kIntRingPitch]: this channel's point differences x(r, c), staged coalesced
   const int H = prm.rows, Wd = prm.cols, NP = H * Wd, IWp = ii_pitch(Wd);
   const int f = blockIdx.x, ch = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (W.exact_mode && frame_ii_exact(W.crange, f, H, Wd)) return;   // this frame's integral images stay in shared memory (normals_exact_kernel)
   const int k = ch % 3;
   const bool isX = ch < 3;
   const float *ptsf = reinterpret_cast<const float *>(W.pts + (size_t)f * NP) + k;   // component k of pixel i at ptsf[4 * i]
@@ -315,9 +479,9 @@ __global__ void distmap_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
 // ---------------------------------------------------------------------------------------------- P4: normals + plane_d
 __global__ void normals_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   const int H = prm.rows, Wd = prm.cols, NP = H * Wd, IW = ii_pitch(Wd);
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int f = blockIdx.y;
-  if (idx >= NP) return;
+  if (W.exact_mode && frame_ii_exact(W.crange, f, H, Wd)) return;   // done by normals_exact_kernel
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < NP; idx += gridDim.x * blockDim.x) {
   int ri = idx / Wd, ci = idx - ri * Wd;
   const float4 p = W.pts[(size_t)f * NP + idx];
   const float nanf_ = __int_as_float(0x7fc00000);
@@ -354,6 +518,7 @@ __global__ void normals_kernel(PlaneParamsDev prm, PlaneFramePtrs W) {
   }
   float pd = __fadd_rn(__fadd_rn(__fmul_rn(p.x, nx), __fmul_rn(p.y, ny)), __fmul_rn(p.z, nz));   // plane_d = p . n
   W.nrm[(size_t)f * NP + idx] = make_float4(nx, ny, nz, pd);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- P5: connected components
@@ -948,11 +1113,14 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
   ESLAM_CUDA_OK(h, w.cand_root.reserve((size_t)chunk * kMaxRegions * 4)); ESLAM_CUDA_OK(h, w.cand_n.reserve((size_t)chunk * 4));
   ESLAM_CUDA_OK(h, w.cand_coef.reserve((size_t)chunk * kMaxRegions * 16)); ESLAM_CUDA_OK(h, w.cand_valid.reserve((size_t)chunk * kMaxRegions * 4));
   ESLAM_CUDA_OK(h, w.cand_size.reserve((size_t)chunk * kMaxRegions * 4));
+  ESLAM_CUDA_OK(h, w.crange.reserve((size_t)chunk * 6 * sizeof(unsigned)));
+  ESLAM_CUDA_OK(h, w.cpart.reserve((size_t)chunk * ((NP + 255) / 256) * 6 * sizeof(unsigned)));
   ESLAM_CUDA_OK(h, w.out_plane.reserve((size_t)chunk * 32)); ESLAM_CUDA_OK(h, w.out_found.reserve((size_t)chunk * 4)); ESLAM_CUDA_OK(h, w.out_inl.reserve((size_t)chunk * 4));
   PlaneFramePtrs P;
   P.pts = w.pts.as<float4>(); P.nrm = w.nrm.as<float4>(); P.iiX = w.iiX.as<double>(); P.iiY = w.iiY.as<double>(); P.dm = w.dm.as<float>();
   P.parent = w.parent.as<int>(); P.label = w.label.as<int>(); P.count = w.count.as<int>(); P.maxidx = w.maxidx.as<int>(); P.cmin = w.cmin.as<int>(); P.cmax = w.cmax.as<int>();
   P.cand_root = w.cand_root.as<int>(); P.cand_n = w.cand_n.as<int>(); P.cand_coef = w.cand_coef.as<float4>(); P.cand_valid = w.cand_valid.as<int>();
+  P.crange = w.crange.as<unsigned>(); P.cpart = w.cpart.as<unsigned>(); P.exact_mode = h->plane_exact ? 1 : 0;
   P.cand_size = w.cand_size.as<int>(); P.out_plane = w.out_plane.as<double>(); P.out_found = w.out_found.as<int>(); P.out_inl = w.out_inl.as<int>();
   PlaneParamsDev prm;
   prm.fx = h->cam.fx; prm.fy = h->cam.fy; prm.cx = h->cam.cx; prm.cy = h->cam.cy; prm.scale = h->cam.scale; prm.rows = H; prm.cols = Wd;
@@ -968,18 +1136,47 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
     ESLAM_CUDA_OK(h, cudaFuncSetAttribute(integral_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // 2 CTAs (2 x 97 KB) per SM
     ESLAM_CUDA_OK(h, cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFitSmemBytes));
     ESLAM_CUDA_OK(h, cudaFuncSetAttribute(ccl_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, strip_bytes));
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(normals_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNxSmemBytes));
     h->attr_plane = true;
   }
   const size_t frame_stride = (size_t)H * pitch;
+  // A chunk runs as two halves on two streams: most kernels of the stage are latency bound with one CTA per frame (distance map,
+  // refinement, candidates, fit), so kernels of the two halves overlap on the SMs; the second stream is ordered after the caller's.
+  const int nblocks = (int)((NP + 255) / 256);
+  auto shifted = [&](const PlaneFramePtrs &B, int o) {
+    PlaneFramePtrs Q = B;
+    Q.pts += (size_t)o * NP; Q.nrm += (size_t)o * NP; Q.iiX += (size_t)o * NI; Q.iiY += (size_t)o * NI; Q.dm += (size_t)o * NP;
+    Q.parent += (size_t)o * NP; Q.label += (size_t)o * NP; Q.count += (size_t)o * NP; Q.maxidx += (size_t)o * NP; Q.cmin += (size_t)o * NP; Q.cmax += (size_t)o * NP;
+    Q.cand_root += (size_t)o * kMaxRegions; Q.cand_n += o; Q.cand_coef += (size_t)o * kMaxRegions; Q.cand_valid += (size_t)o * kMaxRegions; Q.cand_size += (size_t)o * kMaxRegions;
+    Q.out_plane += (size_t)o * 4; Q.out_found += o; Q.out_inl += o; Q.crange += (size_t)o * 6; Q.cpart += (size_t)o * nblocks * 6;
+    return Q;
+  };
+  if (!h->plane_stream2) {
+    ESLAM_CUDA_OK(h, cudaStreamCreateWithFlags(&h->plane_stream2, cudaStreamNonBlocking));
+    ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->plane_ev[0], cudaEventDisableTiming));
+    ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->plane_ev[1], cudaEventDisableTiming));
+  }
   for (int f0 = 0; f0 < n_frames; f0 += chunk) {
-    const int F = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;
-    const uint16_t *d0 = depth_dev + (size_t)f0 * frame_stride;
+    const int Fc = (n_frames - f0) < chunk ? (n_frames - f0) : chunk;
+    const int nsub = (debug_stage == 0 && Fc >= 32 && h->plane_streams > 1) ? 2 : 1;
+    if (nsub == 2) { ESLAM_CUDA_OK(h, cudaEventRecord(h->plane_ev[0], s)); ESLAM_CUDA_OK(h, cudaStreamWaitEvent(h->plane_stream2, h->plane_ev[0], 0)); }
+    for (int sub = 0; sub < nsub; sub++) {
+    const int o = sub == 0 ? 0 : Fc / 2, F = nsub == 1 ? Fc : (sub == 0 ? Fc / 2 : Fc - Fc / 2);
+    cudaStream_t s_outer = s;
+    {
+    cudaStream_t s = sub == 0 ? s_outer : h->plane_stream2;
+    const PlaneFramePtrs P_outer = P;
+    const PlaneFramePtrs P = shifted(P_outer, o);
+    const int f0s = f0 + o;
+    const uint16_t *d0 = depth_dev + (size_t)f0s * frame_stride;
     dim3 gpix((unsigned)((NP + 255) / 256), (unsigned)F);
     points_kernel<<<gpix, 256, 0, s>>>(d0, pitch, frame_stride, prm, P); ESLAM_LAUNCHED(h);
+    crange_kernel<<<F, 192, 0, s>>>(P, (int)gpix.x); ESLAM_LAUNCHED(h);
     integral_kernel<<<F, 32 * kIntWarps, kIntSmemBytes, s>>>(prm, P); ESLAM_LAUNCHED(h);
     distmap_kernel<<<F, tpc, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
     if (debug_stage == 1) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.dm, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
-    normals_kernel<<<gpix, 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);
+    normals_kernel<<<dim3((gpix.x + 7) / 8, (unsigned)F), 256, 0, s>>>(prm, P); ESLAM_LAUNCHED(h);   // frames that need the recurrence (exit at once otherwise)
+    normals_exact_kernel<<<dim3((unsigned)((Wd + kNxT - 1) / kNxT), (unsigned)((H + kNxT - 1) / kNxT), (unsigned)F), 512, kNxSmemBytes, s>>>(prm, P); ESLAM_LAUNCHED(h);
     if (debug_stage == 2) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.nrm, NP * 16, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
     const int nstrips = (H + kStripRows - 1) / kStripRows;
     ccl_strip_kernel<<<dim3((unsigned)nstrips, (unsigned)F), tpc, strip_bytes, s>>>(prm, P); ESLAM_LAUNCHED(h);
@@ -994,10 +1191,13 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
     if (debug_stage == 4) { ESLAM_CUDA_OK(h, cudaMemcpyAsync(debug_out, P.label, NP * 4, cudaMemcpyDeviceToHost, s)); ESLAM_CUDA_OK(h, cudaStreamSynchronize(s)); return ESLAM_OK; }
     select_kernel<<<(F + 63) / 64, 64, 0, s>>>(prm, P, F); ESLAM_LAUNCHED(h);
     ESLAM_CUDA_OK(h, cudaGetLastError());
-    ESLAM_CUDA_OK(h, cudaMemcpyAsync(plane_cam_host + 4 * (size_t)f0, P.out_plane, sizeof(double) * 4 * F, cudaMemcpyDeviceToHost, s));
-    ESLAM_CUDA_OK(h, cudaMemcpyAsync(found_host + f0, P.out_found, sizeof(int) * F, cudaMemcpyDeviceToHost, s));
-    if (n_inliers_host) ESLAM_CUDA_OK(h, cudaMemcpyAsync(n_inliers_host + f0, P.out_inl, sizeof(int) * F, cudaMemcpyDeviceToHost, s));
-    ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
+    ESLAM_CUDA_OK(h, cudaMemcpyAsync(plane_cam_host + 4 * (size_t)f0s, P.out_plane, sizeof(double) * 4 * F, cudaMemcpyDeviceToHost, s));
+    ESLAM_CUDA_OK(h, cudaMemcpyAsync(found_host + f0s, P.out_found, sizeof(int) * F, cudaMemcpyDeviceToHost, s));
+    if (n_inliers_host) ESLAM_CUDA_OK(h, cudaMemcpyAsync(n_inliers_host + f0s, P.out_inl, sizeof(int) * F, cudaMemcpyDeviceToHost, s));
+    }
+    }
+    if (nsub == 2) { ESLAM_CUDA_OK(h, cudaEventRecord(h->plane_ev[1], h->plane_stream2)); ESLAM_CUDA_OK(h, cudaStreamWaitEvent(s, h->plane_ev[1], 0)); }
+    ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));   // the results of the chunk are on the host (the one host synchronisation of the entry)
   }
   return ESLAM_OK;
 }
@@ -1011,9 +1211,10 @@ void plane_free(EslamHandle *h) {
   if (!h->pl) return;
   PlaneWorkspace &w = *h->pl;
   DevBuf *bufs[] = {&w.pts, &w.nrm, &w.iiX, &w.iiY, &w.dm, &w.parent, &w.label, &w.count, &w.maxidx, &w.cmin, &w.cmax, &w.cand_root, &w.cand_n, &w.cand_coef, &w.cand_valid, &w.cand_size,
-                    &w.out_plane, &w.out_found, &w.out_inl};
+                    &w.out_plane, &w.out_found, &w.out_inl, &w.crange, &w.cpart};
   for (DevBuf *b : bufs) b->release();
   w.pin.release();
+  if (h->plane_stream2) { cudaStreamDestroy(h->plane_stream2); cudaEventDestroy(h->plane_ev[0]); cudaEventDestroy(h->plane_ev[1]); h->plane_stream2 = nullptr; }
   delete h->pl; h->pl = nullptr;
 }
 

@@ -587,3 +587,20 @@ def test_device_resident_submit_collect_equals_blocking_call(handle):
     stream.synchronize()
     for b, w in zip(bufs, want):
         assert b.cpu().numpy().tobytes() == w
+
+
+def test_plane_normals_fused_tiles_and_recurrence_fallback():
+    """Frames whose integral images are provably exact take the fused tile kernel (tile-local integral images in shared memory), the
+    others the wavefront recurrence: both must give the oracle's normals bit for bit.  ESLAM_PLANE_EXACT=0 forces the recurrence;
+    a raw depth of 1 (0.2 mm) next to the optical axis breaks the exactness bound, so that frame falls back on its own."""
+    depth = synth.make_batch(1, "one_box")[0][0]
+    tiny = depth.copy(); tiny[247:249, 318:322] = 1
+    for d in (depth, tiny):
+        normals = orc.extract_planes_debug(d)[0]
+        ok = ~np.isnan(normals[..., 0])
+        for env in ({}, {"ESLAM_PLANE_EXACT": "0"}):
+            h = _handle_with_env(env)
+            g = h.debug_plane_stage(d, 2)
+            h.close()
+            assert np.array_equal(np.isnan(g[..., 0]), ~ok)
+            assert np.array_equal(g[..., :3][ok], normals[ok]), np.abs(g[..., :3][ok] - normals[ok]).max()
