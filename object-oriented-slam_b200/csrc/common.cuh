@@ -73,7 +73,7 @@ struct EslamHandle {
   eslam::DevBuf sym_pool_nn, sym_pool_px, sym_slotmask;   // round-1 kernel (ESLAM_SYM_IMPL=1) only
   eslam::DevBuf sym_pool256, sym_pool512, sym_slotmask2, sym_smid_map;
   cudaStream_t plane_stream2 = nullptr; cudaEvent_t plane_ev[2] = {nullptr, nullptr};   // second half of a ground-plane chunk
-XX
+  int plane_streams = 1;    // env ESLAM_PLANE_STREAMS=2: a chunk as two halves on two streams (measured slower: 15.2 vs 12.3 ms per 296 frames)
   bool plane_exact = true;  // env ESLAM_PLANE_EXACT=0: every frame takes the integral-image recurrence (A/B, fallback test)
   bool pull_tma = true;    // SM pull of the box rectangles through cp.async.bulk (TMA); env ESLAM_PULL_TMA=0: the LDG/STG pull kernel
   int sym_occ = 0;         // env ESLAM_SYM_OCC (tuning): 2 / 4 resident CTAs per SM instead of kSymCtas256
