@@ -539,10 +539,11 @@ def main():
         mine = torch.empty(n_obj * rec_bytes, dtype=torch.uint8, device="cuda")
         allrec = torch.empty(world * n_obj * rec_bytes, dtype=torch.uint8, device="cuda")
 
+        from eslam_b200 import shard
+
         def step_c5():
             step_resident()
-            h.copy_ellipsoids_dev(n_obj, mine.data_ptr(), stream=sptr)
-            dist.all_gather_into_tensor(allrec, mine)       # NCCL on the current (= launching) stream, no host round trip
+            shard.gather_records_dev(h, n_obj, stream_ptr=sptr, out=allrec)   # D2D copy + ncclAllGather on the launching stream, no host round trip
         for _ in range(3):
             step_c5()
         barrier()

@@ -60,3 +60,23 @@ def gather_records(local_records, local_obj_ids, n_obj_total, device="cpu", grou
         for k in range(int(cnts[r].item())):
             C.memmove(C.byref(out, int(gid[k]) * RECORD_BYTES), buf[k * RECORD_BYTES:(k + 1) * RECORD_BYTES].ctypes.data, RECORD_BYTES)
     return out
+
+
+def gather_records_dev(handle, n_obj, stream_ptr=0, group=None, out=None):
+    """Device-side "gather of map": the records of the handle's last *_dev batch go D2D into a torch buffer on the caller's stream and
+    are all-gathered over NCCL (all_gather_into_tensor) on the same stream -- no host round trip, no per-record Python.  Every rank
+    must own the same number of objects.  Returns a uint8 CUDA tensor [world, n_obj * RECORD_BYTES] in rank order; records_view()
+    turns a rank's row (after .cpu()) into an EslamEllipsoidOut array."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mine = torch.empty(n_obj * RECORD_BYTES, dtype=torch.uint8, device="cuda")
+    if out is None:
+        out = torch.empty(world * n_obj * RECORD_BYTES, dtype=torch.uint8, device="cuda")
+    handle.copy_ellipsoids_dev(n_obj, mine.data_ptr(), stream=stream_ptr)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out.view(world, n_obj * RECORD_BYTES)
+
+
+def records_view(row_u8_cpu, n):
+    return bytes_to_records(row_u8_cpu.numpy() if hasattr(row_u8_cpu, "numpy") else row_u8_cpu, n)
