@@ -447,13 +447,18 @@ __device__ __noinline__ void classify_chunk(const SymObj<CAP> &O, SymSeed<CAP> &
   const int li = chunk * 32 + lane;
   int cls = 0; bool rob = true, safe = false, hit = false;
   if (li < M) {
-    const float4 c = S.nnc[S.cur][h0 + li];   // both cache entries are requested before the fp64 classification chain
+    float4 c = S.nnc[S.cur][h0 + li];   // the cache entries are requested before the fp64 classification chain
+    const float4 c2 = S.nnc[wbank][h0 + li];   // the other bank: the entry of an earlier (rejected) trial -- any entry ever written is valid
     const uint4 pc = S.pxc[h0 + li];
     const d3 pm = mirror_q(load_pt(O, li), q, n, down);
     cls = classify(O, pm, pc, S.pxc + h0 + li, rob);
     double lnp = -0.0;
     if (cls == 1) {
       hit = nn_cached(c, (float)pm.x, (float)pm.y, (float)pm.z, safe);
+      if (!hit && wbank != S.cur) {   // a shorter step after a rejected trial often lands near that trial's query
+        bool safe2;
+        if (nn_cached(c2, (float)pm.x, (float)pm.y, (float)pm.z, safe2)) { hit = true; safe = safe2; c = c2; }
+      }
       if (hit) {
         const int best = (int)(__float_as_uint(c.w) & kIdxMask);
         const double dis = dist_to_neighbour(O, pm, best);
