@@ -618,7 +618,7 @@ def main():
                     "api": "eslam_estimate_ellipsoids_submit / _wait, two batches in flight (host pinned buffers in, records out, every step)",
                     "single_blocking_call_value": e2e_sync,
                     "pageable_input": {"value": e2e_pageable, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_pg) * world,
-                                       "api": "eslam_estimate_ellipsoids_host on a pageable numpy array (batched DMA of the box rectangles)"}},
+                                       "api": "eslam_estimate_ellipsoids_host on a pageable numpy array (box rows staged into pinned memory by host threads, then pulled by the bulk-copy kernel)"}},
             "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline}
     if stages is not None:

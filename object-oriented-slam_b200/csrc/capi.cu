@@ -3,13 +3,46 @@
 // There is no CPU implementation of any hot-path stage in this library.
 #include <math.h>
 #include <stdlib.h>
+#include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <thread>
 #include "common.cuh"
 #include "extract_types.cuh"
 #include "internal.h"
 
 using namespace eslam;
+
+namespace eslam {
+// Fork-join pool for the host-side staging copies of pageable input (box rows -> pinned memory).  Workers sleep between jobs.
+struct CopyPool {
+  std::vector<std::thread> th;
+  std::mutex m; std::condition_variable cv_go, cv_done;
+  std::function<void(int)> job; int n_items = 0; std::atomic<int> next{0}; int gen = 0, running = 0; bool quit = false;
+  explicit CopyPool(int n) {
+    for (int i = 0; i < n; i++) th.emplace_back([this] {
+      int seen = 0;
+      while (true) {
+        { std::unique_lock<std::mutex> lk(m); cv_go.wait(lk, [&] { return quit || gen != seen; }); if (quit) return; seen = gen; }
+        for (int it; (it = next.fetch_add(1)) < n_items;) job(it);
+        { std::lock_guard<std::mutex> lk(m); if (--running == 0) cv_done.notify_one(); }
+      }
+    });
+  }
+  ~CopyPool() { { std::lock_guard<std::mutex> lk(m); quit = true; } cv_go.notify_all(); for (auto &t : th) t.join(); }
+  void run(int n, std::function<void(int)> fn) {   // the calling thread works too
+    if (n <= 0) return;
+    { std::lock_guard<std::mutex> lk(m); job = std::move(fn); n_items = n; next = 0; running = (int)th.size(); gen++; }
+    cv_go.notify_all();
+    for (int it; (it = next.fetch_add(1)) < n_items;) job(it);
+    std::unique_lock<std::mutex> lk(m); cv_done.wait(lk, [&] { return running == 0; });
+  }
+};
+}  // namespace eslam
 
 namespace {
 
@@ -211,6 +244,44 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
           const int x0 = m.x1 & ~7, x1 = (m.x2 + 8) & ~7, y1 = m.y2 + 1;
           h->h2d_bytes += (size_t)((x1 < cols ? x1 : cols) - x0) * (size_t)((y1 < rows ? y1 : rows) - m.y1) * sizeof(uint16_t);
         }
+      } else if (h->h2d_mode == 4 && (pitch % 8) == 0 && (h->cam.cols % 8) == 0 && ((uintptr_t)depth_dev % 16) == 0) {
+        // Pageable host input (a plain cv::Mat): the rows of this chunk's box rectangles are copied by a few host threads into the
+        // workspace's pinned staging buffer (same layout as the frame batch), then pulled by the bulk-copy kernel like mapped input.
+        // The host copies chunk c + 1 while the GPU works on chunk c.
+        ExtractWorkspace &ww = *h->ex;
+        const size_t need = (size_t)n_frames * frame_stride * sizeof(uint16_t);
+        if (ww.pin_depth.bytes < need) ESLAM_CUDA_OK(h, ww.pin_depth.reserve(need));
+        uint16_t *stage = ww.pin_depth.as<uint16_t>();
+        if (!h->copy_pool) { unsigned hw = std::thread::hardware_concurrency(); int nt = hw >= 16 ? 7 : (hw >= 4 ? (int)hw / 2 - 1 : 0); h->copy_pool = new eslam::CopyPool(nt); }
+        std::vector<int> &rows_of = ww.stage_rows;   // prefix of row counts per object of the chunk
+        rows_of.assign((size_t)(o1 - o) + 1, 0);
+        for (int k = o; k < o1; k++) {
+          const ObjMeta &m = w.meta_host[k];
+          int nr = 0;
+          if (m.pre_status == 0 && m.nx != 0) { const int y1 = m.y2 + 1 < rows ? m.y2 + 1 : rows; nr = y1 - m.y1; }
+          rows_of[(size_t)(k - o) + 1] = rows_of[(size_t)(k - o)] + (nr > 0 ? nr : 0);
+        }
+        const int total_rows = rows_of.back(), per = 16, n_items = (total_rows + per - 1) / per;
+        const int obase = o;
+        h->copy_pool->run(n_items, [&, stage, obase](int it) {
+          int r0 = it * per, r1 = r0 + per < total_rows ? r0 + per : total_rows;
+          int k = (int)(std::upper_bound(rows_of.begin(), rows_of.end(), r0) - rows_of.begin()) - 1;
+          for (int r = r0; r < r1; r++) {
+            while (rows_of[(size_t)k + 1] <= r) k++;
+            const ObjMeta &m = w.meta_host[obase + k];
+            const int x0 = m.x1 & ~7, x1a = (m.x2 + 8) & ~7, x1 = x1a < cols ? x1a : cols;
+            const size_t off = (size_t)m.frame * frame_stride + (size_t)(m.y1 + (r - rows_of[(size_t)k])) * pitch + x0;
+            memcpy(stage + off, host_depth + off, (size_t)(x1 - x0) * sizeof(uint16_t));
+          }
+        });
+        for (int k = o; k < o1; k++) {
+          const ObjMeta &m = w.meta_host[k];
+          if (m.pre_status != 0 || m.nx == 0) continue;
+          const int x0 = m.x1 & ~7, x1 = (m.x2 + 8) & ~7, y1 = m.y2 + 1;
+          h->h2d_bytes += (size_t)((x1 < cols ? x1 : cols) - x0) * (size_t)((y1 < rows ? y1 : rows) - m.y1) * sizeof(uint16_t);
+        }
+        ESLAM_CUDA_OK(h, cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[16], 0));   // needs the ObjMeta table
+        if ((rc = pull_rects_launch(h, h->copy_stream, stage, const_cast<uint16_t *>(depth_dev), pitch, frame_stride, o, o1 - o))) return rc;
       } else if (sorted && h->h2d_mode != 0) {
         // The kernels only ever read pixels inside the (int-truncated) boxes: crop and GetCenter sample inside the box, the lazy range
         // image is read where isInRange holds.  Upload the union rectangle of each frame's boxes (64-byte aligned columns) instead
@@ -379,6 +450,7 @@ void eslam_destroy(EslamHandle *h) {
   }
   h->sym_pool_nn.release(); h->sym_pool_px.release(); h->sym_slotmask.release(); h->plane_depth.release();
   h->sym_pool256.release(); h->sym_pool512.release(); h->sym_slotmask2.release(); h->sym_smid_map.release();
+  delete h->copy_pool; h->copy_pool = nullptr;
   slam_free(h);
   graph_free(h);
   plane_free(h);

@@ -50,6 +50,7 @@ struct ExtractWorkspace;  // extract.cu
 struct GraphWorkspace;    // edges.cu
 struct SlamWorkspace;     // slam.cu
 struct PlaneWorkspace;    // plane.cu
+struct CopyPool;          // capi.cu: host threads that stage pageable input into pinned memory
 
 }  // namespace eslam
 
@@ -99,6 +100,7 @@ struct EslamHandle {
   eslam::GraphWorkspace *gr = nullptr;
   eslam::SlamWorkspace *sl = nullptr;
   eslam::PlaneWorkspace *pl = nullptr;
+  eslam::CopyPool *copy_pool = nullptr;
 };
 
 #define ESLAM_CUDA_OK(h, call)                                                                       \

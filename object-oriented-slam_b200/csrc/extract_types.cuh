@@ -75,6 +75,7 @@ struct ExtractWorkspace {
   PinBuf pin_meta, pin_out, pin_depth;
   std::vector<ObjMeta> meta_host;
   std::vector<cudaMemcpy3DBatchOp> copy_ops;   // per-chunk upload list of the host entry
+  std::vector<int> stage_rows;                 // staged pull of pageable input: row-count prefix of the chunk's objects
   long long cap_total = 0;
   int n_obj = 0;
 };
