@@ -48,6 +48,7 @@ extern "C" {
 #define ESLAM_OBJ_NO_POINTS 3    /* EllipsoidExtractor.cpp:127 */
 #define ESLAM_OBJ_NO_POINTS_AFTER_PLANE 4 /* EllipsoidExtractor.cpp:118 */
 #define ESLAM_OBJ_BBOX_OUTSIDE 5 /* not in the reference: bbox leaves the image (the reference reads out of bounds) */
+#define ESLAM_OBJ_INTERNAL 6     /* not in the reference: the device pipeline did not finish the object (never expected; reported instead of a partial record) */
 
 /* camera_intrinsic (include/core/Geometry.h:27-33) + image size */
 typedef struct EslamCamera {

@@ -158,6 +158,13 @@ int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const
     ESLAM_CUDA_OK(h, cudaMemcpy(h->sym_slotmask2.p, mask.data(), mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
     ESLAM_CUDA_OK(h, cudaMemcpy(h->sym_smid_map.p, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
+  if (h->sym_impl == 3) {   // round pipeline: the seeds' state and caches live in HBM / L2 between the launches of a chunk
+    ESLAM_CUDA_OK(h, w.symseed.reserve(symmetry_round_seed_bytes() * (size_t)n_obj));
+    ESLAM_CUDA_OK(h, w.symcache.reserve(symmetry_round_cache_bytes() * (size_t)n_obj));
+    ESLAM_CUDA_OK(h, w.symchunk.reserve(symmetry_round_desc_bytes() * (size_t)kMaxChunks));
+    ESLAM_CUDA_OK(h, w.symlive.reserve(sizeof(int) * (size_t)kMaxChunks * (kSymMaxRounds + 2)));
+    ESLAM_CUDA_OK(h, w.pin_symchunk.reserve(symmetry_round_desc_bytes() * (size_t)kMaxChunks));
+  }
   P.sympool256 = h->sym_pool256.as<unsigned char>(); P.sympool512 = h->sym_pool512.as<unsigned char>();
   P.slotmask2 = h->sym_slotmask2.as<unsigned>(); P.smid_map = h->sym_smid_map.as<int>(); P.sm_count = h->sm_count;
   P.d_crop = P.d_voxel = P.d_world = P.d_sym = P.d_final = nullptr; P.d_label = nullptr;
@@ -345,7 +352,7 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
     }
     if (cs != s) ESLAM_CUDA_OK(h, cudaStreamWaitEvent(cs, h->chunk_ev[16], 0));
     if ((rc = extract_launch(h, cs, depth_dev, pitch, frame_stride, o, o1 - o, prm, P))) return rc;
-    if ((rc = symmetry_finalize_launch(h, cs, depth_dev, pitch, frame_stride, o, o1 - o, prm, P))) return rc;
+    if ((rc = symmetry_finalize_launch(h, cs, depth_dev, pitch, frame_stride, o, o1 - o, prm, P, c))) return rc;
     if (cs != s) { ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_done[c], cs)); ESLAM_CUDA_OK(h, cudaStreamWaitEvent(s, h->chunk_done[c], 0)); }
     o = o1;
   }
@@ -420,11 +427,12 @@ int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHa
   if (!h) return ESLAM_ERR_CUDA;
   h->prm = *p; h->cam = *c; h->device = device; h->sm_count = prop.multiProcessorCount;
   if (const char *e = getenv("ESLAM_H2D_MODE")) { int v = atoi(e); if (v >= 0 && v <= 4) h->h2d_mode = v; }
-  if (const char *e = getenv("ESLAM_SYM_IMPL")) { int v = atoi(e); if (v == 1 || v == 2) h->sym_impl = v; }
+  if (const char *e = getenv("ESLAM_SYM_IMPL")) { int v = atoi(e); if (v >= 1 && v <= 3) h->sym_impl = v; }
   if (const char *e = getenv("ESLAM_PLANE_STREAMS")) h->plane_streams = atoi(e);
   if (const char *e = getenv("ESLAM_PLANE_EXACT")) h->plane_exact = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_PULL_TMA")) h->pull_tma = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_SYM_OCC")) h->sym_occ = atoi(e);
+  if (const char *e = getenv("ESLAM_SYM_GRAPH")) h->sym_graph = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_SYM_VERIFY")) h->sym_verify = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_DEV_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= kMaxChunks) h->dev_chunks = v; }
   if (const char *e = getenv("ESLAM_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= kMaxChunks) h->host_chunks = v; }
@@ -442,6 +450,8 @@ void eslam_destroy(EslamHandle *h) {
     DevBuf *bufs[] = {&w.meta, &w.state, &w.out, &w.ptsA, &w.ptsB, &w.ptsC, &w.k0, &w.k1, &w.v0, &w.v1, &w.parent, &w.count, &w.objn, &w.objnf,
                       &w.d_crop, &w.d_voxel, &w.d_world, &w.d_sym, &w.d_final, &w.d_label, &w.depth};
     for (DevBuf *b : bufs) b->release();
+    w.symseed.release(); w.symcache.release(); w.symchunk.release(); w.symlive.release(); w.pin_symchunk.release();
+    for (auto &g : w.symgraph) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     w.pin_meta.release(); w.pin_out.release(); w.pin_depth.release();
     delete h->ex_slot[sl];
     if (h->slot_stream[sl]) cudaStreamDestroy(h->slot_stream[sl]);
@@ -618,7 +628,7 @@ int eslam_batch_counters(EslamHandle *h, unsigned long long out[12]) {
     out[0] += o.n_ref_evals; out[1] += o.n_ref_points; out[2] += o.n_evals; out[3] += o.n_points; out[4] += o.n_queries; out[5] += o.n_hits;
     if ((unsigned long long)o.n_sym > out[6]) out[6] = (unsigned long long)o.n_sym;
     out[8] += o.n_verify_fail;
-    for (int k = 0; k < 3; k++) out[9 + k] += (unsigned long long)o.sym_clk[k == 2 ? 3 : k];
+    for (int k = 0; k < 3; k++) out[9 + k] += (unsigned long long)o.sym_clk[k == 2 ? 3 : k];   // scalar phases, task phases, whole CTA
     if (o.run_sym) out[7]++;
   }
   return ESLAM_OK;

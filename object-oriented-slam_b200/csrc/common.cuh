@@ -78,7 +78,8 @@ struct EslamHandle {
   bool plane_exact = true;  // env ESLAM_PLANE_EXACT=0: every frame takes the integral-image recurrence (A/B, fallback test)
   bool pull_tma = true;    // SM pull of the box rectangles through cp.async.bulk (TMA); env ESLAM_PULL_TMA=0: the LDG/STG pull kernel
   int sym_occ = 0;         // env ESLAM_SYM_OCC (tuning): 2 / 4 resident CTAs per SM instead of kSymCtas256
-  int sym_impl = 2;        // env ESLAM_SYM_IMPL: 1 = round-1 kernel (A/B baseline), 2 = current
+  int sym_impl = 3;        // env ESLAM_SYM_IMPL: 1 = round-1 kernel (A/B baseline), 2 = single launch (CTA per object, rounds inside), 3 = round pipeline (phase-pure launches)
+  bool sym_graph = true;   // round pipeline: a chunk's ~115 launches are captured once and replayed as a CUDA graph (env ESLAM_SYM_GRAPH=0: plain launches)
   bool sym_verify = false; // env ESLAM_SYM_VERIFY=1: every shortcut decision of the symmetry kernel is re-derived the long way and counted when it differs
   eslam::DevBuf plane_depth;           // staging of eslam_extract_ground_plane_host (separate from the extraction slots)
   bool attr_extract = false, attr_symmetry = false, attr_symmetry_v1 = false, attr_plane = false;   // kernel attributes are per device: set once per handle, not once per process

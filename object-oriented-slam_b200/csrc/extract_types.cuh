@@ -26,7 +26,8 @@ struct ObjState {  // device resident, one per object
   double seed_prob[9], seed_init[9], seed_final[9], seed_plane[9][4], seed_dual[9];
   long long phase_clk[9];   // clock64() stamps of the extraction phases (thread 0): start, crop, voxel sort, voxel+plane filter, cluster sort,
                             // neighbour search, flatten+select+gather, PCA, symmetry grid (tools/extract_phases.py)
-  long long sym_clk[4];     // symmetry kernel, summed over the 9 seed warps: classification, NN scans, ordered sums, rest
+  long long sym_clk[4];     // single-launch symmetry kernel, cycles of the CTA: scalar phases, task phases, scan phases, whole CTA (round-1 kernel: per-warp sums)
+  double sym_R2;            // radius of the object-normalised cloud (bounds the finite-difference displacement), round pipeline
   unsigned long long n_evals, n_queries, n_points, n_hits;   // symmetry work counters (cost evaluations, NN scans, mirrored points, NN cache hits)
   unsigned long long n_ref_evals, n_ref_points;              // what the reference's call sequence performs (incl. the evaluations memoised here)
   unsigned long long n_verify_fail;                          // ESLAM_SYM_VERIFY=1: shortcut decisions that disagreed with the full path (must stay 0)
@@ -71,6 +72,9 @@ struct ExtractPtrs {  // device pointers of the per-point workspace (total capac
 struct ExtractWorkspace {
   DevBuf meta, state, out, ptsA, ptsB, ptsC, k0, k1, v0, v1, parent, count, objn, objnf;
   DevBuf d_crop, d_voxel, d_world, d_sym, d_final, d_label;
+  DevBuf symseed, symcache, symchunk, symlive;   // symmetry round pipeline: seed state, NN / pixel caches, per-chunk descriptors and live counters
+  PinBuf pin_symchunk;
+  struct SymGraph { cudaGraphExec_t exec = nullptr; int n_obj = 0, rounds = 0, verify = 0; const void *desc = nullptr, *live = nullptr; } symgraph[16];   // replayable launch sequence per chunk
   DevBuf depth;   // staging for the *_host entry point
   PinBuf pin_meta, pin_out, pin_depth;
   std::vector<ObjMeta> meta_host;

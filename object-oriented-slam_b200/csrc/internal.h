@@ -25,7 +25,11 @@ int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, si
                    const ExtractPtrs &ptrs);
 int pull_rects_launch(EslamHandle *h, cudaStream_t s, const uint16_t *host_mapped, uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj);
 int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj,
-                             const ExtractParamsDev &prm, const ExtractPtrs &ptrs);
+                             const ExtractParamsDev &prm, const ExtractPtrs &ptrs, int chunk = 0);
+size_t symmetry_round_seed_bytes();    // round pipeline (ESLAM_SYM_IMPL=3): persistent state per object (nine seeds)
+size_t symmetry_round_cache_bytes();   // NN + pixel caches per object
+size_t symmetry_round_desc_bytes();    // one chunk descriptor
+constexpr int kSymMaxRounds = 126;     // live counters per chunk (rounds + 2)
 
 size_t symmetry_pool_bytes(int cap);   // NN + pixel cache bytes of one resident symmetry CTA
 

@@ -73,11 +73,12 @@ struct SymObj {
   unsigned long long X2[CAP / 2], Y2[CAP / 2], Z2[CAP / 2];
 };
 enum { kActDone = 0, kActInit = 1, kActFd = 2, kActTrial = 3 };
-template <int CAP>
-struct SymSeed {
+// Levenberg-Marquardt state of one seed: everything that survives from one cost evaluation to the next (no per-evaluation scratch).
+// The single-launch kernel keeps it in shared memory; the round pipeline (sym_eval_kernel / sym_step_kernel) keeps it in HBM / L2
+// between launches and stages it through shared memory inside an evaluation launch.
+struct SeedCore {
   float4 *nnc[2];          // NN cache, two banks: [bank][point] = (q0.x, q0.y, q0.z, rho^2 | neighbour index)
   uint4 *pxc;              // pixel cache: [point] = (x | y << 16, ushort range value, depth = value / scale as a double)
-  // ---- Levenberg-Marquardt state of the one-vertex problem
   PlanePair pp, base, fd[6];
   dplane est, backup;
   double H[9], b[3], x[3], J[3];
@@ -87,14 +88,17 @@ struct SymSeed {
   unsigned n_evals, n_queries, n_points, n_hits, n_ref, n_verify_fail;
   SeedResult res;
   int inv_s[6];
-  // ---- per-evaluation scratch
+};
+template <int CAP>
+struct SymSeed : SeedCore {
+  unsigned mA[2][2][CAP / 32];        // [bank][half][word]: point needs work for a finite-difference plane (cost != 0, or not robust)
+  unsigned mF[2][2][CAP / 32];        //                     point is robust, carries a distance and its cached neighbour is final
+  // ---- per-evaluation scratch (everything from here on is dead between two evaluations)
   alignas(16) double lnp[2 * CAP];    // ln P of every mirrored point (-0.0 where it carries no distance), point order; FD passes stage their tiles here
   alignas(16) unsigned short queue[2 * CAP];   // points that need a scan: li | half << 9 | robust << 15 (FD passes keep their side buffer here)
   unsigned short list[CAP];           // FD pass: active points of the current half
   unsigned short slow[kSlowMax];
-  unsigned mA[2][2][CAP / 32];        // [bank][half][word]: point needs work for a finite-difference plane (cost != 0, or not robust)
-  unsigned mF[2][2][CAP / 32];        //                     point is robust, carries a distance and its cached neighbour is final
-  double pad_[2];                     // sizeof % 128 == 16: the nine lanes of the scalar step hit different banks
+  double pad_[2];                     // the nine lanes of the scalar step hit different banks
 };
 static_assert(6 * 33 <= 256 && 6 * kSlowMax * 2 <= 256, "FD staging tiles alias lnp / queue");
 
@@ -654,9 +658,7 @@ __device__ __forceinline__ bool fd_pair_ok(const PlanePair &A, const PlanePair &
 // It consumes the result of the seed's last action (S.err_last / S.J) and prepares the next one.  Exact economy over the literal call
 // sequence: computeActiveErrors() at the top of an iteration re-evaluates the plane whose error is already known (the accepted trial,
 // or the restored backup) -- the cost is a pure function, so the value is reused.
-template <int CAP>
-__device__ __noinline__ void lm_step(const SymObj<CAP> &O, SymSeed<CAP> &S) {
-  const int symtype = O.symtype;
+__device__ __noinline__ void lm_step(const int symtype, const int iters, SeedCore &S) {
   const int dim = (symtype == 1) ? 2 : 3;
   bool start_trial = false, begin_iter = false;
   if (S.action == kActInit) {
@@ -708,7 +710,7 @@ __device__ __noinline__ void lm_step(const SymObj<CAP> &O, SymSeed<CAP> &S) {
     }
   }
   if (begin_iter) {
-    if (S.it >= O.iters || !S.ok) {
+    if (S.it >= iters || !S.ok) {
       S.res.final_err = S.err_last;   // e->error() after optimize(): value of the LAST computeError call (possibly a rejected trial)
       S.res.prob = exp(-S.err_last);
       S.res.plane = S.est;
@@ -949,7 +951,11 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
   const int dim = (O.symtype == 1) ? 2 : 3;
   const int nchunks = (M + 31) >> 5, nhalves = (npts > M) ? 2 : 1;
   bool first = true;
+  // phase clocks of the CTA (thread 0): [0] scalar phases, [1] task phases, [2] scan phases, [3] whole CTA (tools/sym_counters.py)
+  long long clk_scalar = 0, clk_task = 0, clk_scan = 0, clk_t = 0;
+  const long long clk_begin = clock64();
   while (true) {
+    if (threadIdx.x == 0) clk_t = clock64();
     if (wid == 0) {
       if (lane < kSeeds) {
         SymSeed<CAP> &T = seeds[lane];
@@ -970,7 +976,7 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
               T.n_evals += nhalves; T.n_queries += (unsigned)T.qn; T.n_points += (unsigned)npts;
             }
           }
-          lm_step(O, T);
+          lm_step(O.symtype, O.iters, T);
           T.wbank = T.cur ^ 1; T.qn = 0; T.invalid = 0;
         }
       }
@@ -989,6 +995,7 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
     }
     first = false;
     __syncthreads();
+    if (threadIdx.x == 0) { const long long t = clock64(); clk_scalar += t - clk_t; clk_t = t; }
     if (O.n_live == 0) break;
     while (true) {
       int t = 0;
@@ -1036,6 +1043,7 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
       }
     }
     __syncthreads();
+    if (threadIdx.x == 0) { const long long t = clock64(); clk_task += t - clk_t; clk_t = t; }
     if (O.in_smem) {   // scan tasks: 32 queued points of one trial plane each
       if (wid == 0) {
         int cnt = (lane < O.n_tr) ? (seeds[O.tr_seed[lane]].qn + 31) >> 5 : 0, incl = cnt;
@@ -1058,7 +1066,9 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
       }
     }
     __syncthreads();
+    if (threadIdx.x == 0) clk_scan += clock64() - clk_t;
   }
+  if (threadIdx.x == 0) { st.sym_clk[0] = clk_scalar; st.sym_clk[1] = clk_task; st.sym_clk[2] = clk_scan; st.sym_clk[3] = clock64() - clk_begin; }
   // all seeds done: results to the object state, the slot back to the SM, completion by warp 0
   if (lane == 0) {
     const SeedResult &r = S.res;
@@ -1076,6 +1086,281 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
     atomicAnd(W.slotmask2 + (small ? 0 : W.sm_count) + O.sm, ~(1u << O.slotbit));
   }
   if (wid == 0) finalize_object(m, st, prm, W, out);
+}
+
+// ================================================================================================================ round pipeline
+// The same search as symmetry_finalize_kernel, cut into PHASE-PURE launches (default; ESLAM_SYM_IMPL=2 selects the single launch):
+//   sym_step_kernel   one thread per seed of the whole chunk (plus seven helper lanes): the scalar Levenberg-Marquardt step, the
+//                     finite-difference planes of the next linearisation, results of finished seeds
+//   sym_eval_kernel   one CTA per object: the cost evaluations the seeds are waiting for (finite-difference passes, trial planes)
+//   sym_final_kernel  one warp per object: completion, extents, ellipsoid record
+// issued as step(0), { eval(r), step(r + 1) } for r < 1 + 11 * iters (the longest possible LM run: every iteration 1 linearisation
+// + 10 trials); a launch whose chunk has no running seed left exits at once.  Why: the single launch spends a quarter of every
+// CTA's life in its scalar phase -- one warp streaming ~35 KB of cold fp64 code (oplus, trigonometry, LDLT, divisions) through a
+// 32 KB instruction cache that the evaluation code of the co-resident CTAs keeps flushing -- while its eight other warps wait at
+// the barrier.  Here that code runs once per round for ALL seeds of a chunk with every group busy, and the evaluation launches hold
+// nothing but evaluation code.  The seeds' state (SeedCore + robust masks, kSeedStride bytes) and their NN / pixel caches live in
+// HBM / L2 between launches; an evaluation CTA stages its nine seeds through shared memory.
+constexpr int kRoundCap = 256;                                        // clouds of up to 256 points; larger ones take the single-launch kernel
+constexpr int kSeedPersist = (int)((sizeof(SeedCore) + 2 * sizeof(unsigned[2][2][kRoundCap / 32]) + 15) & ~(size_t)15);
+constexpr int kSeedStride = kSeedPersist;
+constexpr size_t kRoundCacheBytes = (size_t)kRoundCap * 96;           // per seed: two NN banks + the pixel cache, 2 * CAP entries each
+constexpr int kStepThreads = 128;                                     // eight lanes per seed: 16 seeds per CTA
+static_assert(sizeof(SeedCore) % 8 == 0, "SeedCore is followed by the masks without padding");
+static_assert(sizeof(SymSeed<kRoundCap>) >= (size_t)kSeedPersist, "persistent prefix");
+#pragma nv_diag_suppress 1427
+static_assert(__builtin_offsetof(SymSeed<kRoundCap>, mA) == sizeof(SeedCore) && __builtin_offsetof(SymSeed<kRoundCap>, lnp) == (size_t)kSeedPersist,
+              "the persistent prefix is SeedCore + the robust masks; the scratch starts right behind it");
+#pragma nv_diag_default 1427
+
+struct SymChunk {   // descriptor of a chunk's launches (device memory, fixed address per chunk: the launches can be replayed as a graph)
+  const uint16_t *depth; size_t pitch, frame_stride;
+  const ObjMeta *metas; ObjState *states; EslamEllipsoidOut *outs;
+  unsigned char *seedp;   // [n_obj][kSeeds][kSeedStride]
+  unsigned char *cache;   // [n_obj][kSeeds][kRoundCacheBytes]
+  int *live;              // [rounds + 2]: seeds of the chunk waiting for evaluation r (zeroed before step(0))
+  int n_obj, rounds;
+  ExtractParamsDev prm; ExtractPtrs W;
+};
+__device__ __forceinline__ SeedCore *seed_core(const SymChunk &C, int obj, int sd) {
+  return reinterpret_cast<SeedCore *>(C.seedp + ((size_t)obj * kSeeds + sd) * kSeedStride);
+}
+__device__ __forceinline__ bool round_owned(const ObjState &st) { return st.status == 0 && st.run_sym && st.n_sym <= kRoundCap; }
+
+// step(0): seed planes (GenerateInitPlanes, Symmetry.cpp:44-86).  step(k > 0): consumes evaluation k - 1.
+__global__ void __launch_bounds__(kStepThreads) sym_step_kernel(const SymChunk *__restrict__ Cp, int k) {
+  const SymChunk &C = *Cp;
+  if (k > 0 && *((volatile const int *)(C.live + k - 1)) == 0) return;   // chunk uniform
+  const int lane = threadIdx.x & 31, sub = threadIdx.x & 7;
+  const int g = (blockIdx.x * kStepThreads + threadIdx.x) >> 3;
+  const int obj = g / kSeeds, sd = g - obj * kSeeds;
+  bool valid = obj < C.n_obj;
+  ObjState *st = valid ? C.states + obj : nullptr;
+  if (valid) valid = round_owned(*st);
+  const int symtype = valid ? C.metas[obj].symtype : 2;
+  const int dim = (symtype == 1) ? 2 : 3;
+  SeedCore *S = valid ? seed_core(C, obj, sd) : nullptr;
+  int action = kActDone;
+  if (valid && sub == 0) {
+    if (k == 0) {
+      unsigned char *cb = C.cache + ((size_t)obj * kSeeds + sd) * kRoundCacheBytes;
+      float4 *nn0 = reinterpret_cast<float4 *>(cb), *nn1 = nn0 + 2 * kRoundCap;
+      S->nnc[0] = nn0; S->nnc[1] = nn1; S->pxc = reinterpret_cast<uint4 *>(nn1 + 2 * kRoundCap);
+      S->cur = 0; S->fd_ok = 0; S->action = kActInit;
+      S->n_evals = S->n_queries = S->n_points = S->n_hits = S->n_ref = S->n_verify_fail = 0;
+      const double diff_dis = 0.2, diff_angle = M_PI / 180.0 * 5;
+      const double start_dis = -diff_dis * 1, start_angle = -diff_angle * 1;
+      const int si = sd / 3, sm_ = sd % 3;
+      const double dis = start_dis + diff_dis * si, angle = start_angle + diff_angle * sm_;
+      S->est.p[0] = sin(angle); S->est.p[1] = -cos(angle); S->est.p[2] = 0; S->est.p[3] = -dis; S->est.dual = 0;   // fromDisAngleTrans
+      make_pair(S->pp, S->est);
+      S->wbank = 0; S->qn = 0; S->invalid = 0;
+      action = kActInit;
+    } else if (S->action != kActDone) {
+      lm_step(symtype, C.prm.symmetry_iters, *S);
+      S->wbank = S->cur ^ 1; S->qn = 0; S->invalid = 0;
+      action = S->action;
+      if (action == kActDone) {   // results to the object state; the last seed of an object is seen by sym_final_kernel through st->done
+        const SeedResult &r = S->res;
+        st->seed_prob[sd] = r.prob; st->seed_init[sd] = r.init_err; st->seed_final[sd] = r.final_err; st->seed_dual[sd] = r.plane.dual;
+        for (int q = 0; q < 4; q++) st->seed_plane[sd][q] = r.plane.p[q];
+        atomicAdd(&st->n_evals, (unsigned long long)S->n_evals); atomicAdd(&st->n_queries, (unsigned long long)S->n_queries);
+        atomicAdd(&st->n_points, (unsigned long long)S->n_points); atomicAdd(&st->n_hits, (unsigned long long)S->n_hits);
+        const unsigned long long npts = (unsigned long long)((symtype == 2) ? 2 * st->n_sym : st->n_sym);
+        atomicAdd(&st->n_ref_evals, (unsigned long long)S->n_ref); atomicAdd(&st->n_ref_points, (unsigned long long)S->n_ref * npts);
+        atomicAdd(&st->n_verify_fail, (unsigned long long)S->n_verify_fail);
+        __threadfence();
+        atomicAdd(&st->done, 1);
+      }
+    }
+  }
+  __syncwarp();
+  action = __shfl_sync(0xffffffffu, action, lane & ~7);
+  // linearizeOplus (numeric, delta 1e-9): the 2*dim perturbed planes by 2*dim lanes of the seed's group, the base pair by lane 6
+  if (action == kActFd) {
+    if (sub < 2 * dim) {
+      const int d = sub >> 1;
+      const double del = (sub & 1) ? -1e-9 : 1e-9;
+      double add[3];
+      add[0] = (d == 0) ? del : 0.0; add[1] = (d == 1) ? del : 0.0; add[2] = (d == 2) ? del : 0.0;
+      dplane tp = S->est;
+      sym_oplus(tp, add, symtype);
+      make_pair(S->fd[sub], tp);
+    } else if (sub == 6) {
+      make_pair(S->base, S->est);
+    }
+  }
+  __syncwarp();
+  bool pair_ok = true;
+  if (action == kActFd && sub < 2 * dim) pair_ok = fd_pair_ok(S->base, S->fd[sub], st->sym_R2);
+  const unsigned bad = __ballot_sync(0xffffffffu, !pair_ok) & (0xffu << (lane & ~7));
+  if (action == kActFd && sub == 0) S->fd_ok = bad ? 0 : 1;
+  const unsigned lv = __ballot_sync(0xffffffffu, sub == 0 && action != kActDone);
+  if (lane == 0 && lv) atomicAdd(C.live + k, __popc(lv));
+}
+
+// eval(r): the evaluations the seeds of one object wait for -- the round body of symmetry_finalize_kernel without its scalar phase.
+template <bool VERIFY>
+__global__ void __launch_bounds__(32 * kSeeds, kSymCtas256) sym_eval_kernel(const SymChunk *__restrict__ Cp, int r) {
+  constexpr int CAP = kRoundCap;
+  extern __shared__ __align__(16) unsigned char sym_smem_raw[];
+  SymObj<CAP> &O = *reinterpret_cast<SymObj<CAP> *>(sym_smem_raw);
+  SymSeed<CAP> *seeds = reinterpret_cast<SymSeed<CAP> *>(sym_smem_raw + sizeof(SymObj<CAP>));
+  const SymChunk &C = *Cp;
+  if (*((volatile const int *)(C.live + r)) == 0) return;   // chunk uniform
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int obj = blockIdx.x;
+  ObjState &st = C.states[obj];
+  if (!round_owned(st) || *((volatile int *)&st.done) >= kSeeds) return;   // CTA uniform
+  const ObjMeta &m = C.metas[obj];
+  const int M = st.n_sym;
+  const int npts = (m.symtype == 2) ? 2 * M : M;
+  const double *objn = C.W.objn + 3 * (size_t)m.off;
+  const float4 *objnf = C.W.objnf + m.off;
+  if (threadIdx.x == 0) {
+    const ExtractParamsDev &prm = C.prm;
+    O.sm = 0; O.slotbit = 0;
+    O.img = C.depth + (size_t)m.frame * C.frame_stride; O.pitch = C.pitch; O.st = &st;
+    O.objn = objn; O.nn_g = objnf; O.M = M; O.symtype = m.symtype; O.npts = npts; O.in_smem = 1;
+    for (int i = 0; i < 12; i++) O.P[i] = st.P[i];
+    O.A0 = fabs(O.P[0]) + fabs(O.P[1]) + fabs(O.P[2]); O.A1 = fabs(O.P[4]) + fabs(O.P[5]) + fabs(O.P[6]); O.A2 = fabs(O.P[8]) + fabs(O.P[9]) + fabs(O.P[10]);
+    O.cam[0] = st.T_oc[0]; O.cam[1] = st.T_oc[1]; O.cam[2] = st.T_oc[2];
+    O.bx0 = st.bbox_i[0]; O.by1 = st.bbox_i[1]; O.bx2 = st.bbox_i[2]; O.by3 = st.bbox_i[3];
+    O.rows = prm.rows; O.cols = prm.cols; O.fx = prm.fx; O.cx = prm.cx; O.cy = prm.cy; O.scale = prm.scale;
+    const double sinv = 1.0 / prm.sigma;
+    O.coef = -0.5 * sinv * sinv;
+    O.iters = prm.symmetry_iters; O.n_live = 0; O.R2 = 0.0;
+  }
+  SymSeed<CAP> &S = seeds[wid];
+  uint4 *gseed = reinterpret_cast<uint4 *>(C.seedp + ((size_t)obj * kSeeds + wid) * kSeedStride);
+  {   // stage this warp's seed
+    uint4 *dst = reinterpret_cast<uint4 *>(&S);
+    for (int i = lane; i < kSeedPersist / 16; i += 32) dst[i] = gseed[i];
+  }
+  for (int j = threadIdx.x; j < (M + 1) / 2; j += blockDim.x) {
+    const float4 a = objnf[2 * j];
+    const float far_ = 1.0e30f;   // (q - 1e30)^2 overflows to +inf: never < FLT_MAX, so the pad can never win
+    const float4 b = (2 * j + 1 < M) ? objnf[2 * j + 1] : make_float4(far_, far_, far_, 0.0f);
+    O.X2[j] = f2_pack(a.x, b.x); O.Y2[j] = f2_pack(a.y, b.y); O.Z2[j] = f2_pack(a.z, b.z);
+  }
+  __syncwarp();
+  if (r == 0) {   // invalidate this seed's caches: a NaN x never equals / is never within rho of a float query; no pixel has x = y = 65535
+    float4 *nn0 = S.nnc[0], *nn1 = S.nnc[1]; uint4 *pxc = S.pxc;
+    for (int j = lane; j < npts; j += 32) {
+      nn0[j] = make_float4(__uint_as_float(0x7fffffffu), 0.0f, 0.0f, 0.0f);
+      nn1[j] = make_float4(__uint_as_float(0x7fffffffu), 0.0f, 0.0f, 0.0f);
+      pxc[j] = make_uint4(0xffffffffu, 0u, 0u, 0u);
+    }
+    if (wid == 0) {
+      double r2 = 0.0;
+      for (int j = lane; j < M; j += 32) { const double x = objn[3 * j], y = objn[3 * j + 1], z = objn[3 * j + 2]; r2 = fmax(r2, x * x + y * y + z * z); }
+      r2 = warp_max_d(r2);
+      if (lane == 0) st.sym_R2 = sqrt(r2) * 1.000001 + 1e-9;
+    }
+  }
+  __syncthreads();
+  const int dim = (O.symtype == 1) ? 2 : 3;
+  const int nchunks = (M + 31) >> 5, nhalves = (npts > M) ? 2 : 1;
+  if (wid == 0) {   // task list: FD passes first (the longest tasks), then the classification chunks of the trial planes
+    const int act = lane < kSeeds ? seeds[lane].action : kActDone;
+    const unsigned mfd = __ballot_sync(0xffffffffu, act == kActFd), mtr = __ballot_sync(0xffffffffu, act == kActInit || act == kActTrial);
+    const unsigned lt = (1u << lane) - 1u;
+    if (act == kActFd) O.fd_seed[__popc(mfd & lt)] = (unsigned char)lane;
+    if (act == kActInit || act == kActTrial) O.tr_seed[__popc(mtr & lt)] = (unsigned char)lane;
+    if (lane == 0) { O.n_fd = __popc(mfd); O.n_tr = __popc(mtr); O.n_tasks = O.n_fd + O.n_tr * nhalves * nchunks; O.next_task = 0; }
+  }
+  __syncthreads();
+  while (true) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&O.next_task, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= O.n_tasks) break;
+    if (t >= O.n_fd) {
+      const int u = t - O.n_fd, per = nhalves * nchunks, q = u / per, rr = u - q * per, hf = rr / nchunks;
+      classify_chunk<CAP, VERIFY>(O, seeds[O.tr_seed[q]], hf, rr - hf * nchunks);
+    } else {
+      SymSeed<CAP> &T = seeds[O.fd_seed[t]];
+      bool done = false;
+      if (T.fd_ok) done = (dim == 2) ? eval_fd<CAP, 2, VERIFY>(O, T) : eval_fd<CAP, 3, VERIFY>(O, T);
+      if (!done) {
+        for (int d = 0; d < dim; d++) {
+          const double e1 = eval_single<CAP, VERIFY>(O, T, T.fd[2 * d], -1);
+          const double e2 = eval_single<CAP, VERIFY>(O, T, T.fd[2 * d + 1], -1);
+          if (lane == 0) T.J[d] = (1.0 / (2 * 1e-9)) * (e1 - e2);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (O.n_tr > 0) {   // scan tasks: 32 queued points of one trial plane each (block uniform)
+    if (wid == 0) {
+      int cnt = (lane < O.n_tr) ? (seeds[O.tr_seed[lane]].qn + 31) >> 5 : 0, incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (lane <= kSeeds) O.scan_first[lane] = incl - cnt;
+      if (lane == 0) O.next_task = 0;
+      const int total = __shfl_sync(0xffffffffu, incl, 15);
+      if (lane == 0) O.n_tasks = total;
+    }
+    __syncthreads();
+    while (true) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(&O.next_task, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= O.n_tasks) break;
+      int q = 0;
+      while (q + 1 < O.n_tr && O.scan_first[q + 1] <= t) q++;
+      scan_chunk<CAP, VERIFY>(O, seeds[O.tr_seed[q]], (t - O.scan_first[q]) << 5);
+    }
+    __syncthreads();
+    // the evaluation of S.pp is complete: sum ln P in point order (every lane runs the same chain on broadcast loads)
+    if (S.action == kActInit || S.action == kActTrial) {
+      double ln_total = 0.0;
+      int q = 0;
+      for (; q + 4 <= npts; q += 4) {
+        const double2 u = *reinterpret_cast<const double2 *>(&S.lnp[q]), v = *reinterpret_cast<const double2 *>(&S.lnp[q + 2]);
+        ln_total += u.x; ln_total += u.y; ln_total += v.x; ln_total += v.y;
+      }
+      for (; q < npts; q++) ln_total += S.lnp[q];
+      const int num_valid = npts - S.invalid;
+      const double aver = (num_valid > 0) ? (ln_total / (double)num_valid) : -INFINITY;
+      __syncwarp();
+      if (lane == 0) { S.err_last = -aver; S.n_evals += nhalves; S.n_queries += (unsigned)S.qn; S.n_points += (unsigned)npts; }
+      __syncwarp();
+    }
+  }
+  {   // persistent state back (only a live seed changed)
+    const uint4 *src = reinterpret_cast<const uint4 *>(&S);
+    if (S.action != kActDone) for (int i = lane; i < kSeedPersist / 16; i += 32) gseed[i] = src[i];
+  }
+}
+
+// completion (and the records of the objects that never reach the symmetry search)
+__global__ void __launch_bounds__(128) sym_final_kernel(const SymChunk *__restrict__ Cp) {
+  const SymChunk &C = *Cp;
+  const int obj = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (obj >= C.n_obj) return;   // warp uniform
+  const ObjMeta &m = C.metas[obj];
+  ObjState &st = C.states[obj];
+  EslamEllipsoidOut &out = C.outs[obj];
+  const int status = st.status;
+  if (status == 0 && st.run_sym && st.n_sym > kRoundCap) return;   // owned by the single-launch kernel (CAP = 512 / generic path)
+  if (lane == 0) {
+    for (int i = 0; i < 10; i++) out.ellipsoid[i] = 0;
+    out.prob = 0; out.status = status; out.symmetry_type = m.symtype > 0 ? m.symtype : 0; out.symmetry_result = 0; out.best_seed = -1;
+    for (int i = 0; i < 4; i++) { out.sym_plane_world[i] = 0; out.sym_plane2_world[i] = 0; }
+    for (int i = 0; i < 3; i++) out.sym_center_world[i] = 0;
+    out.n_crop = st.n_crop; out.n_voxel = st.n_voxel; out.n_plane = st.n_plane; out.n_clusters = st.n_clusters; out.n_cluster = st.n_cluster;
+    out.n_sym = st.n_sym; out.n_final = 0; out.reserved = 0;
+    if (!C.prm.symmetry_open) out.symmetry_type = 0;
+  }
+  __syncwarp();
+  if (status != 0) return;
+  if (st.run_sym && *((volatile int *)&st.done) != kSeeds) {   // cannot happen (the round count covers the longest LM run); never emit a half-finished record
+    if (lane == 0) out.status = ESLAM_OBJ_INTERNAL;
+    return;
+  }
+  finalize_object(m, st, C.prm, C.W, out);
 }
 
 template <int CAP, int MINB, bool VERIFY>
@@ -1102,11 +1387,87 @@ int symmetry_v1_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev
 
 size_t symmetry_pool_bytes(int cap) { return (size_t)kSeeds * (size_t)cap * 96; }   // cache bytes of one resident CTA
 
+size_t symmetry_round_seed_bytes() { return (size_t)kSeeds * kSeedStride; }
+size_t symmetry_round_cache_bytes() { return (size_t)kSeeds * kRoundCacheBytes; }
+size_t symmetry_round_desc_bytes() { return sizeof(SymChunk); }
+
+// Round pipeline of one chunk on stream s: descriptor upload, live counters, step(0), { eval(r), step(r + 1) }, completion, and the
+// single-launch kernel for the (rare) clouds of more than kRoundCap points.
+static int symmetry_rounds_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj,
+                                  const ExtractParamsDev &prm, const ExtractPtrs &ptrs, int chunk) {
+  ExtractWorkspace &w = *h->ex;
+  const int rounds = 1 + 11 * (prm.symmetry_iters > 0 ? prm.symmetry_iters : 0);   // 1 initial cost + per iteration 1 linearisation + at most 10 trials
+  SymChunk d;
+  d.depth = depth_dev; d.pitch = pitch; d.frame_stride = frame_stride;
+  d.metas = w.meta.as<ObjMeta>() + obj0; d.states = w.state.as<ObjState>() + obj0; d.outs = w.out.as<EslamEllipsoidOut>() + obj0;
+  d.seedp = w.symseed.as<unsigned char>() + (size_t)obj0 * symmetry_round_seed_bytes();
+  d.cache = w.symcache.as<unsigned char>() + (size_t)obj0 * symmetry_round_cache_bytes();
+  d.live = w.symlive.as<int>() + (size_t)chunk * (kSymMaxRounds + 2);
+  d.n_obj = n_obj; d.rounds = rounds; d.prm = prm; d.W = ptrs;
+  SymChunk *pin = w.pin_symchunk.as<SymChunk>() + chunk, *dev = w.symchunk.as<SymChunk>() + chunk;
+  memcpy(pin, &d, sizeof(d));
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(dev, pin, sizeof(d), cudaMemcpyHostToDevice, s));
+  const size_t smem = sym_smem_bytes<kRoundCap>();
+  int dev_id = 0; cudaGetDevice(&dev_id);
+  static bool attr[16][2] = {};
+  const int vi = h->sym_verify ? 1 : 0;
+  if (dev_id < 16 && !attr[dev_id][vi]) {
+    if (vi) {
+      ESLAM_CUDA_OK(h, cudaFuncSetAttribute(sym_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ESLAM_CUDA_OK(h, cudaFuncSetAttribute(sym_eval_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    } else {
+      ESLAM_CUDA_OK(h, cudaFuncSetAttribute(sym_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ESLAM_CUDA_OK(h, cudaFuncSetAttribute(sym_eval_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+    attr[dev_id][vi] = true;
+  }
+  const int step_grid = (n_obj * kSeeds * 8 + kStepThreads - 1) / kStepThreads;
+  auto issue = [&](cudaStream_t q) -> cudaError_t {
+    cudaError_t e = cudaMemsetAsync(d.live, 0, sizeof(int) * (size_t)(rounds + 2), q);
+    if (e != cudaSuccess) return e;
+    sym_step_kernel<<<step_grid, kStepThreads, 0, q>>>(dev, 0);
+    for (int r = 0; r < rounds; r++) {
+      if (vi) sym_eval_kernel<true><<<n_obj, 32 * kSeeds, smem, q>>>(dev, r);
+      else sym_eval_kernel<false><<<n_obj, 32 * kSeeds, smem, q>>>(dev, r);
+      sym_step_kernel<<<step_grid, kStepThreads, 0, q>>>(dev, r + 1);
+    }
+    sym_final_kernel<<<(n_obj + 3) / 4, 128, 0, q>>>(dev);
+    return cudaGetLastError();
+  };
+  bool replayed = false;
+  if (h->sym_graph) {   // the sequence depends on (n_obj, rounds) and two fixed addresses only: capture once per chunk, replay afterwards
+    ExtractWorkspace::SymGraph &g = w.symgraph[chunk];
+    if (g.exec && !(g.n_obj == n_obj && g.rounds == rounds && g.verify == vi && g.desc == dev && g.live == d.live)) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    if (!g.exec) {
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const cudaError_t e1 = issue(s);
+        const cudaError_t e2 = cudaStreamEndCapture(s, &graph);
+        if (e1 == cudaSuccess && e2 == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+          g.n_obj = n_obj; g.rounds = rounds; g.verify = vi; g.desc = dev; g.live = d.live;
+        } else g.exec = nullptr;
+        if (graph) cudaGraphDestroy(graph);
+      }
+      cudaGetLastError();
+    }
+    if (g.exec) { ESLAM_CUDA_OK(h, cudaGraphLaunch(g.exec, s)); replayed = true; }
+  }
+  if (!replayed) ESLAM_CUDA_OK(h, issue(s));
+  h->launches += 2 * rounds + 2;
+  cudaError_t e = vi ? launch_variant<512, 1, true>(s, n_obj, depth_dev, pitch, frame_stride, d.metas, d.states, prm, ptrs, d.outs)
+                     : launch_variant<512, kSymCtas512, false>(s, n_obj, depth_dev, pitch, frame_stride, d.metas, d.states, prm, ptrs, d.outs);
+  ESLAM_CUDA_OK(h, e);
+  ESLAM_LAUNCHED(h);
+  return ESLAM_OK;
+}
+
 int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, size_t pitch, size_t frame_stride, int obj0, int n_obj,
-                             const ExtractParamsDev &prm, const ExtractPtrs &ptrs) {
+                             const ExtractParamsDev &prm, const ExtractPtrs &ptrs, int chunk) {
   ExtractWorkspace &w = *h->ex;
   if (n_obj <= 0) return ESLAM_OK;
   if (h->sym_impl == 1) return symmetry_v1_launch(h, s, depth_dev, pitch, frame_stride, obj0, n_obj, prm, ptrs);
+  if (h->sym_impl == 3 && 1 + 11 * prm.symmetry_iters <= kSymMaxRounds && chunk >= 0 && chunk < kMaxChunks && w.symseed.p)
+    return symmetry_rounds_launch(h, s, depth_dev, pitch, frame_stride, obj0, n_obj, prm, ptrs, chunk);
   const ObjMeta *metas = w.meta.as<ObjMeta>() + obj0;
   ObjState *states = w.state.as<ObjState>() + obj0;
   EslamEllipsoidOut *outs = w.out.as<EslamEllipsoidOut>() + obj0;
@@ -1116,6 +1477,7 @@ int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *dep
     if (e == cudaSuccess) e = launch_variant<512, 1, true>(s, n_obj, depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs);
   } else {
     switch (h->sym_occ) {   // env ESLAM_SYM_OCC: resident CTAs per SM of the CAP = 256 instantiation (register budget), tuning hook
+      case 1: e = launch_variant<256, 1, false>(s, n_obj, depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs); break;
       case 2: e = launch_variant<256, 2, false>(s, n_obj, depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs); break;
       case 4: e = launch_variant<256, 4, false>(s, n_obj, depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs); break;
       default: e = launch_variant<256, kSymCtas256, false>(s, n_obj, depth_dev, pitch, frame_stride, metas, states, prm, ptrs, outs); break;

@@ -157,6 +157,7 @@ long long orc_estimate_ellipsoids(const EslamParams *prm, const EslamCamera *cam
   }
   return evals;
 }
+void orc_last_seed_evals(long long *out9) { for (int s = 0; s < 9; s++) out9[s] = g_last_seed_evals[s]; }
 // stage helpers for stage-isolated parity tests
 int orc_voxel_grid(const float *xyz, int n, double leaf, int unstable, float *out_xyz, int cap) {
   std::vector<P3f> in(n), o; for (int i = 0; i < n; i++) in[i] = P3f{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};

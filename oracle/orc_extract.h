@@ -437,6 +437,7 @@ inline SymResult optimize_symmetry(SymContext &c, const Plane &init, int symType
 }
 
 // ---------------- the extractor ----------------
+static long long g_last_seed_evals[9];
 struct ExtractorState { bool plane_set = false; double plane[4] = {0, 0, 1, 0}; bool unstable_voxel_sort = false; };
 inline int symmetry_type_of_label(int label) {  // LoadSymmetryPrior :52-79 ; -1 = label unknown
   switch (label) { case 58: return 0; case 59: case 62: case 57: case 66: case 63: case 64: case 41: return 1; case 28: return 2; default: return -1; }
@@ -532,8 +533,10 @@ inline void estimate_local_ellipsoid(const ExtractorState &st, const EslamParams
     for (int i = 0; i < 3; i++) for (int m = 0; m < 3; m++) {
       double dis = start_dis + diff_dis * i, angle = start_angle + diff_angle * m;
       Plane init = plane_from_dis_angle_trans(dis, angle, 0);
+      const long long evals_before = ctx.n_cost_evals;
       SymResult r = optimize_symmetry(ctx, init, symmetryType, prm.symmetry_iters);
       int s = i * 3 + m;
+      g_last_seed_evals[s] = ctx.n_cost_evals - evals_before;   // diagnostics: work per seed of the last object (tools/seed_balance.py)
       if (dump) { dump->seed_prob[s] = r.prob; dump->seed_init_err[s] = r.init_error; dump->seed_final_err[s] = r.final_error; for (int k = 0; k < 4; k++) dump->seed_plane[s][k] = r.plane.p[k]; dump->seed_dual_dis[s] = r.plane.dual_dis; }
       // sort(desc by prob) of 9 elements = insertion sort = stable: first maximum wins (Symmetry.cpp:122-126)
       if (best_i < 0 || r.prob > best.prob) { best = r; best_i = s; }

@@ -18,15 +18,17 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=1024)
 ap.add_argument("--seed", type=int, default=1000)
 ap.add_argument("--verify", action="store_true")
-ap.add_argument("--variants", default="1:0,2:2,2:3,2:4")
+ap.add_argument("--variants", default="2:3,3:0:8:1,3:0:8:0,3:0:4:1", help="impl:occ[:dev_chunks[:graph]], impl 1 = round-1 kernel, 2 = single launch, 3 = round pipeline")
 args = ap.parse_args()
 depth, fo, bb, lb, tw = make_frames("one_box", args.frames, args.seed)
 dev = torch.from_numpy(depth.view(np.int16)).cuda()
 ref = None
 for var in args.variants.split(","):
-    impl, occ = var.split(":")
+    impl, occ, chunks, graph = (var.split(":") + ["8", "1"])[:4]
+    os.environ["ESLAM_SYM_GRAPH"] = graph
     os.environ["ESLAM_SYM_IMPL"] = impl
     os.environ["ESLAM_SYM_OCC"] = occ
+    os.environ["ESLAM_DEV_CHUNKS"] = chunks
     h = E.Handle()
     h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
@@ -47,10 +49,10 @@ for var in args.variants.split(","):
     c = h.batch_counters()
     if ref is None:
         ref = rec
-    print(json.dumps({"impl": impl, "occ": occ, "step_ms": step_ms, "extract_ms": k_ms[0], "symmetry_ms": k_ms[1], "records_equal_first": rec == ref, "counters": c}))
+    print(json.dumps({"impl": impl, "occ": occ, "chunks": chunks, "graph": graph, "launches_per_call": h.launches // 14, "step_ms": step_ms, "extract_ms": k_ms[0], "symmetry_ms": k_ms[1], "records_equal_first": rec == ref, "counters": c}))
     h.close()
 if args.verify:
-    os.environ["ESLAM_SYM_IMPL"] = "2"; os.environ["ESLAM_SYM_OCC"] = "0"; os.environ["ESLAM_SYM_VERIFY"] = "1"
+    os.environ["ESLAM_SYM_IMPL"] = "3"; os.environ["ESLAM_SYM_OCC"] = "0"; os.environ["ESLAM_SYM_VERIFY"] = "1"
     h = E.Handle()
     h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
     h.estimate_ellipsoids_dev(dev.data_ptr(), args.frames, 640, fo, bb, lb, tw); torch.cuda.synchronize()
