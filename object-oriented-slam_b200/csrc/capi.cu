@@ -468,6 +468,7 @@ void eslam_destroy(EslamHandle *h) {
   for (int i = 0; i < 17; i++) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int i = 0; i < kMaxChunks; i++) { if (h->chunk_stream[i]) cudaStreamDestroy(h->chunk_stream[i]); if (h->chunk_done[i]) cudaEventDestroy(h->chunk_done[i]); }
+  for (int i = 0; i < kMaxChunks; i++) { if (h->chunk_aux[i]) cudaStreamDestroy(h->chunk_aux[i]); if (h->aux_fork[i]) cudaEventDestroy(h->aux_fork[i]); if (h->aux_join[i]) cudaEventDestroy(h->aux_join[i]); }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

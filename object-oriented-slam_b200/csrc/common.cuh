@@ -64,6 +64,8 @@ struct EslamHandle {
   cudaEvent_t chunk_ev[17] = {};       // [16]: metadata upload of the batch
   cudaStream_t chunk_stream[16] = {};   // per-chunk compute streams: chunks overlap each other and the remaining uploads
   cudaEvent_t chunk_done[16] = {};
+  cudaStream_t chunk_aux[16] = {};      // round pipeline: the single-launch kernel of a chunk's large clouds (n_sym > 256) runs beside the rounds
+  cudaEvent_t aux_fork[16] = {}, aux_join[16] = {};
   int h2d_mode = 4;      // upload: 4 = SMs pull each box rectangle from pinned host memory (falls back to 3 for pageable input);
                          // 3 = union rectangle of each frame's boxes, one batched DMA call per chunk; 2 = same, one call per frame;
                          // 1 = the boxes' rows (contiguous), 0 = whole frames (env ESLAM_H2D_MODE)

@@ -46,7 +46,7 @@ constexpr double kPixMargin = 4.04e-6;     // kFdDelta * 1.01 (denominator shift
 constexpr double kDepthMargin = 5.0e-6;    // |s - t| >= kDepthMargin * (2 + s + t)  =>  |sqrt s - sqrt t| >= 1e-5 > sqrt(3) * kFdDelta
 constexpr float kNnSafe = 1.0e-5f;         // a cached neighbour is final for the finite-difference planes when rho - |q - q0| exceeds this
 constexpr double kQMax = 14.0;             // float rounding of a query (2^-23 |q|) stays below kNnSafe - sqrt(3) kFdDelta for |q| <= kQMax
-constexpr int kSlowMax = 16;               // non-robust points of one half handled by the finite-difference pass (more: generic evaluations)
+constexpr int kSlowMax = 48;               // non-robust points of one half handled by the finite-difference pass (more: generic evaluations)
 constexpr int kSeeds = 9;
 constexpr unsigned kIdxMask = 1023u;       // neighbour index packed into the low mantissa bits of rho^2 (rounded down: conservative)
 
@@ -71,6 +71,7 @@ struct SymObj {
   int scan_first[kSeeds + 1];
   // float cloud, pair-interleaved SoA (odd tail padded far away)
   unsigned long long X2[CAP / 2], Y2[CAP / 2], Z2[CAP / 2];
+  double PX[CAP], PY[CAP], PZ[CAP];   // the object-normalised cloud itself (objn), SoA
 };
 enum { kActDone = 0, kActInit = 1, kActFd = 2, kActTrial = 3 };
 // Levenberg-Marquardt state of one seed: everything that survives from one cost evaluation to the next (no per-evaluation scratch).
@@ -96,11 +97,11 @@ struct SymSeed : SeedCore {
   // ---- per-evaluation scratch (everything from here on is dead between two evaluations)
   alignas(16) double lnp[2 * CAP];    // ln P of every mirrored point (-0.0 where it carries no distance), point order; FD passes stage their tiles here
   alignas(16) unsigned short queue[2 * CAP];   // points that need a scan: li | half << 9 | robust << 15 (FD passes keep their side buffer here)
-  unsigned short list[CAP];           // FD pass: active points of the current half
-  unsigned short slow[kSlowMax];
-  double pad_[2];                     // the nine lanes of the scalar step hit different banks
 };
-static_assert(6 * 33 <= 256 && 6 * kSlowMax * 2 <= 256, "FD staging tiles alias lnp / queue");
+// scratch of a finite-difference pass (the seed runs no other evaluation meanwhile): staging tile [6][33] and the slow points' values
+// [6][kSlowMax] in lnp, the active-point list [CAP] and the slow-point list [kSlowMax] in queue
+constexpr int kFdSideOff = 200;
+static_assert(6 * 33 <= kFdSideOff && kFdSideOff + 6 * kSlowMax <= 2 * 256 && 256 + kSlowMax <= 2 * 256, "FD scratch aliases lnp / queue");
 
 __device__ __forceinline__ int x86_int(double a) { return (a > -2147483649.0 && a < 2147483648.0) ? (int)a : (int)0x80000000; }
 __device__ __forceinline__ double rcp_fast(double a) {   // ~1 ulp reciprocal without the special-case path (guarded use only)
@@ -160,7 +161,10 @@ __device__ __forceinline__ d3 mirror_q(d3 pt, const double *q, const double *n, 
   return mk3(pt.x + kk * n[0], pt.y + kk * n[1], pt.z + kk * n[2]);
 }
 template <int CAP>
-__device__ __forceinline__ d3 load_pt(const SymObj<CAP> &O, int j) { return mk3(O.objn[3 * j], O.objn[3 * j + 1], O.objn[3 * j + 2]); }
+__device__ __forceinline__ d3 load_pt(const SymObj<CAP> &O, int j) {
+  if (O.in_smem) return mk3(O.PX[j], O.PY[j], O.PZ[j]);
+  return mk3(O.objn[3 * j], O.objn[3 * j + 1], O.objn[3 * j + 2]);
+}
 
 // Classification of a mirrored point (SymmetrySolver.cpp:62-116): 0 = cost 0 (occluded / no depth), 1 = needs the nearest-neighbour
 // distance, 2 = invalid (not counted).  `rob` = every decision holds for any point within kFdDelta (per coordinate) of pm.
@@ -527,7 +531,8 @@ __device__ __noinline__ bool eval_fd(const SymObj<CAP> &O, SymSeed<CAP> &S) {
   const double coef = O.coef;
   const float4 *rc = S.nnc[cur];
   double (*stage)[33] = reinterpret_cast<double (*)[33]>(S.lnp);
-  double (*side)[kSlowMax] = reinterpret_cast<double (*)[kSlowMax]>(S.queue);
+  double (*side)[kSlowMax] = reinterpret_cast<double (*)[kSlowMax]>(S.lnp + kFdSideOff);
+  unsigned short *list = S.queue, *slow = S.queue + CAP;
   double ln_tot = 0.0;   // lanes < NFD: ordered sum of plane `lane`
   if (lane < 6) S.inv_s[lane] = 0;
   unsigned visited = 0;
@@ -537,8 +542,8 @@ __device__ __noinline__ bool eval_fd(const SymObj<CAP> &O, SymSeed<CAP> &S) {
     int n_act = 0, n_slow = 0;
     for (int w = 0; w * 32 < M; w++) {
       const unsigned A = S.mA[cur][half][w], F = S.mF[cur][half][w], Sl = A & ~F;
-      if (A >> lane & 1u) S.list[n_act + __popc(A & lt)] = (unsigned short)(w * 32 + lane);
-      if (Sl >> lane & 1u) { const int k = n_slow + __popc(Sl & lt); if (k < kSlowMax) S.slow[k] = (unsigned short)(w * 32 + lane); }
+      if (A >> lane & 1u) list[n_act + __popc(A & lt)] = (unsigned short)(w * 32 + lane);
+      if (Sl >> lane & 1u) { const int k = n_slow + __popc(Sl & lt); if (k < kSlowMax) slow[k] = (unsigned short)(w * 32 + lane); }
       n_act += __popc(A); n_slow += __popc(Sl);
     }
     if (n_slow > kSlowMax) return false;   // warp uniform
@@ -547,7 +552,7 @@ __device__ __noinline__ bool eval_fd(const SymObj<CAP> &O, SymSeed<CAP> &S) {
     // slow points: one lane per (point, plane), full classification, cached or scanned neighbour
     for (int it = lane; it < n_slow * NFD; it += 32) {
       const int s = it / NFD, k = it - s * NFD;
-      const int li = S.slow[s];
+      const int li = slow[s];
       const PlanePair &Q = S.fd[k];
       const d3 pm = mirror_q(load_pt(O, li), half ? Q.p2 : Q.p1, half ? Q.n2 : Q.n1, half ? Q.down2 : Q.down1);
       bool rob, safe;
@@ -567,22 +572,21 @@ __device__ __noinline__ bool eval_fd(const SymObj<CAP> &O, SymSeed<CAP> &S) {
       side[k][s] = val;
     }
     __syncwarp();
-    const double *objn = O.objn;
     for (int base = 0; base < n_act; base += 32) {
       const bool e = base + lane < n_act;
-      const int li = e ? (int)S.list[base + lane] : 0;
+      const int li = e ? (int)list[base + lane] : 0;
       const bool fast = e && ((S.mF[cur][half][li >> 5] >> (li & 31)) & 1u);
       d3 pt = mk3(0, 0, 0);
       double bx = 0, by = 0, bz = 0;
       int best = 0, sslot = 0;
       if (fast) {
         best = (int)(__float_as_uint(rc[h0 + li].w) & kIdxMask);
-        pt = mk3(objn[3 * li], objn[3 * li + 1], objn[3 * li + 2]);
+        pt = load_pt(O, li);
         const unsigned long long X = O.X2[best >> 1], Y = O.Y2[best >> 1], Z = O.Z2[best >> 1];
         const int sh = (best & 1) * 32;
         bx = (double)__uint_as_float((unsigned)(X >> sh)); by = (double)__uint_as_float((unsigned)(Y >> sh)); bz = (double)__uint_as_float((unsigned)(Z >> sh));
       } else if (e) {
-        for (int s = 0; s < n_slow; s++) if ((int)S.slow[s] == li) sslot = s;
+        for (int s = 0; s < n_slow; s++) if ((int)slow[s] == li) sslot = s;
       }
 #pragma unroll 2
       for (int k = 0; k < NFD; k++) {
@@ -923,6 +927,7 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
         const float4 b = (2 * j + 1 < M) ? objnf[2 * j + 1] : make_float4(far_, far_, far_, 0.0f);
         O.X2[j] = f2_pack(a.x, b.x); O.Y2[j] = f2_pack(a.y, b.y); O.Z2[j] = f2_pack(a.z, b.z);
       }
+      for (int j = threadIdx.x; j < M; j += blockDim.x) { O.PX[j] = objn[3 * j]; O.PY[j] = objn[3 * j + 1]; O.PZ[j] = objn[3 * j + 2]; }
       if (wid == 0) {
         double r2 = 0.0;
         for (int j = lane; j < M; j += 32) { const double x = objn[3 * j], y = objn[3 * j + 1], z = objn[3 * j + 2]; r2 = fmax(r2, x * x + y * y + z * z); }
@@ -1127,6 +1132,27 @@ __device__ __forceinline__ SeedCore *seed_core(const SymChunk &C, int obj, int s
 }
 __device__ __forceinline__ bool round_owned(const ObjState &st) { return st.status == 0 && st.run_sym && st.n_sym <= kRoundCap; }
 
+// copies of a seed's state between HBM / L2 and shared memory with all loads of a batch in flight before the first store
+template <int NLANES>
+__device__ __forceinline__ void copy_words8(unsigned long long *dst, const unsigned long long *src, int n, int l) {
+  for (int base = 0; base < n; base += 8 * NLANES) {
+    unsigned long long t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { const int i = base + u * NLANES + l; t[u] = (i < n) ? src[i] : 0ull; }
+#pragma unroll
+    for (int u = 0; u < 8; u++) { const int i = base + u * NLANES + l; if (i < n) dst[i] = t[u]; }
+  }
+}
+__device__ __forceinline__ void copy_quads4(uint4 *dst, const uint4 *src, int n, int lane) {
+  for (int base = 0; base < n; base += 128) {
+    uint4 t[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = base + u * 32 + lane; t[u] = (i < n) ? src[i] : make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int i = base + u * 32 + lane; if (i < n) dst[i] = t[u]; }
+  }
+}
+
 // step(0): seed planes (GenerateInitPlanes, Symmetry.cpp:44-86).  step(k > 0): consumes evaluation k - 1.
 __global__ void __launch_bounds__(kStepThreads) sym_step_kernel(const SymChunk *__restrict__ Cp, int k) {
   const SymChunk &C = *Cp;
@@ -1139,7 +1165,16 @@ __global__ void __launch_bounds__(kStepThreads) sym_step_kernel(const SymChunk *
   if (valid) valid = round_owned(*st);
   const int symtype = valid ? C.metas[obj].symtype : 2;
   const int dim = (symtype == 1) ? 2 : 3;
-  SeedCore *S = valid ? seed_core(C, obj, sd) : nullptr;
+  // the seed's state is staged through shared memory by its eight lanes (the scalar code touches ~150 fields: one coalesced copy
+  // instead of that many dependent L2 round trips)
+  __shared__ __align__(16) unsigned long long s_seed[kStepThreads / 8][sizeof(SeedCore) / 8];
+  SeedCore *G = valid ? seed_core(C, obj, sd) : nullptr;
+  SeedCore *S = reinterpret_cast<SeedCore *>(s_seed[threadIdx.x >> 3]);
+  if (valid && k > 0) {
+    copy_words8<8>(s_seed[threadIdx.x >> 3], reinterpret_cast<const unsigned long long *>(G), (int)(sizeof(SeedCore) / 8), sub);
+  }
+  __syncwarp();
+  const bool was_live = valid && (k == 0 || S->action != kActDone);
   int action = kActDone;
   if (valid && sub == 0) {
     if (k == 0) {
@@ -1195,6 +1230,8 @@ __global__ void __launch_bounds__(kStepThreads) sym_step_kernel(const SymChunk *
   if (action == kActFd && sub < 2 * dim) pair_ok = fd_pair_ok(S->base, S->fd[sub], st->sym_R2);
   const unsigned bad = __ballot_sync(0xffffffffu, !pair_ok) & (0xffu << (lane & ~7));
   if (action == kActFd && sub == 0) S->fd_ok = bad ? 0 : 1;
+  __syncwarp();
+  if (was_live) copy_words8<8>(reinterpret_cast<unsigned long long *>(G), s_seed[threadIdx.x >> 3], (int)(sizeof(SeedCore) / 8), sub);
   const unsigned lv = __ballot_sync(0xffffffffu, sub == 0 && action != kActDone);
   if (lane == 0 && lv) atomicAdd(C.live + k, __popc(lv));
 }
@@ -1233,16 +1270,14 @@ __global__ void __launch_bounds__(32 * kSeeds, kSymCtas256) sym_eval_kernel(cons
   }
   SymSeed<CAP> &S = seeds[wid];
   uint4 *gseed = reinterpret_cast<uint4 *>(C.seedp + ((size_t)obj * kSeeds + wid) * kSeedStride);
-  {   // stage this warp's seed
-    uint4 *dst = reinterpret_cast<uint4 *>(&S);
-    for (int i = lane; i < kSeedPersist / 16; i += 32) dst[i] = gseed[i];
-  }
+  copy_quads4(reinterpret_cast<uint4 *>(&S), gseed, kSeedPersist / 16, lane);   // stage this warp's seed
   for (int j = threadIdx.x; j < (M + 1) / 2; j += blockDim.x) {
     const float4 a = objnf[2 * j];
     const float far_ = 1.0e30f;   // (q - 1e30)^2 overflows to +inf: never < FLT_MAX, so the pad can never win
     const float4 b = (2 * j + 1 < M) ? objnf[2 * j + 1] : make_float4(far_, far_, far_, 0.0f);
     O.X2[j] = f2_pack(a.x, b.x); O.Y2[j] = f2_pack(a.y, b.y); O.Z2[j] = f2_pack(a.z, b.z);
   }
+  for (int j = threadIdx.x; j < M; j += blockDim.x) { O.PX[j] = objn[3 * j]; O.PY[j] = objn[3 * j + 1]; O.PZ[j] = objn[3 * j + 2]; }
   __syncwarp();
   if (r == 0) {   // invalidate this seed's caches: a NaN x never equals / is never within rho of a float query; no pixel has x = y = 65535
     float4 *nn0 = S.nnc[0], *nn1 = S.nnc[1]; uint4 *pxc = S.pxc;
@@ -1282,6 +1317,7 @@ __global__ void __launch_bounds__(32 * kSeeds, kSymCtas256) sym_eval_kernel(cons
       SymSeed<CAP> &T = seeds[O.fd_seed[t]];
       bool done = false;
       if (T.fd_ok) done = (dim == 2) ? eval_fd<CAP, 2, VERIFY>(O, T) : eval_fd<CAP, 3, VERIFY>(O, T);
+      if (lane == 0) { atomicAdd((unsigned long long *)&st.sym_clk[0], 1ull); if (!done) atomicAdd((unsigned long long *)&st.sym_clk[1], 1ull); }
       if (!done) {
         for (int d = 0; d < dim; d++) {
           const double e1 = eval_single<CAP, VERIFY>(O, T, T.fd[2 * d], -1);
@@ -1330,8 +1366,7 @@ __global__ void __launch_bounds__(32 * kSeeds, kSymCtas256) sym_eval_kernel(cons
     }
   }
   {   // persistent state back (only a live seed changed)
-    const uint4 *src = reinterpret_cast<const uint4 *>(&S);
-    if (S.action != kActDone) for (int i = lane; i < kSeedPersist / 16; i += 32) gseed[i] = src[i];
+    if (S.action != kActDone) copy_quads4(gseed, reinterpret_cast<const uint4 *>(&S), kSeedPersist / 16, lane);
   }
 }
 
@@ -1421,6 +1456,26 @@ static int symmetry_rounds_launch(EslamHandle *h, cudaStream_t s, const uint16_t
     }
     attr[dev_id][vi] = true;
   }
+  // The clouds of more than kRoundCap points (rare: 1 in ~8000 objects of the bench stream) take the single-launch kernel.  It runs on
+  // a side stream next to the rounds: alone, one such CTA lives ~2 ms, and behind the rounds it was the straggler of its whole rank.
+  cudaStream_t big = s;
+  if (!h->profiling) {
+    if (!h->chunk_aux[chunk]) {
+      ESLAM_CUDA_OK(h, cudaStreamCreateWithFlags(&h->chunk_aux[chunk], cudaStreamNonBlocking));
+      ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->aux_fork[chunk], cudaEventDisableTiming));
+      ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&h->aux_join[chunk], cudaEventDisableTiming));
+    }
+    big = h->chunk_aux[chunk];
+    ESLAM_CUDA_OK(h, cudaEventRecord(h->aux_fork[chunk], s));
+    ESLAM_CUDA_OK(h, cudaStreamWaitEvent(big, h->aux_fork[chunk], 0));
+  }
+  if (big != s) {
+    cudaError_t e = vi ? launch_variant<512, 1, true>(big, n_obj, depth_dev, pitch, frame_stride, d.metas, d.states, prm, ptrs, d.outs)
+                       : launch_variant<512, kSymCtas512, false>(big, n_obj, depth_dev, pitch, frame_stride, d.metas, d.states, prm, ptrs, d.outs);
+    ESLAM_CUDA_OK(h, e);
+    ESLAM_LAUNCHED(h);
+    ESLAM_CUDA_OK(h, cudaEventRecord(h->aux_join[chunk], big));
+  }
   const int step_grid = (n_obj * kSeeds * 8 + kStepThreads - 1) / kStepThreads;
   auto issue = [&](cudaStream_t q) -> cudaError_t {
     cudaError_t e = cudaMemsetAsync(d.live, 0, sizeof(int) * (size_t)(rounds + 2), q);
@@ -1454,10 +1509,14 @@ static int symmetry_rounds_launch(EslamHandle *h, cudaStream_t s, const uint16_t
   }
   if (!replayed) ESLAM_CUDA_OK(h, issue(s));
   h->launches += 2 * rounds + 2;
-  cudaError_t e = vi ? launch_variant<512, 1, true>(s, n_obj, depth_dev, pitch, frame_stride, d.metas, d.states, prm, ptrs, d.outs)
-                     : launch_variant<512, kSymCtas512, false>(s, n_obj, depth_dev, pitch, frame_stride, d.metas, d.states, prm, ptrs, d.outs);
-  ESLAM_CUDA_OK(h, e);
-  ESLAM_LAUNCHED(h);
+  if (big != s) {
+    ESLAM_CUDA_OK(h, cudaStreamWaitEvent(s, h->aux_join[chunk], 0));
+  } else {
+    cudaError_t e = vi ? launch_variant<512, 1, true>(s, n_obj, depth_dev, pitch, frame_stride, d.metas, d.states, prm, ptrs, d.outs)
+                       : launch_variant<512, kSymCtas512, false>(s, n_obj, depth_dev, pitch, frame_stride, d.metas, d.states, prm, ptrs, d.outs);
+    ESLAM_CUDA_OK(h, e);
+    ESLAM_LAUNCHED(h);
+  }
   return ESLAM_OK;
 }
 

@@ -235,7 +235,7 @@ class Handle:
         out = (C.c_ulonglong * 12)()
         self.check(self.lib.eslam_batch_counters(self._h, out), "eslam_batch_counters")
         keys = ("ref_evals", "ref_points", "evals", "points", "nn_scans", "nn_hits", "max_n_sym", "objects_with_symmetry", "verify_failures",
-                "clk_scalar_phase", "clk_task_phase", "clk_cta_total")
+                "clk_scalar_phase", "clk_task_phase", "clk_cta_total")   # round pipeline: FD passes, FD fallbacks, -
         return {k: int(v) for k, v in zip(keys, out)}
 
     def init_quadric(self, Twc, det5, K, rows=None, cols=None):

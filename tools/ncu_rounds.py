@@ -16,9 +16,9 @@ for r in rows[1:]:
     seq.append((name, us))
 for k, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f"{k[:50]:50s} launches {n:4d}  total {t:10.1f} us")
-ev = [u for n, u in seq if n.startswith("sym_eval")]
-stp = [u for n, u in seq if n.startswith("sym_step")]
-per = len(ev) // max(1, sum(1 for n, _ in seq if n.startswith("sym_final")))
+ev = [u for n, u in seq if "sym_eval" in n]
+stp = [u for n, u in seq if "sym_step" in n]
+per = len(ev) // max(1, sum(1 for n, _ in seq if "sym_final" in n))
 print("rounds per sequence", per)
 print("eval us :", " ".join(f"{u:.0f}" for u in ev[:per]))
 print("step us :", " ".join(f"{u:.0f}" for u in stp[:per + 1]))
