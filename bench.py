@@ -320,13 +320,14 @@ def run_stages(args, h, torch, stream, plane, peak, peak_src):
                                 "note": "fp64-ALU bound (19 residual evaluations per edge), not bandwidth bound"},
                    "cpu_baseline": {"value": E_ / cpu_ms * 1e3, "unit": "edges/s", "cores": 1, "kind": "port", "sample": "the same graph once, %.2f s" % (cpu_ms / 1e3)},
                    "parity_in_run": {"max_abs_residual_diff": float(np.abs(r_ - ro).max()), "max_rel_chi2_diff": float(np.max(np.abs(c_ - co) / np.maximum(1.0, np.abs(co))))}})
-    h.optimize_objects(gg, p["init"], 2)
+    t0 = time.perf_counter(); h.optimize_objects(gg, p["init"], 10); lm_first_ms = (time.perf_counter() - t0) * 1e3   # first call of this shape: plain launches
+    h.optimize_objects(gg, p["init"], 10)                                                                                 # second call: captures the per-iteration graph
     l0 = h.launches
     t0 = time.perf_counter(); eg, sg = h.optimize_objects(gg, p["init"], 10); lm_ms = (time.perf_counter() - t0) * 1e3
     lm_launches = h.launches - l0
     t0 = time.perf_counter(); eo, so = orc.optimize_objects(go, p["init"], 10); cpu_ms = (time.perf_counter() - t0) * 1e3
     stages.append({"stage": "config3_optimize_mapping", "config": "Optimizer::GlobalObjectGraphOptimization, graph.optimize(10), fixed poses (mapping mode), same graph",
-                   "value": lm_ms, "unit": "ms per optimize(10)", "higher_is_better": False, "iterations": sg.iterations, "trials": sg.trials_total, "gpu_launches_per_batch": int(lm_launches),
+                   "value": lm_ms, "unit": "ms per optimize(10)", "higher_is_better": False, "first_call_ms": lm_first_ms, "iterations": sg.iterations, "trials": sg.trials_total, "gpu_launches_per_batch": int(lm_launches),
                    "chi2": [sg.chi2_initial, sg.chi2_final],
                    "e2e": {"value": lm_ms, "unit": "ms per optimize(10)", "api": "eslam_optimize_objects_host (host graph in, ellipsoids out; wall clock)"},
                    "cpu_baseline": {"value": cpu_ms, "unit": "ms per optimize(10)", "cores": 1, "kind": "port", "sample": "the same graph, optimize(10), %d iterations" % so.iterations},
@@ -584,7 +585,7 @@ def main():
     crop_bytes = float(sum(2 * ((int(b[2]) - int(b[0]) + 2) // 3) * ((int(b[3]) - int(b[1]) + 2) // 3) for b in bb))   # 2 B per stride-3 sample
     sym_bytes = 14.0 * counters["ref_points"]   # 12 B float point + 2 B depth pixel per mirrored point of every cost evaluation of the reference's call sequence
     if k_ms[1] >= k_ms[0]:
-        dom, alg, t_ms = "symmetry_finalize_kernel", sym_bytes, k_ms[1]
+        dom, alg, t_ms = "symmetry_stage", sym_bytes, k_ms[1]
     else:
         dom, alg, t_ms = "extract_kernel", crop_bytes, k_ms[0]
     achieved = alg / (t_ms / 1e3) / 1e9
@@ -592,10 +593,12 @@ def main():
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (float(tr["dram_bytes_per_object"]) * n_obj if tr else None),
                 "traffic_source": (tr_src + " (dram__bytes_read.sum + dram__bytes_write.sum per object x objects per launch; not re-measured in this run)") if tr else None,
-                "peak_source": peak_src, "kernel_ms": {"extract_kernel": k_ms[0], "symmetry_finalize_kernel": k_ms[1]},
+                "peak_source": peak_src, "kernel_ms": {"extract_kernel": k_ms[0], "symmetry_stage": k_ms[1]},
+                "kernels_of_stage": {"symmetry_stage": "sym_step_kernel(0), 56 x { sym_eval_kernel(r), sym_step_kernel(r + 1) }, sym_final_kernel: the round pipeline of the symmetry search "
+                                                       "(launches past the last running seed exit at once), replayed as one CUDA graph per chunk"},
                 "algorithmic_bytes_per_launch": alg, "work_counters": counters,
-                "note": "kernel_ms: CUDA events on the launching stream of one profiled batch (kernels back to back); algorithmic bytes of the symmetry kernel = 14 B x mirrored points "
-                        "visited by the reference's cost evaluations, counted by the kernel for this batch.  Both kernels are instruction-issue bound (per-object working set << L2), see DESIGN.md"}
+                "note": "kernel_ms: CUDA events on the launching stream of one profiled batch (one stream, launches back to back); algorithmic bytes of the symmetry stage = 14 B x mirrored points "
+                        "visited by the reference's cost evaluations, counted by the kernels for this batch.  Both stages are latency / instruction-issue bound (per-object working set << L2), see DESIGN.md"}
     # ---- cpu baseline (1 thread, bounded sample): rank 0 at N = 1 only
     cpu_baseline = None
     stages = None

@@ -12,11 +12,18 @@ struct GraphWorkspace {
   DevBuf obj_start, obj_edges;   // CSR: edges of each object in graph order
   DevBuf H, b, x, xtmp, okflag, lm;  // H [No*81], b [No*9], x [No*9]
   PinBuf pin;
+  // mapping-mode optimize(iters) as one replayable launch sequence (device-resident control flow): valid for this key only
+  cudaGraphExec_t lm_exec = nullptr;
+  struct LmKey { int iters, n_edges, n_objects; const void *p[14]; } lm_key = {};
+  const void *lm_more[5] = {};
 };
 
-struct LmState {  // lives in device memory, mirrored to pinned host memory after every decision
+struct LmState {  // lives in device memory; mirrored to pinned host memory (SLAM mode: after every decision, mapping mode: once at the end)
   double lambda, ni, currentChi, tempChi, rho, iniChi;
   int accepted, all_ok, pad0, pad1;
+  // device-resident control flow of the mapping-mode LM (edges.cu): every launch of the fixed sequence looks at these and exits when it has nothing to do
+  int trial_active, terminated, qmax, nBad, iterations, trials_total;
+  double chi2_initial, chi2_final;
 };
 
 __device__ __forceinline__ int edge_dim(int t) { return t == ESLAM_EDGE_PROJ ? 4 : (t == ESLAM_EDGE_9DOF ? 9 : 1); }
@@ -74,7 +81,8 @@ static __device__ double warp_ordered_sum(const double *v, int n, double acc = 0
 // rows >= dim of every Jacobian are stored as zeros, so all 9 rows are summed (adding +0.0 is exact).
 static __global__ void __launch_bounds__(96) build_system_kernel(const int *__restrict__ obj_start, const int *__restrict__ obj_edges, const int *__restrict__ type,
                                                           const double *__restrict__ info, const double *__restrict__ res, const double *__restrict__ jac,
-                                                          double *__restrict__ H, double *__restrict__ b) {
+                                                          double *__restrict__ H, double *__restrict__ b, const LmState *ctl) {
+  if (ctl && ctl->terminated) return;   // mapping-mode sequence: the optimisation has already stopped
   constexpr int CH = 16;
   __shared__ double Js[CH][81], rs[CH][9], ws[CH];
   __shared__ int ts[CH];

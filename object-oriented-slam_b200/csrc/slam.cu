@@ -657,7 +657,7 @@ int slam_optimize(EslamHandle *h, const EslamEdgeBatch *g, const double *odom_me
   for (int it = 0; it < iters; it++) {
     if ((rc = slam_eval(h, s, q.T.as<double>(), w.ell.as<double>(), true))) return rc;
     build_system_kernel<<<No, 96, 0, s>>>(w.obj_start.as<int>(), w.obj_edges.as<int>(), w.type.as<int>(), w.info.as<double>(), w.res.as<double>(),
-                                          w.jac.as<double>(), w.H.as<double>(), w.b.as<double>());
+                                          w.jac.as<double>(), w.H.as<double>(), w.b.as<double>(), nullptr);
     ESLAM_LAUNCHED(h);
     if (NP > 0) {
       ESLAM_CUDA_OK(h, cudaMemsetAsync(q.W.p, 0, (size_t)rows * ncols * 8, s));

@@ -1110,6 +1110,7 @@ constexpr int kRoundCap = 256;                                        // clouds 
 constexpr int kSeedPersist = (int)((sizeof(SeedCore) + 2 * sizeof(unsigned[2][2][kRoundCap / 32]) + 15) & ~(size_t)15);
 constexpr int kSeedStride = kSeedPersist;
 constexpr size_t kRoundCacheBytes = (size_t)kRoundCap * 96;           // per seed: two NN banks + the pixel cache, 2 * CAP entries each
+constexpr int kRoundsMinObjects = 16;                                  // smaller launches take the single-launch kernel
 constexpr int kStepThreads = 128;                                     // eight lanes per seed: 16 seeds per CTA
 static_assert(sizeof(SeedCore) % 8 == 0, "SeedCore is followed by the masks without padding");
 static_assert(sizeof(SymSeed<kRoundCap>) >= (size_t)kSeedPersist, "persistent prefix");
@@ -1237,8 +1238,8 @@ __global__ void __launch_bounds__(kStepThreads) sym_step_kernel(const SymChunk *
 }
 
 // eval(r): the evaluations the seeds of one object wait for -- the round body of symmetry_finalize_kernel without its scalar phase.
-template <bool VERIFY>
-__global__ void __launch_bounds__(32 * kSeeds, kSymCtas256) sym_eval_kernel(const SymChunk *__restrict__ Cp, int r) {
+template <bool VERIFY, int MINB>
+__global__ void __launch_bounds__(32 * kSeeds, MINB) sym_eval_kernel(const SymChunk *__restrict__ Cp, int r) {
   constexpr int CAP = kRoundCap;
   extern __shared__ __align__(16) unsigned char sym_smem_raw[];
   SymObj<CAP> &O = *reinterpret_cast<SymObj<CAP> *>(sym_smem_raw);
@@ -1444,17 +1445,15 @@ static int symmetry_rounds_launch(EslamHandle *h, cudaStream_t s, const uint16_t
   ESLAM_CUDA_OK(h, cudaMemcpyAsync(dev, pin, sizeof(d), cudaMemcpyHostToDevice, s));
   const size_t smem = sym_smem_bytes<kRoundCap>();
   int dev_id = 0; cudaGetDevice(&dev_id);
-  static bool attr[16][2] = {};
+  static bool attr[16][3] = {};
   const int vi = h->sym_verify ? 1 : 0;
-  if (dev_id < 16 && !attr[dev_id][vi]) {
-    if (vi) {
-      ESLAM_CUDA_OK(h, cudaFuncSetAttribute(sym_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      ESLAM_CUDA_OK(h, cudaFuncSetAttribute(sym_eval_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    } else {
-      ESLAM_CUDA_OK(h, cudaFuncSetAttribute(sym_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      ESLAM_CUDA_OK(h, cudaFuncSetAttribute(sym_eval_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    }
-    attr[dev_id][vi] = true;
+  // evaluation kernel variant: 0 = three resident CTAs per SM (72 registers), 1 = verification build, 2 = two CTAs per SM (env ESLAM_SYM_OCC=2, tuning)
+  const int variant = vi ? 1 : (h->sym_occ == 2 ? 2 : 0);
+  void (*eval_fn)(const SymChunk *, int) = variant == 1 ? sym_eval_kernel<true, 1> : (variant == 2 ? sym_eval_kernel<false, 2> : sym_eval_kernel<false, kSymCtas256>);
+  if (dev_id < 16 && !attr[dev_id][variant]) {
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(eval_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(eval_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr[dev_id][variant] = true;
   }
   // The clouds of more than kRoundCap points (rare: 1 in ~8000 objects of the bench stream) take the single-launch kernel.  It runs on
   // a side stream next to the rounds: alone, one such CTA lives ~2 ms, and behind the rounds it was the straggler of its whole rank.
@@ -1482,8 +1481,7 @@ static int symmetry_rounds_launch(EslamHandle *h, cudaStream_t s, const uint16_t
     if (e != cudaSuccess) return e;
     sym_step_kernel<<<step_grid, kStepThreads, 0, q>>>(dev, 0);
     for (int r = 0; r < rounds; r++) {
-      if (vi) sym_eval_kernel<true><<<n_obj, 32 * kSeeds, smem, q>>>(dev, r);
-      else sym_eval_kernel<false><<<n_obj, 32 * kSeeds, smem, q>>>(dev, r);
+      eval_fn<<<n_obj, 32 * kSeeds, smem, q>>>(dev, r);
       sym_step_kernel<<<step_grid, kStepThreads, 0, q>>>(dev, r + 1);
     }
     sym_final_kernel<<<(n_obj + 3) / 4, 128, 0, q>>>(dev);
@@ -1491,16 +1489,18 @@ static int symmetry_rounds_launch(EslamHandle *h, cudaStream_t s, const uint16_t
   };
   bool replayed = false;
   if (h->sym_graph) {   // the sequence depends on (n_obj, rounds) and two fixed addresses only: capture once per chunk, replay afterwards
+    // captured on the second consecutive call with the same shape (a frame stream in fixed batches); a caller whose batches change
+    // from call to call (the per-frame tracking driver: 1..8 boxes) keeps plain launches instead of paying an instantiation per call
     ExtractWorkspace::SymGraph &g = w.symgraph[chunk];
-    if (g.exec && !(g.n_obj == n_obj && g.rounds == rounds && g.verify == vi && g.desc == dev && g.live == d.live)) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-    if (!g.exec) {
+    const bool same = g.n_obj == n_obj && g.rounds == rounds && g.verify == variant && g.desc == dev && g.live == d.live;
+    if (g.exec && !same) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    if (!same) { g.n_obj = n_obj; g.rounds = rounds; g.verify = variant; g.desc = dev; g.live = d.live; }
+    if ((same || h->profiling) && !g.exec) {   // (a profiled batch is timed: it never pays for plain launches of a sequence this long)
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
         const cudaError_t e1 = issue(s);
         const cudaError_t e2 = cudaStreamEndCapture(s, &graph);
-        if (e1 == cudaSuccess && e2 == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
-          g.n_obj = n_obj; g.rounds = rounds; g.verify = vi; g.desc = dev; g.live = d.live;
-        } else g.exec = nullptr;
+        if (!(e1 == cudaSuccess && e2 == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess)) g.exec = nullptr;
         if (graph) cudaGraphDestroy(graph);
       }
       cudaGetLastError();
@@ -1525,7 +1525,9 @@ int symmetry_finalize_launch(EslamHandle *h, cudaStream_t s, const uint16_t *dep
   ExtractWorkspace &w = *h->ex;
   if (n_obj <= 0) return ESLAM_OK;
   if (h->sym_impl == 1) return symmetry_v1_launch(h, s, depth_dev, pitch, frame_stride, obj0, n_obj, prm, ptrs);
-  if (h->sym_impl == 3 && 1 + 11 * prm.symmetry_iters <= kSymMaxRounds && chunk >= 0 && chunk < kMaxChunks && w.symseed.p)
+  // round pipeline for batches; a handful of objects (the per-frame tracking driver) is latency bound either way and takes the single
+  // launch: one CTA per object and two launches instead of ~115 mostly idle ones
+  if (h->sym_impl == 3 && n_obj >= kRoundsMinObjects && 1 + 11 * prm.symmetry_iters <= kSymMaxRounds && chunk >= 0 && chunk < kMaxChunks && w.symseed.p)
     return symmetry_rounds_launch(h, s, depth_dev, pitch, frame_stride, obj0, n_obj, prm, ptrs, chunk);
   const ObjMeta *metas = w.meta.as<ObjMeta>() + obj0;
   ObjState *states = w.state.as<ObjState>() + obj0;
