@@ -352,6 +352,9 @@ int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *de
     }
     if (cs != s) ESLAM_CUDA_OK(h, cudaStreamWaitEvent(cs, h->chunk_ev[16], 0));
     if ((rc = extract_launch(h, cs, depth_dev, pitch, frame_stride, o, o1 - o, prm, P))) return rc;
+    // ESLAM_SYM_WINDOW=k (tuning): the symmetry rounds of chunk c start when chunk c - k is done, so that at most k chunks' seed
+    // caches (~123 KB per object) compete for L2; extraction of the later chunks is not held back
+    if (h->sym_window > 0 && c >= h->sym_window && cs != s) ESLAM_CUDA_OK(h, cudaStreamWaitEvent(cs, h->chunk_done[c - h->sym_window], 0));
     if ((rc = symmetry_finalize_launch(h, cs, depth_dev, pitch, frame_stride, o, o1 - o, prm, P, c))) return rc;
     if (cs != s) { ESLAM_CUDA_OK(h, cudaEventRecord(h->chunk_done[c], cs)); ESLAM_CUDA_OK(h, cudaStreamWaitEvent(s, h->chunk_done[c], 0)); }
     o = o1;
@@ -432,6 +435,9 @@ int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHa
   if (const char *e = getenv("ESLAM_PLANE_EXACT")) h->plane_exact = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_PULL_TMA")) h->pull_tma = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_SYM_OCC")) h->sym_occ = atoi(e);
+  if (const char *e = getenv("ESLAM_SYM_WINDOW")) h->sym_window = atoi(e);
+  if (const char *e = getenv("ESLAM_EXTRACT_UQ")) h->extract_uq = atoi(e) != 0;
+  if (const char *e = getenv("ESLAM_EXTRACT_PF")) h->extract_pf = atoi(e) == 2 ? 2 : 1;
   if (const char *e = getenv("ESLAM_SYM_GRAPH")) h->sym_graph = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_SYM_VERIFY")) h->sym_verify = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_DEV_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= kMaxChunks) h->dev_chunks = v; }

@@ -81,6 +81,9 @@ struct EslamHandle {
   bool pull_tma = true;    // SM pull of the box rectangles through cp.async.bulk (TMA); env ESLAM_PULL_TMA=0: the LDG/STG pull kernel
   int sym_occ = 0;         // env ESLAM_SYM_OCC (tuning): 2 / 4 resident CTAs per SM instead of kSymCtas256
   int sym_impl = 3;        // env ESLAM_SYM_IMPL: 1 = round-1 kernel (A/B baseline), 2 = single launch (CTA per object, rounds inside), 3 = round pipeline (phase-pure launches)
+  int sym_window = 0;      // env ESLAM_SYM_WINDOW (tuning): chunks whose symmetry rounds may run at the same time (0 = all)
+  bool extract_uq = true;  // cluster unions through a per-warp queue (env ESLAM_EXTRACT_UQ=0: inline unions, the A/B baseline)
+  int extract_pf = 1;      // env ESLAM_EXTRACT_PF=2 (tuning): neighbour candidates requested two ahead instead of one
   bool sym_graph = true;   // round pipeline: a chunk's ~115 launches are captured once and replayed as a CUDA graph (env ESLAM_SYM_GRAPH=0: plain launches)
   bool sym_verify = false; // env ESLAM_SYM_VERIFY=1: every shortcut decision of the symmetry kernel is re-derived the long way and counted when it differs
   eslam::DevBuf plane_depth;           // staging of eslam_extract_ground_plane_host (separate from the extraction slots)

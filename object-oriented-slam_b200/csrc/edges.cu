@@ -291,11 +291,36 @@ int graph_optimize(EslamHandle *h, int iters, double *ell_inout, EslamLmStats *s
       cudaGetLastError();
     }
   }
-  for (int it = 0; it < iters; it++) {
-    if (w.lm_exec && h->sym_graph) ESLAM_CUDA_OK(h, cudaGraphLaunch(w.lm_exec, s));
-    else if ((rc = issue_iteration(s))) { if (rc == ESLAM_ERR_CUDA) h->err = "graph_optimize: launch failed"; return rc; }
+  if (!(w.lm_exec && h->sym_graph) && E < 8192) {
+    // small graph that does not repeat its shape (the online case: one optimisation per frame on a graph that grows by a few edges):
+    // the worst-case sequence would be ~430 mostly idle launches, more than the work itself -- issue one trial at a time and read
+    // the control block back after each (same kernels, same device state machine)
+    long long n = 0;
+    for (int it = 0; it < iters; it++) {
+      if ((rc = launch_eval(h, s, w.ell.as<double>(), true, 1))) return rc;
+      build_system_kernel<<<No, 96, 0, s>>>(w.obj_start.as<int>(), w.obj_edges.as<int>(), w.type.as<int>(), w.info.as<double>(), w.res.as<double>(),
+                                            w.jac.as<double>(), w.H.as<double>(), w.b.as<double>(), st);
+      lm_begin_kernel<<<1, 32, 0, s>>>(st, w.chi2.as<double>(), E, w.H.as<double>(), No);
+      n += 3;
+      do {
+        lm_solve_kernel<<<(No + 31) / 32, 32, 0, s>>>(st, w.H.as<double>(), w.b.as<double>(), w.xtmp.as<double>(), No);
+        lm_update_kernel<<<(No + 31) / 32, 32, 0, s>>>(st, w.xtmp.as<double>(), w.x.as<double>(), w.ell.as<double>(), w.ell_trial.as<double>(), No);
+        if ((rc = launch_eval(h, s, w.ell_trial.as<double>(), false, 2))) return rc;
+        lm_decide_kernel<<<1, 32, 0, s>>>(st, w.chi2.as<double>(), E, w.x.as<double>(), w.b.as<double>(), No, w.ell.as<double>(), w.ell_trial.as<double>(), 0);
+        n += 4;
+        ESLAM_CUDA_OK(h, cudaMemcpyAsync(hs, st, sizeof(LmState), cudaMemcpyDeviceToHost, s));
+        ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));
+      } while (hs->trial_active);
+      if (hs->terminated) break;
+    }
+    h->launches = launches_before + n;
+  } else {
+    for (int it = 0; it < iters; it++) {
+      if (w.lm_exec && h->sym_graph) ESLAM_CUDA_OK(h, cudaGraphLaunch(w.lm_exec, s));
+      else if ((rc = issue_iteration(s))) { if (rc == ESLAM_ERR_CUDA) h->err = "graph_optimize: launch failed"; return rc; }
+    }
+    h->launches = launches_before + (long long)iters * (3 + 4 * maxTrials);
   }
-  h->launches = launches_before + (long long)iters * (3 + 4 * maxTrials);
   ESLAM_CUDA_OK(h, cudaMemcpyAsync(hs, st, sizeof(LmState), cudaMemcpyDeviceToHost, s));
   ESLAM_CUDA_OK(h, cudaMemcpyAsync(ell_inout, w.ell.p, (size_t)No * 80, cudaMemcpyDeviceToHost, s));
   ESLAM_CUDA_OK(h, cudaStreamSynchronize(s));

@@ -157,13 +157,15 @@ __device__ __forceinline__ bool voxel_tile_centroid(const float4 *pts, const uns
   return head;
 }
 
-template <int MINB, int SMEM_PARENTS>
+template <int MINB, int SMEM_PARENTS, bool UQ, int PF>
 __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const uint16_t *__restrict__ depth, size_t pitch, size_t frame_stride, const ObjMeta *__restrict__ metas,
                                                       ObjState *__restrict__ states, ExtractParamsDev prm, ExtractPtrs W) {
   __shared__ BlockScratch S;
   __shared__ RadixScratch RS;
   __shared__ ScanScratch SS;
   __shared__ int s_sel;
+  // UQ: per-warp queue of the (i, j) pairs that still need a union (packed 16 + 16 bits: at most 34 080 stride-3 samples per box)
+  __shared__ unsigned s_uq[UQ ? kExtractThreads / 32 : 1][UQ ? 64 : 1];
   VoxelTile &VT = *reinterpret_cast<VoxelTile *>(&RS);
   extern __shared__ int s_parent[];   // union-find parents / cluster labels when the filtered cloud fits (kSmemParents), else HBM
   int phase = 0;
@@ -338,6 +340,12 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
     // cell x+1 by walking on from the point's own sorted position, then rows (dz,dy) = (0,+1), (+1,-1), (+1,0), (+1,+1) over x-1..x+1.
     // The data-dependent scan of a row is re-converged with __any_sync each step, so divergent union-find retries never serialise
     // the rest of the warp.
+    // UQ: a pair inside the radius whose points do not share a parent yet is rare per lane and iteration (the union-find code ran
+    // with ~4 of 32 lanes active, 16 % of the kernel's issued instructions); the pairs go to a per-warp queue instead and are united
+    // 32 at a time with every lane busy.  The final partition does not depend on the order of the unions.
+    const unsigned lt_ = (1u << (tid & 31)) - 1u;
+    unsigned *wq = s_uq[UQ ? (tid >> 5) : 0];
+    int wcnt = 0;
     for (int base = 0; base < n3; base += blockDim.x) {
       const int pos = base + tid;
       const bool act = pos < n3;
@@ -359,22 +367,51 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
         }
         // software pipelined walk: key and point of candidate q+1 are requested before candidate q is tested (a second lower bound for
         // the end of the row instead of the key loads was measured slower: 65 instructions per search against ~3 per candidate)
+        // (PF = 2: two candidates ahead -- one iteration of the resident warps is shorter than an L2 round trip)
         unsigned kq = 0xffffffffu; float4 pq = make_float4(0, 0, 0, 0);
+        unsigned kq1 = 0xffffffffu; float4 pq1 = make_float4(0, 0, 0, 0);
         if (valid && q < n3) { kq = k0[q]; pq = Bs[q]; }
+        if (PF == 2 && valid && q + 1 < n3) { kq1 = k0[q + 1]; pq1 = Bs[q + 1]; }
         while (true) {
           const bool more = valid && q < n3 && kq <= khi;
           if (!__any_sync(0xffffffffu, more)) break;
           unsigned kn = 0xffffffffu; float4 pn = make_float4(0, 0, 0, 0);
-          if (more && q + 1 < n3) { kn = k0[q + 1]; pn = Bs[q + 1]; }
+          if (more && q + PF < n3) { kn = k0[q + PF]; pn = Bs[q + PF]; }
+          bool want = false; int j = 0;
           if (more) {
             if (l2_simple(p, pq) < r2) {   // RadiusResultSet::addPoint: dist < radius^2
-              const int j = __float_as_int(pq.w);
-              if (vload(parent + i) != vload(parent + j)) uf_union(parent, i, j);   // same parent => same set already: skip the finds
+              j = __float_as_int(pq.w);
+              want = vload(parent + i) != vload(parent + j);   // same parent => same set already: skip the finds
+              if (!UQ && want) uf_union(parent, i, j);
             }
-            q++; kq = kn; pq = pn;
+            q++;
+            if (PF == 2) { kq = kq1; pq = pq1; kq1 = kn; pq1 = pn; } else { kq = kn; pq = pn; }
+          }
+          if (UQ) {
+            const unsigned wm = __ballot_sync(0xffffffffu, want);
+            if (wm) {
+              if (want) wq[wcnt + __popc(wm & lt_)] = (unsigned)i | ((unsigned)j << 16);
+              wcnt += __popc(wm);
+              if (wcnt >= 32) {
+                __syncwarp();
+                const unsigned e = wq[tid & 31];
+                uf_union(parent, (int)(e & 0xffffu), (int)(e >> 16));
+                const int rest = wcnt - 32;
+                unsigned t = 0;
+                if ((tid & 31) < rest) t = wq[32 + (tid & 31)];
+                __syncwarp();
+                if ((tid & 31) < rest) wq[tid & 31] = t;
+                wcnt = rest;
+                __syncwarp();
+              }
+            }
           }
         }
       }
+    }
+    if (UQ) {   // drain
+      __syncwarp();
+      if ((tid & 31) < wcnt) { const unsigned e = wq[tid & 31]; uf_union(parent, (int)(e & 0xffffu), (int)(e >> 16)); }
     }
     __syncthreads();
     if (tid == 0) st.phase_clk[5] = clock64();
@@ -685,13 +722,14 @@ int extract_launch(EslamHandle *h, cudaStream_t s, const uint16_t *depth_dev, si
   if (n_obj <= 0) return ESLAM_OK;
   // Shape: 3 CTAs/SM (80 registers, 48 KB of parents).  Measured alternative: 4 CTAs/SM with a 64-register cap and 32 KB of parents is
   // 9 % slower (profiles/r01_kernel_shape_ab.txt).
+  void (*fn)(const uint16_t *, size_t, size_t, const ObjMeta *, ObjState *, ExtractParamsDev, ExtractPtrs) =
+      !h->extract_uq ? extract_kernel<3, kSmemParents, false, 1> : (h->extract_pf == 2 ? extract_kernel<3, kSmemParents, true, 2> : extract_kernel<3, kSmemParents, true, 1>);
   if (!h->attr_extract) {
-    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(extract_kernel<3, kSmemParents>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemParents * (int)sizeof(int)));
-    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(extract_kernel<3, kSmemParents>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemParents * (int)sizeof(int)));
+    ESLAM_CUDA_OK(h, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     h->attr_extract = true;
   }
-  extract_kernel<3, kSmemParents><<<n_obj, kExtractThreads, kSmemParents * sizeof(int), s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0,
-                                                                                              w.state.as<ObjState>() + obj0, prm, ptrs);
+  fn<<<n_obj, kExtractThreads, kSmemParents * sizeof(int), s>>>(depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, w.state.as<ObjState>() + obj0, prm, ptrs);
   ESLAM_LAUNCHED(h);
   ESLAM_CUDA_OK(h, cudaGetLastError());
   return ESLAM_OK;

@@ -494,6 +494,20 @@ def test_symmetry_kernel_equals_the_round1_kernel_bit_for_bit():
     assert all(r == recs[0] for r in recs[1:])
 
 
+def test_cluster_unions_through_the_warp_queue_give_the_same_records(handle):
+    """The unions of the Euclidean clustering go through a per-warp queue (32 at a time, every lane busy; ESLAM_EXTRACT_UQ=0 = the
+    inline unions of round 1): the partition, and with it every record, must not depend on it -- nor on the candidate prefetch distance."""
+    batch = _mixed_batch()
+    handle.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+    want = bytes(handle.estimate_ellipsoids(*batch)[0])
+    for env in ({"ESLAM_EXTRACT_UQ": "0"}, {"ESLAM_EXTRACT_PF": "2"}):
+        h = _handle_with_env(env)
+        h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
+        got = bytes(h.estimate_ellipsoids(*batch)[0])
+        h.close()
+        assert got == want, env
+
+
 def test_symmetry_verify_mode_finds_no_disagreement(handle):
     """ESLAM_SYM_VERIFY=1 re-derives every shortcut decision the long way inside the kernel (full classification + brute-force scan)
     and counts disagreements: none, and the records equal the normal run's."""
