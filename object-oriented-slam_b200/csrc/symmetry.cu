@@ -86,6 +86,7 @@ struct SeedCore {
   double lambda, ni, currentChi, iniChi, err_last, err_est;   // err_last: value of the last computeError call; err_est: error of `est`
   int nBad, ok, qmax, ok2, it, cur, fd_ok, action;
   int wbank, qn, invalid;  // the running single-plane evaluation: bank it writes, points queued for a scan, invalid points
+  int stale;               // round pipeline (one NN bank): the last trial was rejected, so the bank no longer holds the evaluation of `est`
   unsigned n_evals, n_queries, n_points, n_hits, n_ref, n_verify_fail;
   SeedResult res;
   int inv_s[6];
@@ -666,7 +667,7 @@ __device__ __noinline__ void lm_step(const int symtype, const int iters, SeedCor
   const int dim = (symtype == 1) ? 2 : 3;
   bool start_trial = false, begin_iter = false;
   if (S.action == kActInit) {
-    S.n_ref = 1; S.res.init_err = S.err_last; S.err_est = S.err_last;
+    S.n_ref = 1; S.res.init_err = S.err_last; S.err_est = S.err_last; S.stale = 0;
     S.lambda = -1; S.ni = 2; S.nBad = 0; S.x[0] = S.x[1] = S.x[2] = 0; S.ok = 1; S.it = 0;
     begin_iter = true;
   } else if (S.action == kActFd) {
@@ -698,8 +699,10 @@ __device__ __noinline__ void lm_step(const int symtype, const int iters, SeedCor
       const double sf = fmax(1. / 3., alpha);
       S.lambda *= sf; S.ni = 2; S.currentChi = tempChi;
       S.err_est = err; S.cur ^= 1;   // the trial's evaluation is the state of `est` from now on
+      S.stale = 0;
     } else {
       S.lambda *= S.ni; S.ni *= 2; S.est = S.backup;
+      S.stale = 1;
     }
     S.qmax++;
     if (rho < 0 && S.qmax < 10) start_trial = true;
@@ -1109,7 +1112,7 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
 constexpr int kRoundCap = 256;                                        // clouds of up to 256 points; larger ones take the single-launch kernel
 constexpr int kSeedPersist = (int)((sizeof(SeedCore) + 2 * sizeof(unsigned[2][2][kRoundCap / 32]) + 15) & ~(size_t)15);
 constexpr int kSeedStride = kSeedPersist;
-constexpr size_t kRoundCacheBytes = (size_t)kRoundCap * 96;           // per seed: two NN banks + the pixel cache, 2 * CAP entries each
+constexpr size_t kRoundCacheBytes = (size_t)kRoundCap * 64;           // per seed: one NN bank + the pixel cache, 2 * CAP entries of 16 bytes each
 constexpr int kRoundsMinObjects = 16;                                  // smaller launches take the single-launch kernel
 constexpr int kStepThreads = 128;                                     // eight lanes per seed: 16 seeds per CTA
 static_assert(sizeof(SeedCore) % 8 == 0, "SeedCore is followed by the masks without padding");
@@ -1180,8 +1183,11 @@ __global__ void __launch_bounds__(kStepThreads) sym_step_kernel(const SymChunk *
   if (valid && sub == 0) {
     if (k == 0) {
       unsigned char *cb = C.cache + ((size_t)obj * kSeeds + sd) * kRoundCacheBytes;
-      float4 *nn0 = reinterpret_cast<float4 *>(cb), *nn1 = nn0 + 2 * kRoundCap;
-      S->nnc[0] = nn0; S->nnc[1] = nn1; S->pxc = reinterpret_cast<uint4 *>(nn1 + 2 * kRoundCap);
+      // ONE NN bank (both names point at it): a linearisation always follows an accepted trial, whose evaluation is the last writer
+      // of the bank; any entry ever written stays a valid (query, neighbour, radius) triple for the trials in between.  The one
+      // exception -- a rejected trial followed by a linearisation (non-finite rho) -- is flagged `stale` and takes full evaluations.
+      float4 *nn0 = reinterpret_cast<float4 *>(cb);
+      S->nnc[0] = nn0; S->nnc[1] = nn0; S->pxc = reinterpret_cast<uint4 *>(nn0 + 2 * kRoundCap);
       S->cur = 0; S->fd_ok = 0; S->action = kActInit;
       S->n_evals = S->n_queries = S->n_points = S->n_hits = S->n_ref = S->n_verify_fail = 0;
       const double diff_dis = 0.2, diff_angle = M_PI / 180.0 * 5;
@@ -1230,7 +1236,7 @@ __global__ void __launch_bounds__(kStepThreads) sym_step_kernel(const SymChunk *
   bool pair_ok = true;
   if (action == kActFd && sub < 2 * dim) pair_ok = fd_pair_ok(S->base, S->fd[sub], st->sym_R2);
   const unsigned bad = __ballot_sync(0xffffffffu, !pair_ok) & (0xffu << (lane & ~7));
-  if (action == kActFd && sub == 0) S->fd_ok = bad ? 0 : 1;
+  if (action == kActFd && sub == 0) S->fd_ok = (bad || S->stale) ? 0 : 1;
   __syncwarp();
   if (was_live) copy_words8<8>(reinterpret_cast<unsigned long long *>(G), s_seed[threadIdx.x >> 3], (int)(sizeof(SeedCore) / 8), sub);
   const unsigned lv = __ballot_sync(0xffffffffu, sub == 0 && action != kActDone);
