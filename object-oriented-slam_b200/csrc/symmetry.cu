@@ -78,18 +78,26 @@ enum { kActDone = 0, kActInit = 1, kActFd = 2, kActTrial = 3 };
 // The single-launch kernel keeps it in shared memory; the round pipeline (sym_eval_kernel / sym_step_kernel) keeps it in HBM / L2
 // between launches and stages it through shared memory inside an evaluation launch.
 struct SeedCore {
+  // ---- A: read (and partly written) by every cost evaluation
   float4 *nnc[2];          // NN cache, two banks: [bank][point] = (q0.x, q0.y, q0.z, rho^2 | neighbour index)
   uint4 *pxc;              // pixel cache: [point] = (x | y << 16, ushort range value, depth = value / scale as a double)
-  PlanePair pp, base, fd[6];
-  dplane est, backup;
-  double H[9], b[3], x[3], J[3];
-  double lambda, ni, currentChi, iniChi, err_last, err_est;   // err_last: value of the last computeError call; err_est: error of `est`
+  PlanePair pp;            // the trial plane being evaluated
+  double J[3];
+  double err_last;         // value of the last computeError call
   int nBad, ok, qmax, ok2, it, cur, fd_ok, action;
   int wbank, qn, invalid;  // the running single-plane evaluation: bank it writes, points queued for a scan, invalid points
   int stale;               // round pipeline (one NN bank): the last trial was rejected, so the bank no longer holds the evaluation of `est`
   unsigned n_evals, n_queries, n_points, n_hits, n_ref, n_verify_fail;
-  SeedResult res;
   int inv_s[6];
+  // ---- B: finite-difference passes only
+  alignas(16) PlanePair base;
+  PlanePair fd[6];
+  // ---- C: the scalar Levenberg-Marquardt step only
+  alignas(16) dplane est;
+  dplane backup;
+  double H[9], b[3], x[3];
+  double lambda, ni, currentChi, iniChi, err_est;   // err_est: error of `est`
+  SeedResult res;
 };
 template <int CAP>
 struct SymSeed : SeedCore {
@@ -1115,7 +1123,13 @@ constexpr int kSeedStride = kSeedPersist;
 constexpr size_t kRoundCacheBytes = (size_t)kRoundCap * 64;           // per seed: one NN bank + the pixel cache, 2 * CAP entries of 16 bytes each
 constexpr int kRoundsMinObjects = 16;                                  // smaller launches take the single-launch kernel
 constexpr int kStepThreads = 128;                                     // eight lanes per seed: 16 seeds per CTA
-static_assert(sizeof(SeedCore) % 8 == 0, "SeedCore is followed by the masks without padding");
+static_assert(sizeof(SeedCore) % 16 == 0, "SeedCore is followed by the masks without padding");
+#pragma nv_diag_suppress 1427
+constexpr int kSeedA16 = (int)(__builtin_offsetof(SeedCore, base) / 16);    // part A in 16-byte units
+constexpr int kSeedC16 = (int)(__builtin_offsetof(SeedCore, est) / 16);     // parts A + B
+#pragma nv_diag_default 1427
+constexpr int kSeedCore16 = (int)(sizeof(SeedCore) / 16);
+static_assert(kSeedA16 <= 32 && __builtin_offsetof(SeedCore, base) % 16 == 0 && __builtin_offsetof(SeedCore, est) % 16 == 0, "part A is one 16-byte load per lane");
 static_assert(sizeof(SymSeed<kRoundCap>) >= (size_t)kSeedPersist, "persistent prefix");
 #pragma nv_diag_suppress 1427
 static_assert(__builtin_offsetof(SymSeed<kRoundCap>, mA) == sizeof(SeedCore) && __builtin_offsetof(SymSeed<kRoundCap>, lnp) == (size_t)kSeedPersist,
@@ -1277,7 +1291,14 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) sym_eval_kernel(const SymCh
   }
   SymSeed<CAP> &S = seeds[wid];
   uint4 *gseed = reinterpret_cast<uint4 *>(C.seedp + ((size_t)obj * kSeeds + wid) * kSeedStride);
-  copy_quads4(reinterpret_cast<uint4 *>(&S), gseed, kSeedPersist / 16, lane);   // stage this warp's seed
+  {   // stage this warp's seed: part A and the robust masks always, the finite-difference planes (part B) when a pass is due; the
+      // scalar LM state (part C) never comes here
+    uint4 *dst = reinterpret_cast<uint4 *>(&S);
+    if (lane < kSeedA16) dst[lane] = gseed[lane];
+    for (int i = kSeedCore16 + lane; i < kSeedPersist / 16; i += 32) dst[i] = gseed[i];
+    __syncwarp();
+    if (S.action == kActFd) copy_quads4(dst + kSeedA16, gseed + kSeedA16, kSeedC16 - kSeedA16, lane);
+  }
   for (int j = threadIdx.x; j < (M + 1) / 2; j += blockDim.x) {
     const float4 a = objnf[2 * j];
     const float far_ = 1.0e30f;   // (q - 1e30)^2 overflows to +inf: never < FLT_MAX, so the pad can never win
@@ -1373,7 +1394,11 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) sym_eval_kernel(const SymCh
     }
   }
   {   // persistent state back (only a live seed changed)
-    if (S.action != kActDone) copy_quads4(gseed, reinterpret_cast<const uint4 *>(&S), kSeedPersist / 16, lane);
+    if (S.action != kActDone) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(&S);
+      if (lane < kSeedA16) gseed[lane] = src[lane];
+      for (int i = kSeedCore16 + lane; i < kSeedPersist / 16; i += 32) gseed[i] = src[i];
+    }
   }
 }
 

@@ -25,7 +25,17 @@ tot = dt.sum(axis=1).mean()
 print("stage ms", h.stage_ms(), " mean cycles per CTA %.0f (%.3f ms at 1.965 GHz)" % (tot, tot / 1.965e6))
 for k, nm in enumerate(names):
     print("  %-32s %9.0f cycles  %5.1f %%" % (nm, dt[:, k].mean(), 100 * dt[:, k].mean() / tot))
-st = sclk.sum(axis=1).mean()
-print("symmetry kernel: mean cycles per seed warp %.0f (%.3f ms)" % (st / 9, st / 9 / 1.965e6))
-for k, nm in enumerate(["classification passes (mirror + project + caches)", "nearest-neighbour scans", "ordered ln P sums", "rest (LM scalar code, oplus, plane pairs, set-up)"]):
-    print("  %-52s %9.0f cycles  %5.1f %%" % (nm, sclk[:, k].mean() / 9, 100 * sclk[:, k].mean() / st))
+# symmetry: the slots mean different things per implementation (ESLAM_SYM_IMPL)
+impl = os.environ.get("ESLAM_SYM_IMPL", "3")
+if impl == "2":     # single launch: cycles of the CTA's phases (thread 0)
+    tot = sclk[:, 3].mean()
+    print("symmetry_finalize_kernel (single launch): mean cycles per CTA %.0f (%.3f ms)" % (tot, tot / 1.965e6))
+    for k, nm in enumerate(["scalar phases (LM step of the nine seeds, one warp)", "task phases (FD passes + classification)", "scan phases + ordered sums"]):
+        print("  %-52s %9.0f cycles  %5.1f %%" % (nm, sclk[:, k].mean(), 100 * sclk[:, k].mean() / tot))
+elif impl == "1":   # round-1 kernel: per-warp sums
+    st = sclk.sum(axis=1).mean()
+    print("round-1 symmetry kernel: mean cycles per seed warp %.0f (%.3f ms)" % (st / 9, st / 9 / 1.965e6))
+    for k, nm in enumerate(["classification passes (mirror + project + caches)", "nearest-neighbour scans", "ordered ln P sums", "rest (LM scalar code, oplus, plane pairs, set-up)"]):
+        print("  %-52s %9.0f cycles  %5.1f %%" % (nm, sclk[:, k].mean() / 9, 100 * sclk[:, k].mean() / st))
+else:               # round pipeline: finite-difference passes and how many fell back to full evaluations
+    print("symmetry round pipeline: finite-difference passes per object %.1f, fallbacks per object %.3f (per-round times: tools/ncu_rounds.py over an ncu launch list)" % (sclk[:, 0].mean(), sclk[:, 1].mean()))
