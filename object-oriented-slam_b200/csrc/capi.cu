@@ -167,6 +167,7 @@ int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const
   }
   P.sympool256 = h->sym_pool256.as<unsigned char>(); P.sympool512 = h->sym_pool512.as<unsigned char>();
   P.slotmask2 = h->sym_slotmask2.as<unsigned>(); P.smid_map = h->sym_smid_map.as<int>(); P.sm_count = h->sm_count;
+  P.l2_discard = (h->l2_discard && !want_dump) ? 1 : 0;
   P.d_crop = P.d_voxel = P.d_world = P.d_sym = P.d_final = nullptr; P.d_label = nullptr;
   if (want_dump) {
     ESLAM_CUDA_OK(h, w.d_crop.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_voxel.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_world.reserve(CAP * 24));
@@ -435,6 +436,7 @@ int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHa
   if (const char *e = getenv("ESLAM_PLANE_EXACT")) h->plane_exact = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_PULL_TMA")) h->pull_tma = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_SYM_OCC")) h->sym_occ = atoi(e);
+  if (const char *e = getenv("ESLAM_L2_DISCARD")) h->l2_discard = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_SYM_WINDOW")) h->sym_window = atoi(e);
   if (const char *e = getenv("ESLAM_EXTRACT_UQ")) h->extract_uq = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_EXTRACT_PF")) h->extract_pf = atoi(e) == 2 ? 2 : 1;

@@ -81,6 +81,7 @@ struct EslamHandle {
   bool pull_tma = true;    // SM pull of the box rectangles through cp.async.bulk (TMA); env ESLAM_PULL_TMA=0: the LDG/STG pull kernel
   int sym_occ = 0;         // env ESLAM_SYM_OCC (tuning): 2 / 4 resident CTAs per SM instead of kSymCtas256
   int sym_impl = 3;        // env ESLAM_SYM_IMPL: 1 = round-1 kernel (A/B baseline), 2 = single launch (CTA per object, rounds inside), 3 = round pipeline (phase-pure launches)
+  bool l2_discard = true;  // env ESLAM_L2_DISCARD=0: keep the dead scratch lines in L2 (they are written back to HBM when evicted)
   int sym_window = 0;      // env ESLAM_SYM_WINDOW (tuning): chunks whose symmetry rounds may run at the same time (0 = all)
   bool extract_uq = true;  // cluster unions through a per-warp queue (env ESLAM_EXTRACT_UQ=0: inline unions, the A/B baseline)
   int extract_pf = 1;      // env ESLAM_EXTRACT_PF=2 (tuning): neighbour candidates requested two ahead instead of one
@@ -121,3 +122,14 @@ struct EslamHandle {
   } while (0)
 
 #define ESLAM_LAUNCHED(h) ((h)->launches++)
+
+#ifdef __CUDACC__
+namespace eslam {
+// Drops the 128-byte lines of [p, p + bytes) from L2 WITHOUT write-back (PTX discard.global.L2, SASS CCTL.RML2): for scratch whose last
+// reader is done.  p must be 128-byte aligned and the range must not share a line with live data; `tid` / `nthreads` spread the lines.
+__device__ __forceinline__ void l2_discard_lines(const void *p, size_t bytes, int tid, int nthreads) {
+  const char *a = reinterpret_cast<const char *>(p);
+  for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)nthreads * 128) asm volatile("discard.global.L2 [%0], 128;" ::"l"(a + off) : "memory");
+}
+}  // namespace eslam
+#endif

@@ -600,6 +600,20 @@ __global__ void __launch_bounds__(kExtractThreads, MINB) extract_kernel(const ui
     st.n_sym = M;
     st.run_sym = (prm.symmetry_open && m.symtype > 0 && M >= 1) ? 1 : 0;
   }
+  // Everything but the object-normalised symmetry cloud (objn / objnf, M points) is dead now.  Its dirty lines would sit in L2 until
+  // evicted and then be written back to HBM for nothing (the kernel wrote 1.04 MB per object to DRAM, more than it read): drop them.
+  // A slice starts on a 128-byte boundary and holds a multiple of 128 bytes per array (cap is a multiple of 32 elements).
+  if (W.l2_discard) {
+    __syncthreads();
+    const size_t r1 = (((size_t)n1 + 31) & ~(size_t)31), r3 = (((size_t)n3 + 31) & ~(size_t)31), rc = (((size_t)nc + 31) & ~(size_t)31);
+    l2_discard_lines(A, r1 * 16, tid, kExtractThreads);
+    l2_discard_lines(B, r3 * 16, tid, kExtractThreads);
+    l2_discard_lines(Cc, rc * 16, tid, kExtractThreads);
+    l2_discard_lines(k0, r1 * 4, tid, kExtractThreads); l2_discard_lines(k1, r1 * 4, tid, kExtractThreads);
+    l2_discard_lines(v0, r1 * 4, tid, kExtractThreads); l2_discard_lines(v1, r1 * 4, tid, kExtractThreads);
+    l2_discard_lines(W.count + m.off, r3 * 4, tid, kExtractThreads);
+    if (n3 > SMEM_PARENTS) l2_discard_lines(W.parent + m.off, r3 * 4, tid, kExtractThreads);
+  }
 }
 
 // Host entry, pinned (mapped) input: the SMs pull each object's box rectangle straight out of host memory over PCIe (16-byte

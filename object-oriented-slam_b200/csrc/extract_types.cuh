@@ -64,6 +64,7 @@ struct ExtractPtrs {  // device pointers of the per-point workspace (total capac
   unsigned *slotmask2;   // [2][sm_count]: CAP = 256 words, then CAP = 512 words; bits beyond the variant's slot count are pre-set
   int *smid_map;         // [kMaxSmId + 1]: dense SM index per %smid (first touch), last entry = next free index
   int sm_count;
+  int l2_discard;        // 1: dead per-object scratch is dropped from L2 without write-back when its last reader is done (discard.global.L2)
   // optional stage dump (device mirrors, NULL when no dump requested)
   double *d_crop, *d_voxel, *d_world, *d_sym, *d_final;  // d_final has 4x capacity
   int *d_label;

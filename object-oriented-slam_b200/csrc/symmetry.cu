@@ -1119,7 +1119,7 @@ __global__ void __launch_bounds__(32 * kSeeds, MINB) symmetry_finalize_kernel(co
 // HBM / L2 between launches; an evaluation CTA stages its nine seeds through shared memory.
 constexpr int kRoundCap = 256;                                        // clouds of up to 256 points; larger ones take the single-launch kernel
 constexpr int kSeedPersist = (int)((sizeof(SeedCore) + 2 * sizeof(unsigned[2][2][kRoundCap / 32]) + 15) & ~(size_t)15);
-constexpr int kSeedStride = kSeedPersist;
+constexpr int kSeedStride = (kSeedPersist + 127) / 128 * 128;          // whole 128-byte lines per seed: an object's state can be dropped from L2 line by line
 constexpr size_t kRoundCacheBytes = (size_t)kRoundCap * 64;           // per seed: one NN bank + the pixel cache, 2 * CAP entries of 16 bytes each
 constexpr int kRoundsMinObjects = 16;                                  // smaller launches take the single-launch kernel
 constexpr int kStepThreads = 128;                                     // eight lanes per seed: 16 seeds per CTA
@@ -1428,6 +1428,18 @@ __global__ void __launch_bounds__(128) sym_final_kernel(const SymChunk *__restri
     return;
   }
   finalize_object(m, st, C.prm, C.W, out);
+  // the seeds of this object are done: their state and the touched part of their caches are dead -- dropped from L2 without write-back
+  if (C.W.l2_discard && st.run_sym) {
+    __syncwarp();
+    const int npts = (m.symtype == 2) ? 2 * st.n_sym : st.n_sym;
+    l2_discard_lines(C.seedp + (size_t)obj * kSeeds * kSeedStride, (size_t)kSeeds * kSeedStride, lane, 32);
+    const size_t touched = (((size_t)npts * 16) + 127) & ~(size_t)127;
+    for (int sd = 0; sd < kSeeds; sd++) {
+      const unsigned char *cb = C.cache + ((size_t)obj * kSeeds + sd) * kRoundCacheBytes;
+      l2_discard_lines(cb, touched, lane, 32);                                   // NN bank
+      l2_discard_lines(cb + (size_t)2 * kRoundCap * 16, touched, lane, 32);      // pixel cache
+    }
+  }
 }
 
 template <int CAP, int MINB, bool VERIFY>
