@@ -242,6 +242,19 @@ int eslam_estimate_ellipsoids_dev_collect(EslamHandle *h, void *stream, int tick
 int eslam_init_quadric(EslamHandle *h, int n_obs, const double *Twc7, const double *det5, const double K[9],
                        int rows, int cols, double ellipsoid10[10], int *ok);
 
+/* ------------------------------------------------------------------ automatic data association (batched over frames) */
+/* replaces DataAssociationSolver::Solve(pFrame, true) + SolveCostMat (src/core/DataAssociation.cpp:16-135) for n_frames frames
+ * against ONE map snapshot: det_start [n_frames + 1] = row ranges of the frames (rows in frame order), Twc7 [n_frames*7],
+ * det_pose7_cam [n_det*7] = pose of each single-frame ellipsoid in its camera frame (pFrame->mpLocalObjects[i]->pose),
+ * valid [n_det] = 0 where mpLocalObjects[i] == NULL, map_center3 [n_map*3] = centres of the map objects in ascending instance
+ * order (std::map order).  assoc_out [n_det]: -1 for an invalid row; the COLUMN index of the matched map object (the reference
+ * returns the column, DataAssociation.cpp:113-114); or a new instance id, numbered from first_new_instance in (frame, row)
+ * order (miInstanceNum++, :137-140).  *n_new_out = instances created.  At most 64 rows per frame and 1024 map objects
+ * (ESLAM_ERR_CAPACITY beyond). */
+int eslam_associate_frames_host(EslamHandle *h, int n_frames, const int *det_start, const double *Twc7, int n_det,
+                                const double *det_pose7_cam, const int *valid, int n_map, const double *map_center3,
+                                int first_new_instance, int *assoc_out, int *n_new_out);
+
 /* ------------------------------------------------------------------ graph edges / BA */
 /* One launch: residuals + g2o numeric Jacobians (delta 1e-9 central differences, base_binary_edge.hpp:131-205)
  * w.r.t. the 9-DoF ellipsoid vertex for all edges.

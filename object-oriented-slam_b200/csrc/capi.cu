@@ -466,6 +466,7 @@ void eslam_destroy(EslamHandle *h) {
     if (h->slot_done[sl]) cudaEventDestroy(h->slot_done[sl]);
     if (h->slot_start[sl]) cudaEventDestroy(h->slot_start[sl]);
   }
+  h->assoc_buf.release();
   h->sym_pool_nn.release(); h->sym_pool_px.release(); h->sym_slotmask.release(); h->plane_depth.release();
   h->sym_pool256.release(); h->sym_pool512.release(); h->sym_slotmask2.release(); h->sym_smid_map.release();
   delete h->copy_pool; h->copy_pool = nullptr;
@@ -762,6 +763,13 @@ int eslam_optimize_objects_host(EslamHandle *h, const EslamEdgeBatch *g, int ite
   int rc = eslam_edges_upload(h, g, ell);
   if (rc) return rc;
   return graph_optimize(h, iters, ell, stats, h->stream);
+}
+
+int eslam_associate_frames_host(EslamHandle *h, int n_frames, const int *det_start, const double *Twc7, int n_det, const double *det_pose7_cam, const int *valid,
+                                int n_map, const double *map_center3, int first_new_instance, int *assoc_out, int *n_new_out) {
+  if (!h || !det_start || !Twc7 || !assoc_out || !n_new_out || (n_det > 0 && (!det_pose7_cam || !valid)) || (n_map > 0 && !map_center3)) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  return associate_frames(h, h->stream, n_frames, det_start, Twc7, n_det, det_pose7_cam, valid, n_map, map_center3, first_new_instance, assoc_out, n_new_out);
 }
 
 void eslam_pose_inverse(const double T[7], double Ti[7]) {  // SE3Quat::inverse, se3quat.h:129-134

@@ -87,6 +87,7 @@ struct EslamHandle {
   int extract_pf = 1;      // env ESLAM_EXTRACT_PF=2 (tuning): neighbour candidates requested two ahead instead of one
   bool sym_graph = true;   // round pipeline: a chunk's ~115 launches are captured once and replayed as a CUDA graph (env ESLAM_SYM_GRAPH=0: plain launches)
   bool sym_verify = false; // env ESLAM_SYM_VERIFY=1: every shortcut decision of the symmetry kernel is re-derived the long way and counted when it differs
+  eslam::DevBuf assoc_buf;             // batched data association (associate.cu)
   eslam::DevBuf plane_depth;           // staging of eslam_extract_ground_plane_host (separate from the extraction slots)
   bool attr_extract = false, attr_symmetry = false, attr_symmetry_v1 = false, attr_plane = false;   // kernel attributes are per device: set once per handle, not once per process
   unsigned long long h2d_bytes = 0;    // depth bytes uploaded by the *_host extraction entry (running total)

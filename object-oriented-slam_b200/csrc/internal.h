@@ -40,6 +40,10 @@ int plane_extract_dbg(EslamHandle *h, cudaStream_t s, int n_frames, const uint16
                       int *n_inliers_host, int debug_stage, void *debug_out);
 void plane_free(EslamHandle *h);
 
+// associate.cu (N4: batched data association)
+int associate_frames(EslamHandle *h, cudaStream_t s, int n_frames, const int *det_start_host, const double *Twc7, int n_det, const double *det_pose7, const int *valid,
+                     int n_map, const double *map_center3, int first_new_instance, int *assoc_out, int *n_new_out);
+
 // init_quadric.cu
 int init_quadric_device(EslamHandle *h, cudaStream_t s, int n_obs, const double *Twc7, const double *det5, const double K[9], int rows, int cols,
                         double ellipsoid10[10], int *ok);

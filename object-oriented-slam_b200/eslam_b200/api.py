@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "eslam_launch_count", "eslam_h2d_bytes", "eslam_extract_ground_plane_host", "eslam_extract_ground_plane_dev", "eslam_plane_to_world",
     "eslam_set_supporting_plane", "eslam_calibrate_measurement", "eslam_estimate_ellipsoids_host", "eslam_estimate_ellipsoids_dev",
     "eslam_fetch_ellipsoids", "eslam_estimate_ellipsoids_dev_submit", "eslam_estimate_ellipsoids_dev_collect", "eslam_copy_ellipsoids_dev", "eslam_batch_counters", "eslam_estimate_ellipsoids_submit", "eslam_estimate_ellipsoids_wait", "eslam_init_quadric", "eslam_edges_eval_host", "eslam_edges_upload", "eslam_edges_eval_dev",
-    "eslam_edges_download", "eslam_optimize_objects_host", "eslam_optimize_slam_host", "eslam_pose_inverse", "eslam_pose_mul", "eslam_set_profiling", "eslam_get_stage_ms",
+    "eslam_edges_download", "eslam_optimize_objects_host", "eslam_optimize_slam_host", "eslam_pose_inverse", "eslam_pose_mul", "eslam_set_profiling", "eslam_get_stage_ms", "eslam_associate_frames_host",
 ]
 
 
@@ -237,6 +237,18 @@ class Handle:
         keys = ("ref_evals", "ref_points", "evals", "points", "nn_scans", "nn_hits", "max_n_sym", "objects_with_symmetry", "verify_failures",
                 "clk_scalar_phase", "clk_task_phase", "clk_cta_total")   # round pipeline: FD passes, FD fallbacks, -
         return {k: int(v) for k, v in zip(keys, out)}
+
+    def associate_frames(self, det_start, Twc, det_pose7_cam, valid, map_center3, first_new_instance=0):
+        """Batched DataAssociationSolver::Solve (src/core/DataAssociation.cpp:16-135) of n_frames frames against one map snapshot on the device.
+        Returns (assoc [n_det] int32, n_new)."""
+        ds = np.ascontiguousarray(det_start, dtype=np.int32); tw = _d(Twc).reshape(-1, 7)
+        dp = _d(det_pose7_cam).reshape(-1, 7); va = np.ascontiguousarray(valid, dtype=np.int32); mc = _d(map_center3).reshape(-1, 3)
+        n_det = len(dp)
+        out = np.zeros(max(1, n_det), dtype=np.int32); n_new = C.c_int(0)
+        self.check(self.lib.eslam_associate_frames_host(self._h, C.c_int(len(ds) - 1), _ip(ds), _dp(tw), C.c_int(n_det), _dp(dp) if n_det else None,
+                                                        _ip(va) if n_det else None, C.c_int(len(mc)), _dp(mc) if len(mc) else None, C.c_int(first_new_instance),
+                                                        _ip(out), C.byref(n_new)), "eslam_associate_frames_host")
+        return out[:n_det], int(n_new.value)
 
     def init_quadric(self, Twc, det5, K, rows=None, cols=None):
         tw, d, k = _d(Twc).reshape(-1, 7), _d(det5).reshape(-1, 5), _d(K).reshape(-1)

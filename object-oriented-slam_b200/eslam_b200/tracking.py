@@ -37,6 +37,17 @@ def pose_inverse_np(T):
     return np.concatenate([v + qc[3] * uv + np.cross(qc[:3], uv), qc])
 
 
+def ellipsoid_to_minimal_vector(vec10):
+    """ellipsoid::toMinimalVector (src/core/Ellipsoid.cpp:144-149): x y z roll pitch yaw a b c with SE3Quat::toXYZPRYVector's ZYX Euler
+    angles of the quaternion (Thirdparty/g2o/g2o/types/se3quat.h:184-207)."""
+    v = np.asarray(vec10, float)
+    qx, qy, qz, qw = v[3:7]
+    roll = np.arctan2(2.0 * (qw * qx + qy * qz), 1.0 - 2.0 * (qx * qx + qy * qy))
+    pitch = np.arcsin(2.0 * (qw * qy - qz * qx))
+    yaw = np.arctan2(2.0 * (qw * qz + qx * qy), 1.0 - 2.0 * (qy * qy + qz * qz))
+    return np.concatenate([v[:3], [roll, pitch, yaw], v[7:10]])
+
+
 class DataAssociationSolver:
     """N4: src/core/DataAssociation.cpp:16-135 -- greedy nearest-centre association (threshold 1 m) of the frame's single-frame
     ellipsoids with the map, used when withAssociation=False ("not steady" per Tracking.cpp:505-518).  Quirks kept: the value returned
@@ -74,6 +85,25 @@ class DataAssociationSolver:
         return assoc
 
 
+    def SolveBatch(self, frames, map_ellipsoids, backend=None):
+        """The frames of a batch against ONE map snapshot (the frame-parallel use of the path): what calling Solve frame by frame would
+        return while the map does not change -- matches as column indices, new instances numbered in (frame, row) order.  With a
+        `backend` that has associate_frames (eslam_b200.api.Handle) the batch runs on the device (csrc/associate.cu, one warp per frame)."""
+        if backend is None or not hasattr(backend, "associate_frames"):
+            return [self.Solve(f, map_ellipsoids) for f in frames]
+        insts = sorted(map_ellipsoids)
+        centres = np.array([np.asarray(map_ellipsoids[i]["vec"], float)[:3] for i in insts]).reshape(-1, 3)
+        start, poses, valid = [0], [], []
+        for f in frames:
+            for obj in f.mpLocalObjects[:len(f.mmObservations)]:
+                valid.append(0 if obj is None else 1)
+                poses.append(np.zeros(7) if obj is None else np.asarray(obj["vec"], float)[:7])
+            start.append(len(valid))
+        assoc, n_new = backend.associate_frames(start, np.array([f.cam_pose_Twc for f in frames]), np.array(poses).reshape(-1, 7), valid, centres, self.miInstanceNum)
+        self.miInstanceNum += n_new
+        return [[int(v) for v in assoc[start[k]:start[k + 1]]] for k in range(len(frames))]
+
+
 class Tracking:
     def __init__(self, backend, optimizer_cls, K, rows=480, cols=640, keyframe_check_close=True, min_init_frames=MINIMUM_INITIALIZATION_FRAME):
         self.h = backend
@@ -88,9 +118,33 @@ class Tracking:
         self.mmObjectObservations = {}       # instance -> [Observation]
         self.mmObjectObservations3D = {}     # instance -> [(frame, ellipsoid dict)]
         self.map_ellipsoids = {}             # instance -> ellipsoid dict (world frame)  == Map::GetAllEllipsoidsMap()
+        self.mmObjectHistory = {}            # instance -> rows [n_obs, valid, minimal vector(9)]   (Tracking.h mmObjectHistory)
         self.pDASolver = DataAssociationSolver()
 
     # ---- :716-799
+    # ---- Tracking::RefreshObjectHistory (src/core/Tracking.cpp:810-852): one row per (instance, number of 2-D observations) --
+    # [observation count, valid = 1, x y z roll pitch yaw a b c]; a new optimisation with the same observation count overwrites the last row
+    def RefreshObjectHistory(self):
+        for inst in sorted(self.map_ellipsoids):
+            hist = self.mmObjectHistory.setdefault(inst, [])
+            n_obs = len(self.mmObjectObservations.get(inst, []))     # the reference asserts that the instance has 2-D observations
+            row = np.concatenate([[float(n_obs), 1.0], ellipsoid_to_minimal_vector(self.map_ellipsoids[inst]["vec"])])
+            if hist and int(round(hist[-1][0])) == n_obs:
+                hist[-1] = row
+            else:
+                hist.append(row)
+
+    # ---- Tracking::SaveObjectHistory (src/core/Tracking.cpp:855-896): "TotalInstanceNum", then per instance "id historyNum" and its rows;
+    # values go through a default-precision ostream (6 significant digits)
+    def SaveObjectHistory(self, path):
+        with open(path, "w") as f:
+            f.write(f"{len(self.mmObjectHistory)}\n")
+            for inst in sorted(self.mmObjectHistory):
+                rows = self.mmObjectHistory[inst]
+                f.write(f"{inst} {len(rows)}\n")
+                for r in rows:
+                    f.write(" ".join(f"{float(v):.6g}" for v in r) + "\n")
+
     def ProcessGroundPlaneEstimation(self, frame):
         pl, found, _ = self.h.extract_ground_plane(frame.frame_img)
         if not found[0]:
@@ -169,6 +223,7 @@ class Tracking:
         # ---- ProcessCurrentFrame :219-226
         if self.map_ellipsoids:
             self.optimizer.GlobalObjectGraphOptimization(self.mvpFrames, self.map_ellipsoids, self.rows, self.cols, self.K, self.mmObjectObservations, iters=iters)
+            self.RefreshObjectHistory()                                   # :228
         return frame
 
     # ---- :567-638
