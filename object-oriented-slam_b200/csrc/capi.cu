@@ -94,6 +94,9 @@ int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const
                   bool want_dump, ExtractPtrs &P) {
   if (!h->ex) use_slot(h, 0);
   ExtractWorkspace &w = *h->ex;
+  // next generation of the page-locked staging; wait (normally not at all) for the batch that used it two calls ago
+  w.pin_cur ^= 1;
+  if (w.pin_done[w.pin_cur]) ESLAM_CUDA_OK(h, cudaEventSynchronize(w.pin_done[w.pin_cur]));
   w.meta_host.resize(n_obj);
   long long off = 0;
   for (int i = 0; i < n_obj; i++) {
@@ -163,11 +166,12 @@ int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const
     ESLAM_CUDA_OK(h, w.symcache.reserve(symmetry_round_cache_bytes() * (size_t)n_obj));
     ESLAM_CUDA_OK(h, w.symchunk.reserve(symmetry_round_desc_bytes() * (size_t)kMaxChunks));
     ESLAM_CUDA_OK(h, w.symlive.reserve(sizeof(int) * (size_t)kMaxChunks * (kSymMaxRounds + 2)));
-    ESLAM_CUDA_OK(h, w.pin_symchunk.reserve(symmetry_round_desc_bytes() * (size_t)kMaxChunks));
+    for (int g = 0; g < 2; g++) ESLAM_CUDA_OK(h, w.pin_symchunk2[g].reserve(symmetry_round_desc_bytes() * (size_t)kMaxChunks));
   }
   P.sympool256 = h->sym_pool256.as<unsigned char>(); P.sympool512 = h->sym_pool512.as<unsigned char>();
   P.slotmask2 = h->sym_slotmask2.as<unsigned>(); P.smid_map = h->sym_smid_map.as<int>(); P.sm_count = h->sm_count;
   P.l2_discard = (h->l2_discard && !want_dump) ? 1 : 0;
+  P.uf_jump = h->uf_jump;
   P.d_crop = P.d_voxel = P.d_world = P.d_sym = P.d_final = nullptr; P.d_label = nullptr;
   if (want_dump) {
     ESLAM_CUDA_OK(h, w.d_crop.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_voxel.reserve(CAP * 24)); ESLAM_CUDA_OK(h, w.d_world.reserve(CAP * 24));
@@ -175,16 +179,29 @@ int prepare_batch(EslamHandle *h, cudaStream_t s, int n_frames, int n_obj, const
     P.d_crop = w.d_crop.as<double>(); P.d_voxel = w.d_voxel.as<double>(); P.d_world = w.d_world.as<double>();
     P.d_sym = w.d_sym.as<double>(); P.d_final = w.d_final.as<double>(); P.d_label = w.d_label.as<int>();
   }
-  ESLAM_CUDA_OK(h, w.pin_meta.reserve(sizeof(ObjMeta) * (size_t)n_obj));
-  memcpy(w.pin_meta.p, w.meta_host.data(), sizeof(ObjMeta) * (size_t)n_obj);
-  ESLAM_CUDA_OK(h, cudaMemcpyAsync(w.meta.p, w.pin_meta.p, sizeof(ObjMeta) * (size_t)n_obj, cudaMemcpyHostToDevice, s));
+  PinBuf &pm = w.pin_meta2[w.pin_cur];
+  ESLAM_CUDA_OK(h, pm.reserve(sizeof(ObjMeta) * (size_t)n_obj));
+  memcpy(pm.p, w.meta_host.data(), sizeof(ObjMeta) * (size_t)n_obj);
+  ESLAM_CUDA_OK(h, cudaMemcpyAsync(w.meta.p, pm.p, sizeof(ObjMeta) * (size_t)n_obj, cudaMemcpyHostToDevice, s));
   return ESLAM_OK;
 }
 
 // host_depth != nullptr: pipelined host entry -- the depth batch is uploaded in chunks on copy_stream while the kernels of the
 // previous chunk run on `s` (objects must be ordered by frame, which is how a frame stream arrives; otherwise one chunk).
+int run_extract_impl(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *depth_dev, size_t pitch, int n_obj, const int *frame_of_obj, const double *bbox4,
+                     const int *label, const double *Twc7, bool want_dump, ExtractPtrs &P, const uint16_t *host_depth);
 int run_extract(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *depth_dev, size_t pitch, int n_obj, const int *frame_of_obj, const double *bbox4,
                 const int *label, const double *Twc7, bool want_dump, ExtractPtrs &P, const uint16_t *host_depth = nullptr) {
+  const int rc = run_extract_impl(h, s, n_frames, depth_dev, pitch, n_obj, frame_of_obj, bbox4, label, Twc7, want_dump, P, host_depth);
+  if (rc == ESLAM_OK && h->ex) {   // everything the batch reads from the staging generation is ordered before this point of s
+    ExtractWorkspace &w = *h->ex;
+    if (!w.pin_done[w.pin_cur]) ESLAM_CUDA_OK(h, cudaEventCreateWithFlags(&w.pin_done[w.pin_cur], cudaEventDisableTiming));
+    ESLAM_CUDA_OK(h, cudaEventRecord(w.pin_done[w.pin_cur], s));
+  }
+  return rc;
+}
+int run_extract_impl(EslamHandle *h, cudaStream_t s, int n_frames, const uint16_t *depth_dev, size_t pitch, int n_obj, const int *frame_of_obj, const double *bbox4,
+                     const int *label, const double *Twc7, bool want_dump, ExtractPtrs &P, const uint16_t *host_depth) {
   if (!h->plane_set) { h->err = "supporting plane not set (eslam_set_supporting_plane)"; return ESLAM_ERR_NO_PLANE; }
   if (n_obj <= 0 || n_frames <= 0 || !depth_dev || !frame_of_obj || !bbox4 || !label || !Twc7) return ESLAM_ERR_BAD_ARG;
   if (pitch < (size_t)h->cam.cols) return ESLAM_ERR_BAD_ARG;
@@ -439,6 +456,7 @@ int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHa
   if (const char *e = getenv("ESLAM_L2_DISCARD")) h->l2_discard = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_SYM_WINDOW")) h->sym_window = atoi(e);
   if (const char *e = getenv("ESLAM_EXTRACT_UQ")) h->extract_uq = atoi(e) != 0;
+  if (const char *e = getenv("ESLAM_UF_JUMP")) { int v = atoi(e); if (v >= 0 && v <= 64) h->uf_jump = v; }
   if (const char *e = getenv("ESLAM_EXTRACT_PF")) h->extract_pf = atoi(e) == 2 ? 2 : 1;
   if (const char *e = getenv("ESLAM_SYM_GRAPH")) h->sym_graph = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_SYM_VERIFY")) h->sym_verify = atoi(e) != 0;
@@ -458,9 +476,10 @@ void eslam_destroy(EslamHandle *h) {
     DevBuf *bufs[] = {&w.meta, &w.state, &w.out, &w.ptsA, &w.ptsB, &w.ptsC, &w.k0, &w.k1, &w.v0, &w.v1, &w.parent, &w.count, &w.objn, &w.objnf,
                       &w.d_crop, &w.d_voxel, &w.d_world, &w.d_sym, &w.d_final, &w.d_label, &w.depth};
     for (DevBuf *b : bufs) b->release();
-    w.symseed.release(); w.symcache.release(); w.symchunk.release(); w.symlive.release(); w.pin_symchunk.release();
+    w.symseed.release(); w.symcache.release(); w.symchunk.release(); w.symlive.release(); w.pin_symchunk2[0].release(); w.pin_symchunk2[1].release();
+    for (int g = 0; g < 2; g++) if (w.pin_done[g]) cudaEventDestroy(w.pin_done[g]);
     for (auto &g : w.symgraph) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-    w.pin_meta.release(); w.pin_out.release(); w.pin_depth.release();
+    w.pin_meta2[0].release(); w.pin_meta2[1].release(); w.pin_out.release(); w.pin_depth.release();
     delete h->ex_slot[sl];
     if (h->slot_stream[sl]) cudaStreamDestroy(h->slot_stream[sl]);
     if (h->slot_done[sl]) cudaEventDestroy(h->slot_done[sl]);

@@ -84,6 +84,7 @@ struct EslamHandle {
   bool l2_discard = true;  // env ESLAM_L2_DISCARD=0: keep the dead scratch lines in L2 (they are written back to HBM when evicted)
   int sym_window = 0;      // env ESLAM_SYM_WINDOW (tuning): chunks whose symmetry rounds may run at the same time (0 = all)
   bool extract_uq = true;  // cluster unions through a per-warp queue (env ESLAM_EXTRACT_UQ=0: inline unions, the A/B baseline)
+  int uf_jump = 0;         // env ESLAM_UF_JUMP=n (tuning): pointer jumping over the cluster parents every n-th batch of 256 points; measured slower (0 = never)
   int extract_pf = 1;      // env ESLAM_EXTRACT_PF=2 (tuning): neighbour candidates requested two ahead instead of one
   bool sym_graph = true;   // round pipeline: a chunk's ~115 launches are captured once and replayed as a CUDA graph (env ESLAM_SYM_GRAPH=0: plain launches)
   bool sym_verify = false; // env ESLAM_SYM_VERIFY=1: every shortcut decision of the symmetry kernel is re-derived the long way and counted when it differs

@@ -64,6 +64,7 @@ struct ExtractPtrs {  // device pointers of the per-point workspace (total capac
   unsigned *slotmask2;   // [2][sm_count]: CAP = 256 words, then CAP = 512 words; bits beyond the variant's slot count are pre-set
   int *smid_map;         // [kMaxSmId + 1]: dense SM index per %smid (first touch), last entry = next free index
   int sm_count;
+  int uf_jump;           // clustering: pointer jumping over all parents every uf_jump-th batch of points (0 = never)
   int l2_discard;        // 1: dead per-object scratch is dropped from L2 without write-back when its last reader is done (discard.global.L2)
   // optional stage dump (device mirrors, NULL when no dump requested)
   double *d_crop, *d_voxel, *d_world, *d_sym, *d_final;  // d_final has 4x capacity
@@ -74,10 +75,15 @@ struct ExtractWorkspace {
   DevBuf meta, state, out, ptsA, ptsB, ptsC, k0, k1, v0, v1, parent, count, objn, objnf;
   DevBuf d_crop, d_voxel, d_world, d_sym, d_final, d_label;
   DevBuf symseed, symcache, symchunk, symlive;   // symmetry round pipeline: seed state, NN / pixel caches, per-chunk descriptors and live counters
-  PinBuf pin_symchunk;
+  PinBuf pin_symchunk2[2];   // per-chunk descriptors, page-locked staging (two generations, see pin_cur)
   struct SymGraph { cudaGraphExec_t exec = nullptr; int n_obj = 0, rounds = 0, verify = 0; const void *desc = nullptr, *live = nullptr; } symgraph[16];   // replayable launch sequence per chunk
   DevBuf depth;   // staging for the *_host entry point
-  PinBuf pin_meta, pin_out, pin_depth;
+  PinBuf pin_meta2[2], pin_out, pin_depth;
+  // The page-locked staging of the metadata / chunk descriptors is written by the CPU at issue time and read by an asynchronous copy
+  // later: two generations, and a generation is rewritten only after the batch that used it has completed (pin_done) -- a caller
+  // may issue the stream-based entry points back to back without synchronising in between.
+  cudaEvent_t pin_done[2] = {nullptr, nullptr};
+  int pin_cur = 0;
   std::vector<ObjMeta> meta_host;
   std::vector<cudaMemcpy3DBatchOp> copy_ops;   // per-chunk upload list of the host entry
   std::vector<int> stage_rows;                 // staged pull of pageable input: row-count prefix of the chunk's objects

@@ -1483,7 +1483,7 @@ static int symmetry_rounds_launch(EslamHandle *h, cudaStream_t s, const uint16_t
   d.cache = w.symcache.as<unsigned char>() + (size_t)obj0 * symmetry_round_cache_bytes();
   d.live = w.symlive.as<int>() + (size_t)chunk * (kSymMaxRounds + 2);
   d.n_obj = n_obj; d.rounds = rounds; d.prm = prm; d.W = ptrs;
-  SymChunk *pin = w.pin_symchunk.as<SymChunk>() + chunk, *dev = w.symchunk.as<SymChunk>() + chunk;
+  SymChunk *pin = w.pin_symchunk2[w.pin_cur].as<SymChunk>() + chunk, *dev = w.symchunk.as<SymChunk>() + chunk;
   memcpy(pin, &d, sizeof(d));
   ESLAM_CUDA_OK(h, cudaMemcpyAsync(dev, pin, sizeof(d), cudaMemcpyHostToDevice, s));
   const size_t smem = sym_smem_bytes<kRoundCap>();
