@@ -453,6 +453,8 @@ int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHa
   if (const char *e = getenv("ESLAM_PLANE_EXACT")) h->plane_exact = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_PULL_TMA")) h->pull_tma = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_SYM_OCC")) h->sym_occ = atoi(e);
+  if (const char *e = getenv("ESLAM_PULL_STAGES")) { int v = atoi(e); if (v >= 1 && v <= 8) h->pull_stages = v; }
+  if (const char *e = getenv("ESLAM_PULL_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) h->pull_ctas_per_sm = v; }
   if (const char *e = getenv("ESLAM_L2_DISCARD")) h->l2_discard = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_SYM_WINDOW")) h->sym_window = atoi(e);
   if (const char *e = getenv("ESLAM_EXTRACT_UQ")) h->extract_uq = atoi(e) != 0;

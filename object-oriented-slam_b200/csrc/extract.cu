@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(kPullThreads, 16) pull_rects_kernel(const uint
 // thread per one-warp CTA keeps kTmaStages row segments of its objects in flight -- bulk load host (mapped, pinned) -> shared memory
 // with an mbarrier transaction count, bulk store shared -> device frame buffer -- so the pull costs no load/store issue slots and
 // 352 bytes of registers next to the resident extraction / symmetry CTAs.  Row segments are 16-byte aligned multiples of 16 bytes.
-constexpr int kTmaStages = 8;
+constexpr int kTmaStages = 8;   // upper bound; the launch picks the depth (EslamHandle::pull_stages)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 struct PullCursor {   // (object, row) items of this CTA in a fixed order
   const ObjMeta *metas; int n_obj, rows, cols, k, r, nr, step;
@@ -685,11 +685,11 @@ struct PullCursor {   // (object, row) items of this CTA in a fixed order
   }
 };
 __global__ void __launch_bounds__(32, 8) pull_rects_tma_kernel(const uint16_t *__restrict__ host_src, uint16_t *__restrict__ dst, size_t pitch, size_t frame_stride,
-                                                               const ObjMeta *__restrict__ metas, int n_obj, int rows, int cols, int stage_bytes) {
+                                                               const ObjMeta *__restrict__ metas, int n_obj, int rows, int cols, int stage_bytes, int n_stages) {
   extern __shared__ __align__(128) unsigned char tma_buf[];   // [kTmaStages][stage_bytes]
   __shared__ __align__(8) unsigned long long bar[kTmaStages];
   if (threadIdx.x != 0) return;
-  for (int s = 0; s < kTmaStages; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[s])));
+  for (int s = 0; s < n_stages; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[s])));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   PullCursor ld{metas, n_obj, rows, cols, (int)blockIdx.x, 0, 0, (int)gridDim.x}, st = ld;
   ld.settle(); st.settle();
@@ -702,10 +702,10 @@ __global__ void __launch_bounds__(32, 8) pull_rects_tma_kernel(const uint16_t *_
     ld.next();
   };
   int issued = 0;
-  for (; issued < kTmaStages && ld.valid(); issued++) issue_load(issued);
+  for (; issued < n_stages && ld.valid(); issued++) issue_load(issued);
   for (int i = 0; st.valid(); i++) {
-    const int stage = i % kTmaStages;
-    const unsigned parity = (unsigned)(i / kTmaStages) & 1u, b = smem_u32(&bar[stage]);
+    const int stage = i % n_stages;
+    const unsigned parity = (unsigned)(i / n_stages) & 1u, b = smem_u32(&bar[stage]);
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(b), "r"(parity) : "memory");
     size_t off; unsigned bytes;
     st.item(pitch, frame_stride, off, bytes);
@@ -724,9 +724,10 @@ int pull_rects_launch(EslamHandle *h, cudaStream_t s, const uint16_t *host_mappe
   if (n_obj <= 0) return ESLAM_OK;
   if (h->pull_tma) {   // default: bulk-copy engine instead of LDG/STG (+10 % end to end, profiles/r02_pull_tma_ab.txt); ESLAM_PULL_TMA=0 disables
     const int stage_bytes = (((h->cam.cols + 8) * 2) + 127) & ~127;
-    const int want = 2 * h->sm_count, grid = n_obj < want ? n_obj : want;
-    pull_rects_tma_kernel<<<grid, 32, (size_t)kTmaStages * stage_bytes, s>>>(host_mapped, depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, n_obj, h->cam.rows,
-                                                                              h->cam.cols, stage_bytes);
+    const int want = h->pull_ctas_per_sm * h->sm_count, grid = n_obj < want ? n_obj : want;
+    const int n_stages = h->pull_stages < 1 ? 1 : (h->pull_stages > kTmaStages ? kTmaStages : h->pull_stages);
+    pull_rects_tma_kernel<<<grid, 32, (size_t)n_stages * stage_bytes, s>>>(host_mapped, depth_dev, pitch, frame_stride, w.meta.as<ObjMeta>() + obj0, n_obj, h->cam.rows,
+                                                                              h->cam.cols, stage_bytes, n_stages);
     ESLAM_LAUNCHED(h);
     ESLAM_CUDA_OK(h, cudaGetLastError());
     return ESLAM_OK;

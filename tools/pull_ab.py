@@ -18,13 +18,15 @@ from bench import make_frames  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=1024)
 ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--settings", default="0:8:2,1:8:2", help="comma-separated pull_tma:stages:ctas_per_sm")
 args = ap.parse_args()
 depth, fo, bb, lb, tw = make_frames("one_box", args.frames, 1000)
 host = torch.from_numpy(depth.view(np.int16)).pin_memory().numpy().view(np.uint16)
 ref = None
 for rep in range(2):
-    for tma in ("0", "1"):
-        os.environ["ESLAM_PULL_TMA"] = tma
+    for setting in args.settings.split(","):
+        tma, stages, ctas = (setting.split(":") + ["8", "2"])[:3]
+        os.environ["ESLAM_PULL_TMA"] = tma; os.environ["ESLAM_PULL_STAGES"] = stages; os.environ["ESLAM_PULL_CTAS"] = ctas
         h = E.Handle(); h.set_supporting_plane(synth.GROUND_PLANE_WORLD)
 
         def pipelined(steps):
@@ -44,5 +46,5 @@ for rep in range(2):
         dtb = time.perf_counter() - t0
         if ref is None:
             ref = rec
-        print(json.dumps({"pull_tma": tma, "rep": rep, "e2e_pipelined_fps": args.frames * args.steps / dt, "e2e_blocking_fps": args.frames * args.steps / dtb, "records_equal": rec == ref}))
+        print(json.dumps({"pull_tma": tma, "stages": stages, "ctas_per_sm": ctas, "rep": rep, "e2e_pipelined_fps": args.frames * args.steps / dt, "e2e_blocking_fps": args.frames * args.steps / dtb, "records_equal": rec == ref}))
         h.close()
