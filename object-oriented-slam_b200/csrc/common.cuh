@@ -78,7 +78,7 @@ struct EslamHandle {
   cudaStream_t plane_stream2 = nullptr; cudaEvent_t plane_ev[2] = {nullptr, nullptr};   // second half of a ground-plane chunk
   int plane_streams = 1;    // env ESLAM_PLANE_STREAMS=2: a chunk as two halves on two streams (measured slower: 15.2 vs 12.3 ms per 296 frames)
   bool plane_exact = true;  // env ESLAM_PLANE_EXACT=0: every frame takes the integral-image recurrence (A/B, fallback test)
-  int pull_stages = 8, pull_ctas_per_sm = 2;   // env ESLAM_PULL_STAGES (1..8 row segments in flight per pull CTA), ESLAM_PULL_CTAS (pull CTAs per SM)
+  int pull_stages = 4, pull_ctas_per_sm = 2;   // env ESLAM_PULL_STAGES (1..8 row segments in flight per pull CTA), ESLAM_PULL_CTAS (pull CTAs per SM)
   bool pull_tma = true;    // SM pull of the box rectangles through cp.async.bulk (TMA); env ESLAM_PULL_TMA=0: the LDG/STG pull kernel
   int sym_occ = 0;         // env ESLAM_SYM_OCC (tuning): 2 / 4 resident CTAs per SM instead of kSymCtas256
   int sym_impl = 3;        // env ESLAM_SYM_IMPL: 1 = round-1 kernel (A/B baseline), 2 = single launch (CTA per object, rounds inside), 3 = round pipeline (phase-pure launches)
