@@ -456,6 +456,7 @@ int eslam_create(const EslamParams *p, const EslamCamera *c, int device, EslamHa
   if (const char *e = getenv("ESLAM_PULL_STAGES")) { int v = atoi(e); if (v >= 1 && v <= 8) h->pull_stages = v; }
   if (const char *e = getenv("ESLAM_PULL_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) h->pull_ctas_per_sm = v; }
   if (const char *e = getenv("ESLAM_L2_DISCARD")) h->l2_discard = atoi(e) != 0;
+  if (const char *e = getenv("ESLAM_STEP_THREADS")) h->step_threads = atoi(e);
   if (const char *e = getenv("ESLAM_SYM_WINDOW")) h->sym_window = atoi(e);
   if (const char *e = getenv("ESLAM_EXTRACT_UQ")) h->extract_uq = atoi(e) != 0;
   if (const char *e = getenv("ESLAM_UF_JUMP")) { int v = atoi(e); if (v >= 0 && v <= 64) h->uf_jump = v; }

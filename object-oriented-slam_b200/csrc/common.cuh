@@ -83,6 +83,7 @@ struct EslamHandle {
   int sym_occ = 0;         // env ESLAM_SYM_OCC (tuning): 2 / 4 resident CTAs per SM instead of kSymCtas256
   int sym_impl = 3;        // env ESLAM_SYM_IMPL: 1 = round-1 kernel (A/B baseline), 2 = single launch (CTA per object, rounds inside), 3 = round pipeline (phase-pure launches)
   bool l2_discard = true;  // env ESLAM_L2_DISCARD=0: keep the dead scratch lines in L2 (they are written back to HBM when evicted)
+  int step_threads = 0;    // env ESLAM_STEP_THREADS (tuning): 32 / 64 / 128 (default) threads per CTA of the symmetry step kernel
   int sym_window = 0;      // env ESLAM_SYM_WINDOW (tuning): chunks whose symmetry rounds may run at the same time (0 = all)
   bool extract_uq = true;  // cluster unions through a per-warp queue (env ESLAM_EXTRACT_UQ=0: inline unions, the A/B baseline)
   int uf_jump = 0;         // env ESLAM_UF_JUMP=n (tuning): pointer jumping over the cluster parents every n-th batch of 256 points; measured slower (0 = never)

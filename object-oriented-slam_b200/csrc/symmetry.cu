@@ -1122,7 +1122,7 @@ constexpr int kSeedPersist = (int)((sizeof(SeedCore) + 2 * sizeof(unsigned[2][2]
 constexpr int kSeedStride = (kSeedPersist + 127) / 128 * 128;          // whole 128-byte lines per seed: an object's state can be dropped from L2 line by line
 constexpr size_t kRoundCacheBytes = (size_t)kRoundCap * 64;           // per seed: one NN bank + the pixel cache, 2 * CAP entries of 16 bytes each
 constexpr int kRoundsMinObjects = 16;                                  // smaller launches take the single-launch kernel
-constexpr int kStepThreads = 128;                                     // eight lanes per seed: 16 seeds per CTA
+constexpr int kStepThreadsDefault = 128;                              // eight lanes per seed: 16 seeds per CTA (one-warp CTAs that slip in beside three resident compute CTAs were measured: no gain)
 static_assert(sizeof(SeedCore) % 16 == 0, "SeedCore is followed by the masks without padding");
 #pragma nv_diag_suppress 1427
 constexpr int kSeedA16 = (int)(__builtin_offsetof(SeedCore, base) / 16);    // part A in 16-byte units
@@ -1172,6 +1172,7 @@ __device__ __forceinline__ void copy_quads4(uint4 *dst, const uint4 *src, int n,
 }
 
 // step(0): seed planes (GenerateInitPlanes, Symmetry.cpp:44-86).  step(k > 0): consumes evaluation k - 1.
+template <int kStepThreads>
 __global__ void __launch_bounds__(kStepThreads) sym_step_kernel(const SymChunk *__restrict__ Cp, int k) {
   const SymChunk &C = *Cp;
   if (k > 0 && *((volatile const int *)(C.live + k - 1)) == 0) return;   // chunk uniform
@@ -1518,14 +1519,16 @@ static int symmetry_rounds_launch(EslamHandle *h, cudaStream_t s, const uint16_t
     ESLAM_LAUNCHED(h);
     ESLAM_CUDA_OK(h, cudaEventRecord(h->aux_join[chunk], big));
   }
-  const int step_grid = (n_obj * kSeeds * 8 + kStepThreads - 1) / kStepThreads;
+  const int step_threads = (h->step_threads == 32 || h->step_threads == 64) ? h->step_threads : kStepThreadsDefault;   // env ESLAM_STEP_THREADS (tuning)
+  void (*step_fn)(const SymChunk *, int) = step_threads == 128 ? sym_step_kernel<128> : (step_threads == 64 ? sym_step_kernel<64> : sym_step_kernel<32>);
+  const int step_grid = (n_obj * kSeeds * 8 + step_threads - 1) / step_threads;
   auto issue = [&](cudaStream_t q) -> cudaError_t {
     cudaError_t e = cudaMemsetAsync(d.live, 0, sizeof(int) * (size_t)(rounds + 2), q);
     if (e != cudaSuccess) return e;
-    sym_step_kernel<<<step_grid, kStepThreads, 0, q>>>(dev, 0);
+    step_fn<<<step_grid, step_threads, 0, q>>>(dev, 0);
     for (int r = 0; r < rounds; r++) {
       eval_fn<<<n_obj, 32 * kSeeds, smem, q>>>(dev, r);
-      sym_step_kernel<<<step_grid, kStepThreads, 0, q>>>(dev, r + 1);
+      step_fn<<<step_grid, step_threads, 0, q>>>(dev, r + 1);
     }
     sym_final_kernel<<<(n_obj + 3) / 4, 128, 0, q>>>(dev);
     return cudaGetLastError();
@@ -1535,9 +1538,9 @@ static int symmetry_rounds_launch(EslamHandle *h, cudaStream_t s, const uint16_t
     // captured on the second consecutive call with the same shape (a frame stream in fixed batches); a caller whose batches change
     // from call to call (the per-frame tracking driver: 1..8 boxes) keeps plain launches instead of paying an instantiation per call
     ExtractWorkspace::SymGraph &g = w.symgraph[chunk];
-    const bool same = g.n_obj == n_obj && g.rounds == rounds && g.verify == variant && g.desc == dev && g.live == d.live;
+    const bool same = g.n_obj == n_obj && g.rounds == rounds && g.verify == variant + 8 * step_threads && g.desc == dev && g.live == d.live;
     if (g.exec && !same) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-    if (!same) { g.n_obj = n_obj; g.rounds = rounds; g.verify = variant; g.desc = dev; g.live = d.live; }
+    if (!same) { g.n_obj = n_obj; g.rounds = rounds; g.verify = variant + 8 * step_threads; g.desc = dev; g.live = d.live; }
     if ((same || h->profiling) && !g.exec) {   // (a profiled batch is timed: it never pays for plain launches of a sequence this long)
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
