@@ -123,7 +123,7 @@ __device__ void voxel_sort(const float4 *pts, int n, float leaf, unsigned *k0, u
 }
 
 constexpr int kExtractThreads = 256;   // 3 CTAs/SM: different objects sit in different phases, hiding the many block barriers
-constexpr int kSmemParents = 12288;    // 48 KB of dynamic shared memory per CTA (3 CTAs/SM still fit in 227 KB)
+constexpr int kSmemParents = 11264;    // 44 KB of dynamic shared memory per CTA: three CTAs (72.4 KB each with the static part) leave ~13 KB per SM for the small kernels that run beside them (bulk-copy pull, symmetry step)
 
 // One tile (kExtractThreads sorted positions) of (voxel key, point) staged in shared memory -- every thread issues its own
 // independent gather -- after which the first position of each voxel sums its members from shared memory.  Aliases RadixScratch
