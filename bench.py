@@ -247,7 +247,11 @@ def run_stages(args, h, torch, stream, plane, peak, peak_src):
     pl, found, ninl = res["plane"]
     alg = 614400.0 * F
     tr, tr_src = _ncu_traffic("plane_stage")
-    t0 = time.perf_counter(); h.extract_ground_plane(host_np); e2e_ms = (time.perf_counter() - t0) * 1e3
+    h.extract_ground_plane(host_np)                                      # first call: allocates the library's staging buffer
+    e2e_runs = []
+    for _ in range(3):
+        t0 = time.perf_counter(); h.extract_ground_plane(host_np); e2e_runs.append((time.perf_counter() - t0) * 1e3)
+    e2e_ms = float(np.median(e2e_runs))
     import orc
     n_cpu = min(F, 16)
     t0 = time.perf_counter(); po, fo_, no = orc.extract_ground_plane(depth[:n_cpu]); cpu_dt = time.perf_counter() - t0
