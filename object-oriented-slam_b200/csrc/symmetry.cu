@@ -1,5 +1,11 @@
 // symmetry.cu -- symmetry-plane estimation (9 seeds x Levenberg-Marquardt on the symmetry cost) + point-cloud completion +
-// final ellipsoid.  ONE CTA PER OBJECT, ONE WARP PER SEED, the nine seeds advancing in ROUNDS.
+// final ellipsoid.  The nine seeds of an object advance in ROUNDS (one cost evaluation per seed and round, then the scalar LM step);
+// two drivers share the device functions below:
+//   * the ROUND PIPELINE (default for batches; second half of this file): phase-pure launches per chunk of objects --
+//     sym_step_kernel (LM step of all seeds), sym_eval_kernel (one CTA per object, one warp per seed, any warp takes any task),
+//     sym_final_kernel -- replayed as one CUDA graph, seed state in HBM / L2 between launches;
+//   * the SINGLE LAUNCH (symmetry_finalize_kernel: one CTA per object, the rounds inside the CTA, state in shared memory): handfuls
+//     of objects and clouds of 257..512 points (cached path) or more (generic global-memory path).
 //
 // Replaces
 //   Symmetry::estimateSymmetry / GenerateInitPlanes / getProjDepthMat     src/symmetry/Symmetry.cpp:44-161
