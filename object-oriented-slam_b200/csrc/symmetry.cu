@@ -470,15 +470,16 @@ __device__ __noinline__ void classify_chunk(const SymObj<CAP> &O, SymSeed<CAP> &
   const int li = chunk * 32 + lane;
   int cls = 0; bool rob = true, safe = false, hit = false;
   if (li < M) {
+    const bool two_banks = S.nnc[0] != S.nnc[1];   // (the round pipeline keeps ONE bank: both names point at it)
     float4 c = S.nnc[S.cur][h0 + li];   // the cache entries are requested before the fp64 classification chain
-    const float4 c2 = S.nnc[wbank][h0 + li];   // the other bank: the entry of an earlier (rejected) trial -- any entry ever written is valid
+    const float4 c2 = two_banks ? S.nnc[wbank][h0 + li] : c;   // the other bank: the entry of an earlier (rejected) trial -- any entry ever written is valid
     const uint4 pc = S.pxc[h0 + li];
     const d3 pm = mirror_q(load_pt(O, li), q, n, down);
     cls = classify(O, pm, pc, S.pxc + h0 + li, rob);
     double lnp = -0.0;
     if (cls == 1) {
       hit = nn_cached(c, (float)pm.x, (float)pm.y, (float)pm.z, safe);
-      if (!hit && wbank != S.cur) {   // a shorter step after a rejected trial often lands near that trial's query
+      if (!hit && two_banks && wbank != S.cur) {   // a shorter step after a rejected trial often lands near that trial's query
         bool safe2;
         if (nn_cached(c2, (float)pm.x, (float)pm.y, (float)pm.z, safe2)) { hit = true; safe = safe2; c = c2; }
       }
@@ -490,7 +491,7 @@ __device__ __noinline__ void classify_chunk(const SymObj<CAP> &O, SymSeed<CAP> &
       }
     }
     S.lnp[h0 + li] = lnp;
-    if (!(cls == 1 && !hit)) S.nnc[wbank][h0 + li] = c;   // carried forward (the scanned points write their new entry later)
+    if (two_banks && !(cls == 1 && !hit)) S.nnc[wbank][h0 + li] = c;   // carried forward (the scanned points write their new entry later)
   }
   const unsigned need = __ballot_sync(0xffffffffu, cls == 1 && !hit);
   const unsigned a = __ballot_sync(0xffffffffu, cls == 1 || !rob), f = __ballot_sync(0xffffffffu, cls == 1 && rob && safe);
