@@ -329,6 +329,40 @@ class Optimizer {
   Context &ctx_; bool mbGroundPlaneSet = false; Plane4 mGroundPlaneNormal{};
 };
 
+// DataAssociationSolver (include/core/DataAssociation.h, src/core/DataAssociation.cpp:16-135).  The reference resolves one frame against the
+// Map it holds; here the map snapshot is passed as (instance id -> ellipsoid) and a whole list of frames can be resolved in ONE device
+// launch (Solve(frames, map)): every frame against the same snapshot, new instances numbered in (frame, row) order.  A match returns
+// the COLUMN index of the instance-ordered map like the reference (DataAssociation.cpp:113-114).
+class DataAssociationSolver {
+ public:
+  explicit DataAssociationSolver(Context &c) : ctx_(c) {}
+  std::vector<int> Solve(Frame *pFrame, const std::map<int, ellipsoid_pod> &map) { std::vector<Frame *> one{pFrame}; return Solve(one, map)[0]; }
+  std::vector<std::vector<int>> Solve(const std::vector<Frame *> &frames, const std::map<int, ellipsoid_pod> &map) {
+    std::vector<int> start{0}, valid; std::vector<double> twc, poses, centres;
+    for (Frame *f : frames) {
+      for (int k = 0; k < 7; k++) twc.push_back(f->cam_pose_Twc[k]);
+      for (size_t i = 0; i < f->mmObservations.size(); i++) {
+        const ellipsoid_pod *o = i < f->mpLocalObjects.size() ? f->mpLocalObjects[i] : nullptr;
+        valid.push_back(o ? 1 : 0);
+        for (int k = 0; k < 7; k++) poses.push_back(o ? o->vec[k] : 0.0);
+      }
+      start.push_back((int)valid.size());
+    }
+    for (auto &kv : map) for (int k = 0; k < 3; k++) centres.push_back(kv.second.vec[k]);   // std::map: ascending instance id
+    std::vector<int> assoc(valid.size() ? valid.size() : 1); int n_new = 0;
+    int rc = eslam_associate_frames_host(ctx_.get(), (int)frames.size(), start.data(), twc.data(), (int)valid.size(), poses.data(), valid.data(), (int)map.size(),
+                                         centres.data(), miInstanceNum, assoc.data(), &n_new);
+    ctx_.check(rc, "eslam_associate_frames_host");
+    miInstanceNum += n_new;
+    std::vector<std::vector<int>> out;
+    for (size_t f = 0; f < frames.size(); f++) out.emplace_back(assoc.begin() + start[f], assoc.begin() + start[f + 1]);
+    return out;
+  }
+  int CreateInstance() { return miInstanceNum++; }
+ private:
+  Context &ctx_; int miInstanceNum = 0;
+};
+
 #ifdef ESLAM_HAVE_EIGEN_OPENCV
 // ellipsoid_pod -> the reference's g2o::ellipsoid (or any type with fromVector(Vector10d), prob, miLabel, miInstanceID)
 template <class EllipsoidT> EllipsoidT to_reference(const ellipsoid_pod &p) {

@@ -12,7 +12,7 @@ int main() {
   double bb[4] = {50, 50, 300, 300};
   if (eslam_calibrate_measurement(&p, &c, bb) != 0) return 3;
   bool threw = false;
-  try { EllipsoidSLAM::Context ctx(p, c, 0); EllipsoidSLAM::EllipsoidExtractor ex(ctx); EllipsoidSLAM::PlaneExtractor pe(ctx); EllipsoidSLAM::Optimizer op(ctx); EllipsoidSLAM::Initializer in(ctx, 480, 640); (void)ex; (void)pe; (void)op; (void)in; }
+  try { EllipsoidSLAM::Context ctx(p, c, 0); EllipsoidSLAM::EllipsoidExtractor ex(ctx); EllipsoidSLAM::PlaneExtractor pe(ctx); EllipsoidSLAM::Optimizer op(ctx); EllipsoidSLAM::Initializer in(ctx, 480, 640); EllipsoidSLAM::DataAssociationSolver da(ctx); (void)ex; (void)pe; (void)op; (void)in; (void)da; }
   catch (const std::exception &e) { threw = true; std::printf("no device: %s\n", e.what()); }
   std::printf("adapter ok (device %s)\n", threw ? "absent" : "present");
   return 0;
