@@ -787,6 +787,13 @@ int eslam_optimize_objects_host(EslamHandle *h, const EslamEdgeBatch *g, int ite
   return graph_optimize(h, iters, ell, stats, h->stream);
 }
 
+// test hook (not in eslam.h): out2 = { ordered sum as the LM kernels compute it (32 terms per step), the plain one-by-one loop }
+int eslam_debug_ordered_sum(EslamHandle *h, int n, const double *v, double acc, double out2[2]) {
+  if (!h || !out2) return ESLAM_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  return graph_debug_ordered_sum(h, h->stream, n, v, acc, out2);
+}
+
 int eslam_associate_frames_host(EslamHandle *h, int n_frames, const int *det_start, const double *Twc7, int n_det, const double *det_pose7_cam, const int *valid,
                                 int n_map, const double *map_center3, int first_new_instance, int *assoc_out, int *n_new_out) {
   if (!h || !det_start || !Twc7 || !assoc_out || !n_new_out || (n_det > 0 && (!det_pose7_cam || !valid)) || (n_map > 0 && !map_center3)) return ESLAM_ERR_BAD_ARG;

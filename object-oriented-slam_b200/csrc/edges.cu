@@ -156,6 +156,26 @@ __global__ void lm_decide_kernel(LmState *st, const double *chi2, int n_edges, c
   if (accepted) for (int i = threadIdx.x; i < 10 * n_obj; i += 32) ell[i] = ell_trial[i];
 }
 
+// test hook: out[0] = warp_ordered_sum, out[1] = the plain one-by-one loop, of the same device array
+__global__ void ordered_sum_test_kernel(const double *v, int n, double acc, double *out) {
+  const double a = warp_ordered_sum(v, n, acc), b = warp_ordered_sum_plain(v, n, acc);
+  if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+int graph_debug_ordered_sum(EslamHandle *h, cudaStream_t s, int n, const double *v_host, double acc, double out2[2]) {
+  if (n < 0 || (n > 0 && !v_host)) return ESLAM_ERR_BAD_ARG;
+  DevBuf buf;
+  ESLAM_CUDA_OK(h, buf.reserve((size_t)(n + 2) * 8 + 16));
+  double *d = buf.as<double>();
+  if (n > 0) ESLAM_CUDA_OK(h, cudaMemcpyAsync(d + 2, v_host, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+  ordered_sum_test_kernel<<<1, 32, 0, s>>>(d + 2, n, acc, d);
+  ESLAM_LAUNCHED(h);
+  cudaError_t e = cudaMemcpyAsync(out2, d, 16, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  buf.release();
+  ESLAM_CUDA_OK(h, e);
+  return ESLAM_OK;
+}
+
 static int upload(EslamHandle *h, DevBuf &buf, const void *src, size_t bytes, cudaStream_t s) {
   ESLAM_CUDA_OK(h, buf.reserve(bytes ? bytes : 8));
   if (bytes) ESLAM_CUDA_OK(h, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, s));

@@ -51,27 +51,90 @@ static __device__ void edge_error(int type, const se3 &Tcw, const ellipsoid &obj
   }
 }
 
-// sequential (graph-order) sum acc + v[0] + v[1] + ... by one warp: the lanes stage 256 values in shared memory (coalesced, the
-// next chunk already in flight), lane 0 adds them strictly in order.  Every lane returns the same value.
+// Sequential (graph-order) sum acc + v[0] + v[1] + ... by one warp, 256 (or 32) terms per step, BIT-IDENTICAL to the one-by-one loop
+// (g2o's activeChi2: `chi += e->chi2()` over the active edges) -- every lane returns the same value.
+// While the running sum s stays inside one binade [2^e, 2^(e+1)) its ulp u is fixed and s = S u with an integer S; a term
+// c >= 0 is c = (q + f) u with an integer q and 0 <= f < 1, and RN(s + c) = (S + q + [f > 1/2]) u: the rounding of each step depends
+// on the term alone (ties f = 1/2 excepted, where it depends on the parity of S + q).  So the increments d = q + [f > 1/2] of a block of terms are
+// computed independently, added up with an integer warp reduction, and the result is exact provided no term is a tie, negative,
+// subnormal, non-finite or above the binade, and S + sum d stays below 2^53 (no carry into the next binade at any prefix, because
+// the increments are non-negative).  A step that fails any of these runs the plain 32-step loop instead -- in a chi-square sum of
+// 25 000 edges that is the ~20 steps in which the sum crosses a power of two.
+// increment of the integer mantissa S of a running sum in binade `es` (biased exponent) by the term c; ok = false where the term does
+// not allow the shortcut (negative, subnormal, non-finite, above the binade, or a tie)
+__device__ __forceinline__ unsigned long long ordered_sum_inc(int es, double c, bool &ok) {
+  const unsigned long long kMant = (1ull << 52) - 1ull;
+  if (c == 0.0) return 0ull;                                     // +-0 adds nothing
+  const unsigned long long cb = (unsigned long long)__double_as_longlong(c);
+  const int ec = (int)((cb >> 52) & 0x7ffull);
+  const int shift = es - ec;
+  if ((cb >> 63) != 0ull || ec == 0 || ec == 0x7ff || shift < 0) { ok = false; return 0ull; }
+  if (shift >= 54) return 0ull;                                  // c < u / 2: the sum does not move
+  const unsigned long long mc = (cb & kMant) | (1ull << 52);
+  if (shift == 0) return mc;
+  const unsigned long long q = mc >> shift, f = mc & ((1ull << shift) - 1ull), half = 1ull << (shift - 1);
+  if (f == half) { ok = false; return 0ull; }                    // tie: round-to-even needs the running parity
+  return q + (f > half ? 1ull : 0ull);
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+// s <- s + (terms whose increments add up to `total`) when that stays inside the binade; false otherwise (s untouched)
+__device__ __forceinline__ bool ordered_sum_commit(double &s, unsigned long long total) {
+  const unsigned long long kMant = (1ull << 52) - 1ull;
+  const unsigned long long sb = (unsigned long long)__double_as_longlong(s);
+  const unsigned long long ms = (sb & kMant) | (1ull << 52);
+  if (total >= (1ull << 53) || ms + total >= (1ull << 53)) return false;
+  s = __longlong_as_double((long long)((sb & ~kMant) | ((ms + total) & kMant)));
+  return true;
+}
 static __device__ double warp_ordered_sum(const double *v, int n, double acc = 0.0) {
-  __shared__ double stage[256];
-  int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  double s = acc;
   double nxt[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) nxt[j] = (j * 32 + lane < n) ? v[j * 32 + lane] : 0.0;
   for (int base = 0; base < n; base += 256) {
+    double cur[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) stage[j * 32 + lane] = nxt[j];
-    __syncwarp();
-    int nb = base + 256;
+    for (int j = 0; j < 8; j++) cur[j] = nxt[j];
+    const int nb = base + 256;
 #pragma unroll
-    for (int j = 0; j < 8; j++) nxt[j] = (nb + j * 32 + lane < n) ? v[nb + j * 32 + lane] : 0.0;
-    if (lane == 0) {
-      int cnt = min(256, n - base);
-      for (int k = 0; k < cnt; k++) acc += stage[k];
+    for (int j = 0; j < 8; j++) nxt[j] = (nb + j * 32 + lane < n) ? v[nb + j * 32 + lane] : 0.0;   // the next 256 terms are in flight during this block
+    // (1) the whole block of 256 terms at once (term j * 32 + lane of the block sits in cur[j] of this lane; missing terms are +0)
+    {
+      const unsigned long long sb = (unsigned long long)__double_as_longlong(s);
+      const int es = (int)((sb >> 52) & 0x7ffull);
+      bool ok = (sb >> 63) == 0ull && es > 0 && es < 0x7ff;   // s positive and normal
+      unsigned long long dsum = 0ull;
+      if (ok) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) dsum += ordered_sum_inc(es, cur[j], ok);
+      }
+      if (__all_sync(0xffffffffu, ok) && ordered_sum_commit(s, warp_sum_u64(dsum))) continue;
     }
-    __syncwarp();
+    // (2) 32 terms at a time, (3) one by one
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+      const int cnt = min(32, n - (base + j * 32));
+      if (cnt <= 0) break;
+      const double c = cur[j];
+      const unsigned long long sb = (unsigned long long)__double_as_longlong(s);
+      const int es = (int)((sb >> 52) & 0x7ffull);
+      bool ok = (sb >> 63) == 0ull && es > 0 && es < 0x7ff;
+      unsigned long long d = 0ull;
+      if (ok) d = ordered_sum_inc(es, c, ok);
+      if (__all_sync(0xffffffffu, ok) && ordered_sum_commit(s, warp_sum_u64(d))) continue;
+      for (int k = 0; k < cnt; k++) s += __shfl_sync(0xffffffffu, c, k);
+    }
   }
+  return s;
+}
+// the plain loop (A/B baseline and checker of the routine above)
+static __device__ double warp_ordered_sum_plain(const double *v, int n, double acc = 0.0) {
+  if ((threadIdx.x & 31) == 0) for (int k = 0; k < n; k++) acc += v[k];
   return __shfl_sync(0xffffffffu, acc, 0);
 }
 

@@ -14,6 +14,7 @@ int graph_eval(EslamHandle *h, cudaStream_t s, bool jac);
 int graph_download(EslamHandle *h, double *res, double *jac, double *chi2, cudaStream_t s);
 int graph_optimize(EslamHandle *h, int iters, double *ell_inout, EslamLmStats *stats, cudaStream_t s);
 void graph_free(EslamHandle *h);
+int graph_debug_ordered_sum(EslamHandle *h, cudaStream_t s, int n, const double *v_host, double acc, double out2[2]);   // test hook
 
 // slam.cu (SLAM mode: free poses + odometry edges)
 int slam_optimize(EslamHandle *h, const EslamEdgeBatch *g, const double *odom_meas7, double odom_info, int iters, double *ell_inout, double *Tcw_out,

@@ -1128,6 +1128,7 @@ constexpr int kRoundCap = 256;                                        // clouds 
 constexpr int kSeedPersist = (int)((sizeof(SeedCore) + 2 * sizeof(unsigned[2][2][kRoundCap / 32]) + 15) & ~(size_t)15);
 constexpr int kSeedStride = (kSeedPersist + 127) / 128 * 128;          // whole 128-byte lines per seed: an object's state can be dropped from L2 line by line
 constexpr size_t kRoundCacheBytes = (size_t)kRoundCap * 64;           // per seed: one NN bank + the pixel cache, 2 * CAP entries of 16 bytes each
+constexpr int kGraphAtFirstSight = 64;                                // chunks of this many objects are captured into a graph on their first call
 constexpr int kRoundsMinObjects = 16;                                  // smaller launches take the single-launch kernel
 constexpr int kStepThreadsDefault = 128;                              // eight lanes per seed: 16 seeds per CTA (one-warp CTAs that slip in beside three resident compute CTAs were measured: no gain)
 static_assert(sizeof(SeedCore) % 16 == 0, "SeedCore is followed by the masks without padding");
@@ -1542,13 +1543,17 @@ static int symmetry_rounds_launch(EslamHandle *h, cudaStream_t s, const uint16_t
   };
   bool replayed = false;
   if (h->sym_graph) {   // the sequence depends on (n_obj, rounds) and two fixed addresses only: capture once per chunk, replay afterwards
-    // captured on the second consecutive call with the same shape (a frame stream in fixed batches); a caller whose batches change
-    // from call to call (the per-frame tracking driver: 1..8 boxes) keeps plain launches instead of paying an instantiation per call
+    // small launches are captured on the second consecutive call with the same shape; a caller whose small batches change from call
+    // to call keeps plain launches instead of paying an instantiation per call (the per-frame tracking driver, 1..8 boxes, does not
+    // come here at all: fewer than 16 objects take the single-launch kernel)
     ExtractWorkspace::SymGraph &g = w.symgraph[chunk];
     const bool same = g.n_obj == n_obj && g.rounds == rounds && g.verify == variant + 8 * step_threads && g.desc == dev && g.live == d.live;
     if (g.exec && !same) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     if (!same) { g.n_obj = n_obj; g.rounds = rounds; g.verify = variant + 8 * step_threads; g.desc = dev; g.live = d.live; }
-    if ((same || h->profiling) && !g.exec) {   // (a profiled batch is timed: it never pays for plain launches of a sequence this long)
+    // (a profiled batch is timed: it never pays for plain launches of a sequence this long; a chunk of a streamed batch -- 64 objects
+    // and more -- is expected to come back with the same shape, so its graph is instantiated at first sight: with two workspaces in
+    // flight the "second call" of the second workspace would otherwise land ~10 ms of instantiation in the caller's steady state)
+    if ((same || h->profiling || n_obj >= kGraphAtFirstSight) && !g.exec) {
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
         const cudaError_t e1 = issue(s);

@@ -539,6 +539,27 @@ def test_symmetry_cloud_sizes_beyond_the_small_instantiation(grid, lo, hi):
     assert not msgs, "\n".join(msgs)
 
 
+def test_ordered_sum_in_steps_of_32_is_bit_identical_to_the_plain_loop(handle):
+    """The chi-square sums of the LM kernels (g2o's activeChi2 order) run 32 terms per step by exact integer arithmetic inside a
+    binade and fall back to the plain loop at ties, binade crossings and odd values: same bits as one-by-one fp64 addition."""
+    import ctypes as C
+    rng = np.random.default_rng(0)
+    cases = [rng.exponential(20.0, 25050) ** 2, 10.0 ** rng.uniform(-30, 30, 5000), np.r_[1.0, [2.0 ** -53] * 40, [2.0 ** -52] * 40, [1.5 * 2.0 ** -53] * 40, rng.exponential(1e-15, 500)],
+             np.r_[rng.exponential(5.0, 100), -1.0, rng.exponential(5.0, 100), 5e-324, np.inf], np.zeros(70), np.array([]), rng.exponential(1.0, 31), np.abs(rng.normal(size=4000)) * 2.0 ** rng.integers(-60, 60, 4000)]
+    for k, v in enumerate(cases):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        for acc in (0.0, 3.7):
+            out = (C.c_double * 2)()
+            rc = handle.lib.eslam_debug_ordered_sum(handle._h, C.c_int(len(v)), v.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(acc), out)
+            assert rc == 0
+            ref = np.float64(acc)
+            with np.errstate(all="ignore"):
+                for x in v:
+                    ref = np.float64(ref + x)
+            a, b = np.float64(out[0]), np.float64(out[1])
+            assert a.tobytes() == b.tobytes() == np.float64(ref).tobytes() or (np.isnan(a) and np.isnan(b) and np.isnan(ref)), (k, acc, a, b, ref)
+
+
 # ------------------------------------------------------------------ C++ host adapter on the device
 def test_cpp_adapter_end_to_end(tmp_path):
     """host/eslam_adapter.hpp (reference-named C++ classes over the C-ABI) run end to end on the device -- ground plane, one local
